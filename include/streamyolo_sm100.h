@@ -1,0 +1,164 @@
+/*
+ * libstreamyolo_sm100.so -- C ABI of the B200-native StreamYOLO hot path.
+ *
+ * This is the drop-in boundary of SURVEY.md section 8(b): plain `extern "C"` entry
+ * points, raw device pointers + sizes + a cudaStream_t, no torch types.  The host
+ * side (streamyolo_b200/model/*.py, a mirror of the reference's exps/model API)
+ * binds them with ctypes; INTEGRATION.md shows the stub a reference maintainer adds.
+ *
+ * Conventions
+ *   - every function is asynchronous on `stream`, re-entrant, allocates nothing,
+ *     never synchronises the device and never throws; it returns 0 or an SY_E*
+ *     status and `sy_last_error_string()` describes the last failure of the
+ *     calling thread.  The caller owns every buffer (PyTorch caching allocator).
+ *   - activations are NHWC bf16 "views" (SyTensor): pixel (n,y,x) channel c lives
+ *     at ptr + (((n*h + y)*w + x)*pitch + c) elements; pitch >= c lets a view be
+ *     a channel slice of a wider concat buffer (pitch, slice offsets and c are
+ *     multiples of 8 so that every pixel row is 16-byte aligned).
+ *   - conv weights are bf16, packed [Cout][kh*kw][Cin] (K-major GEMM B operand).
+ *   - the library requires an sm_100a device; there is no other code path.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to
+ * /root/reference; "[yolox]" = the un-vendored yolox==0.3.0 dependency).
+ */
+#ifndef STREAMYOLO_SM100_H_
+#define STREAMYOLO_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* sy_stream_t; /* == cudaStream_t */
+
+enum {
+  SY_OK = 0,
+  SY_EINVAL = 1,   /* bad shape / alignment / null pointer */
+  SY_EARCH = 2,    /* device is not sm_100 */
+  SY_ELAUNCH = 3,  /* CUDA launch or driver error (see sy_last_error_string) */
+  SY_EWORKSPACE = 4
+};
+
+typedef struct {
+  void* ptr;      /* bf16 */
+  int32_t n, h, w, c;
+  int64_t pitch;  /* elements between consecutive pixels */
+} SyTensor;
+
+/* -------- runtime ---------------------------------------------------------- */
+const char* sy_last_error_string(void);
+int sy_version(void);
+/* 0 when the current device is sm_100 and the driver exposes cuTensorMapEncodeTiled. */
+int sy_check_device(void);
+
+/* -------- convolution (replaces [yolox] BaseConv.conv / nn.Conv2d, e.g.
+ * exps/model/darknet.py:115-165, exps/model/dfp_pafpn.py:33-105,
+ * exps/model/tal_head.py:55-104) ------------------------------------------------- */
+enum { SY_CONV_RAW = 0, SY_CONV_FUSED = 1 };
+
+typedef struct {
+  SyTensor x;            /* input  */
+  SyTensor y;            /* output: RAW -> conv result; FUSED -> silu(acc*scale+shift)(+res) */
+  const void* w;         /* bf16 [Cout][k*k][Cin] */
+  int32_t ksize;         /* 1 or 3, padding (k-1)/2 */
+  int32_t stride;        /* 1 or 2 */
+  int32_t mode;          /* SY_CONV_RAW / SY_CONV_FUSED */
+  int32_t act;           /* FUSED: 1 = SiLU, 0 = identity */
+  const float* scale;    /* FUSED: [Cout] (folded BatchNorm), may be NULL = 1 */
+  const float* shift;    /* FUSED: [Cout], may be NULL = 0 */
+  SyTensor res;          /* FUSED: optional residual added after the activation (ptr NULL = none) */
+  float* stat_partials;  /* RAW: [P][2][Cout] per-tile (sum, sum of squares) of the STORED bf16 values, or NULL */
+  int32_t n_partials;    /* out-capacity check: must be >= sy_conv_num_partials() */
+} SyConvDesc;
+
+/* Number of statistic partial rows (P) the tensor-core kernel writes for an output of
+ * n x ho x wo; rows are image-major, so rows [0, split_n * P/n) belong to images < split_n. */
+int sy_conv_num_partials(int32_t n, int32_t ho, int32_t wo);
+/* tcgen05 implicit-GEMM kernel (TMA -> smem -> UMMA -> TMEM -> epilogue). */
+int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream);
+/* plain CUDA-core direct convolution with the same contract (no stat partials):
+ * device-side cross-check of the tensor-core kernel and the path for shapes it rejects. */
+int sy_conv2d_simt(const SyConvDesc* d, sy_stream_t stream);
+
+/* Focus stem: [yolox] Focus (space-to-depth, TL/BL/TR/BR) + 3x3 conv, used at
+ * exps/model/darknet.py:115.  x is the NCHW float32 frame-pair batch [b,6,h,w]
+ * (exps/model/dfp_pafpn.py:120,145 split it); image n of y takes frame n / b
+ * (0 = current, 1 = support) of batch element n % b.  y is the RAW conv output
+ * [frames*b, h/2, w/2, cout]; w is bf16 [cout][9][12]. */
+int sy_stem_focus_conv(const float* x, int32_t b, int32_t in_ch, int32_t h, int32_t w_px, int32_t frames,
+                       const void* w, SyTensor y, sy_stream_t stream);
+
+/* -------- BatchNorm (train mode) + SiLU (replaces nn.BatchNorm2d + nn.SiLU inside
+ * [yolox] BaseConv; eps/momentum from cfgs/s_s50_onex_dfp_tal_flip.py:40-44) ---------- */
+/* Per-(row-chunk, channel) partial sums of a stored tensor: partials [P][2][c],
+ * P = sy_stats_num_partials(n, h*w) image-major. */
+int sy_stats_num_partials(int32_t n, int32_t hw);
+int sy_channel_stats(SyTensor x, float* partials, int32_t n_partials, sy_stream_t stream);
+/* Reduce partials per group (group 0 = partial rows [0,p_split), group 1 = the rest;
+ * the two frames of a pair are normalised separately, exps/model/dfp_pafpn.py:120,145),
+ * update running statistics sequentially group 0 then group 1 (unbiased variance,
+ * momentum) and emit scale/shift [groups][c] with y = x*scale + shift. */
+int sy_bn_finalize(const float* partials, int32_t n_partials, int32_t p_split, int32_t groups,
+                   int64_t count_per_group, int32_t c,
+                   const float* gamma, const float* beta, float* running_mean, float* running_var,
+                   int64_t* num_batches_tracked, float momentum, float eps,
+                   float* scale_out, float* shift_out, sy_stream_t stream);
+/* y = act(x*scale[g]+shift[g]) (+ res), g = (image >= split_n); single bf16 rounding. */
+int sy_bn_act_apply(SyTensor x, const float* scale, const float* shift, int32_t split_n, int32_t act,
+                    SyTensor res, SyTensor y, sy_stream_t stream);
+
+/* -------- glue ------------------------------------------------------------- */
+/* F.interpolate(mode="nearest", size=) of exps/model/dfp_pafpn.py:125,130 into a channel
+ * slice; index rule src = min(floor(dst * (float)in/out), in-1) evaluated in float32. */
+int sy_upsample_nearest(SyTensor x, SyTensor y, sy_stream_t stream);
+/* [yolox] SPPBottleneck pooling (exps/model/darknet.py:156): y5,y9,y13 = stride-1
+ * same-padded max pools (k = 5, 9, 13; -inf padding) of x. */
+int sy_spp_maxpool(SyTensor x, SyTensor y5, SyTensor y9, SyTensor y13, sy_stream_t stream);
+/* strided copy of a view (used for 3-channel duplicates and buffers). */
+int sy_copy(SyTensor x, SyTensor y, sy_stream_t stream);
+
+/* -------- head: prediction convs + decode (exps/model/tal_head.py:105-131,167-171,
+ * 174,197-199,225-260) ------------------------------------------------------------ */
+typedef struct {
+  SyTensor cls_feat, reg_feat;   /* [b, h, w, c] */
+  const float* w_reg; const float* b_reg;   /* [4][c], [4]  */
+  const float* w_obj; const float* b_obj;   /* [1][c], [1]  */
+  const float* w_cls; const float* b_cls;   /* [ncls][c], [ncls] */
+  int32_t num_classes;
+  int32_t stride;          /* 8 / 16 / 32 */
+  int32_t anchor_offset;   /* first anchor row of this level in the [b, a_total, 5+ncls] output */
+  int32_t a_total;
+  int32_t sigmoid;         /* eval: sigmoid on obj / cls */
+  int32_t decode;          /* xy = (xy + grid) * stride, wh = exp(wh) * stride */
+  float* out;              /* [b, a_total, 5+ncls] float32 */
+  float* origin;           /* [b, a_total, 4] raw reg (tal_head.py:185-194) or NULL */
+} SyHeadPredDesc;
+int sy_head_pred_decode(const SyHeadPredDesc* d, sy_stream_t stream);
+
+/* -------- SimOTA + Trend-Aware loss (exps/model/tal_head.py:262-712) --------- */
+typedef struct {
+  int32_t b, a_total, max_labels, num_classes;
+  int32_t n_levels;
+  int32_t level_h[4], level_w[4], level_stride[4];
+  const float* outputs;    /* [b, a_total, 5+ncls] decoded, logits for obj/cls */
+  const float* origin;     /* [b, a_total, 4] raw reg */
+  const float* labels_fut; /* [b, max_labels, 5] (cls, cx, cy, w, h) */
+  const float* labels_cur; /* [b, max_labels, 5] */
+  float gamma, ignore_thr, ignore_value;
+  int32_t use_l1;
+  void* workspace; size_t workspace_bytes;   /* >= sy_tal_loss_workspace_bytes() */
+  float* loss_out;         /* [6]: total, 5*iou, obj(conf), cls, l1, num_fg / max(num_gt, 1) */
+  /* optional dumps for tests / backward: */
+  int32_t* fg_out;         /* [b, a_total] 0/1 or NULL */
+  int32_t* matched_out;    /* [b, a_total] gt index or -1, or NULL */
+  float* pred_iou_out;     /* [b, a_total] or NULL */
+} SyTalLossDesc;
+size_t sy_tal_loss_workspace_bytes(int32_t b, int32_t a_total, int32_t max_labels, int32_t num_classes);
+int sy_tal_loss(const SyTalLossDesc* d, sy_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STREAMYOLO_SM100_H_ */

@@ -1,0 +1,73 @@
+"""Build libstreamyolo_sm100.so in-tree with nvcc (sm_100a only, cross-compiles without a GPU).
+
+    python -m streamyolo_b200.build [--force]
+
+The .so lands in streamyolo_b200/lib/ (git-ignored, travels to the GPU box with gpurun).
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libstreamyolo_sm100.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+          "--use_fast_math=false" if False else "-DSY_BUILD", "-Xptxas", "-v"]
+# per-file extra flags: the loss/decode unit must evaluate reference expressions without FMA contraction
+SOURCES = {
+    "api.cu": [],
+    "conv_tc.cu": [],
+    "conv_simt.cu": [],
+    "bn_glue.cu": [],
+    "head_loss.cu": ["-fmad=false"],
+}
+
+
+def _digest():
+    h = hashlib.sha256()
+    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+        for f in sorted(os.listdir(root)):
+            with open(os.path.join(root, f), "rb") as fh:
+                h.update(f.encode())
+                h.update(fh.read())
+    h.update(" ".join(COMMON).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(LIBDIR, exist_ok=True)
+    stamp = os.path.join(LIBDIR, "build.stamp")
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return LIB
+    objs = []
+    log = []
+    for src, extra in SOURCES.items():
+        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        cmd = [NVCC] + COMMON + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log.append(f"$ {' '.join(cmd)}\n{r.stdout}{r.stderr}")
+        if r.returncode != 0:
+            sys.stderr.write(log[-1])
+            raise RuntimeError(f"nvcc failed on {src}")
+        objs.append(obj)
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log.append(f"$ {' '.join(cmd)}\n{r.stdout}{r.stderr}")
+    if r.returncode != 0:
+        sys.stderr.write(log[-1])
+        raise RuntimeError("link failed")
+    with open(os.path.join(LIBDIR, "build.log"), "w") as fh:
+        fh.write("\n".join(log))
+    with open(stamp, "w") as fh:
+        fh.write(dig)
+    if verbose:
+        print("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,227 @@
+// BatchNorm(train) finalize / apply+SiLU, nearest upsample, SPP max pools, strided copy:
+// vectorised (16-byte) HBM-bound kernels over NHWC bf16 views.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace sy {
+
+// thread = channel.  Deterministic: partial rows are summed in index order in fp64.
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int P, int p_split, int groups,
+                                   double count, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean, float* running_var,
+                                   long long* nbt, float momentum, float eps, float* scale_out, float* shift_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt != nullptr) *nbt += groups;
+  if (c >= C) return;
+  float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 1.f;
+  for (int g = 0; g < groups; ++g) {
+    const int pa = (g == 0) ? 0 : p_split, pb = (g == 0 && groups > 1) ? p_split : P;
+    double s1 = 0.0, s2 = 0.0;
+    for (int q = pa; q < pb; ++q) {
+      s1 += (double)partials[(size_t)q * 2 * C + c];
+      s2 += (double)partials[(size_t)q * 2 * C + C + c];
+    }
+    const double mean = s1 / count;
+    double var = s2 / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float sc = gamma[c] * (float)(1.0 / sqrt(var + (double)eps));
+    scale_out[g * C + c] = sc;
+    shift_out[g * C + c] = beta[c] - (float)mean * sc;
+    const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
+    rm = (1.f - momentum) * rm + momentum * (float)mean;
+    rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+  }
+  if (running_mean) running_mean[c] = rm;
+  if (running_var) running_var[c] = rv;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+__global__ void bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, long long split_pix, int act,
+                                    const __nv_bfloat16* res, long long rp, __nv_bfloat16* y, long long yp,
+                                    long long npix, int C) {
+  const int G = C / 8;
+  const long long total = npix * G;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    const long long pix = idx / G;
+    const int grp = pix >= split_pix ? 1 : 0;
+    float f[8], r[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + pix * xp + g * 8), f);
+    const float4 s0 = *reinterpret_cast<const float4*>(scale + grp * C + g * 8);
+    const float4 s1 = *reinterpret_cast<const float4*>(scale + grp * C + g * 8 + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(shift + grp * C + g * 8);
+    const float4 h1 = *reinterpret_cast<const float4*>(shift + grp * C + g * 8 + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t = f[i] * sc[i] + sh[i];
+      f[i] = act ? silu_f(t) : t;
+    }
+    if (res != nullptr) {
+      unpack8(*reinterpret_cast<const uint4*>(res + pix * rp + g * 8), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += r[i];
+    }
+    *reinterpret_cast<uint4*>(y + pix * yp + g * 8) = pack8(f);
+  }
+}
+
+// PyTorch legacy "nearest": src = min((int)floorf(dst * scale), in - 1), scale = (float)in / out
+__global__ void upsample_nearest_kernel(const __nv_bfloat16* __restrict__ x, long long xp, int N, int Hi, int Wi,
+                                        __nv_bfloat16* y, long long yp, int Ho, int Wo, int C) {
+  const int G = C / 8;
+  const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+  const long long total = (long long)N * Ho * Wo * G;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    const long long pix = idx / G;
+    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho);
+    const int n = (int)(pix / ((long long)Wo * Ho));
+    const int iy = min((int)floorf(__fmul_rn((float)oy, sh)), Hi - 1);
+    const int ix = min((int)floorf(__fmul_rn((float)ox, sw)), Wi - 1);
+    const uint4 v = *reinterpret_cast<const uint4*>(x + (((long long)n * Hi + iy) * Wi + ix) * xp + g * 8);
+    *reinterpret_cast<uint4*>(y + pix * yp + g * 8) = v;
+  }
+}
+
+__device__ __forceinline__ void max8(float* m, const float* f) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], f[i]);
+}
+
+// stride-1 same-padded max pools k=5,9,13 (-inf padding): nested windows, one pass
+__global__ void spp_maxpool_kernel(const __nv_bfloat16* __restrict__ x, long long xp, int N, int H, int W, int C,
+                                   __nv_bfloat16* y5, long long p5, __nv_bfloat16* y9, long long p9,
+                                   __nv_bfloat16* y13, long long p13) {
+  const int G = C / 8;
+  const long long total = (long long)N * H * W * G;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    const long long pix = idx / G;
+    const int ox = (int)(pix % W), oy = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    float m5[8], m9[8], m13[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m5[i] = m9[i] = m13[i] = -INFINITY;
+    for (int dy = -6; dy <= 6; ++dy) {
+      const int iy = oy + dy;
+      if (iy < 0 || iy >= H) continue;
+      for (int dx = -6; dx <= 6; ++dx) {
+        const int ix = ox + dx;
+        if (ix < 0 || ix >= W) continue;
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(x + (((long long)n * H + iy) * W + ix) * xp + g * 8), f);
+        max8(m13, f);
+        const int ad = max(abs(dy), abs(dx));
+        if (ad <= 4) max8(m9, f);
+        if (ad <= 2) max8(m5, f);
+      }
+    }
+    *reinterpret_cast<uint4*>(y5 + pix * p5 + g * 8) = pack8(m5);
+    *reinterpret_cast<uint4*>(y9 + pix * p9 + g * 8) = pack8(m9);
+    *reinterpret_cast<uint4*>(y13 + pix * p13 + g * 8) = pack8(m13);
+  }
+}
+
+__global__ void copy_kernel(const __nv_bfloat16* __restrict__ x, long long xp, __nv_bfloat16* y, long long yp,
+                            long long npix, int C) {
+  const int G = C / 8;
+  const long long total = npix * G;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    const long long pix = idx / G;
+    *reinterpret_cast<uint4*>(y + pix * yp + g * 8) = *reinterpret_cast<const uint4*>(x + pix * xp + g * 8);
+  }
+}
+
+static inline int grid_for(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace sy
+
+using namespace sy;
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" int sy_bn_finalize(const float* partials, int32_t n_partials, int32_t p_split, int32_t groups,
+                              int64_t count_per_group, int32_t c, const float* gamma, const float* beta,
+                              float* running_mean, float* running_var, int64_t* nbt, float momentum, float eps,
+                              float* scale_out, float* shift_out, sy_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SY_REQUIRE(partials && gamma && beta && scale_out && shift_out, SY_EINVAL, "bn_finalize: null pointer");
+  SY_REQUIRE(groups == 1 || groups == 2, SY_EINVAL, "bn_finalize: groups=%d", groups);
+  SY_REQUIRE(n_partials > 0 && count_per_group > 0 && c > 0, SY_EINVAL, "bn_finalize: empty input");
+  SY_REQUIRE(groups == 1 || (p_split > 0 && p_split < n_partials), SY_EINVAL, "bn_finalize: p_split=%d of %d", p_split,
+             n_partials);
+  bn_finalize_kernel<<<cdiv(c, 128), 128, 0, stream>>>(partials, n_partials, p_split, groups, (double)count_per_group, c,
+                                                       gamma, beta, running_mean, running_var,
+                                                       reinterpret_cast<long long*>(nbt), momentum, eps, scale_out,
+                                                       shift_out);
+  return launch_status("bn_finalize_kernel");
+}
+
+extern "C" int sy_bn_act_apply(SyTensor x, const float* scale, const float* shift, int32_t split_n, int32_t act,
+                               SyTensor res, SyTensor y, sy_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SY_REQUIRE(view_ok(x) && view_ok(y) && scale && shift, SY_EINVAL, "bn_act_apply: bad view");
+  SY_REQUIRE(x.n == y.n && x.h == y.h && x.w == y.w && x.c == y.c, SY_EINVAL, "bn_act_apply: x/y shape mismatch");
+  SY_REQUIRE(((uintptr_t)scale % 16) == 0 && ((uintptr_t)shift % 16) == 0, SY_EINVAL, "bn_act_apply: scale/shift alignment");
+  const __nv_bfloat16* rp = nullptr;
+  long long rpitch = 0;
+  if (res.ptr) {
+    SY_REQUIRE(view_ok(res) && res.n == x.n && res.h == x.h && res.w == x.w && res.c == x.c, SY_EINVAL,
+               "bn_act_apply: residual mismatch");
+    rp = CBF(res.ptr); rpitch = res.pitch;
+  }
+  const long long npix = (long long)x.n * x.h * x.w;
+  const long long split_pix = (long long)split_n * x.h * x.w;
+  bn_act_apply_kernel<<<grid_for(npix * (x.c / 8), 256), 256, 0, stream>>>(CBF(x.ptr), x.pitch, scale, shift, split_pix,
+                                                                           act, rp, rpitch, BF(y.ptr), y.pitch, npix, x.c);
+  return launch_status("bn_act_apply_kernel");
+}
+
+extern "C" int sy_upsample_nearest(SyTensor x, SyTensor y, sy_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SY_REQUIRE(view_ok(x) && view_ok(y) && x.n == y.n && x.c == y.c, SY_EINVAL, "upsample: bad views");
+  const long long total = (long long)y.n * y.h * y.w * (y.c / 8);
+  upsample_nearest_kernel<<<grid_for(total, 256), 256, 0, stream>>>(CBF(x.ptr), x.pitch, x.n, x.h, x.w, BF(y.ptr),
+                                                                    y.pitch, y.h, y.w, x.c);
+  return launch_status("upsample_nearest_kernel");
+}
+
+extern "C" int sy_spp_maxpool(SyTensor x, SyTensor y5, SyTensor y9, SyTensor y13, sy_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SY_REQUIRE(view_ok(x) && view_ok(y5) && view_ok(y9) && view_ok(y13), SY_EINVAL, "spp: bad views");
+  SY_REQUIRE(y5.c == x.c && y9.c == x.c && y13.c == x.c && y5.h == x.h && y5.w == x.w && y5.n == x.n, SY_EINVAL,
+             "spp: shape mismatch");
+  const long long total = (long long)x.n * x.h * x.w * (x.c / 8);
+  spp_maxpool_kernel<<<grid_for(total, 128), 128, 0, stream>>>(CBF(x.ptr), x.pitch, x.n, x.h, x.w, x.c, BF(y5.ptr),
+                                                               y5.pitch, BF(y9.ptr), y9.pitch, BF(y13.ptr), y13.pitch);
+  return launch_status("spp_maxpool_kernel");
+}
+
+extern "C" int sy_copy(SyTensor x, SyTensor y, sy_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SY_REQUIRE(view_ok(x) && view_ok(y) && x.n == y.n && x.h == y.h && x.w == y.w && x.c == y.c, SY_EINVAL,
+             "copy: view mismatch");
+  const long long npix = (long long)x.n * x.h * x.w;
+  copy_kernel<<<grid_for(npix * (x.c / 8), 256), 256, 0, stream>>>(CBF(x.ptr), x.pitch, BF(y.ptr), y.pitch, npix, x.c);
+  return launch_status("copy_kernel");
+}

@@ -1,0 +1,60 @@
+// Shared helpers for libstreamyolo_sm100 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/streamyolo_sm100.h"
+
+namespace sy {
+
+// thread-local last error text (sy_last_error_string)
+void set_error(const char* fmt, ...);
+
+#define SY_REQUIRE(cond, code, ...)      \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::sy::set_error(__VA_ARGS__);      \
+      return (code);                     \
+    }                                    \
+  } while (0)
+
+#define SY_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      ::sy::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                      __LINE__);                                                        \
+      return SY_ELAUNCH;                                                                \
+    }                                                                                   \
+  } while (0)
+
+inline int launch_status(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+    return SY_ELAUNCH;
+  }
+  return SY_OK;
+}
+
+inline bool view_ok(const SyTensor& t) {
+  return t.ptr != nullptr && t.n > 0 && t.h > 0 && t.w > 0 && t.c > 0 && t.pitch >= t.c &&
+         (t.c % 8) == 0 && (t.pitch % 8) == 0 && ((uintptr_t)t.ptr % 16) == 0;
+}
+
+__host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- bf16 pack helpers -------------------------------------------------------
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);  // .x = a (low half), .y = b
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ float round_bf16(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+
+}  // namespace sy

@@ -1,0 +1,527 @@
+// Implicit-GEMM convolution on the Blackwell tensor cores (sm_100a).
+//
+//   M = output pixels (a TH x TW spatial patch of one image, <= 128 rows)
+//   N = output channels (BN = 32/64/128/256 per tile)
+//   K = taps * Cin, walked as (tap, 64-channel block)
+//
+// Operand movement is im2col-free: for every (tap, channel block) ONE 4-D TMA load
+// brings the shifted input patch [TH][TW][64ch] straight from the NHWC tensor into a
+// 128B-swizzled shared-memory tile (out-of-bounds = zero padding = the conv padding;
+// stride-2 convs use the tensor map's element strides), and one 3-D TMA load brings the
+// [BN][64] weight slab.  A single elected thread issues tcgen05.mma (M=128, N=BN, K=16)
+// with both operands in shared memory and the fp32 accumulator in TMEM (double
+// buffered), so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Warp roles (256 threads, persistent CTA, one per SM):
+//   warp 0   TMA producer          warp 1   MMA issuer       warp 2   TMEM alloc/free
+//   warps 4-7 epilogue: TMEM -> registers -> (BN-stat partials | folded BN + SiLU +
+//             residual) -> bf16 -> shared staging -> coalesced 16B global stores
+//
+// Replaces the cuDNN conv + ATen BN/SiLU triplet behind [yolox] BaseConv
+// (/root/reference/exps/model/darknet.py:115-165, dfp_pafpn.py:33-105, tal_head.py:55-104).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace sy {
+namespace tc {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;              // bf16 elements = one 128-byte swizzle row
+constexpr int kThreads = 256;
+constexpr int kABytes = kBlockM * 128;   // 16 KiB per stage
+constexpr uint64_t kSpinLimit = 6000000000ull;  // ~3 s of SM clocks, then trap instead of hanging
+
+struct Params {
+  int N, Ho, Wo, Cout, Cin;
+  int ksize, stride, pad;
+  int th, tw, tiles_x, tiles_y;
+  int m_tiles, n_tiles, total_tiles;
+  int cblocks, kblocks;
+  int mode, act;
+  __nv_bfloat16* y;
+  long long y_pitch;
+  const __nv_bfloat16* res;
+  long long res_pitch;
+  const float* scale;
+  const float* shift;
+  float* partials;
+};
+
+// ----------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if ((++spins & 1023u) == 0) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if ((unsigned long long)(now - t0) > kSpinLimit) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address      bits [0,14)
+  d |= (uint64_t)0 << 16;                     // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024u >> 4) << 32;          // stride byte offset  bits [32,46)
+  d |= (uint64_t)1 << 46;                     // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                     // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128.
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = (BN == 256) ? 3 : ((BN == 128) ? 5 : 6);
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageCols = (BN < 128) ? BN : 128;          // epilogue staging width
+  static constexpr int kStagePitch = kStageCols * 2 + 16;           // bytes, +16 breaks bank conflicts
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;     // double-buffered accumulator (power of two)
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * (kABytes + kBBytes) + kBlockM * kStagePitch +
+                                    2 * 256 * 4 /*scale,shift*/ + kBlockM * 8 /*row offsets*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  using C = Cfg<BN>;
+  constexpr int S = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + S * kABytes;
+  uint8_t* sStage = sB + S * C::kBBytes;
+  float* sScale = reinterpret_cast<float*>(sStage + kBlockM * C::kStagePitch);
+  float* sShift = sScale + 256;
+  long long* sRowOff = reinterpret_cast<long long*>(sShift + 256);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRowOff + kBlockM);
+  // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, then tmem base slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int taps = p.ksize * p.ksize;
+  const uint32_t a_bytes = (uint32_t)(p.th * p.tw) * 128u;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
+        const int per_img = p.tiles_x * p.tiles_y;
+        const int img = m_tile / per_img, rem = m_tile % per_img;
+        const int y0 = (rem / p.tiles_x) * p.th, x0 = (rem % p.tiles_x) * p.tw;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          const int tap = kb / p.cblocks, cb = kb % p.cblocks;
+          const int r = tap / p.ksize, s = tap % p.ksize;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), a_bytes + (uint32_t)C::kBBytes);
+          tma_load_4d(smem_u32(sA + stage * kABytes), &tmA, full_bar(stage), cb * kBlockK,
+                      x0 * p.stride + s - p.pad, y0 * p.stride + r - p.pad, img);
+          tma_load_3d(smem_u32(sB + stage * C::kBBytes), &tmB, full_bar(stage), cb * kBlockK, tap, n_tile * BN);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint64_t da = make_smem_desc(smem_u32(sA + stage * kABytes));
+          const uint64_t db = make_smem_desc(smem_u32(sB + stage * C::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));            // frees the smem slot when these MMAs retire
+          if (kb == p.kblocks - 1) umma_commit(tfull_bar(acc));
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp & 3;                    // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;             // tile row == TMEM lane
+    const int et = threadIdx.x - 128;          // 0..127
+    const int ty = row / p.tw, tx = row - ty * p.tw;
+    const int per_img = p.tiles_x * p.tiles_y;
+    constexpr int SC = C::kStageCols;
+    constexpr int CH = SC / 8;                 // 16-byte chunks per staged row
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
+      const int img = m_tile / per_img, rem = m_tile % per_img;
+      const int oy = (rem / p.tiles_x) * p.th + ty, ox = (rem % p.tiles_x) * p.tw + tx;
+      const bool valid = (row < p.th * p.tw) && (oy < p.Ho) && (ox < p.Wo);
+      const long long pix = ((long long)img * p.Ho + oy) * p.Wo + ox;
+      const int n0 = n_tile * BN;
+      sRowOff[row] = valid ? pix : -1;
+      if (p.mode == SY_CONV_FUSED) {
+        for (int c = et; c < BN; c += 128) {
+          const int cg = n0 + c;
+          sScale[c] = (cg < p.Cout && p.scale) ? p.scale[cg] : 1.0f;
+          sShift[c] = (cg < p.Cout && p.shift) ? p.shift[cg] : 0.0f;
+        }
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      epi_bar();
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int h0 = 0; h0 < BN; h0 += SC) {
+#pragma unroll 1
+        for (int j = 0; j < SC / 32; ++j) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)(h0 + j * 32), v);
+          tmem_ld_wait();
+          uint32_t packed[16];
+          if (p.mode == SY_CONV_RAW) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              packed[i] = valid ? pack_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) : 0u;
+          } else {
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = h0 + j * 32 + i;
+              float t = __uint_as_float(v[i]) * sScale[c] + sShift[c];
+              f[i] = p.act ? silu_f(t) : t;
+            }
+            if (p.res != nullptr && valid) {
+              const __nv_bfloat16* rp = p.res + pix * p.res_pitch + n0 + h0 + j * 32;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (n0 + h0 + j * 32 + g * 8 < p.Cout) {
+                  const uint4 rv = *reinterpret_cast<const uint4*>(rp + g * 8);
+                  f[g * 8 + 0] += bf16_lo(rv.x); f[g * 8 + 1] += bf16_hi(rv.x);
+                  f[g * 8 + 2] += bf16_lo(rv.y); f[g * 8 + 3] += bf16_hi(rv.y);
+                  f[g * 8 + 4] += bf16_lo(rv.z); f[g * 8 + 5] += bf16_hi(rv.z);
+                  f[g * 8 + 6] += bf16_lo(rv.w); f[g * 8 + 7] += bf16_hi(rv.w);
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) packed[i] = valid ? pack_bf16(f[2 * i], f[2 * i + 1]) : 0u;
+          }
+          uint4* dst = reinterpret_cast<uint4*>(sStage + row * C::kStagePitch + j * 64);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            dst[g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+        }
+        if (h0 + SC >= BN) {
+          // every TMEM read of this accumulator is complete: hand it back to the MMA warp
+          tcgen05_fence_before();
+          mbar_arrive(tempty_bar(acc));
+        }
+        epi_bar();
+        // ---- per-channel statistic partials of the STORED (bf16-rounded) values
+        if (p.mode == SY_CONV_RAW && p.partials != nullptr && et < SC) {
+          const int cg = n0 + h0 + et;
+          if (cg < p.Cout) {
+            float s1 = 0.f, s2 = 0.f;
+            const uint8_t* col = sStage + et * 2;
+#pragma unroll 8
+            for (int r = 0; r < kBlockM; ++r) {
+              const float x = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(col + r * C::kStagePitch)) << 16);
+              s1 += x;
+              s2 += x * x;
+            }
+            float* pp = p.partials + (size_t)m_tile * 2 * p.Cout;
+            pp[cg] = s1;
+            pp[p.Cout + cg] = s2;
+          }
+        }
+        // ---- coalesced stores: consecutive threads write consecutive 16-byte chunks of a pixel row
+        for (int qd = et; qd < kBlockM * CH; qd += 128) {
+          const int r = qd / CH, cc = qd - r * CH;
+          const long long po = sRowOff[r];
+          const int cg = n0 + h0 + cc * 8;
+          if (po >= 0 && cg < p.Cout) {
+            const uint4 val = *reinterpret_cast<const uint4*>(sStage + r * C::kStagePitch + cc * 16);
+            *reinterpret_cast<uint4*>(p.y + po * p.y_pitch + cg) = val;
+          }
+        }
+        epi_bar();
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// choose the TH x TW output patch (<= 128 pixels) that needs the fewest tiles
+static void pick_patch(int ho, int wo, int stride, int* th, int* tw) {
+  long best = -1;
+  for (int w = 1; w <= 128 && w <= ((wo + 7) / 8) * 8; ++w) {
+    int h = 128 / w;
+    if (h < 1) break;
+    if (h > ho) h = ho;
+    if (w * stride > 256 || h * stride > 256) continue;
+    long tiles = (long)cdiv(ho, h) * cdiv(wo, w);
+    // prefer fewer tiles, then fuller tiles (larger h*w)
+    long score = tiles * 1000 - (long)h * w;
+    if (best < 0 || score < best) {
+      best = score;
+      *th = h;
+      *tw = w;
+    }
+  }
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  conv_tc_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(ta, tb, p);
+  return launch_status("conv_tc_kernel");
+}
+
+}  // namespace tc
+}  // namespace sy
+
+using namespace sy;
+
+extern "C" int sy_conv_num_partials(int32_t n, int32_t ho, int32_t wo) {
+  int th = 1, tw = 1;
+  tc::pick_patch(ho, wo, 1, &th, &tw);
+  return n * cdiv(ho, th) * cdiv(wo, tw);
+}
+
+extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SY_REQUIRE(d != nullptr, SY_EINVAL, "null descriptor");
+  const SyTensor& x = d->x;
+  const SyTensor& y = d->y;
+  SY_REQUIRE(view_ok(x) && view_ok(y) && d->w != nullptr, SY_EINVAL, "conv2d_tc: bad x/y view or null weights");
+  SY_REQUIRE((d->ksize == 1 || d->ksize == 3) && (d->stride == 1 || d->stride == 2), SY_EINVAL,
+             "conv2d_tc: ksize %d stride %d unsupported", d->ksize, d->stride);
+  const int pad = (d->ksize - 1) / 2;
+  const int ho = (x.h + 2 * pad - d->ksize) / d->stride + 1, wo = (x.w + 2 * pad - d->ksize) / d->stride + 1;
+  SY_REQUIRE(y.n == x.n && y.h == ho && y.w == wo, SY_EINVAL, "conv2d_tc: output view %dx%dx%d, expected %dx%dx%d",
+             y.n, y.h, y.w, x.n, ho, wo);
+  SY_REQUIRE(((uintptr_t)d->w % 16) == 0, SY_EINVAL, "conv2d_tc: weights not 16B aligned");
+  tc::EncodeTiledFn enc = tc::get_encode();
+  SY_REQUIRE(enc != nullptr, SY_EARCH, "cuTensorMapEncodeTiled not available from the driver");
+
+  tc::Params p{};
+  p.N = x.n; p.Ho = ho; p.Wo = wo; p.Cout = y.c; p.Cin = x.c;
+  p.ksize = d->ksize; p.stride = d->stride; p.pad = pad;
+  // the same patch rule as sy_conv_num_partials (stride does not change it for this net's shapes)
+  tc::pick_patch(ho, wo, 1, &p.th, &p.tw);
+  SY_REQUIRE(p.th * d->stride <= 256 && p.tw * d->stride <= 256, SY_EINVAL, "conv2d_tc: patch too large for TMA box");
+  p.tiles_y = cdiv(ho, p.th); p.tiles_x = cdiv(wo, p.tw);
+  p.m_tiles = x.n * p.tiles_y * p.tiles_x;
+  int bn = 32;
+  if (y.c > 128) bn = 256; else if (y.c > 64) bn = 128; else if (y.c > 32) bn = 64;
+  p.n_tiles = cdiv(y.c, bn);
+  p.total_tiles = p.m_tiles * p.n_tiles;
+  p.cblocks = cdiv(x.c, tc::kBlockK);
+  p.kblocks = d->ksize * d->ksize * p.cblocks;
+  p.mode = d->mode; p.act = d->act;
+  p.y = reinterpret_cast<__nv_bfloat16*>(y.ptr); p.y_pitch = y.pitch;
+  p.res = nullptr; p.res_pitch = 0;
+  if (d->mode == SY_CONV_FUSED && d->res.ptr != nullptr) {
+    SY_REQUIRE(view_ok(d->res) && d->res.n == y.n && d->res.h == ho && d->res.w == wo && d->res.c == y.c, SY_EINVAL,
+               "conv2d_tc: residual view mismatch");
+    p.res = reinterpret_cast<const __nv_bfloat16*>(d->res.ptr); p.res_pitch = d->res.pitch;
+  }
+  p.scale = d->scale; p.shift = d->shift;
+  p.partials = (d->mode == SY_CONV_RAW) ? d->stat_partials : nullptr;
+  if (p.partials) SY_REQUIRE(d->n_partials >= p.m_tiles, SY_EWORKSPACE, "conv2d_tc: %d stat partial rows, need %d",
+                             d->n_partials, p.m_tiles);
+
+  // A: input view as (C, W, H, N), box (64, TW*s, TH*s, 1) traversed with element strides (1, s, s, 1)
+  CUtensorMap ta, tb;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)x.c, (cuuint64_t)x.w, (cuuint64_t)x.h, (cuuint64_t)x.n};
+    cuuint64_t strides[3] = {(cuuint64_t)x.pitch * 2, (cuuint64_t)x.pitch * 2 * x.w, (cuuint64_t)x.pitch * 2 * x.w * x.h};
+    cuuint32_t box[4] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)(p.tw * d->stride), (cuuint32_t)(p.th * d->stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x.ptr, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SY_REQUIRE(r == CUDA_SUCCESS, SY_ELAUNCH, "cuTensorMapEncodeTiled(A) failed: %d (c=%d w=%d h=%d n=%d pitch=%lld box=%u,%u,%u)",
+               (int)r, x.c, x.w, x.h, x.n, (long long)x.pitch, box[0], box[1], box[2]);
+  }
+  {
+    const int taps = d->ksize * d->ksize;
+    cuuint64_t dims[3] = {(cuuint64_t)x.c, (cuuint64_t)taps, (cuuint64_t)y.c};
+    cuuint64_t strides[2] = {(cuuint64_t)x.c * 2, (cuuint64_t)x.c * 2 * taps};
+    cuuint32_t box[3] = {(cuuint32_t)tc::kBlockK, 1, (cuuint32_t)bn};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SY_REQUIRE(r == CUDA_SUCCESS, SY_ELAUNCH, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+  }
+  switch (bn) {
+    case 32: return tc::launch<32>(ta, tb, p, stream);
+    case 64: return tc::launch<64>(ta, tb, p, stream);
+    case 128: return tc::launch<128>(ta, tb, p, stream);
+    default: return tc::launch<256>(ta, tb, p, stream);
+  }
+}

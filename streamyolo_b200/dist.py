@@ -1,0 +1,55 @@
+"""Data-parallel plumbing for the frame-pair hot path.
+
+Frame pairs are independent units, BatchNorm statistics and the loss normaliser are per GPU
+(/root/reference/exps/train_utils/double_trainer.py:171 ``broadcast_buffers=False``, no SyncBN), so
+forward+loss needs no data-path collective: each rank takes ``global_batch / world`` pairs
+(/root/reference/cfgs/s_s50_onex_dfp_tal_flip.py:93-94).  The only exchanges are the timing
+reduction of the benchmark (max over ranks) and, for training, the gradient all-reduce that
+``DistributedDataParallel`` adds around the model.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def env_world():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def init(backend=None):
+    rank, local_rank, world = env_world()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, local_rank, world
+
+
+def shard_pairs(global_batch: int, world: int, rank: int):
+    """[start, end) of the frame pairs rank ``rank`` owns; sizes differ by at most one."""
+    base, extra = divmod(global_batch, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def barrier():
+    if dist.is_initialized():
+        dist.barrier()
+
+
+def max_over_ranks(value: float, device="cpu") -> float:
+    if not dist.is_initialized():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device="cpu") -> float:
+    if not dist.is_initialized():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())

@@ -1,0 +1,257 @@
+"""Layer executor: walks the module tree with NHWC bf16 views and launches the CUDA ops.
+
+Train mode (``model.training``): every BaseConv = tcgen05 conv writing the raw bf16 result + per-tile
+statistic partials  ->  bn_finalize (batch statistics, running-stat update)  ->  bn_act_apply
+(normalise + SiLU + optional residual, written straight into its consumer's concat slice).
+The two frames of a pair are batched through the shared-weight backbone as 2B images with
+*grouped* statistics (group 0 = current frames, group 1 = support frames), which reproduces the
+reference's two sequential passes (/root/reference/exps/model/dfp_pafpn.py:120,145) exactly,
+including the order of the two running-statistic updates.
+
+Eval mode: BatchNorm is folded into a per-channel scale/shift applied in the conv epilogue
+together with SiLU and the residual (what yolox ``fuse_model`` + ``fuseforward`` achieve).
+"""
+import os
+
+import torch
+
+from .. import ops
+from ..ops import View
+
+
+class Ctx:
+    """Per-forward execution context."""
+
+    def __init__(self, train, n, split, device):
+        self.train = train
+        self.n = n              # images in the batched tensor
+        self.split = split      # first image of statistics group 1 (== n: single group)
+        self.groups = 2 if split < n else 1
+        self.device = device
+        self.impl = os.environ.get("SY_CONV_IMPL", "tc")
+
+
+def _packed(m):
+    w = m.conv.weight
+    key = (w._version, w.data_ptr(), w.device)
+    if getattr(m, "_pk_key", None) != key:
+        m._pk = ops.pack_conv_weight(w)
+        m._pk_key = key
+    return m._pk
+
+
+def _folded(m):
+    """Eval: scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale (fp32)."""
+    bn = m.bn
+    key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+           getattr(m, "_stats_epoch", 0), bn.weight.data_ptr(), bn.eps)
+    if getattr(m, "_fold_key", None) != key:
+        with torch.no_grad():
+            scale = bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+            shift = bn.bias.float() - bn.running_mean.float() * scale
+        m._fold = (scale.contiguous(), shift.contiguous())
+        m._fold_key = key
+    return m._fold
+
+
+def base_conv(ctx: Ctx, m, x: View, y: View = None, res: View = None) -> View:
+    """[yolox] BaseConv: act(bn(conv(x))) (+ res).  ``y`` may be a slice of a concat buffer."""
+    k, s = m.ksize, m.stride
+    ho, wo = ops.conv_out_hw(x.h, x.w, k, s)
+    cout = m.conv.out_channels
+    if y is None:
+        y = View.empty(x.n, ho, wo, cout, ctx.device)
+    wpk = _packed(m)
+    act = 1 if m.act_name == "silu" else 0
+    if not ctx.train:
+        scale, shift = _folded(m)
+        ops.conv2d(x, wpk, y, k, s, ops.SY_CONV_FUSED, impl=ctx.impl, scale=scale, shift=shift, act=act, res=res)
+        return y
+    raw = View.empty(x.n, ho, wo, cout, ctx.device)
+    if ctx.impl == "tc":
+        P = ops.conv_num_partials(x.n, ho, wo)
+        partials = torch.empty((P, 2, cout), dtype=torch.float32, device=ctx.device)
+        ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="tc", partials=partials)
+    else:
+        ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="simt")
+        P = ops.stats_num_partials(x.n, ho * wo)
+        partials = torch.empty((P, 2, cout), dtype=torch.float32, device=ctx.device)
+        ops.channel_stats(raw, partials)
+    bn_apply(ctx, m, raw, partials, y, res, act)
+    return y
+
+
+def bn_apply(ctx: Ctx, m, raw: View, partials, y: View, res: View, act: int):
+    """Batch statistics -> running-stat update -> normalise + act (+res) into ``y``."""
+    bn = m.bn
+    cout = raw.c
+    n = raw.n
+    groups = ctx.groups
+    split = ctx.split if groups == 2 else n
+    P = partials.shape[0]
+    sc = torch.empty((2, 2, cout), dtype=torch.float32, device=ctx.device)   # [scale|shift][group][c]
+    mom = 0.1 if bn.momentum is None else bn.momentum
+    ops.bn_finalize(partials, (P // n) * split if groups == 2 else 0, groups, split * raw.h * raw.w,
+                    bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                    float(mom), float(bn.eps), sc[0], sc[1])
+    m._stats_epoch = getattr(m, "_stats_epoch", 0) + 1
+    ops.bn_act_apply(raw, sc[0].data_ptr(), sc[1].data_ptr(), split, act, res, y)
+    return sc
+
+
+def csp_layer(ctx: Ctx, m, x: View, out: View = None) -> View:
+    """[yolox] CSPLayer: conv3(cat(m(conv1 x), conv2 x)); the concat never materialises as a copy --
+    producers write into channel slices of one buffer and the bottleneck chain runs in place."""
+    hid = m.conv1.conv.out_channels
+    u = View.empty(x.n, x.h, x.w, 2 * hid, ctx.device)
+    a, b = u.ch(0, hid), u.ch(hid, hid)
+    base_conv(ctx, m.conv1, x, a)
+    base_conv(ctx, m.conv2, x, b)
+    for blk in m.m:
+        t = base_conv(ctx, blk.conv1, a)
+        base_conv(ctx, blk.conv2, t, a, res=a if blk.use_add else None)
+    return base_conv(ctx, m.conv3, u, out)
+
+
+def focus_stem(ctx: Ctx, m, x, frames) -> View:
+    """[yolox] Focus + BaseConv straight from the NCHW float frame-pair batch."""
+    b, ch, h, w = x.shape
+    bc = m.conv
+    cout = bc.conv.out_channels
+    n = frames * b
+    raw = View.empty(n, h // 2, w // 2, cout, ctx.device)
+    ops.stem_focus_conv(x, frames, _packed(bc), raw)
+    y = View.empty(n, h // 2, w // 2, cout, ctx.device)
+    if ctx.train:
+        P = ops.stats_num_partials(n, (h // 2) * (w // 2))
+        partials = torch.empty((P, 2, cout), dtype=torch.float32, device=ctx.device)
+        ops.channel_stats(raw, partials)
+        bn_apply(ctx, bc, raw, partials, y, None, 1)
+    else:
+        scale, shift = _folded(bc)
+        ops.bn_act_apply(raw, scale.data_ptr(), shift.data_ptr(), n, 1, None, y)
+    return y
+
+
+def spp_bottleneck(ctx: Ctx, m, x: View) -> View:
+    hid = m.conv1.conv.out_channels
+    s = View.empty(x.n, x.h, x.w, 4 * hid, ctx.device)
+    base_conv(ctx, m.conv1, x, s.ch(0, hid))
+    ops.spp_maxpool(s.ch(0, hid), s.ch(hid, hid), s.ch(2 * hid, hid), s.ch(3 * hid, hid))
+    return base_conv(ctx, m.conv2, s)
+
+
+def pafpn_frames(ctx: Ctx, net, x, frames):
+    """CSPDarknet + PAFPN for ``frames`` x B images (/root/reference/exps/model/darknet.py:167-179,
+    dfp_pafpn.py:120-140).  Returns the un-fused (pan_out2, pan_out1, pan_out0) views."""
+    bb = net.backbone
+    dev = ctx.device
+    c3 = net.C3_p3.conv3.conv.out_channels
+    c4 = net.C3_p4.conv3.conv.out_channels
+    t = focus_stem(ctx, bb.stem, x, frames)
+    t = base_conv(ctx, bb.dark2[0], t)
+    t = csp_layer(ctx, bb.dark2[1], t)
+    t = base_conv(ctx, bb.dark3[0], t)
+    n, h8, w8 = t.n, t.h, t.w
+    f1 = View.empty(n, h8, w8, 2 * c3, dev)              # cat(up(fpn_out1), dark3)
+    x2 = csp_layer(ctx, bb.dark3[1], t, f1.ch(c3, c3))
+    t = base_conv(ctx, bb.dark4[0], x2)
+    h16, w16 = t.h, t.w
+    f0 = View.empty(n, h16, w16, 2 * c4, dev)            # cat(up(fpn_out0), dark4)
+    x1 = csp_layer(ctx, bb.dark4[1], t, f0.ch(c4, c4))
+    t = base_conv(ctx, bb.dark5[0], x1)
+    h32, w32 = t.h, t.w
+    t = spp_bottleneck(ctx, bb.dark5[1], t)
+    x0 = csp_layer(ctx, bb.dark5[2], t)
+    z0 = View.empty(n, h32, w32, 2 * c4, dev)            # cat(bu_conv1, fpn_out0)
+    fpn0 = base_conv(ctx, net.lateral_conv0, x0, z0.ch(c4, c4))
+    ops.upsample_nearest(fpn0, f0.ch(0, c4))
+    fo0 = csp_layer(ctx, net.C3_p4, f0)
+    z1 = View.empty(n, h16, w16, 2 * c3, dev)            # cat(bu_conv2, fpn_out1)
+    fpn1 = base_conv(ctx, net.reduce_conv1, fo0, z1.ch(c3, c3))
+    ops.upsample_nearest(fpn1, f1.ch(0, c3))
+    pan2 = csp_layer(ctx, net.C3_p3, f1)
+    base_conv(ctx, net.bu_conv2, pan2, z1.ch(0, c3))
+    pan1 = csp_layer(ctx, net.C3_n3, z1)
+    base_conv(ctx, net.bu_conv1, pan1, z0.ch(0, c4))
+    pan0 = csp_layer(ctx, net.C3_n4, z0)
+    return pan2, pan1, pan0
+
+
+def dfp_fuse(ctx: Ctx, net, cur, sup):
+    """Dual-Flow Perception fusion (/root/reference/exps/model/dfp_pafpn.py:168-170, 211-221):
+    out = cat(jian(cur), jian(sup)) + cur, a single bf16 rounding after the residual add.
+    ``cur`` / ``sup`` are per-level views with the same image count."""
+    outs = []
+    for m, c, s in zip((net.jian2, net.jian1, net.jian0), cur, sup):
+        half = m.conv.out_channels
+        nb = c.n
+        out = View.empty(nb, c.h, c.w, 2 * half, ctx.device)
+        wpk = _packed(m)
+        if not ctx.train:
+            scale, shift = _folded(m)
+            ops.conv2d(c, wpk, out.ch(0, half), 1, 1, ops.SY_CONV_FUSED, impl=ctx.impl, scale=scale, shift=shift,
+                       act=1, res=c.ch(0, half))
+            ops.conv2d(s, wpk, out.ch(half, half), 1, 1, ops.SY_CONV_FUSED, impl=ctx.impl, scale=scale,
+                       shift=shift, act=1, res=c.ch(half, half))
+        else:
+            # the reference runs jian(cur) then jian(sup): two BN batches, two running-stat updates.
+            # Batched here when cur/sup are the two halves of one buffer, else two launches.
+            same = (c.buf is s.buf) and s.n0 == c.n0 + nb and c.c0 == s.c0
+            if same:
+                both = View(c.buf, c.c0, c.c, c.n0, 2 * nb)
+                raw = View.empty(2 * nb, c.h, c.w, half, ctx.device)
+                sub = Ctx(True, 2 * nb, nb, ctx.device)
+                sc = _raw_conv_stats(sub, m, both, raw)
+                ops.bn_act_apply(raw.imgs(0, nb), sc[0, 0].data_ptr(), sc[1, 0].data_ptr(), nb, 1, c.ch(0, half),
+                                 out.ch(0, half))
+                ops.bn_act_apply(raw.imgs(nb, nb), sc[0, 1].data_ptr(), sc[1, 1].data_ptr(), nb, 1,
+                                 c.ch(half, half), out.ch(half, half))
+            else:
+                sub = Ctx(True, nb, nb, ctx.device)
+                for src, dst, r in ((c, out.ch(0, half), c.ch(0, half)), (s, out.ch(half, half), c.ch(half, half))):
+                    raw = View.empty(nb, c.h, c.w, half, ctx.device)
+                    sc = _raw_conv_stats(sub, m, src, raw)
+                    ops.bn_act_apply(raw, sc[0, 0].data_ptr(), sc[1, 0].data_ptr(), nb, 1, r, dst)
+        outs.append(out)
+    return tuple(outs)
+
+
+def _raw_conv_stats(ctx: Ctx, m, x: View, raw: View):
+    """conv (raw) + statistics + finalize; returns the [2(scale|shift)][2(group)][c] tensor."""
+    cout = raw.c
+    wpk = _packed(m)
+    if ctx.impl == "tc":
+        P = ops.conv_num_partials(x.n, raw.h, raw.w)
+        partials = torch.empty((P, 2, cout), dtype=torch.float32, device=ctx.device)
+        ops.conv2d(x, wpk, raw, m.ksize, m.stride, ops.SY_CONV_RAW, impl="tc", partials=partials)
+    else:
+        ops.conv2d(x, wpk, raw, m.ksize, m.stride, ops.SY_CONV_RAW, impl="simt")
+        P = ops.stats_num_partials(x.n, raw.h * raw.w)
+        partials = torch.empty((P, 2, cout), dtype=torch.float32, device=ctx.device)
+        ops.channel_stats(raw, partials)
+    bn = m.bn
+    groups, n = ctx.groups, x.n
+    split = ctx.split if groups == 2 else n
+    sc = torch.empty((2, 2, cout), dtype=torch.float32, device=ctx.device)
+    mom = 0.1 if bn.momentum is None else bn.momentum
+    ops.bn_finalize(partials, (P // n) * split if groups == 2 else 0, groups, split * raw.h * raw.w,
+                    bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                    float(mom), float(bn.eps), sc[0], sc[1])
+    m._stats_epoch = getattr(m, "_stats_epoch", 0) + 1
+    return sc
+
+
+def as_view(t) -> View:
+    """Accept a View or an NCHW-shaped torch tensor (zero-copy when it is channels-last bf16)."""
+    if isinstance(t, View):
+        return t
+    p = t.permute(0, 2, 3, 1)
+    if t.dtype == torch.bfloat16 and p.is_contiguous():
+        return View(p)
+    return View(p.contiguous().to(torch.bfloat16))
+
+
+def as_nchw(v: View):
+    """NCHW-shaped (channels-last memory) tensor over a view, as the reference API returns."""
+    return v.torch().permute(0, 3, 1, 2)

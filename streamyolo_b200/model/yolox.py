@@ -1,0 +1,25 @@
+"""YOLOX wrapper (mirror of /root/reference/exps/model/yolox.py:11-55)."""
+import torch.nn as nn
+
+from .dfp_pafpn import DFPPAFPN
+from .tal_head import TALHead
+
+
+class YOLOX(nn.Module):
+    def __init__(self, backbone=None, head=None):
+        super().__init__()
+        self.backbone = DFPPAFPN() if backbone is None else backbone
+        self.head = TALHead(20) if head is None else head
+
+    def forward(self, x, targets=None, buffer=None, mode="off_pipe"):
+        assert mode in ["off_pipe", "on_pipe"]
+        if mode == "off_pipe":
+            fpn_outs = self.backbone(x, buffer=buffer, mode="off_pipe")
+            if self.training:
+                assert targets is not None
+                loss, iou_loss, conf_loss, cls_loss, l1_loss, num_fg = self.head(fpn_outs, targets, x)
+                return {"total_loss": loss, "iou_loss": iou_loss, "l1_loss": l1_loss, "conf_loss": conf_loss,
+                        "cls_loss": cls_loss, "num_fg": num_fg}
+            return self.head(fpn_outs)
+        fpn_outs, buffer_ = self.backbone(x, buffer=buffer, mode="on_pipe")
+        return self.head(fpn_outs), buffer_

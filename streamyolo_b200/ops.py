@@ -1,0 +1,271 @@
+"""ctypes binding of libstreamyolo_sm100.so (include/streamyolo_sm100.h) + NHWC view helper.
+
+The library is the product; there is NO fallback: if it is missing or the device is not an
+sm_100 part, every op raises RuntimeError.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libstreamyolo_sm100.so")
+
+SY_CONV_RAW, SY_CONV_FUSED = 0, 1
+
+
+class SyTensor(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+                ("pitch", C.c_int64)]
+
+
+class SyConvDesc(C.Structure):
+    _fields_ = [("x", SyTensor), ("y", SyTensor), ("w", C.c_void_p), ("ksize", C.c_int32), ("stride", C.c_int32),
+                ("mode", C.c_int32), ("act", C.c_int32), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("res", SyTensor), ("stat_partials", C.c_void_p), ("n_partials", C.c_int32)]
+
+
+class SyHeadPredDesc(C.Structure):
+    _fields_ = [("cls_feat", SyTensor), ("reg_feat", SyTensor),
+                ("w_reg", C.c_void_p), ("b_reg", C.c_void_p), ("w_obj", C.c_void_p), ("b_obj", C.c_void_p),
+                ("w_cls", C.c_void_p), ("b_cls", C.c_void_p),
+                ("num_classes", C.c_int32), ("stride", C.c_int32), ("anchor_offset", C.c_int32),
+                ("a_total", C.c_int32), ("sigmoid", C.c_int32), ("decode", C.c_int32),
+                ("out", C.c_void_p), ("origin", C.c_void_p)]
+
+
+class SyTalLossDesc(C.Structure):
+    _fields_ = [("b", C.c_int32), ("a_total", C.c_int32), ("max_labels", C.c_int32), ("num_classes", C.c_int32),
+                ("n_levels", C.c_int32), ("level_h", C.c_int32 * 4), ("level_w", C.c_int32 * 4),
+                ("level_stride", C.c_int32 * 4),
+                ("outputs", C.c_void_p), ("origin", C.c_void_p), ("labels_fut", C.c_void_p),
+                ("labels_cur", C.c_void_p), ("gamma", C.c_float), ("ignore_thr", C.c_float),
+                ("ignore_value", C.c_float), ("use_l1", C.c_int32), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_size_t), ("loss_out", C.c_void_p), ("fg_out", C.c_void_p),
+                ("matched_out", C.c_void_p), ("pred_iou_out", C.c_void_p)]
+
+
+# every symbol include/streamyolo_sm100.h declares: (restype, argtypes)
+_SIG = {
+    "sy_last_error_string": (C.c_char_p, []),
+    "sy_version": (C.c_int, []),
+    "sy_check_device": (C.c_int, []),
+    "sy_conv_num_partials": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    "sy_conv2d_tc": (C.c_int, [C.POINTER(SyConvDesc), C.c_void_p]),
+    "sy_conv2d_simt": (C.c_int, [C.POINTER(SyConvDesc), C.c_void_p]),
+    "sy_stem_focus_conv": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                     SyTensor, C.c_void_p]),
+    "sy_stats_num_partials": (C.c_int, [C.c_int32, C.c_int32]),
+    "sy_channel_stats": (C.c_int, [SyTensor, C.c_void_p, C.c_int32, C.c_void_p]),
+    "sy_bn_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
+    "sy_bn_act_apply": (C.c_int, [SyTensor, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, SyTensor, SyTensor,
+                                  C.c_void_p]),
+    "sy_upsample_nearest": (C.c_int, [SyTensor, SyTensor, C.c_void_p]),
+    "sy_spp_maxpool": (C.c_int, [SyTensor, SyTensor, SyTensor, SyTensor, C.c_void_p]),
+    "sy_copy": (C.c_int, [SyTensor, SyTensor, C.c_void_p]),
+    "sy_head_pred_decode": (C.c_int, [C.POINTER(SyHeadPredDesc), C.c_void_p]),
+    "sy_tal_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "sy_tal_loss": (C.c_int, [C.POINTER(SyTalLossDesc), C.c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIG)
+
+_lib = None
+_device_ok = False
+
+
+def load_library():
+    """dlopen the in-tree library (no GPU needed) and type every entry point."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -m streamyolo_b200.build` "
+                               "(there is no fallback path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIG.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def lib():
+    """Library handle for compute calls: also insists on a CUDA sm_100 device."""
+    global _device_ok
+    l = load_library()
+    if not _device_ok:
+        if not torch.cuda.is_available():
+            raise RuntimeError("streamyolo_b200 needs a CUDA sm_100 (B200) device; there is no CPU path")
+        rc = l.sy_check_device()
+        if rc != 0:
+            raise RuntimeError("streamyolo_b200: " + l.sy_last_error_string().decode())
+        _device_ok = True
+    return l
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(f"libstreamyolo_sm100 error {rc}: " + load_library().sy_last_error_string().decode())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+NULL_T = SyTensor(None, 0, 0, 0, 0, 0)
+
+
+class View:
+    """Channel-slice / image-slice view of an NHWC bf16 buffer ``buf[N,H,W,Ctot]``."""
+    __slots__ = ("buf", "n0", "n", "c0", "c")
+
+    def __init__(self, buf, c0=0, c=None, n0=0, n=None):
+        assert buf.dtype == torch.bfloat16 and buf.dim() == 4 and buf.is_contiguous()
+        self.buf, self.c0, self.n0 = buf, c0, n0
+        self.c = buf.shape[3] - c0 if c is None else c
+        self.n = buf.shape[0] - n0 if n is None else n
+
+    @staticmethod
+    def empty(n, h, w, c, device):
+        return View(torch.empty((n, h, w, c), dtype=torch.bfloat16, device=device))
+
+    @property
+    def h(self):
+        return self.buf.shape[1]
+
+    @property
+    def w(self):
+        return self.buf.shape[2]
+
+    def ch(self, c0, c):
+        return View(self.buf, self.c0 + c0, c, self.n0, self.n)
+
+    def imgs(self, n0, n):
+        return View(self.buf, self.c0, self.c, self.n0 + n0, n)
+
+    def st(self):
+        b = self.buf
+        ptr = b.data_ptr() + 2 * (self.n0 * b.shape[1] * b.shape[2] * b.shape[3] + self.c0)
+        return SyTensor(ptr, self.n, b.shape[1], b.shape[2], self.c, b.shape[3])
+
+    def torch(self):
+        """NHWC torch view (for tests)."""
+        return self.buf[self.n0:self.n0 + self.n, :, :, self.c0:self.c0 + self.c]
+
+    def nchw_float(self):
+        return self.torch().permute(0, 3, 1, 2).float()
+
+
+def from_nchw(x):
+    """float NCHW torch tensor -> bf16 NHWC View (test helper)."""
+    return View(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+
+
+def pack_conv_weight(w):
+    """OIHW float -> bf16 [O][kh*kw][I] contiguous (GEMM B operand, K-major)."""
+    o, i, kh, kw = w.shape
+    return w.detach().permute(0, 2, 3, 1).reshape(o, kh * kw, i).to(torch.bfloat16).contiguous()
+
+
+def conv_out_hw(h, w, k, s):
+    p = (k - 1) // 2
+    return (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+
+
+def conv_num_partials(n, ho, wo):
+    return load_library().sy_conv_num_partials(n, ho, wo)
+
+
+def conv2d(x: View, wpk, y: View, k, s, mode, impl="tc", scale=None, shift=None, act=1, res: View = None,
+           partials=None):
+    d = SyConvDesc()
+    d.x, d.y = x.st(), y.st()
+    d.w = wpk.data_ptr()
+    d.ksize, d.stride, d.mode, d.act = k, s, mode, act
+    d.scale = scale.data_ptr() if scale is not None else None
+    d.shift = shift.data_ptr() if shift is not None else None
+    d.res = res.st() if res is not None else NULL_T
+    if partials is not None:
+        d.stat_partials, d.n_partials = partials.data_ptr(), partials.shape[0]
+    fn = lib().sy_conv2d_tc if impl == "tc" else lib().sy_conv2d_simt
+    _check(fn(C.byref(d), _stream()))
+
+
+def stem_focus_conv(x, frames, wpk, y: View):
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    b, ch, h, w = x.shape
+    _check(lib().sy_stem_focus_conv(x.data_ptr(), b, ch, h, w, frames, wpk.data_ptr(), y.st(), _stream()))
+
+
+def stats_num_partials(n, hw):
+    return load_library().sy_stats_num_partials(n, hw)
+
+
+def channel_stats(x: View, partials):
+    _check(lib().sy_channel_stats(x.st(), partials.data_ptr(), partials.shape[0], _stream()))
+
+
+def bn_finalize(partials, p_split, groups, count, gamma, beta, rmean, rvar, nbt, momentum, eps, scale, shift):
+    c = gamma.numel()
+    _check(lib().sy_bn_finalize(partials.data_ptr(), partials.shape[0], p_split, groups, count, c,
+                                gamma.data_ptr(), beta.data_ptr(),
+                                rmean.data_ptr() if rmean is not None else None,
+                                rvar.data_ptr() if rvar is not None else None,
+                                nbt.data_ptr() if nbt is not None else None,
+                                momentum, eps, scale.data_ptr(), shift.data_ptr(), _stream()))
+
+
+def bn_act_apply(x: View, scale_ptr, shift_ptr, split_n, act, res, y: View):
+    _check(lib().sy_bn_act_apply(x.st(), scale_ptr, shift_ptr, split_n, act,
+                                 res.st() if res is not None else NULL_T, y.st(), _stream()))
+
+
+def upsample_nearest(x: View, y: View):
+    _check(lib().sy_upsample_nearest(x.st(), y.st(), _stream()))
+
+
+def spp_maxpool(x: View, y5: View, y9: View, y13: View):
+    _check(lib().sy_spp_maxpool(x.st(), y5.st(), y9.st(), y13.st(), _stream()))
+
+
+def copy(x: View, y: View):
+    _check(lib().sy_copy(x.st(), y.st(), _stream()))
+
+
+def head_pred_decode(cls_feat: View, reg_feat: View, w_reg, b_reg, w_obj, b_obj, w_cls, b_cls, stride,
+                     anchor_offset, a_total, out, origin, sigmoid, decode):
+    d = SyHeadPredDesc()
+    d.cls_feat, d.reg_feat = cls_feat.st(), reg_feat.st()
+    d.w_reg, d.b_reg, d.w_obj, d.b_obj = w_reg.data_ptr(), b_reg.data_ptr(), w_obj.data_ptr(), b_obj.data_ptr()
+    d.w_cls, d.b_cls = w_cls.data_ptr(), b_cls.data_ptr()
+    d.num_classes = w_cls.shape[0]
+    d.stride, d.anchor_offset, d.a_total = stride, anchor_offset, a_total
+    d.sigmoid, d.decode = int(sigmoid), int(decode)
+    d.out = out.data_ptr()
+    d.origin = origin.data_ptr() if origin is not None else None
+    _check(lib().sy_head_pred_decode(C.byref(d), _stream()))
+
+
+def tal_loss_workspace_bytes(b, a_total, max_labels, num_classes):
+    return load_library().sy_tal_loss_workspace_bytes(b, a_total, max_labels, num_classes)
+
+
+def tal_loss(outputs, origin, labels_fut, labels_cur, hw, strides, gamma, ignore_thr, ignore_value, use_l1,
+             workspace, loss_out, fg_out=None, matched_out=None, pred_iou_out=None):
+    d = SyTalLossDesc()
+    b, a, no = outputs.shape
+    d.b, d.a_total, d.max_labels, d.num_classes = b, a, labels_fut.shape[1], no - 5
+    d.n_levels = len(hw)
+    for i, ((h, w), s) in enumerate(zip(hw, strides)):
+        d.level_h[i], d.level_w[i], d.level_stride[i] = h, w, s
+    d.outputs = outputs.data_ptr()
+    d.origin = origin.data_ptr() if origin is not None else None
+    d.labels_fut, d.labels_cur = labels_fut.data_ptr(), labels_cur.data_ptr()
+    d.gamma, d.ignore_thr, d.ignore_value, d.use_l1 = gamma, ignore_thr, ignore_value, int(use_l1)
+    d.workspace, d.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    d.loss_out = loss_out.data_ptr()
+    d.fg_out = fg_out.data_ptr() if fg_out is not None else None
+    d.matched_out = matched_out.data_ptr() if matched_out is not None else None
+    d.pred_iou_out = pred_iou_out.data_ptr() if pred_iou_out is not None else None
+    _check(lib().sy_tal_loss(C.byref(d), _stream()))

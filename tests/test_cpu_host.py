@@ -1,0 +1,106 @@
+"""CPU: the C-ABI library loads and exports every symbol the header declares, host-side logic,
+state_dict parity of the module mirror, loud failure without a GPU, and the world_size-2
+(gloo) sharding / timing-reduction path of the benchmark."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from streamyolo_b200 import dist as sydist
+from streamyolo_b200 import ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from streamyolo_b200.build import build
+    build()
+    return ops.load_library()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "streamyolo_sm100.h")).read()
+    declared = set(re.findall(r"\b(sy_[a-z0-9_]+)\s*\(", hdr)) - {"sy_stream_t"}
+    assert declared == set(ops.EXPORTED_SYMBOLS), declared ^ set(ops.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.sy_version() >= 100
+
+
+def test_host_logic_no_gpu(lib):
+    # statistic partial rows: image-major, enough 128-pixel tiles to cover the map
+    for (n, h, w) in [(16, 75, 120), (16, 38, 60), (16, 19, 30), (2, 300, 480), (4, 15, 20)]:
+        p = lib.sy_conv_num_partials(n, h, w)
+        assert p % n == 0 and (p // n) * 128 >= h * w
+        assert (p // n) * 128 <= 1.35 * h * w + 128, (n, h, w, p)      # tile waste stays bounded
+    assert lib.sy_stats_num_partials(4, 1000) == 8
+    assert lib.sy_tal_loss_workspace_bytes(8, 11850, 120, 8) > 2 * 8 * 120 * 11850 * 4
+
+
+def test_compute_fails_loudly_without_gpu(lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    v = ops.View(torch.zeros((1, 4, 4, 8), dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.copy(v, v)
+
+
+@pytest.mark.parametrize("tag,dw", [("s", (0.33, 0.5)), ("m", (0.67, 0.75)), ("l", (1.0, 1.0))])
+def test_module_mirror_state_dict(tag, dw):
+    from streamyolo_b200.model import DFPPAFPN, TALHead, YOLOX
+    g = np.load(os.path.join(GOLD, "state_shapes.npz"))
+    m = YOLOX(DFPPAFPN(dw[0], dw[1], in_channels=[256, 512, 1024]), TALHead(8, dw[1], in_channels=[256, 512, 1024]))
+    sd = m.state_dict()
+    assert list(sd) == g[tag + "_keys"].tolist()                       # same keys, same order as the reference
+    assert ["x".join(map(str, v.shape)) for v in sd.values()] == g[tag + "_shapes"].tolist()
+    assert sum(p.numel() for p in m.parameters()) == int(g[tag + "_nparams"])
+    # init_yolo / initialize_biases hooks of cfgs/*.py:40-54 work on the mirror
+    n_bn = sum(isinstance(x, torch.nn.BatchNorm2d) for x in m.modules())
+    assert n_bn == {"s": 77, "m": 101, "l": 125}[tag]
+    m.head.initialize_biases(1e-2)
+    assert abs(float(m.head.cls_preds[0].bias[0]) + 4.59512) < 1e-4
+    assert m.head.use_l1 is False and m.head.decode_in_inference is True and m.head.n_anchors == 1
+
+
+def test_shard_pairs():
+    for gb, w in [(32, 8), (64, 8), (8, 1), (10, 4), (3, 2)]:
+        spans = [sydist.shard_pairs(gb, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == gb
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch
+from streamyolo_b200 import dist as d
+rank, local, world = d.init("gloo")
+a, b = d.shard_pairs(10, world, rank)
+d.barrier()
+t = d.max_over_ranks(1.0 + rank)
+n = d.sum_over_ranks(b - a)
+assert t == float(world) and n == 10.0, (t, n)
+print("ok", rank)
+"""
+
+
+def test_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(WORKER)
+    port = 29600 + os.getpid() % 300
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs

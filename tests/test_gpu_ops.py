@@ -1,0 +1,233 @@
+"""GPU: every kernel of libstreamyolo_sm100 (through the C ABI) against a plain PyTorch fp32
+reference of the same op evaluated on the SAME bf16-rounded operands.
+
+Tolerances (written here once):
+  * conv outputs are stored as bf16: |err| <= 2^-8 * |ref| + 2^-8 * rms(ref)   (one bf16 ulp + accumulation noise)
+  * statistic partial sums (fp32): relative 2e-3 of sqrt(count)*rms
+  * integer / index / max-pool / copy results: bit exact
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from streamyolo_b200 import ops  # noqa: E402
+from streamyolo_b200.ops import View  # noqa: E402
+
+DEV = "cuda"
+
+
+def bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def rand_act(n, c, h, w, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return bf(torch.randn(n, c, h, w, generator=g) * scale).to(DEV)
+
+
+def rand_w(co, ci, k, seed):
+    g = torch.Generator().manual_seed(seed)
+    return bf(torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5).to(DEV)
+
+
+def check_close(got, ref, what, ulp=2.0 ** -8):
+    got, ref = got.float(), ref.float()
+    rms = ref.pow(2).mean().sqrt().item() + 1e-12
+    err = (got - ref).abs()
+    tol = ulp * ref.abs() + ulp * rms
+    bad = (err > tol)
+    frac = bad.float().mean().item()
+    rel = ((got - ref).norm() / (ref.norm() + 1e-12)).item()
+    assert frac == 0.0 and np.isfinite(rel), f"{what}: {bad.sum().item()} / {bad.numel()} outside tolerance, " \
+        f"max err {err.max().item():.4g}, rms {rms:.4g}, rel l2 {rel:.3g}"
+    return rel
+
+
+CONV_CASES = [
+    # n, cin, cout, h, w, k, s
+    (2, 64, 64, 8, 16, 1, 1),
+    (1, 128, 128, 75, 120, 3, 1),
+    (2, 64, 128, 150, 240, 3, 2),
+    (2, 128, 256, 75, 120, 3, 2),      # odd height -> 38
+    (2, 256, 512, 38, 60, 3, 2),
+    (2, 512, 1024, 19, 30, 1, 1),
+    (3, 8, 16, 15, 20, 3, 1),          # tiny test-model widths
+    (2, 16, 32, 15, 20, 3, 2),
+    (2, 48, 96, 38, 60, 1, 1),         # StreamYOLO-m widths (not multiples of 64)
+    (2, 96, 96, 19, 30, 3, 1),
+    (1, 1024, 512, 19, 30, 1, 1),
+    (2, 256, 256, 75, 120, 3, 1),      # head tower conv (largest single conv of l)
+]
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_raw(case, impl):
+    n, ci, co, h, w, k, s = case
+    if impl == "simt" and ci * co * h * w * k * k * n > 3e10:
+        pytest.skip("too slow on the CUDA-core cross-check kernel")
+    x = rand_act(n, ci, h, w, 1)
+    wt = rand_w(co, ci, k, 2)
+    ref = F.conv2d(x, wt, None, s, (k - 1) // 2)
+    xv = ops.from_nchw(x)
+    ho, wo = ops.conv_out_hw(h, w, k, s)
+    y = View.empty(n, ho, wo, co, DEV)
+    y.buf.fill_(float("nan"))
+    P = ops.conv_num_partials(n, ho, wo)
+    partials = torch.full((P, 2, co), float("nan"), device=DEV) if impl == "tc" else None
+    ops.conv2d(xv, ops.pack_conv_weight(wt), y, k, s, ops.SY_CONV_RAW, impl=impl, partials=partials)
+    torch.cuda.synchronize()
+    got = y.nchw_float()
+    check_close(got, ref, f"conv_{impl}{case}")
+    if impl == "tc":
+        st = got    # statistics are defined on the stored (rounded) values
+        s1, s2 = partials[:, 0].sum(0), partials[:, 1].sum(0)
+        cnt = n * ho * wo
+        rms = st.pow(2).mean().sqrt().item()
+        assert torch.allclose(s1, st.sum((0, 2, 3)), rtol=0, atol=2e-3 * rms * cnt ** 0.5 + 1e-3), "sum partials"
+        assert torch.allclose(s2, st.pow(2).sum((0, 2, 3)), rtol=2e-3, atol=1e-3), "sumsq partials"
+        # rows are image-major: the first P/n rows cover image 0 only
+        per = P // n
+        assert torch.allclose(partials[:per, 0].sum(0), st[0].sum((1, 2)), rtol=0, atol=2e-3 * rms * (ho * wo) ** 0.5 + 1e-3)
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_conv_fused_residual_slices(impl):
+    """FUSED epilogue (scale, shift, SiLU, residual) reading and writing channel slices, in place."""
+    n, ci, co, h, w = 2, 64, 64, 19, 30
+    x = rand_act(n, ci, h, w, 3)
+    wt = rand_w(co, ci, 3, 4)
+    g = torch.Generator().manual_seed(5)
+    scale = (torch.rand(co, generator=g) + 0.5).to(DEV)
+    shift = (torch.rand(co, generator=g) - 0.5).to(DEV)
+    resid = rand_act(n, co, h, w, 6)
+    ref = F.silu(F.conv2d(x, wt, None, 1, 1) * scale[None, :, None, None] + shift[None, :, None, None]) + resid
+    big_in = View.empty(n, h, w, 3 * ci, DEV)
+    big_in.buf.fill_(7.0)
+    xin = big_in.ch(ci, ci)
+    xin.torch().copy_(x.permute(0, 2, 3, 1))
+    big_out = View.empty(n, h, w, 2 * co, DEV)
+    big_out.buf.fill_(-3.0)
+    yv = big_out.ch(co, co)
+    yv.torch().copy_(resid.permute(0, 2, 3, 1))      # residual lives where the output goes (in place)
+    ops.conv2d(xin, ops.pack_conv_weight(wt), yv, 3, 1, ops.SY_CONV_FUSED, impl=impl, scale=scale, shift=shift,
+               act=1, res=yv)
+    torch.cuda.synchronize()
+    check_close(yv.nchw_float(), ref, f"conv_fused_{impl}")
+    assert (big_out.ch(0, co).torch() == -3.0).all(), "neighbouring slice was overwritten"
+
+
+def test_conv_tc_matches_simt_bitwise_mostly():
+    """Same operands, two kernels: differences only from fp32 summation order (<= 1 bf16 ulp)."""
+    n, ci, co, h, w, k, s = 2, 128, 128, 38, 60, 3, 1
+    x, wt = rand_act(n, ci, h, w, 11), rand_w(co, ci, k, 12)
+    xv, wp = ops.from_nchw(x), ops.pack_conv_weight(wt)
+    a, b = View.empty(n, h, w, co, DEV), View.empty(n, h, w, co, DEV)
+    ops.conv2d(xv, wp, a, k, s, ops.SY_CONV_RAW, impl="tc")
+    ops.conv2d(xv, wp, b, k, s, ops.SY_CONV_RAW, impl="simt")
+    torch.cuda.synchronize()
+    diff = (a.torch().float() - b.torch().float()).abs()
+    assert (diff > 0).float().mean().item() < 0.05
+    check_close(a.torch().float(), b.torch().float(), "tc vs simt")
+
+
+def test_stem_focus():
+    b, h, w, co = 2, 120, 160, 16
+    g = torch.Generator().manual_seed(0)
+    x = (torch.rand(b, 6, h, w, generator=g) * 255).to(DEV)
+    wt = rand_w(co, 12, 3, 7)
+    y = View.empty(2 * b, h // 2, w // 2, co, DEV)
+    ops.stem_focus_conv(x, 2, ops.pack_conv_weight(wt), y)
+    torch.cuda.synchronize()
+    xs = bf(torch.cat([x[:, 0:3], x[:, 3:6]], 0))
+    foc = torch.cat([xs[..., ::2, ::2], xs[..., 1::2, ::2], xs[..., ::2, 1::2], xs[..., 1::2, 1::2]], 1)
+    ref = F.conv2d(foc, wt, None, 1, 1)
+    check_close(y.nchw_float(), ref, "stem")
+
+
+@pytest.mark.parametrize("groups", [1, 2])
+def test_bn_stats_finalize_apply(groups):
+    n, c, h, w = 4, 64, 19, 30
+    x = rand_act(n, c, h, w, 21, scale=2.0) + 0.7
+    x = bf(x)
+    xv = ops.from_nchw(x)
+    P = ops.stats_num_partials(n, h * w)
+    partials = torch.empty((P, 2, c), device=DEV)
+    ops.channel_stats(xv, partials)
+    g = torch.Generator().manual_seed(22)
+    gamma, beta = (torch.rand(c, generator=g) + 0.5).to(DEV), (torch.rand(c, generator=g) - 0.5).to(DEV)
+    rm, rv = torch.zeros(c, device=DEV) + 0.1, torch.ones(c, device=DEV) * 0.9
+    nbt = torch.zeros((), dtype=torch.long, device=DEV)
+    sc = torch.empty((2, 2, c), device=DEV)
+    split = n // 2 if groups == 2 else n
+    ops.bn_finalize(partials, (P // n) * split if groups == 2 else 0, groups, split * h * w, gamma, beta, rm, rv, nbt,
+                    0.03, 1e-3, sc[0], sc[1])
+    resid = rand_act(n, c, h, w, 23)
+    y = View.empty(n, h, w, c, DEV)
+    ops.bn_act_apply(xv, sc[0].data_ptr(), sc[1].data_ptr(), split, 1, ops.from_nchw(resid), y)
+    torch.cuda.synchronize()
+    rm_ref, rv_ref = torch.zeros(c, device=DEV) + 0.1, torch.ones(c, device=DEV) * 0.9
+    refs = []
+    for gi in range(groups):
+        xs = x[gi * split:(gi + 1) * split]
+        refs.append(F.batch_norm(xs, rm_ref, rv_ref, gamma, beta, True, 0.03, 1e-3))
+    ref = F.silu(torch.cat(refs, 0)) + resid
+    check_close(y.nchw_float(), ref, "bn_apply")
+    assert torch.allclose(rm, rm_ref, rtol=1e-4, atol=1e-5) and torch.allclose(rv, rv_ref, rtol=1e-4, atol=1e-5)
+    assert int(nbt) == groups
+
+
+def test_upsample_nearest_index_exact():
+    for (hi, wi, ho, wo) in [(19, 30, 38, 60), (38, 60, 75, 120), (8, 10, 15, 20), (4, 5, 8, 10)]:
+        x = rand_act(2, 16, hi, wi, 31)
+        y = View.empty(2, ho, wo, 32, DEV)
+        ops.upsample_nearest(ops.from_nchw(x), y.ch(16, 16))
+        torch.cuda.synchronize()
+        ref = F.interpolate(x, size=(ho, wo), mode="nearest")
+        assert torch.equal(y.ch(16, 16).nchw_float(), ref), (hi, wi, ho, wo)
+
+
+def test_spp_and_copy_exact():
+    x = rand_act(2, 32, 19, 30, 41)
+    s = View.empty(2, 19, 30, 128, DEV)
+    ops.copy(ops.from_nchw(x), s.ch(0, 32))
+    ops.spp_maxpool(s.ch(0, 32), s.ch(32, 32), s.ch(64, 32), s.ch(96, 32))
+    torch.cuda.synchronize()
+    ref = torch.cat([x] + [F.max_pool2d(x, k, 1, k // 2) for k in (5, 9, 13)], 1)
+    assert torch.equal(s.nchw_float(), ref)
+
+
+def test_head_pred_decode():
+    b, c, h, w, nc = 2, 64, 15, 20, 8
+    cf, rf = rand_act(b, c, h, w, 51), rand_act(b, c, h, w, 52)
+    g = torch.Generator().manual_seed(53)
+    wr, br = (torch.randn(4, c, generator=g) * 0.05).to(DEV), (torch.randn(4, generator=g) * 0.1).to(DEV)
+    wo_, bo = (torch.randn(1, c, generator=g) * 0.05).to(DEV), (torch.randn(1, generator=g) * 0.1).to(DEV)
+    wc, bc = (torch.randn(nc, c, generator=g) * 0.05).to(DEV), (torch.randn(nc, generator=g) * 0.1).to(DEV)
+    a_total, off, stride = h * w + 37, 37, 16
+    for train in (True, False):
+        out = torch.zeros((b, a_total, 5 + nc), device=DEV)
+        origin = torch.zeros((b, a_total, 4), device=DEV) if train else None
+        ops.head_pred_decode(ops.from_nchw(cf), ops.from_nchw(rf), wr, br, wo_, bo, wc, bc, stride, off, a_total, out,
+                             origin, sigmoid=not train, decode=True)
+        torch.cuda.synchronize()
+        reg = F.conv2d(rf, wr[:, :, None, None], br)
+        obj = F.conv2d(rf, wo_[:, :, None, None], bo)
+        cls = F.conv2d(cf, wc[:, :, None, None], bc)
+        raw = torch.cat([reg, obj, cls], 1).flatten(2).permute(0, 2, 1)
+        yv, xv = torch.meshgrid(torch.arange(h, device=DEV), torch.arange(w, device=DEV), indexing="ij")
+        ref = raw.clone()
+        ref[..., 0] = (raw[..., 0] + xv.reshape(-1)) * stride
+        ref[..., 1] = (raw[..., 1] + yv.reshape(-1)) * stride
+        ref[..., 2:4] = torch.exp(raw[..., 2:4]) * stride
+        if not train:
+            ref[..., 4:] = raw[..., 4:].sigmoid()
+        assert torch.allclose(out[:, off:], ref, rtol=1e-4, atol=1e-4)
+        if train:
+            assert torch.allclose(origin[:, off:], raw[..., :4], rtol=1e-4, atol=1e-5)
+        assert (out[:, :off] == 0).all()
