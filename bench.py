@@ -1,0 +1,366 @@
+"""Benchmark of the StreamYOLO hot path: frame-pairs/s of forward+loss (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model l] [--batch 8]
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  A "step" is one pass of
+the hot path -- DFPPAFPN (CSPDarknet + PAFPN on both frames, DFP fusion) + TALHead + SimOTA/TAL loss,
+model.train() semantics (batch-statistics BatchNorm, running-stat update) -- over one per-GPU batch of
+synthetic 600x960 frame pairs with random-init weights.  Frame pairs are independent, so ranks run
+with no data-path collective (weak scaling: per-GPU batch fixed).
+
+value      whole-job pairs/s with inputs resident in HBM, the step replayed as one CUDA graph,
+           timed with CUDA events, max over ranks.
+e2e        same metric through the public API call ``model(x, targets)`` contract with HOST (pinned)
+           inputs: every step copies the frame pairs + labels host->device (double buffered on a copy
+           stream, like the reference's DataPrefetcher) and reads the 6 loss scalars back.
+roofline   dominant kernel (tcgen05 implicit-GEMM conv) timed alone, live, with CUDA events on its
+           heaviest layer shape; achieved algorithmic TFLOP/s vs the measured cuBLAS bf16 peak.
+cpu_baseline / --impl reference
+           the CPU oracle (oracle/, a restatement of the reference's PyTorch path; the reference itself
+           needs the un-installable yolox package) on the host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+MODELS = {"s": (0.33, 0.50), "m": (0.67, 0.75), "l": (1.0, 1.0), "tiny": (0.33, 0.125)}
+TAL = {"s": (1.0, 0.5, 1.5), "m": (1.0, 0.4, 1.7), "l": (1.0, 0.5, 1.6), "tiny": (1.0, 0.5, 1.5)}   # cfgs/*.py
+GFLOP_PER_PAIR = {"s": 61.43, "m": 176.81, "l": 384.30}     # BASELINE.md section 2 (600x960, convs, 2*MAC)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"burst": d.get("bf16_tflops", 1590.0), "sustained": d.get("bf16_tflops_sustained", 1400.0),
+                "hbm": d.get("hbm_gbs", 6650.0), "source": "measured"}
+    return {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        # "under load": ignore idle samples well below the maximum seen
+        load = [v for v in sm if v >= 0.5 * sm[-1]] if sm else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(tag, device):
+    from streamyolo_b200 import synth
+    from streamyolo_b200.model import DFPPAFPN, TALHead, YOLOX
+    depth, width = MODELS[tag]
+    gamma, thr, val = TAL[tag]
+    ch = [256, 512, 1024]
+    model = YOLOX(DFPPAFPN(depth, width, in_channels=ch), TALHead(8, width, in_channels=ch, gamma=gamma,
+                                                                    ignore_thr=thr, ignore_value=val))
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.eps, m.momentum = 1e-3, 0.03                      # init_yolo, cfgs/*.py:40-44
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.load_state_dict(synth.synth_state_dict(shapes))
+    model.head.use_l1 = True                                    # double_trainer.py:209-216
+    return model.to(device).train()
+
+
+def time_dominant_kernel(tag, batch, peaks):
+    """The heaviest conv of the net (head tower 3x3 at stride 8), alone, CUDA events, warm."""
+    from streamyolo_b200 import ops
+    from streamyolo_b200.ops import View
+    width = MODELS[tag][1]
+    c = int(256 * width)
+    n, h, w = batch, 75, 120
+    x = View(torch.randn((n, h, w, c), device="cuda").to(torch.bfloat16))
+    wt = ops.pack_conv_weight(torch.randn((c, c, 3, 3), device="cuda") * 0.02)
+    y = View.empty(n, h, w, c, "cuda")
+    P = ops.conv_num_partials(n, h, w)
+    part = torch.empty((P, 2, c), device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        ops.conv2d(x, wt, y, 3, 1, ops.SY_CONV_RAW, partials=part)
+    times = []
+    for _ in range(10):
+        flush.zero_()                                           # evict L2 between timed launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.conv2d(x, wt, y, 3, 1, ops.SY_CONV_RAW, partials=part)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    flops = 2.0 * n * h * w * c * c * 9
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": f"conv_tc_kernel<{min(256, c)}> 3x3 s1 {c}->{c} @{n}x{h}x{w}",
+            "achieved": round(ach, 1), "peak": peaks["burst"], "unit": "TFLOP/s", "frac": round(ach / peaks["burst"], 4),
+            "peak_source": peaks["source"] + " cuBLAS bf16 burst", "ms_per_launch": round(ms, 4),
+            "algorithmic_flop_per_launch": flops, "traffic": None}
+
+
+def cpu_oracle_run(tag, pairs, steps, warmup, height=600, width_px=960):
+    """Times the CPU oracle (fp32) forward+loss; returns pairs/s."""
+    from oracle.streamyolo_oracle import OracleCfg, StreamYoloOracle, model_shapes
+    from streamyolo_b200 import synth
+    depth, width = MODELS[tag]
+    gamma, thr, val = TAL[tag]
+    torch.set_num_threads(os.cpu_count())
+    o = StreamYoloOracle(OracleCfg(depth=depth, width=width, gamma=gamma, ignore_thr=thr, ignore_value=val),
+                         synth.synth_state_dict(model_shapes(depth, width)))
+    x = synth.synth_frames(pairs, height, width_px)
+    tg = synth.synth_labels(pairs, height, width_px)
+    ts = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            o.forward(x, tg)
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+    sec = sum(ts) / len(ts)
+    return pairs / sec, sec
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    pairs = 2
+    v, sec = cpu_oracle_run(args.model, pairs, max(1, min(args.steps, 3)), min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "frame-pairs/sec StreamYOLO-%s 600x960 fwd+loss" % args.model,
+            "value": round(v, 4), "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "StreamYOLO-%s 600x960 frame pairs, forward+loss (train-mode BN), CPU" % args.model,
+                       "pairs_per_step": pairs},
+            "cpu_baseline": {"value": round(v, 4), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "%d pairs/step, oracle restatement of the reference PyTorch path (yolox not installable)" % pairs},
+            "e2e": {"value": round(v, 4), "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="l", choices=list(MODELS))
+    ap.add_argument("--batch", type=int, default=8, help="frame pairs per GPU")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    from streamyolo_b200 import dist as sydist
+    rank, local_rank, world = sydist.env_world()
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a B200 (no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    sydist.init("nccl")
+    from streamyolo_b200 import ops, synth
+    from streamyolo_b200.build import build
+    if rank == 0:
+        build()
+    sydist.barrier()
+    ops.lib()
+    peaks = load_peaks()
+    B, H, W = args.batch, 600, 960
+    model = build_model(args.model, dev)
+    # per-rank inputs (different seed per rank = different frame pairs; the shard of a global batch)
+    x_host = synth.synth_frames(B, H, W, seed=1234 + rank).pin_memory()
+    fut, cur = synth.synth_labels(B, H, W, seed=1 + rank)
+    fut_host, cur_host = fut.pin_memory(), cur.pin_memory()
+    x_dev, fut_dev, cur_dev = x_host.to(dev), fut_host.to(dev), cur_host.to(dev)
+
+    ops.LAUNCHES = 0
+    with torch.no_grad():
+        for _ in range(2):                                    # warm caches (weight packing, func attributes)
+            out = model(x_dev, (fut_dev, cur_dev))
+        torch.cuda.synchronize()
+        ops.LAUNCHES = 0
+        out = model(x_dev, (fut_dev, cur_dev))
+        launches_per_step = ops.LAUNCHES
+        torch.cuda.synchronize()
+        loss_ref = float(out["total_loss"])
+        graph = None
+        if not args.no_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                model(x_dev, (fut_dev, cur_dev))
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g_out = model(x_dev, (fut_dev, cur_dev))
+            g_loss = torch.stack([g_out[k] for k in ("total_loss", "iou_loss", "l1_loss", "conf_loss", "cls_loss", "num_fg")])
+
+        def step():
+            if graph is not None:
+                graph.replay()
+                return g_loss
+            o = model(x_dev, (fut_dev, cur_dev))
+            return torch.stack([o[k] for k in ("total_loss", "iou_loss", "l1_loss", "conf_loss", "cls_loss", "num_fg")])
+
+        # ---------------- device-resident timing
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        sydist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            loss_vec = step()
+        e1.record()
+        torch.cuda.synchronize()
+        sydist.barrier()
+        ms_total = sydist.max_over_ranks(e0.elapsed_time(e1), dev)
+        clocks = sampler.stop()
+        ms_step = ms_total / args.steps
+        value = world * B / (ms_step * 1e-3)
+
+        # ---------------- end-to-end: host inputs, H2D every step (double buffered), D2H of the result
+        copy_stream = torch.cuda.Stream()
+        stage = [(torch.empty_like(x_dev), torch.empty_like(fut_dev), torch.empty_like(cur_dev)) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        res_host = torch.empty(6, dtype=torch.float32).pin_memory()
+
+        def prefetch(i):
+            s = stage[i % 2]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[i % 2])
+                s[0].copy_(x_host, non_blocking=True)
+                s[1].copy_(fut_host, non_blocking=True)
+                s[2].copy_(cur_host, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        def e2e_loop(n):
+            for c in consumed:
+                c.record()
+            prefetch(0)
+            for i in range(n):
+                if i + 1 < n:
+                    prefetch(i + 1)
+                cs = torch.cuda.current_stream()
+                cs.wait_event(ready[i % 2])
+                s = stage[i % 2]
+                if graph is not None:
+                    x_dev.copy_(s[0]); fut_dev.copy_(s[1]); cur_dev.copy_(s[2])
+                    consumed[i % 2].record(cs)
+                    graph.replay()
+                    lv = g_loss
+                else:
+                    o = model(s[0], (s[1], s[2]))
+                    consumed[i % 2].record(cs)
+                    lv = torch.stack([o[k] for k in ("total_loss", "iou_loss", "l1_loss", "conf_loss", "cls_loss", "num_fg")])
+                res_host.copy_(lv, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_loop(args.warmup)
+        sydist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record()
+        e2e_loop(args.steps)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        e2e_ms = sydist.max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3), dev) / args.steps
+        e2e_value = world * B / (e2e_ms * 1e-3)
+        h2d = x_host.numel() * 4 + fut_host.numel() * 4 + cur_host.numel() * 4
+        loss_e2e = float(res_host[0])
+
+    if rank != 0:
+        return
+    gf = GFLOP_PER_PAIR.get(args.model)
+    roof = time_dominant_kernel(args.model, B, peaks) if args.model in GFLOP_PER_PAIR else None
+    line = {
+        "metric": "frame-pairs/sec StreamYOLO-%s 600x960 fwd+loss" % args.model,
+        "value": round(value, 2), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "StreamYOLO-%s (random init) 600x960 frame pairs, forward+loss, train-mode BN, "
+                               "%d pairs/GPU" % (args.model, B),
+                   "pairs_per_gpu": B, "global_pairs": world * B, "parallelism": "dp%d (no data-path collective)" % world,
+                   "cuda_graph": graph is not None,
+                   "l2": "per-step inputs (%.0f MB) + activations (>1 GB) exceed the 126 MB L2" % (h2d / 1e6)},
+        "e2e": {"value": round(e2e_value, 2), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 24,
+                "ms_per_step": round(e2e_ms, 4), "note": "pinned fp32 frames+labels copied every step on a copy stream "
+                                                        "(double buffered), 6 loss scalars read back"},
+        "gpu_launches": launches_per_step * args.steps,
+        "launches_per_step": launches_per_step,
+        "clocks": clocks,
+        "loss_check": {"eager": loss_ref, "timed": float(loss_vec[0]), "e2e": loss_e2e},
+    }
+    if gf:
+        tf = value / world * gf / 1e3
+        line["roofline_step"] = {"bound": "tensor", "achieved": round(tf, 1), "peak": peaks["sustained"], "unit": "TFLOP/s",
+                                 "frac": round(tf / peaks["sustained"], 4), "gflop_per_pair": gf,
+                                 "peak_source": peaks["source"] + " cuBLAS bf16 sustained"}
+    if roof:
+        line["roofline"] = roof
+    if not args.no_cpu_baseline:
+        try:
+            v, sec = cpu_oracle_run(args.model, 2, 2, 1)
+            line["cpu_baseline"] = {"value": round(v, 4), "unit": "pairs/s", "cores": torch.get_num_threads(),
+                                    "kind": "port", "sample": "2 pairs/step x 2 steps, fp32 oracle of the reference path"}
+        except Exception as ex:  # never lose the GPU numbers to a host-side problem
+            line["cpu_baseline"] = {"value": None, "error": str(ex)[:200]}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -82,6 +82,9 @@ class StreamYoloOracle:
     def base_conv(self, pfx, x, k, stride, res=None, round_out=True):
         """yolox BaseConv = SiLU(BN(Conv2d(bias=False, pad=(k-1)//2))) [+ residual]."""
         P, q, c = self.P, self.q, self.cfg
+        self._note(pfx + ".in", x)
+        if res is not None:
+            self._note(pfx + ".res", res)
         y = F.conv2d(x, q(P[pfx + ".conv.weight"]), None, stride, (k - 1) // 2)
         g, b = P[pfx + ".bn.weight"], P[pfx + ".bn.bias"]
         if self.training:

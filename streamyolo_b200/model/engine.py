@@ -19,6 +19,19 @@ from .. import ops
 from ..ops import View
 
 
+TRACE = None      # debugging: set to a dict to capture every BaseConv's stored output by module name
+
+
+def name_modules(model):
+    for n, m in model.named_modules():
+        m._sy_name = n
+
+
+def _trace(m, y):
+    if TRACE is not None:
+        TRACE[getattr(m, "_sy_name", str(id(m)))] = y.torch().permute(0, 3, 1, 2).float().cpu()
+
+
 class Ctx:
     """Per-forward execution context."""
 
@@ -66,6 +79,7 @@ def base_conv(ctx: Ctx, m, x: View, y: View = None, res: View = None) -> View:
     if not ctx.train:
         scale, shift = _folded(m)
         ops.conv2d(x, wpk, y, k, s, ops.SY_CONV_FUSED, impl=ctx.impl, scale=scale, shift=shift, act=act, res=res)
+        _trace(m, y)
         return y
     raw = View.empty(x.n, ho, wo, cout, ctx.device)
     if ctx.impl == "tc":
@@ -78,6 +92,7 @@ def base_conv(ctx: Ctx, m, x: View, y: View = None, res: View = None) -> View:
         partials = torch.empty((P, 2, cout), dtype=torch.float32, device=ctx.device)
         ops.channel_stats(raw, partials)
     bn_apply(ctx, m, raw, partials, y, res, act)
+    _trace(m, y)
     return y
 
 
@@ -130,6 +145,7 @@ def focus_stem(ctx: Ctx, m, x, frames) -> View:
     else:
         scale, shift = _folded(bc)
         ops.bn_act_apply(raw, scale.data_ptr(), shift.data_ptr(), n, 1, None, y)
+    _trace(bc, y)
     return y
 
 

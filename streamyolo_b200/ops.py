@@ -73,6 +73,7 @@ EXPORTED_SYMBOLS = tuple(_SIG)
 
 _lib = None
 _device_ok = False
+LAUNCHES = 0      # kernels launched through this binding (bench.py reports it as gpu_launches)
 
 
 def load_library():
@@ -104,7 +105,9 @@ def lib():
     return l
 
 
-def _check(rc):
+def _check(rc, kernels=1):
+    global LAUNCHES
+    LAUNCHES += kernels
     if rc != 0:
         raise RuntimeError(f"libstreamyolo_sm100 error {rc}: " + load_library().sy_last_error_string().decode())
 
@@ -268,4 +271,4 @@ def tal_loss(outputs, origin, labels_fut, labels_cur, hw, strides, gamma, ignore
     d.fg_out = fg_out.data_ptr() if fg_out is not None else None
     d.matched_out = matched_out.data_ptr() if matched_out is not None else None
     d.pred_iou_out = pred_iou_out.data_ptr() if pred_iou_out is not None else None
-    _check(lib().sy_tal_loss(C.byref(d), _stream()))
+    _check(lib().sy_tal_loss(C.byref(d), _stream()), kernels=6)

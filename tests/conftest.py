@@ -9,6 +9,10 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    import torch
+    # GPU-side torch references must be true fp32 (cuDNN / cuBLAS default to TF32 for fp32 inputs)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
 
 

@@ -35,7 +35,7 @@ def rand_w(co, ci, k, seed):
     return bf(torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5).to(DEV)
 
 
-def check_close(got, ref, what, ulp=2.0 ** -8):
+def check_close(got, ref, what, ulp=2.0 ** -7):
     got, ref = got.float(), ref.float()
     rms = ref.pow(2).mean().sqrt().item() + 1e-12
     err = (got - ref).abs()
