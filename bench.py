@@ -145,13 +145,23 @@ def time_dominant_kernel(tag, batch, peaks):
             "algorithmic_flop_per_launch": flops, "traffic": None}
 
 
+def host_threads():
+    """Threads the CPU leg may really use: the affinity mask, capped (torch CPU convs of this size stop
+    scaling -- and on an oversubscribed container collapse -- beyond a few dozen threads)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(n, int(os.environ.get("SY_CPU_THREADS", 32))))
+
+
 def cpu_oracle_run(tag, pairs, steps, warmup, height=600, width_px=960):
     """Times the CPU oracle (fp32) forward+loss; returns pairs/s."""
     from oracle.streamyolo_oracle import OracleCfg, StreamYoloOracle, model_shapes
     from streamyolo_b200 import synth
     depth, width = MODELS[tag]
     gamma, thr, val = TAL[tag]
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(host_threads())
     o = StreamYoloOracle(OracleCfg(depth=depth, width=width, gamma=gamma, ignore_thr=thr, ignore_value=val),
                          synth.synth_state_dict(model_shapes(depth, width)))
     x = synth.synth_frames(pairs, height, width_px)
@@ -242,7 +252,7 @@ def main():
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 g_out = model(x_dev, (fut_dev, cur_dev))
-            g_loss = torch.stack([g_out[k] for k in ("total_loss", "iou_loss", "l1_loss", "conf_loss", "cls_loss", "num_fg")])
+                g_loss = torch.stack([g_out[k] for k in ("total_loss", "iou_loss", "l1_loss", "conf_loss", "cls_loss", "num_fg")])
 
         def step():
             if graph is not None:

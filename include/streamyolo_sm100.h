@@ -82,13 +82,14 @@ int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream);
  * device-side cross-check of the tensor-core kernel and the path for shapes it rejects. */
 int sy_conv2d_simt(const SyConvDesc* d, sy_stream_t stream);
 
-/* Focus stem: [yolox] Focus (space-to-depth, TL/BL/TR/BR) + 3x3 conv, used at
- * exps/model/darknet.py:115.  x is the NCHW float32 frame-pair batch [b,6,h,w]
- * (exps/model/dfp_pafpn.py:120,145 split it); image n of y takes frame n / b
- * (0 = current, 1 = support) of batch element n % b.  y is the RAW conv output
- * [frames*b, h/2, w/2, cout]; w is bf16 [cout][9][12]. */
-int sy_stem_focus_conv(const float* x, int32_t b, int32_t in_ch, int32_t h, int32_t w_px, int32_t frames,
-                       const void* w, SyTensor y, sy_stream_t stream);
+/* Focus stem, part 1: [yolox] Focus space-to-depth (TL/BL/TR/BR channel order), used at
+ * exps/model/darknet.py:115.  x is the NCHW float32 frame-pair batch [b, in_ch, h, w]
+ * (exps/model/dfp_pafpn.py:120,145 split it); image n of y takes frame n / b (0 = current,
+ * 1 = support; channels 3*frame .. 3*frame+2) of batch element n % b.  y = [frames*b, h/2, w/2, 16]
+ * bf16: 12 focus channels + 4 zero channels, so that the stem's 3x3 conv runs on sy_conv2d_tc with
+ * weights packed [cout][9][16] (zero for the pad channels). */
+int sy_focus_pack(const float* x, int32_t b, int32_t in_ch, int32_t h, int32_t w_px, int32_t frames,
+                  SyTensor y, sy_stream_t stream);
 
 /* -------- BatchNorm (train mode) + SiLU (replaces nn.BatchNorm2d + nn.SiLU inside
  * [yolox] BaseConv; eps/momentum from cfgs/s_s50_onex_dfp_tal_flip.py:40-44) ---------- */

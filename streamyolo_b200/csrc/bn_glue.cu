@@ -6,34 +6,53 @@
 
 namespace sy {
 
-// thread = channel.  Deterministic: partial rows are summed in index order in fp64.
-__global__ void bn_finalize_kernel(const float* __restrict__ partials, int P, int p_split, int groups,
-                                   double count, int C, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* running_mean, float* running_var,
-                                   long long* nbt, float momentum, float eps, float* scale_out, float* shift_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && nbt != nullptr) *nbt += groups;
-  if (c >= C) return;
-  float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 1.f;
+// block = 32 channels x 32 row-lanes.  Deterministic: every thread sums a fixed strided subset of the
+// partial rows in fp64, the 32 row-lanes are then combined in a fixed order.
+__global__ void __launch_bounds__(1024)
+bn_finalize_kernel(const float* __restrict__ partials, int P, int p_split, int groups,
+                   double count, int C, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* running_mean, float* running_var,
+                   long long* nbt, float momentum, float eps, float* scale_out, float* shift_out) {
+  __shared__ double red[2][32][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += groups;
+  float rm = 0.f, rv = 1.f;
+  if (rl == 0 && c < C) {
+    rm = running_mean ? running_mean[c] : 0.f;
+    rv = running_var ? running_var[c] : 1.f;
+  }
   for (int g = 0; g < groups; ++g) {
     const int pa = (g == 0) ? 0 : p_split, pb = (g == 0 && groups > 1) ? p_split : P;
     double s1 = 0.0, s2 = 0.0;
-    for (int q = pa; q < pb; ++q) {
-      s1 += (double)partials[(size_t)q * 2 * C + c];
-      s2 += (double)partials[(size_t)q * 2 * C + C + c];
+    if (c < C) {
+      for (int q = pa + rl; q < pb; q += 32) {
+        s1 += (double)partials[(size_t)q * 2 * C + c];
+        s2 += (double)partials[(size_t)q * 2 * C + C + c];
+      }
     }
-    const double mean = s1 / count;
-    double var = s2 / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float sc = gamma[c] * (float)(1.0 / sqrt(var + (double)eps));
-    scale_out[g * C + c] = sc;
-    shift_out[g * C + c] = beta[c] - (float)mean * sc;
-    const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
-    rm = (1.f - momentum) * rm + momentum * (float)mean;
-    rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+    red[0][rl][cl] = s1;
+    red[1][rl][cl] = s2;
+    __syncthreads();
+    if (rl == 0 && c < C) {
+      s1 = 0.0; s2 = 0.0;
+      for (int r = 0; r < 32; ++r) { s1 += red[0][r][cl]; s2 += red[1][r][cl]; }
+      const double mean = s1 / count;
+      double var = s2 / count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float sc = gamma[c] * (float)(1.0 / sqrt(var + (double)eps));
+      scale_out[g * C + c] = sc;
+      shift_out[g * C + c] = beta[c] - (float)mean * sc;
+      const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
+      rm = (1.f - momentum) * rm + momentum * (float)mean;
+      rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+    }
+    __syncthreads();
   }
-  if (running_mean) running_mean[c] = rm;
-  if (running_var) running_var[c] = rv;
+  if (rl == 0 && c < C) {
+    if (running_mean) running_mean[c] = rm;
+    if (running_var) running_var[c] = rv;
+  }
 }
 
 __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
@@ -170,7 +189,7 @@ extern "C" int sy_bn_finalize(const float* partials, int32_t n_partials, int32_t
   SY_REQUIRE(n_partials > 0 && count_per_group > 0 && c > 0, SY_EINVAL, "bn_finalize: empty input");
   SY_REQUIRE(groups == 1 || (p_split > 0 && p_split < n_partials), SY_EINVAL, "bn_finalize: p_split=%d of %d", p_split,
              n_partials);
-  bn_finalize_kernel<<<cdiv(c, 128), 128, 0, stream>>>(partials, n_partials, p_split, groups, (double)count_per_group, c,
+  bn_finalize_kernel<<<cdiv(c, 32), 1024, 0, stream>>>(partials, n_partials, p_split, groups, (double)count_per_group, c,
                                                        gamma, beta, running_mean, running_var,
                                                        reinterpret_cast<long long*>(nbt), momentum, eps, scale_out,
                                                        shift_out);

@@ -67,41 +67,31 @@ __global__ void conv_simt_kernel(const SimtConvParams p) {
   }
 }
 
-// Focus (space-to-depth TL,BL,TR,BR) + 3x3 conv over the 12 focus channels, from the NCHW fp32 batch.
-// thread = one output pixel x 8 output channels.  Input pixels are rounded to bf16 first (storage
-// precision of every activation in this library).
-__global__ void stem_focus_kernel(const float* __restrict__ x, int B, int in_ch, int H, int W, int frames,
-                                  const __nv_bfloat16* __restrict__ w, __nv_bfloat16* y, long long y_pitch,
-                                  int Cout) {
-  const int Ho = H / 2, Wo = W / 2, G = Cout / 8;
-  const long long total = (long long)frames * B * Ho * Wo * G;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % G);
-    const long long pix = idx / G;
+// Focus space-to-depth (TL, BL, TR, BR order) from the NCHW fp32 frame-pair batch into NHWC bf16 with
+// the 12 focus channels padded to 16 (pad = 0), so that the stem becomes an ordinary 3x3 conv for the
+// tensor-core kernel.  thread = one output pixel: 12 strided fp32 reads (coalesced across the warp via
+// L1), one 32-byte store.  Input pixels are rounded to bf16 (storage precision of every activation).
+__global__ void focus_pack_kernel(const float* __restrict__ x, int B, int in_ch, int H, int W, int frames,
+                                  __nv_bfloat16* y, long long y_pitch) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)frames * B * Ho * Wo;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
     const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho);
     const int n = (int)(pix / ((long long)Wo * Ho));
     const int frame = n / B, b = n % B;
     const float* xb = x + ((long long)b * in_ch + frame * 3) * H * W;
-    float acc[8];
+    float v[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int t = 0; t < 9; ++t) {
-      const int fy = oy + t / 3 - 1, fx = ox + t % 3 - 1;
-      if (fy < 0 || fy >= Ho || fx < 0 || fx >= Wo) continue;
-#pragma unroll
-      for (int fc = 0; fc < 12; ++fc) {
-        const int qd = fc / 3, c = fc % 3;
-        const int dy = qd & 1, dx = qd >> 1;   // TL(0,0) BL(1,0) TR(0,1) BR(1,1)
-        const float v = round_bf16(xb[((long long)c * H + (2 * fy + dy)) * W + 2 * fx + dx]);
-#pragma unroll
-        for (int o = 0; o < 8; ++o)
-          acc[o] += v * __bfloat162float(w[((long long)(g * 8 + o) * 9 + t) * 12 + fc]);
-      }
+    for (int fc = 0; fc < 12; ++fc) {
+      const int qd = fc / 3, c = fc % 3;
+      const int dy = qd & 1, dx = qd >> 1;   // TL(0,0) BL(1,0) TR(0,1) BR(1,1)
+      v[fc] = __ldg(xb + ((long long)c * H + (2 * oy + dy)) * W + 2 * ox + dx);
     }
-    uint4 out = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
-                           pack_bf16(acc[6], acc[7]));
-    *reinterpret_cast<uint4*>(y + pix * y_pitch + g * 8) = out;
+    v[12] = v[13] = v[14] = v[15] = 0.f;
+    uint4* dst = reinterpret_cast<uint4*>(y + pix * y_pitch);
+    dst[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
   }
 }
 
@@ -178,18 +168,19 @@ extern "C" int sy_conv2d_simt(const SyConvDesc* d, sy_stream_t stream_) {
   return launch_status("conv_simt_kernel");
 }
 
-extern "C" int sy_stem_focus_conv(const float* x, int32_t b, int32_t in_ch, int32_t h, int32_t w_px, int32_t frames,
-                                  const void* w, SyTensor y, sy_stream_t stream_) {
+extern "C" int sy_focus_pack(const float* x, int32_t b, int32_t in_ch, int32_t h, int32_t w_px, int32_t frames,
+                             SyTensor y, sy_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  SY_REQUIRE(x && w && view_ok(y), SY_EINVAL, "stem: null input or bad output view");
+  SY_REQUIRE(x && view_ok(y), SY_EINVAL, "focus_pack: null input or bad output view");
   SY_REQUIRE(h % 2 == 0 && w_px % 2 == 0 && frames >= 1 && frames * 3 <= in_ch, SY_EINVAL,
-             "stem: h=%d w=%d must be even, frames=%d in_ch=%d", h, w_px, frames, in_ch);
-  SY_REQUIRE(y.n == frames * b && y.h == h / 2 && y.w == w_px / 2, SY_EINVAL, "stem: output view mismatch");
-  const long long total = (long long)y.n * y.h * y.w * (y.c / 8);
-  const int blocks = (int)((total + 127) / 128 < 148 * 32 ? (total + 127) / 128 : 148 * 32);
-  stem_focus_kernel<<<blocks, 128, 0, stream>>>(x, b, in_ch, h, w_px, frames, reinterpret_cast<const __nv_bfloat16*>(w),
-                                                reinterpret_cast<__nv_bfloat16*>(y.ptr), y.pitch, y.c);
-  return launch_status("stem_focus_kernel");
+             "focus_pack: h=%d w=%d must be even, frames=%d in_ch=%d", h, w_px, frames, in_ch);
+  SY_REQUIRE(y.n == frames * b && y.h == h / 2 && y.w == w_px / 2 && y.c == 16, SY_EINVAL,
+             "focus_pack: output view must be [frames*b, h/2, w/2, 16]");
+  const long long total = (long long)y.n * y.h * y.w;
+  const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+  focus_pack_kernel<<<blocks, 256, 0, stream>>>(x, b, in_ch, h, w_px, frames, reinterpret_cast<__nv_bfloat16*>(y.ptr),
+                                                y.pitch);
+  return launch_status("focus_pack_kernel");
 }
 
 extern "C" int sy_stats_num_partials(int32_t n, int32_t hw) { return n * cdiv(hw, kStatChunk); }

@@ -128,23 +128,41 @@ def csp_layer(ctx: Ctx, m, x: View, out: View = None) -> View:
     return base_conv(ctx, m.conv3, u, out)
 
 
+def _packed_stem(bc):
+    w = bc.conv.weight
+    key = (w._version, w.data_ptr(), w.device)
+    if getattr(bc, "_pk_key", None) != key:
+        bc._pk = ops.pack_stem_weight(w)
+        bc._pk_key = key
+    return bc._pk
+
+
 def focus_stem(ctx: Ctx, m, x, frames) -> View:
-    """[yolox] Focus + BaseConv straight from the NCHW float frame-pair batch."""
+    """[yolox] Focus + BaseConv straight from the NCHW float frame-pair batch: space-to-depth into a
+    16-channel NHWC tensor (12 + 4 zero channels), then the ordinary tensor-core 3x3 conv."""
     b, ch, h, w = x.shape
     bc = m.conv
     cout = bc.conv.out_channels
     n = frames * b
-    raw = View.empty(n, h // 2, w // 2, cout, ctx.device)
-    ops.stem_focus_conv(x, frames, _packed(bc), raw)
+    xin = View.empty(n, h // 2, w // 2, 16, ctx.device)
+    ops.focus_pack(x, frames, xin)
+    wpk = _packed_stem(bc)
     y = View.empty(n, h // 2, w // 2, cout, ctx.device)
-    if ctx.train:
-        P = ops.stats_num_partials(n, (h // 2) * (w // 2))
-        partials = torch.empty((P, 2, cout), dtype=torch.float32, device=ctx.device)
-        ops.channel_stats(raw, partials)
-        bn_apply(ctx, bc, raw, partials, y, None, 1)
-    else:
+    if not ctx.train:
         scale, shift = _folded(bc)
-        ops.bn_act_apply(raw, scale.data_ptr(), shift.data_ptr(), n, 1, None, y)
+        ops.conv2d(xin, wpk, y, 3, 1, ops.SY_CONV_FUSED, impl=ctx.impl, scale=scale, shift=shift, act=1)
+    else:
+        raw = View.empty(n, h // 2, w // 2, cout, ctx.device)
+        if ctx.impl == "tc":
+            P = ops.conv_num_partials(n, raw.h, raw.w)
+            partials = torch.empty((P, 2, cout), dtype=torch.float32, device=ctx.device)
+            ops.conv2d(xin, wpk, raw, 3, 1, ops.SY_CONV_RAW, impl="tc", partials=partials)
+        else:
+            ops.conv2d(xin, wpk, raw, 3, 1, ops.SY_CONV_RAW, impl="simt")
+            P = ops.stats_num_partials(n, raw.h * raw.w)
+            partials = torch.empty((P, 2, cout), dtype=torch.float32, device=ctx.device)
+            ops.channel_stats(raw, partials)
+        bn_apply(ctx, bc, raw, partials, y, None, 1)
     _trace(bc, y)
     return y
 

@@ -53,8 +53,8 @@ _SIG = {
     "sy_conv_num_partials": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     "sy_conv2d_tc": (C.c_int, [C.POINTER(SyConvDesc), C.c_void_p]),
     "sy_conv2d_simt": (C.c_int, [C.POINTER(SyConvDesc), C.c_void_p]),
-    "sy_stem_focus_conv": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
-                                     SyTensor, C.c_void_p]),
+    "sy_focus_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, SyTensor,
+                                C.c_void_p]),
     "sy_stats_num_partials": (C.c_int, [C.c_int32, C.c_int32]),
     "sy_channel_stats": (C.c_int, [SyTensor, C.c_void_p, C.c_int32, C.c_void_p]),
     "sy_bn_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p,
@@ -195,10 +195,18 @@ def conv2d(x: View, wpk, y: View, k, s, mode, impl="tc", scale=None, shift=None,
     _check(fn(C.byref(d), _stream()))
 
 
-def stem_focus_conv(x, frames, wpk, y: View):
+def focus_pack(x, frames, y: View):
     assert x.dtype == torch.float32 and x.is_contiguous()
     b, ch, h, w = x.shape
-    _check(lib().sy_stem_focus_conv(x.data_ptr(), b, ch, h, w, frames, wpk.data_ptr(), y.st(), _stream()))
+    _check(lib().sy_focus_pack(x.data_ptr(), b, ch, h, w, frames, y.st(), _stream()))
+
+
+def pack_stem_weight(w):
+    """[O,12,3,3] float -> bf16 [O][9][16], focus channels padded with zeros."""
+    o = w.shape[0]
+    p = torch.zeros((o, 9, 16), dtype=torch.bfloat16, device=w.device)
+    p[:, :, :12] = w.detach().permute(0, 2, 3, 1).reshape(o, 9, 12).to(torch.bfloat16)
+    return p.contiguous()
 
 
 def stats_num_partials(n, hw):

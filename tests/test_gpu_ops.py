@@ -136,16 +136,20 @@ def test_conv_tc_matches_simt_bitwise_mostly():
     check_close(a.torch().float(), b.torch().float(), "tc vs simt")
 
 
-def test_stem_focus():
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_stem_focus(impl):
     b, h, w, co = 2, 120, 160, 16
     g = torch.Generator().manual_seed(0)
     x = (torch.rand(b, 6, h, w, generator=g) * 255).to(DEV)
     wt = rand_w(co, 12, 3, 7)
+    xin = View.empty(2 * b, h // 2, w // 2, 16, DEV)
+    ops.focus_pack(x, 2, xin)
     y = View.empty(2 * b, h // 2, w // 2, co, DEV)
-    ops.stem_focus_conv(x, 2, ops.pack_conv_weight(wt), y)
+    ops.conv2d(xin, ops.pack_stem_weight(wt), y, 3, 1, ops.SY_CONV_RAW, impl=impl)
     torch.cuda.synchronize()
     xs = bf(torch.cat([x[:, 0:3], x[:, 3:6]], 0))
     foc = torch.cat([xs[..., ::2, ::2], xs[..., 1::2, ::2], xs[..., ::2, 1::2], xs[..., 1::2, 1::2]], 1)
+    assert torch.equal(xin.nchw_float()[:, :12], foc) and (xin.nchw_float()[:, 12:] == 0).all()   # exact
     ref = F.conv2d(foc, wt, None, 1, 1)
     check_close(y.nchw_float(), ref, "stem")
 
