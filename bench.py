@@ -122,8 +122,7 @@ def time_dominant_kernel(tag, batch, peaks):
     x = View(torch.randn((n, h, w, c), device="cuda").to(torch.bfloat16))
     wt = ops.pack_conv_weight(torch.randn((c, c, 3, 3), device="cuda") * 0.02)
     y = View.empty(n, h, w, c, "cuda")
-    P = ops.conv_num_partials(n, h, w)
-    part = torch.empty((P, 2, c), device="cuda")
+    part = torch.empty((ops.conv_stat_rows(), 4 * c), device="cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     for _ in range(3):
         ops.conv2d(x, wt, y, 3, 1, ops.SY_CONV_RAW, partials=part)

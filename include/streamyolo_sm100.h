@@ -58,36 +58,55 @@ int sy_check_device(void);
  * exps/model/tal_head.py:55-104) ------------------------------------------------- */
 enum { SY_CONV_RAW = 0, SY_CONV_FUSED = 1 };
 
+/* One BatchNorm parameter set covering output channels [c_begin, next segment's c_begin or Cout):
+ * lets ONE conv launch serve two BaseConv modules that read the same input (CSPLayer conv1 | conv2). */
+typedef struct {
+  const float* gamma; const float* beta;          /* [c] */
+  float* running_mean; float* running_var;        /* [c], updated in place (may be NULL) */
+  int64_t* num_batches_tracked;                   /* += number of statistic groups (may be NULL) */
+  int32_t c_begin;
+} SyBnSegment;
+
 typedef struct {
   SyTensor x;            /* input  */
   SyTensor y;            /* output: RAW -> conv result; FUSED -> silu(acc*scale+shift)(+res) */
-  const void* w;         /* bf16 [Cout][k*k][Cin] */
-  int32_t ksize;         /* 1 or 3, padding (k-1)/2 */
+  const void* w;         /* bf16 [Cout][kh*kw][Cin] */
+  int32_t kh, kw;        /* 1 or 3 each, padding (k-1)/2 */
   int32_t stride;        /* 1 or 2 */
   int32_t mode;          /* SY_CONV_RAW / SY_CONV_FUSED */
   int32_t act;           /* FUSED: 1 = SiLU, 0 = identity */
   const float* scale;    /* FUSED: [Cout] (folded BatchNorm), may be NULL = 1 */
   const float* shift;    /* FUSED: [Cout], may be NULL = 0 */
   SyTensor res;          /* FUSED: optional residual added after the activation (ptr NULL = none) */
-  float* stat_partials;  /* RAW: [P][2][Cout] per-tile (sum, sum of squares) of the STORED bf16 values, or NULL */
-  int32_t n_partials;    /* out-capacity check: must be >= sy_conv_num_partials() */
+  /* ---- RAW mode, train-mode BatchNorm folded into the conv launch (sy_conv2d_tc only) ---- */
+  int32_t split_n;       /* images >= split_n form statistics group 1 (0 or >= n: one group) */
+  float* stat_partials;  /* workspace [n_partials][2 groups][2][Cout] floats, or NULL = no statistics */
+  int32_t n_partials;    /* >= sy_conv_stat_rows() */
+  SyBnSegment bn[2];     /* bn[0].gamma == NULL: write the per-CTA partial rows only */
+  float momentum, eps;
+  float* scale_out;      /* [2 groups][Cout]: y = x*scale + shift, written by the last CTA */
+  float* shift_out;
+  uint32_t* ticket;      /* one zero-initialised counter per concurrently running launch; left at zero */
 } SyConvDesc;
 
-/* Number of statistic partial rows (P) the tensor-core kernel writes for an output of
- * n x ho x wo; rows are image-major, so rows [0, split_n * P/n) belong to images < split_n. */
-int sy_conv_num_partials(int32_t n, int32_t ho, int32_t wo);
-/* tcgen05 implicit-GEMM kernel (TMA -> smem -> UMMA -> TMEM -> epilogue). */
+/* Rows of the statistics workspace (= SM count: one row per persistent CTA). */
+int sy_conv_stat_rows(void);
+/* tcgen05 implicit-GEMM kernel (TMA -> smem -> UMMA -> TMEM -> epilogue).  In RAW mode with
+ * stat_partials it also accumulates per-channel (sum, sum of squares) of the stored values per
+ * statistics group and, with bn[], finalizes BatchNorm (batch statistics -> scale/shift, running
+ * statistics momentum update, unbiased variance) in the last CTA -- deterministic. */
 int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream);
-/* plain CUDA-core direct convolution with the same contract (no stat partials):
- * device-side cross-check of the tensor-core kernel and the path for shapes it rejects. */
+/* plain CUDA-core direct convolution with the same x/y/w/FUSED contract (no statistics):
+ * device-side cross-check of the tensor-core kernel. */
 int sy_conv2d_simt(const SyConvDesc* d, sy_stream_t stream);
 
 /* Focus stem, part 1: [yolox] Focus space-to-depth (TL/BL/TR/BR channel order), used at
  * exps/model/darknet.py:115.  x is the NCHW float32 frame-pair batch [b, in_ch, h, w]
  * (exps/model/dfp_pafpn.py:120,145 split it); image n of y takes frame n / b (0 = current,
- * 1 = support; channels 3*frame .. 3*frame+2) of batch element n % b.  y = [frames*b, h/2, w/2, 16]
- * bf16: 12 focus channels + 4 zero channels, so that the stem's 3x3 conv runs on sy_conv2d_tc with
- * weights packed [cout][9][16] (zero for the pad channels). */
+ * 1 = support; channels 3*frame .. 3*frame+2) of batch element n % b.  y = [frames*b, h/2, w/2, 48]
+ * bf16: for each focus pixel its three horizontal taps (x-1, x, x+1; zero outside the image), each
+ * 12 focus channels + 4 zero channels.  The stem's 3x3 conv then runs on sy_conv2d_tc as a 3x1 conv
+ * over 48 channels with weights packed [cout][3][48]. */
 int sy_focus_pack(const float* x, int32_t b, int32_t in_ch, int32_t h, int32_t w_px, int32_t frames,
                   SyTensor y, sy_stream_t stream);
 

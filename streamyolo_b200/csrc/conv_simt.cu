@@ -10,7 +10,7 @@ struct SimtConvParams {
   __nv_bfloat16* y; long long y_pitch;
   const __nv_bfloat16* res; long long res_pitch;
   const float* scale; const float* shift;
-  int N, H, W, Cin, Ho, Wo, Cout, ksize, stride, pad, mode, act;
+  int N, H, W, Cin, Ho, Wo, Cout, kh, kw, stride, pad_h, pad_w, mode, act;
 };
 
 // one thread = one output pixel x 8 consecutive output channels; fp32 accumulation in (tap, ci) order
@@ -27,10 +27,10 @@ __global__ void conv_simt_kernel(const SimtConvParams p) {
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    const int taps = p.ksize * p.ksize;
+    const int taps = p.kh * p.kw;
     for (int t = 0; t < taps; ++t) {
-      const int iy = oy * p.stride + t / p.ksize - p.pad;
-      const int ix = ox * p.stride + t % p.ksize - p.pad;
+      const int iy = oy * p.stride + t / p.kw - p.pad_h;
+      const int ix = ox * p.stride + t % p.kw - p.pad_w;
       if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) continue;
       const __nv_bfloat16* xp = p.x + (((long long)n * p.H + iy) * p.W + ix) * p.x_pitch;
       for (int c0 = 0; c0 < p.Cin; c0 += 8) {
@@ -67,31 +67,38 @@ __global__ void conv_simt_kernel(const SimtConvParams p) {
   }
 }
 
-// Focus space-to-depth (TL, BL, TR, BR order) from the NCHW fp32 frame-pair batch into NHWC bf16 with
-// the 12 focus channels padded to 16 (pad = 0), so that the stem becomes an ordinary 3x3 conv for the
-// tensor-core kernel.  thread = one output pixel: 12 strided fp32 reads (coalesced across the warp via
-// L1), one 32-byte store.  Input pixels are rounded to bf16 (storage precision of every activation).
+// Focus space-to-depth (TL, BL, TR, BR order) from the NCHW fp32 frame-pair batch into NHWC bf16, already
+// gathered along W for the 3x3 stem conv: pixel (y, x) holds taps x-1, x, x+1 (zero outside the image), each
+// 12 focus channels + 4 zero channels = 48 channels, so that the stem is a 3x1 conv with three 64-deep K
+// blocks for the tensor-core kernel.  thread = (pixel, tap).  Input pixels are rounded to bf16.
 __global__ void focus_pack_kernel(const float* __restrict__ x, int B, int in_ch, int H, int W, int frames,
                                   __nv_bfloat16* y, long long y_pitch) {
   const int Ho = H / 2, Wo = W / 2;
-  const long long total = (long long)frames * B * Ho * Wo;
-  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
-       pix += (long long)gridDim.x * blockDim.x) {
+  const long long total = (long long)frames * B * Ho * Wo * 3;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(idx % 3);
+    const long long pix = idx / 3;
     const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho);
     const int n = (int)(pix / ((long long)Wo * Ho));
     const int frame = n / B, b = n % B;
-    const float* xb = x + ((long long)b * in_ch + frame * 3) * H * W;
-    float v[16];
+    const int fx = ox + s - 1;
+    float v[12];
+    if (fx >= 0 && fx < Wo) {
+      const float* xb = x + ((long long)b * in_ch + frame * 3) * H * W;
 #pragma unroll
-    for (int fc = 0; fc < 12; ++fc) {
-      const int qd = fc / 3, c = fc % 3;
-      const int dy = qd & 1, dx = qd >> 1;   // TL(0,0) BL(1,0) TR(0,1) BR(1,1)
-      v[fc] = __ldg(xb + ((long long)c * H + (2 * oy + dy)) * W + 2 * ox + dx);
+      for (int fc = 0; fc < 12; ++fc) {
+        const int qd = fc / 3, c = fc % 3;
+        const int dy = qd & 1, dx = qd >> 1;   // TL(0,0) BL(1,0) TR(0,1) BR(1,1)
+        v[fc] = __ldg(xb + ((long long)c * H + (2 * oy + dy)) * W + 2 * fx + dx);
+      }
+    } else {
+#pragma unroll
+      for (int fc = 0; fc < 12; ++fc) v[fc] = 0.f;
     }
-    v[12] = v[13] = v[14] = v[15] = 0.f;
-    uint4* dst = reinterpret_cast<uint4*>(y + pix * y_pitch);
+    uint4* dst = reinterpret_cast<uint4*>(y + pix * y_pitch + s * 16);
     dst[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-    dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+    dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), 0u, 0u);
   }
 }
 
@@ -145,13 +152,13 @@ extern "C" int sy_conv2d_simt(const SyConvDesc* d, sy_stream_t stream_) {
   const SyTensor& x = d->x;
   const SyTensor& y = d->y;
   SY_REQUIRE(view_ok(x) && view_ok(y) && d->w != nullptr, SY_EINVAL, "conv2d_simt: bad x/y view or null weights");
-  SY_REQUIRE((d->ksize == 1 || d->ksize == 3) && (d->stride == 1 || d->stride == 2), SY_EINVAL,
-             "conv2d_simt: ksize %d stride %d unsupported", d->ksize, d->stride);
+  SY_REQUIRE((d->kh == 1 || d->kh == 3) && (d->kw == 1 || d->kw == 3) && (d->stride == 1 || d->stride == 2), SY_EINVAL,
+             "conv2d_simt: kernel %dx%d stride %d unsupported", d->kh, d->kw, d->stride);
   SimtConvParams p{};
-  p.pad = (d->ksize - 1) / 2;
-  p.N = x.n; p.H = x.h; p.W = x.w; p.Cin = x.c; p.Cout = y.c; p.ksize = d->ksize; p.stride = d->stride;
-  p.Ho = (x.h + 2 * p.pad - d->ksize) / d->stride + 1;
-  p.Wo = (x.w + 2 * p.pad - d->ksize) / d->stride + 1;
+  p.pad_h = (d->kh - 1) / 2; p.pad_w = (d->kw - 1) / 2;
+  p.N = x.n; p.H = x.h; p.W = x.w; p.Cin = x.c; p.Cout = y.c; p.kh = d->kh; p.kw = d->kw; p.stride = d->stride;
+  p.Ho = (x.h + 2 * p.pad_h - d->kh) / d->stride + 1;
+  p.Wo = (x.w + 2 * p.pad_w - d->kw) / d->stride + 1;
   SY_REQUIRE(y.n == x.n && y.h == p.Ho && y.w == p.Wo, SY_EINVAL, "conv2d_simt: output view mismatch");
   p.x = reinterpret_cast<const __nv_bfloat16*>(x.ptr); p.x_pitch = x.pitch;
   p.w = reinterpret_cast<const __nv_bfloat16*>(d->w);
@@ -174,9 +181,9 @@ extern "C" int sy_focus_pack(const float* x, int32_t b, int32_t in_ch, int32_t h
   SY_REQUIRE(x && view_ok(y), SY_EINVAL, "focus_pack: null input or bad output view");
   SY_REQUIRE(h % 2 == 0 && w_px % 2 == 0 && frames >= 1 && frames * 3 <= in_ch, SY_EINVAL,
              "focus_pack: h=%d w=%d must be even, frames=%d in_ch=%d", h, w_px, frames, in_ch);
-  SY_REQUIRE(y.n == frames * b && y.h == h / 2 && y.w == w_px / 2 && y.c == 16, SY_EINVAL,
-             "focus_pack: output view must be [frames*b, h/2, w/2, 16]");
-  const long long total = (long long)y.n * y.h * y.w;
+  SY_REQUIRE(y.n == frames * b && y.h == h / 2 && y.w == w_px / 2 && y.c == 48, SY_EINVAL,
+             "focus_pack: output view must be [frames*b, h/2, w/2, 48]");
+  const long long total = (long long)y.n * y.h * y.w * 3;
   const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
   focus_pack_kernel<<<blocks, 256, 0, stream>>>(x, b, in_ch, h, w_px, frames, reinterpret_cast<__nv_bfloat16*>(y.ptr),
                                                 y.pitch);

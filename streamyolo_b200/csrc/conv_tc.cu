@@ -1,7 +1,7 @@
 // Implicit-GEMM convolution on the Blackwell tensor cores (sm_100a).
 //
 //   M = output pixels (a TH x TW spatial patch of one image, <= 128 rows)
-//   N = output channels (BN = 32/64/128/256 per tile)
+//   N = output channels (BN = 64/128/256 per tile, chosen per layer)
 //   K = taps * Cin, walked as (tap, 64-channel block)
 //
 // Operand movement is im2col-free: for every (tap, channel block) ONE 4-D TMA load
@@ -12,10 +12,17 @@
 // with both operands in shared memory and the fp32 accumulator in TMEM (double
 // buffered), so the epilogue of tile i overlaps the main loop of tile i+1.
 //
-// Warp roles (256 threads, persistent CTA, one per SM):
+// Warp roles (384 threads, persistent CTA, one per SM):
 //   warp 0   TMA producer          warp 1   MMA issuer       warp 2   TMEM alloc/free
-//   warps 4-7 epilogue: TMEM -> registers -> (BN-stat partials | folded BN + SiLU +
-//             residual) -> bf16 -> shared staging -> coalesced 16B global stores
+//   warps 4-11 epilogue (two warpgroups, each owns half of the columns of a staged slab):
+//             TMEM -> registers -> (raw | folded BN + SiLU + residual) -> bf16 -> shared staging
+//             -> per-channel statistics + coalesced 16B global stores
+//
+// Train-mode BatchNorm is folded into this kernel as far as the grid-wide dependency allows:
+// every CTA accumulates per-channel (sum, sum of squares) of the values it stored, per
+// statistics group (current / support frames), writes ONE partial row, and the last CTA to
+// finish (atomic ticket) reduces the <= 148 rows in a fixed order (deterministic), updates the
+// running statistics and emits scale/shift for the normalise+SiLU pass.
 //
 // Replaces the cuDNN conv + ATen BN/SiLU triplet behind [yolox] BaseConv
 // (/root/reference/exps/model/darknet.py:115-165, dfp_pafpn.py:33-105, tal_head.py:55-104).
@@ -28,16 +35,24 @@ namespace tc {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;              // bf16 elements = one 128-byte swizzle row
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
+constexpr int kEpiThreads = 256;
 constexpr int kABytes = kBlockM * 128;   // 16 KiB per stage
+constexpr int kMaxStages = 8;
 constexpr uint64_t kSpinLimit = 6000000000ull;  // ~3 s of SM clocks, then trap instead of hanging
+
+struct BnSeg {
+  const float* gamma; const float* beta;
+  float* rmean; float* rvar; long long* nbt;
+  int c_begin;
+};
 
 struct Params {
   int N, Ho, Wo, Cout, Cin;
-  int ksize, stride, pad;
+  int kh, kw, stride, pad_h, pad_w;
   int th, tw, tiles_x, tiles_y;
   int m_tiles, n_tiles, total_tiles;
-  int cblocks, kblocks;
+  int cblocks, kblocks, stages;
   int mode, act;
   __nv_bfloat16* y;
   long long y_pitch;
@@ -45,7 +60,14 @@ struct Params {
   long long res_pitch;
   const float* scale;
   const float* shift;
-  float* partials;
+  // statistics / BatchNorm finalize (RAW mode)
+  int split_n;              // images >= split_n form statistics group 1
+  float* partials;          // [gridDim][2 groups][2][Cout] or nullptr (no statistics)
+  int n_seg;                // 0 = partial rows only
+  BnSeg seg[2];
+  float momentum, eps;
+  float* scale_out; float* shift_out;   // [2][Cout]
+  unsigned int* ticket;
 };
 
 // ----------------------------------------------------------------------------- PTX
@@ -136,13 +158,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address      bits [0,14)
-  d |= (uint64_t)0 << 16;                     // leading byte offset (unused for swizzled K-major)
   d |= (uint64_t)(1024u >> 4) << 32;          // stride byte offset  bits [32,46)
   d |= (uint64_t)1 << 46;                     // descriptor version (sm_100)
   d |= (uint64_t)2 << 61;                     // SWIZZLE_128B
@@ -155,20 +176,20 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 
 template <int BN>
 struct Cfg {
-  static constexpr int kStages = (BN == 256) ? 3 : ((BN == 128) ? 5 : 6);
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageCols = (BN < 128) ? BN : 128;          // epilogue staging width
+  static constexpr int kStageCols = (BN < 128) ? BN : 128;          // epilogue staging width (SC)
   static constexpr int kStagePitch = kStageCols * 2 + 16;           // bytes, +16 breaks bank conflicts
-  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;     // double-buffered accumulator (power of two)
-  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * (kABytes + kBBytes) + kBlockM * kStagePitch +
-                                    2 * 256 * 4 /*scale,shift*/ + kBlockM * 8 /*row offsets*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BN;                          // double-buffered accumulator (power of two)
+  // fixed part of dynamic smem (everything but the A/B ring and the per-CTA statistic accumulators)
+  static constexpr int kFixedBytes = 1024 /*align slack*/ + kBlockM * kStagePitch + 2 * 256 * 4 /*scale,shift*/ +
+                                     kBlockM * 8 /*row offsets*/ + 4 * kStageCols * 4 * 2 /*stat scratch*/ + 256 /*barriers*/;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
   using C = Cfg<BN>;
-  constexpr int S = C::kStages;
+  const int S = p.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -177,17 +198,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* sScale = reinterpret_cast<float*>(sStage + kBlockM * C::kStagePitch);
   float* sShift = sScale + 256;
   long long* sRowOff = reinterpret_cast<long long*>(sShift + 256);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRowOff + kBlockM);
-  // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, then tmem base slot
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  float* sScratch = reinterpret_cast<float*>(sRowOff + kBlockM);        // [2][4][SC]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sScratch + 8 * C::kStageCols);
+  // bars: [0,8) full, [8,16) empty, [16,18) tmem_full, [18,20) tmem_empty, then tmem base slot + flag
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  uint32_t* sFlag = tmem_slot + 1;
+  float* sAcc = reinterpret_cast<float*>(bars + 32);                     // [2 groups][2][Cout]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + 2 + a); };
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -198,7 +222,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -208,8 +232,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int taps = p.ksize * p.ksize;
   const uint32_t a_bytes = (uint32_t)(p.th * p.tw) * 128u;
+  const int per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -218,16 +242,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
-        const int per_img = p.tiles_x * p.tiles_y;
         const int img = m_tile / per_img, rem = m_tile % per_img;
         const int y0 = (rem / p.tiles_x) * p.th, x0 = (rem % p.tiles_x) * p.tw;
         for (int kb = 0; kb < p.kblocks; ++kb) {
           const int tap = kb / p.cblocks, cb = kb % p.cblocks;
-          const int r = tap / p.ksize, s = tap % p.ksize;
+          const int r = tap / p.kw, s = tap % p.kw;
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), a_bytes + (uint32_t)C::kBBytes);
           tma_load_4d(smem_u32(sA + stage * kABytes), &tmA, full_bar(stage), cb * kBlockK,
-                      x0 * p.stride + s - p.pad, y0 * p.stride + r - p.pad, img);
+                      x0 * p.stride + s - p.pad_w, y0 * p.stride + r - p.pad_h, img);
           tma_load_3d(smem_u32(sB + stage * C::kBBytes), &tmB, full_bar(stage), cb * kBlockK, tap, n_tile * BN);
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
@@ -264,13 +287,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
-    const int q = warp & 3;                    // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;             // tile row == TMEM lane
-    const int et = threadIdx.x - 128;          // 0..127
-    const int ty = row / p.tw, tx = row - ty * p.tw;
-    const int per_img = p.tiles_x * p.tiles_y;
     constexpr int SC = C::kStageCols;
     constexpr int CH = SC / 8;                 // 16-byte chunks per staged row
+    constexpr int HC = SC / 2;                 // columns per epilogue warpgroup
+    constexpr int RH = kEpiThreads / SC;       // row groups of the statistics pass (2 or 4)
+    const int q = warp & 3;                    // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;          // which half of the staged columns this warpgroup owns
+    const int row = q * 32 + lane;             // tile row == TMEM lane
+    const int et = threadIdx.x - 128;          // 0..255
+    const int ty = row / p.tw, tx = row - ty * p.tw;
+    const bool do_stats = (p.mode == SY_CONV_RAW) && (p.partials != nullptr);
+    if (do_stats) {
+      for (int i = et; i < 4 * p.Cout; i += kEpiThreads) sAcc[i] = 0.f;
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -281,9 +310,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool valid = (row < p.th * p.tw) && (oy < p.Ho) && (ox < p.Wo);
       const long long pix = ((long long)img * p.Ho + oy) * p.Wo + ox;
       const int n0 = n_tile * BN;
-      sRowOff[row] = valid ? pix : -1;
+      const int grp = img >= p.split_n ? 1 : 0;
+      if (half == 0) sRowOff[row] = valid ? pix : -1;
       if (p.mode == SY_CONV_FUSED) {
-        for (int c = et; c < BN; c += 128) {
+        for (int c = et; c < BN; c += kEpiThreads) {
           const int cg = n0 + c;
           sScale[c] = (cg < p.Cout && p.scale) ? p.scale[cg] : 1.0f;
           sShift[c] = (cg < p.Cout && p.shift) ? p.shift[cg] : 0.0f;
@@ -296,9 +326,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
       for (int h0 = 0; h0 < BN; h0 += SC) {
 #pragma unroll 1
-        for (int j = 0; j < SC / 32; ++j) {
+        for (int j = 0; j < HC / 32; ++j) {
+          const int cl = half * HC + j * 32;          // column inside the staged slab
           uint32_t v[32];
-          tmem_ld32(taddr + (uint32_t)(h0 + j * 32), v);
+          tmem_ld32(taddr + (uint32_t)(h0 + cl), v);
           tmem_ld_wait();
           uint32_t packed[16];
           if (p.mode == SY_CONV_RAW) {
@@ -309,15 +340,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float f[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const int c = h0 + j * 32 + i;
+              const int c = h0 + cl + i;
               float t = __uint_as_float(v[i]) * sScale[c] + sShift[c];
               f[i] = p.act ? silu_f(t) : t;
             }
             if (p.res != nullptr && valid) {
-              const __nv_bfloat16* rp = p.res + pix * p.res_pitch + n0 + h0 + j * 32;
+              const __nv_bfloat16* rp = p.res + pix * p.res_pitch + n0 + h0 + cl;
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                if (n0 + h0 + j * 32 + g * 8 < p.Cout) {
+                if (n0 + h0 + cl + g * 8 < p.Cout) {
                   const uint4 rv = *reinterpret_cast<const uint4*>(rp + g * 8);
                   f[g * 8 + 0] += bf16_lo(rv.x); f[g * 8 + 1] += bf16_hi(rv.x);
                   f[g * 8 + 2] += bf16_lo(rv.y); f[g * 8 + 3] += bf16_hi(rv.y);
@@ -329,7 +360,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 16; ++i) packed[i] = valid ? pack_bf16(f[2 * i], f[2 * i + 1]) : 0u;
           }
-          uint4* dst = reinterpret_cast<uint4*>(sStage + row * C::kStagePitch + j * 64);
+          uint4* dst = reinterpret_cast<uint4*>(sStage + row * C::kStagePitch + cl * 2);
 #pragma unroll
           for (int g = 0; g < 4; ++g)
             dst[g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
@@ -340,25 +371,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_arrive(tempty_bar(acc));
         }
         epi_bar();
-        // ---- per-channel statistic partials of the STORED (bf16-rounded) values
-        if (p.mode == SY_CONV_RAW && p.partials != nullptr && et < SC) {
-          const int cg = n0 + h0 + et;
-          if (cg < p.Cout) {
-            float s1 = 0.f, s2 = 0.f;
-            const uint8_t* col = sStage + et * 2;
+        // ---- per-channel statistics of the STORED (bf16-rounded) values: column sums over row groups
+        if (do_stats) {
+          const int col = et % SC, rh = et / SC;
+          float s1 = 0.f, s2 = 0.f;
+          const uint8_t* cp = sStage + col * 2 + (rh * (kBlockM / RH)) * C::kStagePitch;
 #pragma unroll 8
-            for (int r = 0; r < kBlockM; ++r) {
-              const float x = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(col + r * C::kStagePitch)) << 16);
-              s1 += x;
-              s2 += x * x;
-            }
-            float* pp = p.partials + (size_t)m_tile * 2 * p.Cout;
-            pp[cg] = s1;
-            pp[p.Cout + cg] = s2;
+          for (int r = 0; r < kBlockM / RH; ++r) {
+            const float x = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(cp + r * C::kStagePitch)) << 16);
+            s1 += x;
+            s2 += x * x;
           }
+          sScratch[rh * SC + col] = s1;
+          sScratch[(4 + rh) * SC + col] = s2;
         }
         // ---- coalesced stores: consecutive threads write consecutive 16-byte chunks of a pixel row
-        for (int qd = et; qd < kBlockM * CH; qd += 128) {
+        for (int qd = et; qd < kBlockM * CH; qd += kEpiThreads) {
           const int r = qd / CH, cc = qd - r * CH;
           const long long po = sRowOff[r];
           const int cg = n0 + h0 + cc * 8;
@@ -368,6 +396,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         epi_bar();
+        if (do_stats && et < SC) {
+          const int cg = n0 + h0 + et;
+          if (cg < p.Cout) {
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int rh = 0; rh < RH; ++rh) { s1 += sScratch[rh * SC + et]; s2 += sScratch[(4 + rh) * SC + et]; }
+            sAcc[(grp * 2 + 0) * p.Cout + cg] += s1;      // single owner per column: fixed order, deterministic
+            sAcc[(grp * 2 + 1) * p.Cout + cg] += s2;
+          }
+        }
+      }
+    }
+    // ---------------------------------------------- per-CTA partial row, last CTA finalizes BatchNorm
+    if (do_stats) {
+      epi_bar();
+      float* mine = p.partials + (size_t)blockIdx.x * 4 * p.Cout;
+      for (int i = et; i < 4 * p.Cout; i += kEpiThreads) mine[i] = sAcc[i];
+      if (p.n_seg > 0) {
+        __threadfence();
+        epi_bar();
+        if (et == 0) {
+          const unsigned int old = atomicAdd(p.ticket, 1u);
+          *sFlag = (old == gridDim.x - 1) ? 1u : 0u;
+        }
+        epi_bar();
+        if (*sFlag) {
+          __threadfence();
+          const int groups = p.split_n < p.N ? 2 : 1;
+          for (int c = et; c < p.Cout; c += kEpiThreads) {
+            const BnSeg& sg = (p.n_seg > 1 && c >= p.seg[1].c_begin) ? p.seg[1] : p.seg[0];
+            const int cl = c - sg.c_begin;
+            float rm = sg.rmean ? sg.rmean[cl] : 0.f, rv = sg.rvar ? sg.rvar[cl] : 1.f;
+            for (int g = 0; g < groups; ++g) {
+              double s1 = 0.0, s2 = 0.0;
+              for (unsigned int b = 0; b < gridDim.x; ++b) {
+                const float* row_b = p.partials + (size_t)b * 4 * p.Cout;
+                s1 += (double)__ldcg(row_b + (g * 2 + 0) * p.Cout + c);
+                s2 += (double)__ldcg(row_b + (g * 2 + 1) * p.Cout + c);
+              }
+              const double cnt = (double)((g == 0 ? (groups == 2 ? p.split_n : p.N) : p.N - p.split_n)) * p.Ho * p.Wo;
+              const double mean = s1 / cnt;
+              double var = s2 / cnt - mean * mean;
+              if (var < 0.0) var = 0.0;
+              const float sc = sg.gamma[cl] * (float)(1.0 / sqrt(var + (double)p.eps));
+              p.scale_out[g * p.Cout + c] = sc;
+              p.shift_out[g * p.Cout + c] = sg.beta[cl] - (float)mean * sc;
+              const double unbiased = cnt > 1.0 ? var * (cnt / (cnt - 1.0)) : var;
+              rm = (1.f - p.momentum) * rm + p.momentum * (float)mean;
+              rv = (1.f - p.momentum) * rv + p.momentum * (float)unbiased;
+            }
+            if (sg.rmean) sg.rmean[cl] = rm;
+            if (sg.rvar) sg.rvar[cl] = rv;
+          }
+          if (et == 0) {
+            *p.ticket = 0u;                      // self-cleaning: ready for the next launch / graph replay
+            for (int s = 0; s < p.n_seg; ++s)
+              if (p.seg[s].nbt) *p.seg[s].nbt += groups;
+          }
+        }
       }
     }
   }
@@ -399,16 +486,14 @@ static EncodeTiledFn get_encode() {
 }
 
 // choose the TH x TW output patch (<= 128 pixels) that needs the fewest tiles
-static void pick_patch(int ho, int wo, int stride, int* th, int* tw) {
+static void pick_patch(int ho, int wo, int* th, int* tw) {
   long best = -1;
   for (int w = 1; w <= 128 && w <= ((wo + 7) / 8) * 8; ++w) {
     int h = 128 / w;
     if (h < 1) break;
     if (h > ho) h = ho;
-    if (w * stride > 256 || h * stride > 256) continue;
     long tiles = (long)cdiv(ho, h) * cdiv(wo, w);
-    // prefer fewer tiles, then fuller tiles (larger h*w)
-    long score = tiles * 1000 - (long)h * w;
+    long score = tiles * 1000 - (long)h * w;   // fewer tiles first, then fuller tiles
     if (best < 0 || score < best) {
       best = score;
       *th = h;
@@ -428,15 +513,48 @@ static int num_sms() {
   return n;
 }
 
+// Tile width heuristic.  Per 64-deep K block one SM needs max(MMA, shared-memory operand read) cycles:
+// MMA = 2*BN (128 x BN x 64 MACs at 4096 MAC/clk), smem = (16 KiB A + BN*128 B) / 128 B/clk; the
+// epilogue (~1000 + 8*BN cycles per tile) overlaps the next tile's main loop.  Rounds of the persistent
+// grid quantise the total: fewer, fatter tiles lose when they leave SMs idle.
+static int pick_bn(int cout, int m_tiles, int kblocks) {
+  const int cands[3] = {256, 128, 64};
+  int best_bn = 64;
+  double best = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (bn > 64 && bn / 2 >= cout) continue;          // a narrower tile already covers every channel
+    const int tiles = m_tiles * cdiv(cout, bn);
+    const int rounds = cdiv(tiles, num_sms());
+    const double kb = (double)((2 * bn > 128 + bn) ? 2 * bn : 128 + bn);
+    const double epi = 1000.0 + 8.0 * bn;
+    const double main_c = kblocks * kb;
+    const double per_tile = (main_c > epi ? main_c : epi) + 300.0;
+    const double t = rounds * per_tile + (main_c < epi ? main_c : epi);
+    if (t < best) { best = t; best_bn = bn; }
+  }
+  return best_bn;
+}
+
+static const int kSmemLimit = 232448;   // 227 KiB opt-in maximum per CTA
+
 template <int BN>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
+    SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
+  const int acc_bytes = (p.mode == SY_CONV_RAW && p.partials) ? 16 * p.Cout : 0;
+  const int stage_bytes = kABytes + Cfg<BN>::kBBytes;
+  int stages = (kSmemLimit - Cfg<BN>::kFixedBytes - acc_bytes) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > p.kblocks * 2 && p.kblocks * 2 >= 2) stages = p.kblocks * 2 > kMaxStages ? kMaxStages : p.kblocks * 2;
+  SY_REQUIRE(stages >= 2, SY_EINVAL, "conv2d_tc: Cout=%d leaves no room for the operand ring", p.Cout);
+  p.stages = stages;
+  const int smem = Cfg<BN>::kFixedBytes + acc_bytes + stages * stage_bytes;
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_tc_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(ta, tb, p);
+  conv_tc_kernel<BN><<<grid, kThreads, smem, stream>>>(ta, tb, p);
   return launch_status("conv_tc_kernel");
 }
 
@@ -445,11 +563,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
 
 using namespace sy;
 
-extern "C" int sy_conv_num_partials(int32_t n, int32_t ho, int32_t wo) {
-  int th = 1, tw = 1;
-  tc::pick_patch(ho, wo, 1, &th, &tw);
-  return n * cdiv(ho, th) * cdiv(wo, tw);
-}
+extern "C" int sy_conv_stat_rows(void) { return tc::num_sms(); }
 
 extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -457,30 +571,28 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
   const SyTensor& x = d->x;
   const SyTensor& y = d->y;
   SY_REQUIRE(view_ok(x) && view_ok(y) && d->w != nullptr, SY_EINVAL, "conv2d_tc: bad x/y view or null weights");
-  SY_REQUIRE((d->ksize == 1 || d->ksize == 3) && (d->stride == 1 || d->stride == 2), SY_EINVAL,
-             "conv2d_tc: ksize %d stride %d unsupported", d->ksize, d->stride);
-  const int pad = (d->ksize - 1) / 2;
-  const int ho = (x.h + 2 * pad - d->ksize) / d->stride + 1, wo = (x.w + 2 * pad - d->ksize) / d->stride + 1;
+  SY_REQUIRE((d->kh == 1 || d->kh == 3) && (d->kw == 1 || d->kw == 3) && (d->stride == 1 || d->stride == 2), SY_EINVAL,
+             "conv2d_tc: kernel %dx%d stride %d unsupported", d->kh, d->kw, d->stride);
+  const int ph = (d->kh - 1) / 2, pw = (d->kw - 1) / 2;
+  const int ho = (x.h + 2 * ph - d->kh) / d->stride + 1, wo = (x.w + 2 * pw - d->kw) / d->stride + 1;
   SY_REQUIRE(y.n == x.n && y.h == ho && y.w == wo, SY_EINVAL, "conv2d_tc: output view %dx%dx%d, expected %dx%dx%d",
              y.n, y.h, y.w, x.n, ho, wo);
   SY_REQUIRE(((uintptr_t)d->w % 16) == 0, SY_EINVAL, "conv2d_tc: weights not 16B aligned");
+  SY_REQUIRE(y.c <= 2048, SY_EINVAL, "conv2d_tc: Cout=%d > 2048", y.c);
   tc::EncodeTiledFn enc = tc::get_encode();
   SY_REQUIRE(enc != nullptr, SY_EARCH, "cuTensorMapEncodeTiled not available from the driver");
 
   tc::Params p{};
   p.N = x.n; p.Ho = ho; p.Wo = wo; p.Cout = y.c; p.Cin = x.c;
-  p.ksize = d->ksize; p.stride = d->stride; p.pad = pad;
-  // the same patch rule as sy_conv_num_partials (stride does not change it for this net's shapes)
-  tc::pick_patch(ho, wo, 1, &p.th, &p.tw);
-  SY_REQUIRE(p.th * d->stride <= 256 && p.tw * d->stride <= 256, SY_EINVAL, "conv2d_tc: patch too large for TMA box");
+  p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_h = ph; p.pad_w = pw;
+  tc::pick_patch(ho, wo, &p.th, &p.tw);
   p.tiles_y = cdiv(ho, p.th); p.tiles_x = cdiv(wo, p.tw);
   p.m_tiles = x.n * p.tiles_y * p.tiles_x;
-  int bn = 32;
-  if (y.c > 128) bn = 256; else if (y.c > 64) bn = 128; else if (y.c > 32) bn = 64;
+  p.cblocks = cdiv(x.c, tc::kBlockK);
+  p.kblocks = d->kh * d->kw * p.cblocks;
+  const int bn = tc::pick_bn(y.c, p.m_tiles, p.kblocks);
   p.n_tiles = cdiv(y.c, bn);
   p.total_tiles = p.m_tiles * p.n_tiles;
-  p.cblocks = cdiv(x.c, tc::kBlockK);
-  p.kblocks = d->ksize * d->ksize * p.cblocks;
   p.mode = d->mode; p.act = d->act;
   p.y = reinterpret_cast<__nv_bfloat16*>(y.ptr); p.y_pitch = y.pitch;
   p.res = nullptr; p.res_pitch = 0;
@@ -490,9 +602,29 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
     p.res = reinterpret_cast<const __nv_bfloat16*>(d->res.ptr); p.res_pitch = d->res.pitch;
   }
   p.scale = d->scale; p.shift = d->shift;
+  p.split_n = (d->split_n > 0 && d->split_n < x.n) ? d->split_n : x.n;
   p.partials = (d->mode == SY_CONV_RAW) ? d->stat_partials : nullptr;
-  if (p.partials) SY_REQUIRE(d->n_partials >= p.m_tiles, SY_EWORKSPACE, "conv2d_tc: %d stat partial rows, need %d",
-                             d->n_partials, p.m_tiles);
+  if (p.partials) {
+    SY_REQUIRE(d->n_partials >= tc::num_sms(), SY_EWORKSPACE, "conv2d_tc: %d statistic rows, need %d (sy_conv_stat_rows)",
+               d->n_partials, tc::num_sms());
+    p.n_seg = 0;
+    if (d->bn[0].gamma != nullptr) {
+      SY_REQUIRE(d->ticket && d->scale_out && d->shift_out, SY_EINVAL, "conv2d_tc: BN finalize needs ticket/scale_out/shift_out");
+      for (int s = 0; s < 2; ++s) {
+        if (d->bn[s].gamma == nullptr) break;
+        SY_REQUIRE(d->bn[s].beta != nullptr && d->bn[s].c_begin >= 0 && d->bn[s].c_begin < y.c, SY_EINVAL, "conv2d_tc: bad BN segment %d", s);
+        p.seg[s].gamma = d->bn[s].gamma; p.seg[s].beta = d->bn[s].beta;
+        p.seg[s].rmean = d->bn[s].running_mean; p.seg[s].rvar = d->bn[s].running_var;
+        p.seg[s].nbt = reinterpret_cast<long long*>(d->bn[s].num_batches_tracked);
+        p.seg[s].c_begin = d->bn[s].c_begin;
+        p.n_seg = s + 1;
+      }
+      SY_REQUIRE(p.seg[0].c_begin == 0, SY_EINVAL, "conv2d_tc: first BN segment must start at channel 0");
+      p.momentum = d->momentum; p.eps = d->eps;
+      p.scale_out = d->scale_out; p.shift_out = d->shift_out;
+      p.ticket = d->ticket;
+    }
+  }
 
   // A: input view as (C, W, H, N), box (64, TW*s, TH*s, 1) traversed with element strides (1, s, s, 1)
   CUtensorMap ta, tb;
@@ -508,7 +640,7 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
                (int)r, x.c, x.w, x.h, x.n, (long long)x.pitch, box[0], box[1], box[2]);
   }
   {
-    const int taps = d->ksize * d->ksize;
+    const int taps = d->kh * d->kw;
     cuuint64_t dims[3] = {(cuuint64_t)x.c, (cuuint64_t)taps, (cuuint64_t)y.c};
     cuuint64_t strides[2] = {(cuuint64_t)x.c * 2, (cuuint64_t)x.c * 2 * taps};
     cuuint32_t box[3] = {(cuuint32_t)tc::kBlockK, 1, (cuuint32_t)bn};
@@ -519,7 +651,6 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
     SY_REQUIRE(r == CUDA_SUCCESS, SY_ELAUNCH, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
   }
   switch (bn) {
-    case 32: return tc::launch<32>(ta, tb, p, stream);
     case 64: return tc::launch<64>(ta, tb, p, stream);
     case 128: return tc::launch<128>(ta, tb, p, stream);
     default: return tc::launch<256>(ta, tb, p, stream);

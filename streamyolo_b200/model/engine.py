@@ -67,6 +67,63 @@ def _folded(m):
     return m._fold
 
 
+def _ticket(m, device):
+    """One persistent zero-initialised counter per module (the kernel leaves it at zero)."""
+    t = getattr(m, "_sy_ticket", None)
+    if t is None or t.device != device:
+        t = torch.zeros(1, dtype=torch.int32, device=device)
+        m._sy_ticket = t
+    return t
+
+
+def _bn_seg(m, c_begin=0):
+    bn = m.bn
+    return (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, c_begin)
+
+
+def conv_bn_stats(ctx: Ctx, mods, x: View, wpk, raw: View, k, s):
+    """Train mode, tensor-core path: raw conv output + batch statistics + BatchNorm finalize (running
+    statistics update included) in ONE launch.  ``mods``: one BaseConv, or two whose outputs are
+    concatenated along channels (CSPLayer conv1 | conv2).  Returns sc[2 (scale|shift)][2 (group)][cout]."""
+    cout = raw.c
+    bn0 = mods[0].bn
+    mom = 0.1 if bn0.momentum is None else bn0.momentum
+    sc = torch.empty((2, 2, cout), dtype=torch.float32, device=ctx.device)
+    if ctx.impl == "tc":
+        rows = ops.conv_stat_rows()
+        partials = torch.empty((rows, 4 * cout), dtype=torch.float32, device=ctx.device)
+        segs, c0 = [], 0
+        for m in mods:
+            segs.append(_bn_seg(m, c0))
+            c0 += m.conv.out_channels
+        ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="tc", partials=partials,
+                   split_n=ctx.split if ctx.groups == 2 else 0, bn=segs, momentum=float(mom), eps=float(bn0.eps),
+                   scale_out=sc[0], shift_out=sc[1], ticket=_ticket(mods[0], ctx.device))
+    else:
+        # CUDA-core cross-check path: conv, separate statistics pass, separate finalize per module
+        ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="simt")
+        n = x.n
+        groups = ctx.groups
+        split = ctx.split if groups == 2 else n
+        c0 = 0
+        for m in mods:
+            c = m.conv.out_channels
+            rv = raw.ch(c0, c)
+            P = ops.stats_num_partials(n, raw.h * raw.w)
+            partials = torch.empty((P, 2, c), dtype=torch.float32, device=ctx.device)
+            ops.channel_stats(rv, partials)
+            tmp = torch.empty((2, 2, c), dtype=torch.float32, device=ctx.device)
+            bn = m.bn
+            ops.bn_finalize(partials, (P // n) * split if groups == 2 else 0, groups, split * raw.h * raw.w,
+                            bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                            float(mom), float(bn.eps), tmp[0], tmp[1])
+            sc[:, :, c0:c0 + c] = tmp
+            c0 += c
+    for m in mods:
+        m._stats_epoch = getattr(m, "_stats_epoch", 0) + 1
+    return sc
+
+
 def base_conv(ctx: Ctx, m, x: View, y: View = None, res: View = None) -> View:
     """[yolox] BaseConv: act(bn(conv(x))) (+ res).  ``y`` may be a slice of a concat buffer."""
     k, s = m.ksize, m.stride
@@ -82,46 +139,48 @@ def base_conv(ctx: Ctx, m, x: View, y: View = None, res: View = None) -> View:
         _trace(m, y)
         return y
     raw = View.empty(x.n, ho, wo, cout, ctx.device)
-    if ctx.impl == "tc":
-        P = ops.conv_num_partials(x.n, ho, wo)
-        partials = torch.empty((P, 2, cout), dtype=torch.float32, device=ctx.device)
-        ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="tc", partials=partials)
-    else:
-        ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="simt")
-        P = ops.stats_num_partials(x.n, ho * wo)
-        partials = torch.empty((P, 2, cout), dtype=torch.float32, device=ctx.device)
-        ops.channel_stats(raw, partials)
-    bn_apply(ctx, m, raw, partials, y, res, act)
+    sc = conv_bn_stats(ctx, (m,), x, wpk, raw, k, s)
+    ops.bn_act_apply(raw, sc[0].data_ptr(), sc[1].data_ptr(), ctx.split if ctx.groups == 2 else x.n, act, res, y)
     _trace(m, y)
     return y
 
 
-def bn_apply(ctx: Ctx, m, raw: View, partials, y: View, res: View, act: int):
-    """Batch statistics -> running-stat update -> normalise + act (+res) into ``y``."""
-    bn = m.bn
-    cout = raw.c
-    n = raw.n
-    groups = ctx.groups
-    split = ctx.split if groups == 2 else n
-    P = partials.shape[0]
-    sc = torch.empty((2, 2, cout), dtype=torch.float32, device=ctx.device)   # [scale|shift][group][c]
-    mom = 0.1 if bn.momentum is None else bn.momentum
-    ops.bn_finalize(partials, (P // n) * split if groups == 2 else 0, groups, split * raw.h * raw.w,
-                    bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
-                    float(mom), float(bn.eps), sc[0], sc[1])
-    m._stats_epoch = getattr(m, "_stats_epoch", 0) + 1
-    ops.bn_act_apply(raw, sc[0].data_ptr(), sc[1].data_ptr(), split, act, res, y)
-    return sc
+def _packed_pair(m1, m2):
+    """conv1 | conv2 of a CSPLayer as one [2*hidden][1][Cin] GEMM operand."""
+    w1, w2 = m1.conv.weight, m2.conv.weight
+    key = (w1._version, w2._version, w1.data_ptr(), w2.data_ptr(), w1.device)
+    if getattr(m1, "_pk2_key", None) != key:
+        m1._pk2 = torch.cat([ops.pack_conv_weight(w1), ops.pack_conv_weight(w2)], 0).contiguous()
+        m1._pk2_key = key
+    return m1._pk2
+
+
+def _folded_pair(m1, m2):
+    a, b = _folded(m1), _folded(m2)
+    key = (id(a[0]), id(b[0]))
+    if getattr(m1, "_fold2_key", None) != key:
+        m1._fold2 = (torch.cat([a[0], b[0]]).contiguous(), torch.cat([a[1], b[1]]).contiguous())
+        m1._fold2_key = key
+    return m1._fold2
 
 
 def csp_layer(ctx: Ctx, m, x: View, out: View = None) -> View:
-    """[yolox] CSPLayer: conv3(cat(m(conv1 x), conv2 x)); the concat never materialises as a copy --
-    producers write into channel slices of one buffer and the bottleneck chain runs in place."""
+    """[yolox] CSPLayer: conv3(cat(m(conv1 x), conv2 x)).  conv1 and conv2 read the same input, so they
+    run as ONE GEMM with 2*hidden output channels written straight into the concat buffer; the
+    bottleneck chain then updates the first half in place.  No concat copy ever happens."""
     hid = m.conv1.conv.out_channels
     u = View.empty(x.n, x.h, x.w, 2 * hid, ctx.device)
-    a, b = u.ch(0, hid), u.ch(hid, hid)
-    base_conv(ctx, m.conv1, x, a)
-    base_conv(ctx, m.conv2, x, b)
+    a = u.ch(0, hid)
+    wpk = _packed_pair(m.conv1, m.conv2)
+    if not ctx.train:
+        scale, shift = _folded_pair(m.conv1, m.conv2)
+        ops.conv2d(x, wpk, u, 1, 1, ops.SY_CONV_FUSED, impl=ctx.impl, scale=scale, shift=shift, act=1)
+    else:
+        raw = View.empty(x.n, x.h, x.w, 2 * hid, ctx.device)
+        sc = conv_bn_stats(ctx, (m.conv1, m.conv2), x, wpk, raw, 1, 1)
+        ops.bn_act_apply(raw, sc[0].data_ptr(), sc[1].data_ptr(), ctx.split if ctx.groups == 2 else x.n, 1, None, u)
+    _trace(m.conv1, a)
+    _trace(m.conv2, u.ch(hid, hid))
     for blk in m.m:
         t = base_conv(ctx, blk.conv1, a)
         base_conv(ctx, blk.conv2, t, a, res=a if blk.use_add else None)
@@ -138,31 +197,23 @@ def _packed_stem(bc):
 
 
 def focus_stem(ctx: Ctx, m, x, frames) -> View:
-    """[yolox] Focus + BaseConv straight from the NCHW float frame-pair batch: space-to-depth into a
-    16-channel NHWC tensor (12 + 4 zero channels), then the ordinary tensor-core 3x3 conv."""
+    """[yolox] Focus + BaseConv straight from the NCHW float frame-pair batch: space-to-depth + W-gather into
+    a 48-channel NHWC tensor, then the tensor-core kernel runs the 3x3 stem as a 3x1 conv (3 K blocks)."""
     b, ch, h, w = x.shape
     bc = m.conv
     cout = bc.conv.out_channels
     n = frames * b
-    xin = View.empty(n, h // 2, w // 2, 16, ctx.device)
+    xin = View.empty(n, h // 2, w // 2, 48, ctx.device)
     ops.focus_pack(x, frames, xin)
     wpk = _packed_stem(bc)
     y = View.empty(n, h // 2, w // 2, cout, ctx.device)
     if not ctx.train:
         scale, shift = _folded(bc)
-        ops.conv2d(xin, wpk, y, 3, 1, ops.SY_CONV_FUSED, impl=ctx.impl, scale=scale, shift=shift, act=1)
+        ops.conv2d(xin, wpk, y, ops.STEM_K, 1, ops.SY_CONV_FUSED, impl=ctx.impl, scale=scale, shift=shift, act=1)
     else:
         raw = View.empty(n, h // 2, w // 2, cout, ctx.device)
-        if ctx.impl == "tc":
-            P = ops.conv_num_partials(n, raw.h, raw.w)
-            partials = torch.empty((P, 2, cout), dtype=torch.float32, device=ctx.device)
-            ops.conv2d(xin, wpk, raw, 3, 1, ops.SY_CONV_RAW, impl="tc", partials=partials)
-        else:
-            ops.conv2d(xin, wpk, raw, 3, 1, ops.SY_CONV_RAW, impl="simt")
-            P = ops.stats_num_partials(n, raw.h * raw.w)
-            partials = torch.empty((P, 2, cout), dtype=torch.float32, device=ctx.device)
-            ops.channel_stats(raw, partials)
-        bn_apply(ctx, bc, raw, partials, y, None, 1)
+        sc = conv_bn_stats(ctx, (bc,), xin, wpk, raw, ops.STEM_K, 1)
+        ops.bn_act_apply(raw, sc[0].data_ptr(), sc[1].data_ptr(), ctx.split if ctx.groups == 2 else n, 1, None, y)
     _trace(bc, y)
     return y
 
@@ -236,7 +287,7 @@ def dfp_fuse(ctx: Ctx, net, cur, sup):
                 both = View(c.buf, c.c0, c.c, c.n0, 2 * nb)
                 raw = View.empty(2 * nb, c.h, c.w, half, ctx.device)
                 sub = Ctx(True, 2 * nb, nb, ctx.device)
-                sc = _raw_conv_stats(sub, m, both, raw)
+                sc = conv_bn_stats(sub, (m,), both, wpk, raw, 1, 1)
                 ops.bn_act_apply(raw.imgs(0, nb), sc[0, 0].data_ptr(), sc[1, 0].data_ptr(), nb, 1, c.ch(0, half),
                                  out.ch(0, half))
                 ops.bn_act_apply(raw.imgs(nb, nb), sc[0, 1].data_ptr(), sc[1, 1].data_ptr(), nb, 1,
@@ -245,35 +296,10 @@ def dfp_fuse(ctx: Ctx, net, cur, sup):
                 sub = Ctx(True, nb, nb, ctx.device)
                 for src, dst, r in ((c, out.ch(0, half), c.ch(0, half)), (s, out.ch(half, half), c.ch(half, half))):
                     raw = View.empty(nb, c.h, c.w, half, ctx.device)
-                    sc = _raw_conv_stats(sub, m, src, raw)
+                    sc = conv_bn_stats(sub, (m,), src, wpk, raw, 1, 1)
                     ops.bn_act_apply(raw, sc[0, 0].data_ptr(), sc[1, 0].data_ptr(), nb, 1, r, dst)
         outs.append(out)
     return tuple(outs)
-
-
-def _raw_conv_stats(ctx: Ctx, m, x: View, raw: View):
-    """conv (raw) + statistics + finalize; returns the [2(scale|shift)][2(group)][c] tensor."""
-    cout = raw.c
-    wpk = _packed(m)
-    if ctx.impl == "tc":
-        P = ops.conv_num_partials(x.n, raw.h, raw.w)
-        partials = torch.empty((P, 2, cout), dtype=torch.float32, device=ctx.device)
-        ops.conv2d(x, wpk, raw, m.ksize, m.stride, ops.SY_CONV_RAW, impl="tc", partials=partials)
-    else:
-        ops.conv2d(x, wpk, raw, m.ksize, m.stride, ops.SY_CONV_RAW, impl="simt")
-        P = ops.stats_num_partials(x.n, raw.h * raw.w)
-        partials = torch.empty((P, 2, cout), dtype=torch.float32, device=ctx.device)
-        ops.channel_stats(raw, partials)
-    bn = m.bn
-    groups, n = ctx.groups, x.n
-    split = ctx.split if groups == 2 else n
-    sc = torch.empty((2, 2, cout), dtype=torch.float32, device=ctx.device)
-    mom = 0.1 if bn.momentum is None else bn.momentum
-    ops.bn_finalize(partials, (P // n) * split if groups == 2 else 0, groups, split * raw.h * raw.w,
-                    bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
-                    float(mom), float(bn.eps), sc[0], sc[1])
-    m._stats_epoch = getattr(m, "_stats_epoch", 0) + 1
-    return sc
 
 
 def as_view(t) -> View:

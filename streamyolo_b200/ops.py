@@ -19,10 +19,17 @@ class SyTensor(C.Structure):
                 ("pitch", C.c_int64)]
 
 
+class SyBnSegment(C.Structure):
+    _fields_ = [("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p),
+                ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p), ("c_begin", C.c_int32)]
+
+
 class SyConvDesc(C.Structure):
-    _fields_ = [("x", SyTensor), ("y", SyTensor), ("w", C.c_void_p), ("ksize", C.c_int32), ("stride", C.c_int32),
-                ("mode", C.c_int32), ("act", C.c_int32), ("scale", C.c_void_p), ("shift", C.c_void_p),
-                ("res", SyTensor), ("stat_partials", C.c_void_p), ("n_partials", C.c_int32)]
+    _fields_ = [("x", SyTensor), ("y", SyTensor), ("w", C.c_void_p), ("kh", C.c_int32), ("kw", C.c_int32),
+                ("stride", C.c_int32), ("mode", C.c_int32), ("act", C.c_int32), ("scale", C.c_void_p),
+                ("shift", C.c_void_p), ("res", SyTensor), ("split_n", C.c_int32), ("stat_partials", C.c_void_p),
+                ("n_partials", C.c_int32), ("bn", SyBnSegment * 2), ("momentum", C.c_float), ("eps", C.c_float),
+                ("scale_out", C.c_void_p), ("shift_out", C.c_void_p), ("ticket", C.c_void_p)]
 
 
 class SyHeadPredDesc(C.Structure):
@@ -50,7 +57,7 @@ _SIG = {
     "sy_last_error_string": (C.c_char_p, []),
     "sy_version": (C.c_int, []),
     "sy_check_device": (C.c_int, []),
-    "sy_conv_num_partials": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    "sy_conv_stat_rows": (C.c_int, []),
     "sy_conv2d_tc": (C.c_int, [C.POINTER(SyConvDesc), C.c_void_p]),
     "sy_conv2d_simt": (C.c_int, [C.POINTER(SyConvDesc), C.c_void_p]),
     "sy_focus_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, SyTensor,
@@ -176,21 +183,35 @@ def conv_out_hw(h, w, k, s):
     return (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
 
 
-def conv_num_partials(n, ho, wo):
-    return load_library().sy_conv_num_partials(n, ho, wo)
+def conv_stat_rows():
+    return load_library().sy_conv_stat_rows()
 
 
 def conv2d(x: View, wpk, y: View, k, s, mode, impl="tc", scale=None, shift=None, act=1, res: View = None,
-           partials=None):
+           partials=None, split_n=0, bn=None, momentum=0.03, eps=1e-3, scale_out=None, shift_out=None, ticket=None):
+    """``k`` is an int (square) or (kh, kw).  ``bn``: list of up to two
+    (gamma, beta, running_mean, running_var, num_batches_tracked, c_begin) tuples -> BatchNorm finalize in-kernel."""
     d = SyConvDesc()
     d.x, d.y = x.st(), y.st()
     d.w = wpk.data_ptr()
-    d.ksize, d.stride, d.mode, d.act = k, s, mode, act
+    d.kh, d.kw = (k, k) if isinstance(k, int) else k
+    d.stride, d.mode, d.act = s, mode, act
     d.scale = scale.data_ptr() if scale is not None else None
     d.shift = shift.data_ptr() if shift is not None else None
     d.res = res.st() if res is not None else NULL_T
+    d.split_n = split_n
     if partials is not None:
         d.stat_partials, d.n_partials = partials.data_ptr(), partials.shape[0]
+    if bn:
+        for i, (g, b_, rm, rv, nbt, c0) in enumerate(bn):
+            seg = d.bn[i]
+            seg.gamma, seg.beta = g.data_ptr(), b_.data_ptr()
+            seg.running_mean = rm.data_ptr() if rm is not None else None
+            seg.running_var = rv.data_ptr() if rv is not None else None
+            seg.num_batches_tracked = nbt.data_ptr() if nbt is not None else None
+            seg.c_begin = c0
+        d.momentum, d.eps = momentum, eps
+        d.scale_out, d.shift_out, d.ticket = scale_out.data_ptr(), shift_out.data_ptr(), ticket.data_ptr()
     fn = lib().sy_conv2d_tc if impl == "tc" else lib().sy_conv2d_simt
     _check(fn(C.byref(d), _stream()))
 
@@ -201,12 +222,15 @@ def focus_pack(x, frames, y: View):
     _check(lib().sy_focus_pack(x.data_ptr(), b, ch, h, w, frames, y.st(), _stream()))
 
 
+STEM_K = (3, 1)      # the stem runs as a 3x1 conv over the W-gathered 48-channel focus tensor
+
+
 def pack_stem_weight(w):
-    """[O,12,3,3] float -> bf16 [O][9][16], focus channels padded with zeros."""
+    """[O,12,3,3] float -> bf16 [O][3 (row)][48 = 3 taps x (12 focus + 4 zero)]."""
     o = w.shape[0]
-    p = torch.zeros((o, 9, 16), dtype=torch.bfloat16, device=w.device)
-    p[:, :, :12] = w.detach().permute(0, 2, 3, 1).reshape(o, 9, 12).to(torch.bfloat16)
-    return p.contiguous()
+    p = torch.zeros((o, 3, 3, 16), dtype=torch.bfloat16, device=w.device)
+    p[..., :12] = w.detach().permute(0, 2, 3, 1).to(torch.bfloat16)       # [O, r, s, fc]
+    return p.reshape(o, 3, 48).contiguous()
 
 
 def stats_num_partials(n, hw):

@@ -34,11 +34,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_host_logic_no_gpu(lib):
-    # statistic partial rows: image-major, enough 128-pixel tiles to cover the map
-    for (n, h, w) in [(16, 75, 120), (16, 38, 60), (16, 19, 30), (2, 300, 480), (4, 15, 20)]:
-        p = lib.sy_conv_num_partials(n, h, w)
-        assert p % n == 0 and (p // n) * 128 >= h * w
-        assert (p // n) * 128 <= 1.35 * h * w + 128, (n, h, w, p)      # tile waste stays bounded
+    assert lib.sy_conv_stat_rows() >= 1          # one statistics row per persistent CTA (SM count; 148 on B200)
     assert lib.sy_stats_num_partials(4, 1000) == 8
     assert lib.sy_tal_loss_workspace_bytes(8, 11850, 120, 8) > 2 * 8 * 120 * 11850 * 4
 

@@ -78,22 +78,57 @@ def test_conv_raw(case, impl):
     ho, wo = ops.conv_out_hw(h, w, k, s)
     y = View.empty(n, ho, wo, co, DEV)
     y.buf.fill_(float("nan"))
-    P = ops.conv_num_partials(n, ho, wo)
-    partials = torch.full((P, 2, co), float("nan"), device=DEV) if impl == "tc" else None
-    ops.conv2d(xv, ops.pack_conv_weight(wt), y, k, s, ops.SY_CONV_RAW, impl=impl, partials=partials)
+    rows = ops.conv_stat_rows()
+    partials = torch.full((rows, 4 * co), float("nan"), device=DEV) if impl == "tc" else None
+    split = 1 if n > 1 else 0
+    ops.conv2d(xv, ops.pack_conv_weight(wt), y, k, s, ops.SY_CONV_RAW, impl=impl, partials=partials, split_n=split)
     torch.cuda.synchronize()
     got = y.nchw_float()
     check_close(got, ref, f"conv_{impl}{case}")
     if impl == "tc":
+        # per-CTA partial rows [cta][group][sum|sumsq][c]; rows of CTAs that did not run stay NaN
+        pr = torch.nan_to_num(partials.view(rows, 2, 2, co)).sum(0)
         st = got    # statistics are defined on the stored (rounded) values
-        s1, s2 = partials[:, 0].sum(0), partials[:, 1].sum(0)
-        cnt = n * ho * wo
-        rms = st.pow(2).mean().sqrt().item()
-        assert torch.allclose(s1, st.sum((0, 2, 3)), rtol=0, atol=2e-3 * rms * cnt ** 0.5 + 1e-3), "sum partials"
-        assert torch.allclose(s2, st.pow(2).sum((0, 2, 3)), rtol=2e-3, atol=1e-3), "sumsq partials"
-        # rows are image-major: the first P/n rows cover image 0 only
-        per = P // n
-        assert torch.allclose(partials[:per, 0].sum(0), st[0].sum((1, 2)), rtol=0, atol=2e-3 * rms * (ho * wo) ** 0.5 + 1e-3)
+        groups = [(0, split), (split, n)] if split else [(0, n)]
+        for g, (a0, a1) in enumerate(groups):
+            part = st[a0:a1]
+            cnt = (a1 - a0) * ho * wo
+            rms = part.pow(2).mean().sqrt().item()
+            assert torch.allclose(pr[g, 0], part.sum((0, 2, 3)), rtol=0, atol=2e-3 * rms * cnt ** 0.5 + 1e-3), "sum"
+            assert torch.allclose(pr[g, 1], part.pow(2).sum((0, 2, 3)), rtol=2e-3, atol=1e-3), "sumsq"
+
+
+def test_conv_tc_bn_finalize_in_kernel():
+    """RAW conv + statistics + BatchNorm finalize (two groups, two parameter segments) in one launch,
+    against F.batch_norm on the stored conv output; the ticket must come back to zero."""
+    n, ci, co, h, w = 4, 64, 128, 19, 30
+    x, wt = rand_act(n, ci, h, w, 61), rand_w(co, ci, 1, 62)
+    g = torch.Generator().manual_seed(63)
+    gamma, beta = (torch.rand(co, generator=g) + 0.5).to(DEV), (torch.rand(co, generator=g) - 0.5).to(DEV)
+    rm, rv = (torch.rand(co, generator=g) * 0.2).to(DEV), (torch.rand(co, generator=g) + 0.5).to(DEV)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    half = co // 2
+    nbt = [torch.zeros((), dtype=torch.long, device=DEV) for _ in range(2)]
+    segs = [(gamma[:half].contiguous(), beta[:half].contiguous(), rm[:half], rv[:half], nbt[0], 0),
+            (gamma[half:].contiguous(), beta[half:].contiguous(), rm[half:], rv[half:], nbt[1], half)]
+    y = View.empty(n, h, w, co, DEV)
+    rows = ops.conv_stat_rows()
+    partials = torch.empty((rows, 4 * co), device=DEV)
+    sc = torch.empty((2, 2, co), device=DEV)
+    ticket = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for rep in range(2):      # twice: the self-cleaning ticket must allow re-launch (graph replay)
+        ops.conv2d(ops.from_nchw(x), ops.pack_conv_weight(wt), y, 1, 1, ops.SY_CONV_RAW, partials=partials, split_n=2,
+                   bn=segs, momentum=0.03, eps=1e-3, scale_out=sc[0], shift_out=sc[1], ticket=ticket)
+        torch.cuda.synchronize()
+        assert int(ticket) == 0
+        raw = y.nchw_float()
+        for gi in range(2):
+            xs = raw[gi * 2:(gi + 1) * 2]
+            ref = F.batch_norm(xs, rm_ref, rv_ref, gamma, beta, True, 0.03, 1e-3)
+            got = xs * sc[0, gi][None, :, None, None] + sc[1, gi][None, :, None, None]
+            assert torch.allclose(got, ref, rtol=1e-3, atol=1e-3)
+        assert torch.allclose(rm, rm_ref, rtol=1e-4, atol=1e-5) and torch.allclose(rv, rv_ref, rtol=1e-4, atol=1e-5)
+        assert int(nbt[0]) == 2 * (rep + 1) and int(nbt[1]) == 2 * (rep + 1)
 
 
 @pytest.mark.parametrize("impl", ["simt", "tc"])
@@ -142,14 +177,17 @@ def test_stem_focus(impl):
     g = torch.Generator().manual_seed(0)
     x = (torch.rand(b, 6, h, w, generator=g) * 255).to(DEV)
     wt = rand_w(co, 12, 3, 7)
-    xin = View.empty(2 * b, h // 2, w // 2, 16, DEV)
+    xin = View.empty(2 * b, h // 2, w // 2, 48, DEV)
     ops.focus_pack(x, 2, xin)
     y = View.empty(2 * b, h // 2, w // 2, co, DEV)
-    ops.conv2d(xin, ops.pack_stem_weight(wt), y, 3, 1, ops.SY_CONV_RAW, impl=impl)
+    ops.conv2d(xin, ops.pack_stem_weight(wt), y, ops.STEM_K, 1, ops.SY_CONV_RAW, impl=impl)
     torch.cuda.synchronize()
     xs = bf(torch.cat([x[:, 0:3], x[:, 3:6]], 0))
     foc = torch.cat([xs[..., ::2, ::2], xs[..., 1::2, ::2], xs[..., ::2, 1::2], xs[..., 1::2, 1::2]], 1)
-    assert torch.equal(xin.nchw_float()[:, :12], foc) and (xin.nchw_float()[:, 12:] == 0).all()   # exact
+    packed = xin.nchw_float()
+    assert torch.equal(packed[:, 16:28], foc) and (packed[:, 28:32] == 0).all()            # centre tap: exact
+    assert torch.equal(packed[:, 0:12, :, 1:], foc[..., :-1]) and (packed[:, 0:12, :, 0] == 0).all()
+    assert torch.equal(packed[:, 32:44, :, :-1], foc[..., 1:]) and (packed[:, 32:44, :, -1] == 0).all()
     ref = F.conv2d(foc, wt, None, 1, 1)
     check_close(y.nchw_float(), ref, "stem")
 
