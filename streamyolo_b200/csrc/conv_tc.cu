@@ -20,9 +20,9 @@
 //
 // Train-mode BatchNorm is folded into this kernel as far as the grid-wide dependency allows:
 // every CTA accumulates per-channel (sum, sum of squares) of the values it stored, per
-// statistics group (current / support frames), writes ONE partial row, and the last CTA to
-// finish (atomic ticket) reduces the <= 148 rows in a fixed order (deterministic), updates the
-// running statistics and emits scale/shift for the normalise+SiLU pass.
+// statistics group (current / support frames), and writes ONE partial row; the <= 148 rows are
+// reduced in a fixed order (deterministic) by the first blocks of the normalise+SiLU pass
+// (bn_glue.cu), which also updates the running statistics.
 //
 // Replaces the cuDNN conv + ATen BN/SiLU triplet behind [yolox] BaseConv
 // (/root/reference/exps/model/darknet.py:115-165, dfp_pafpn.py:33-105, tal_head.py:55-104).
@@ -41,12 +41,6 @@ constexpr int kABytes = kBlockM * 128;   // 16 KiB per stage
 constexpr int kMaxStages = 8;
 constexpr uint64_t kSpinLimit = 6000000000ull;  // ~3 s of SM clocks, then trap instead of hanging
 
-struct BnSeg {
-  const float* gamma; const float* beta;
-  float* rmean; float* rvar; long long* nbt;
-  int c_begin;
-};
-
 struct Params {
   int N, Ho, Wo, Cout, Cin;
   int kh, kw, stride, pad_h, pad_w;
@@ -63,11 +57,6 @@ struct Params {
   // statistics / BatchNorm finalize (RAW mode)
   int split_n;              // images >= split_n form statistics group 1
   float* partials;          // [gridDim][2 groups][2][Cout] or nullptr (no statistics)
-  int n_seg;                // 0 = partial rows only
-  BnSeg seg[2];
-  float momentum, eps;
-  float* scale_out; float* shift_out;   // [2][Cout]
-  unsigned int* ticket;
 };
 
 // ----------------------------------------------------------------------------- PTX
@@ -202,7 +191,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* bars = reinterpret_cast<uint64_t*>(sScratch + 8 * C::kStageCols);
   // bars: [0,8) full, [8,16) empty, [16,18) tmem_full, [18,20) tmem_empty, then tmem base slot + flag
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
-  uint32_t* sFlag = tmem_slot + 1;
   float* sAcc = reinterpret_cast<float*>(bars + 32);                     // [2 groups][2][Cout]
 
   const int warp = threadIdx.x >> 5;
@@ -408,54 +396,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-    // ---------------------------------------------- per-CTA partial row, last CTA finalizes BatchNorm
+    // ---------------------------------------------- per-CTA partial row (reduced by the normalise pass)
     if (do_stats) {
       epi_bar();
       float* mine = p.partials + (size_t)blockIdx.x * 4 * p.Cout;
       for (int i = et; i < 4 * p.Cout; i += kEpiThreads) mine[i] = sAcc[i];
-      if (p.n_seg > 0) {
-        __threadfence();
-        epi_bar();
-        if (et == 0) {
-          const unsigned int old = atomicAdd(p.ticket, 1u);
-          *sFlag = (old == gridDim.x - 1) ? 1u : 0u;
-        }
-        epi_bar();
-        if (*sFlag) {
-          __threadfence();
-          const int groups = p.split_n < p.N ? 2 : 1;
-          for (int c = et; c < p.Cout; c += kEpiThreads) {
-            const BnSeg& sg = (p.n_seg > 1 && c >= p.seg[1].c_begin) ? p.seg[1] : p.seg[0];
-            const int cl = c - sg.c_begin;
-            float rm = sg.rmean ? sg.rmean[cl] : 0.f, rv = sg.rvar ? sg.rvar[cl] : 1.f;
-            for (int g = 0; g < groups; ++g) {
-              double s1 = 0.0, s2 = 0.0;
-              for (unsigned int b = 0; b < gridDim.x; ++b) {
-                const float* row_b = p.partials + (size_t)b * 4 * p.Cout;
-                s1 += (double)__ldcg(row_b + (g * 2 + 0) * p.Cout + c);
-                s2 += (double)__ldcg(row_b + (g * 2 + 1) * p.Cout + c);
-              }
-              const double cnt = (double)((g == 0 ? (groups == 2 ? p.split_n : p.N) : p.N - p.split_n)) * p.Ho * p.Wo;
-              const double mean = s1 / cnt;
-              double var = s2 / cnt - mean * mean;
-              if (var < 0.0) var = 0.0;
-              const float sc = sg.gamma[cl] * (float)(1.0 / sqrt(var + (double)p.eps));
-              p.scale_out[g * p.Cout + c] = sc;
-              p.shift_out[g * p.Cout + c] = sg.beta[cl] - (float)mean * sc;
-              const double unbiased = cnt > 1.0 ? var * (cnt / (cnt - 1.0)) : var;
-              rm = (1.f - p.momentum) * rm + p.momentum * (float)mean;
-              rv = (1.f - p.momentum) * rv + p.momentum * (float)unbiased;
-            }
-            if (sg.rmean) sg.rmean[cl] = rm;
-            if (sg.rvar) sg.rvar[cl] = rv;
-          }
-          if (et == 0) {
-            *p.ticket = 0u;                      // self-cleaning: ready for the next launch / graph replay
-            for (int s = 0; s < p.n_seg; ++s)
-              if (p.seg[s].nbt) *p.seg[s].nbt += groups;
-          }
-        }
-      }
     }
   }
   tcgen05_fence_before();
@@ -513,10 +458,10 @@ static int num_sms() {
   return n;
 }
 
-// Tile width heuristic.  Per 64-deep K block one SM needs max(MMA, shared-memory operand read) cycles:
-// MMA = 2*BN (128 x BN x 64 MACs at 4096 MAC/clk), smem = (16 KiB A + BN*128 B) / 128 B/clk; the
-// epilogue (~1000 + 8*BN cycles per tile) overlaps the next tile's main loop.  Rounds of the persistent
-// grid quantise the total: fewer, fatter tiles lose when they leave SMs idle.
+// Tile width heuristic.  Per 64-deep K block one SM needs the larger of the MMA time, 2*BN cycles
+// (128 x BN x 64 MACs at 4096 MAC/clk), and the time to pull the A+B operand bytes out of L2,
+// (16 KiB + BN*128 B) / ~44 B/clk/SM (measured: the chip-wide L2->SM path, not the tensor pipe, bounds a
+// 128-row tile), so wide tiles win unless they leave SMs idle: rounds of the persistent grid quantise.
 static int pick_bn(int cout, int m_tiles, int kblocks) {
   const int cands[3] = {256, 128, 64};
   int best_bn = 64;
@@ -526,8 +471,9 @@ static int pick_bn(int cout, int m_tiles, int kblocks) {
     if (bn > 64 && bn / 2 >= cout) continue;          // a narrower tile already covers every channel
     const int tiles = m_tiles * cdiv(cout, bn);
     const int rounds = cdiv(tiles, num_sms());
-    const double kb = (double)((2 * bn > 128 + bn) ? 2 * bn : 128 + bn);
-    const double epi = 1000.0 + 8.0 * bn;
+    const double l2 = (16384.0 + 128.0 * bn) / 44.0;
+    const double kb = (2.0 * bn > l2) ? 2.0 * bn : l2;
+    const double epi = 1200.0 + 10.0 * bn;
     const double main_c = kblocks * kb;
     const double per_tile = (main_c > epi ? main_c : epi) + 300.0;
     const double t = rounds * per_tile + (main_c < epi ? main_c : epi);
@@ -607,24 +553,8 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
   if (p.partials) {
     SY_REQUIRE(d->n_partials >= tc::num_sms(), SY_EWORKSPACE, "conv2d_tc: %d statistic rows, need %d (sy_conv_stat_rows)",
                d->n_partials, tc::num_sms());
-    p.n_seg = 0;
-    if (d->bn[0].gamma != nullptr) {
-      SY_REQUIRE(d->ticket && d->scale_out && d->shift_out, SY_EINVAL, "conv2d_tc: BN finalize needs ticket/scale_out/shift_out");
-      for (int s = 0; s < 2; ++s) {
-        if (d->bn[s].gamma == nullptr) break;
-        SY_REQUIRE(d->bn[s].beta != nullptr && d->bn[s].c_begin >= 0 && d->bn[s].c_begin < y.c, SY_EINVAL, "conv2d_tc: bad BN segment %d", s);
-        p.seg[s].gamma = d->bn[s].gamma; p.seg[s].beta = d->bn[s].beta;
-        p.seg[s].rmean = d->bn[s].running_mean; p.seg[s].rvar = d->bn[s].running_var;
-        p.seg[s].nbt = reinterpret_cast<long long*>(d->bn[s].num_batches_tracked);
-        p.seg[s].c_begin = d->bn[s].c_begin;
-        p.n_seg = s + 1;
-      }
-      SY_REQUIRE(p.seg[0].c_begin == 0, SY_EINVAL, "conv2d_tc: first BN segment must start at channel 0");
-      p.momentum = d->momentum; p.eps = d->eps;
-      p.scale_out = d->scale_out; p.shift_out = d->shift_out;
-      p.ticket = d->ticket;
-    }
   }
+  if (d->rows_written) *d->rows_written = p.total_tiles < tc::num_sms() ? p.total_tiles : tc::num_sms();
 
   // A: input view as (C, W, H, N), box (64, TW*s, TH*s, 1) traversed with element strides (1, s, s, 1)
   CUtensorMap ta, tb;

@@ -67,12 +67,12 @@ def _folded(m):
     return m._fold
 
 
-def _ticket(m, device):
-    """One persistent zero-initialised counter per module (the kernel leaves it at zero)."""
-    t = getattr(m, "_sy_ticket", None)
+def _sync(m, device):
+    """Two persistent zero-initialised counters per module (bn_train_apply leaves them at zero)."""
+    t = getattr(m, "_sy_sync", None)
     if t is None or t.device != device:
-        t = torch.zeros(1, dtype=torch.int32, device=device)
-        m._sy_ticket = t
+        t = torch.zeros(2, dtype=torch.int32, device=device)
+        m._sy_sync = t
     return t
 
 
@@ -81,47 +81,59 @@ def _bn_seg(m, c_begin=0):
     return (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, c_begin)
 
 
-def conv_bn_stats(ctx: Ctx, mods, x: View, wpk, raw: View, k, s):
-    """Train mode, tensor-core path: raw conv output + batch statistics + BatchNorm finalize (running
-    statistics update included) in ONE launch.  ``mods``: one BaseConv, or two whose outputs are
-    concatenated along channels (CSPLayer conv1 | conv2).  Returns sc[2 (scale|shift)][2 (group)][cout]."""
-    cout = raw.c
+def conv_bn_act(ctx: Ctx, mods, x: View, wpk, k, s, y: View, res: View = None, act=1, y_goff1=0, res_goff1=0):
+    """Train mode: conv -> batch statistics -> BatchNorm (running-stat update) -> act (+res) into ``y``.
+    Tensor-core path = 2 launches: the conv writes the raw bf16 result + one statistics row per CTA, the
+    normalise pass reduces those rows in its first blocks and applies.  ``mods``: one BaseConv, or two whose
+    outputs are concatenated along channels (CSPLayer conv1 | conv2)."""
+    kh, kw = (k, k) if isinstance(k, int) else k
+    ho = (x.h + 2 * ((kh - 1) // 2) - kh) // s + 1
+    wo = (x.w + 2 * ((kw - 1) // 2) - kw) // s + 1
+    cout = sum(m.conv.out_channels for m in mods)
+    raw = View.empty(x.n, ho, wo, cout, ctx.device)
     bn0 = mods[0].bn
-    mom = 0.1 if bn0.momentum is None else bn0.momentum
-    sc = torch.empty((2, 2, cout), dtype=torch.float32, device=ctx.device)
+    mom = float(0.1 if bn0.momentum is None else bn0.momentum)
+    n = x.n
+    split = ctx.split if ctx.groups == 2 else 0
+    for m in mods:
+        m._stats_epoch = getattr(m, "_stats_epoch", 0) + 1
     if ctx.impl == "tc":
-        rows = ops.conv_stat_rows()
-        partials = torch.empty((rows, 4 * cout), dtype=torch.float32, device=ctx.device)
+        partials = torch.empty((ops.conv_stat_rows(), 4 * cout), dtype=torch.float32, device=ctx.device)
+        rows = ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="tc", partials=partials, split_n=split)
         segs, c0 = [], 0
         for m in mods:
             segs.append(_bn_seg(m, c0))
             c0 += m.conv.out_channels
-        ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="tc", partials=partials,
-                   split_n=ctx.split if ctx.groups == 2 else 0, bn=segs, momentum=float(mom), eps=float(bn0.eps),
-                   scale_out=sc[0], shift_out=sc[1], ticket=_ticket(mods[0], ctx.device))
-    else:
-        # CUDA-core cross-check path: conv, separate statistics pass, separate finalize per module
-        ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="simt")
-        n = x.n
-        groups = ctx.groups
-        split = ctx.split if groups == 2 else n
-        c0 = 0
-        for m in mods:
-            c = m.conv.out_channels
-            rv = raw.ch(c0, c)
-            P = ops.stats_num_partials(n, raw.h * raw.w)
-            partials = torch.empty((P, 2, c), dtype=torch.float32, device=ctx.device)
-            ops.channel_stats(rv, partials)
-            tmp = torch.empty((2, 2, c), dtype=torch.float32, device=ctx.device)
-            bn = m.bn
-            ops.bn_finalize(partials, (P // n) * split if groups == 2 else 0, groups, split * raw.h * raw.w,
-                            bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
-                            float(mom), float(bn.eps), tmp[0], tmp[1])
-            sc[:, :, c0:c0 + c] = tmp
-            c0 += c
+        ss = torch.empty((2, 2, cout), dtype=torch.float32, device=ctx.device)
+        ops.bn_train_apply(raw, partials, rows, split, segs, mom, float(bn0.eps), ss, _sync(mods[0], ctx.device), act,
+                           res, y, y_goff1, res_goff1)
+        return
+    # CUDA-core cross-check path: conv, separate statistics pass, separate finalize per module, apply
+    ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="simt")
+    sc = torch.empty((2, 2, cout), dtype=torch.float32, device=ctx.device)
+    sp = split if split else n
+    c0 = 0
     for m in mods:
-        m._stats_epoch = getattr(m, "_stats_epoch", 0) + 1
-    return sc
+        c = m.conv.out_channels
+        P = ops.stats_num_partials(n, ho * wo)
+        partials = torch.empty((P, 2, c), dtype=torch.float32, device=ctx.device)
+        ops.channel_stats(raw.ch(c0, c), partials)
+        tmp = torch.empty((2, 2, c), dtype=torch.float32, device=ctx.device)
+        bn = m.bn
+        ops.bn_finalize(partials, (P // n) * sp if split else 0, 2 if split else 1, sp * ho * wo,
+                        bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                        mom, float(bn.eps), tmp[0], tmp[1])
+        sc[:, :, c0:c0 + c] = tmp
+        c0 += c
+    if y_goff1 == 0 and res_goff1 == 0:
+        ops.bn_act_apply(raw, sc[0].data_ptr(), sc[1].data_ptr(), sp, act, res, y)
+    else:   # group-1 images go to a shifted destination (DFP fusion): one call per group
+        nb = sp
+        ops.bn_act_apply(raw.imgs(0, nb), sc[0, 0].data_ptr(), sc[1, 0].data_ptr(), nb, act,
+                         res.imgs(0, nb) if res is not None else None, y.imgs(0, nb))
+        y1 = View(y.buf, y.c0, y.c, y.n0, nb).shifted(y_goff1 + nb * y.img_elems())
+        r1 = View(res.buf, res.c0, res.c, res.n0, nb).shifted(res_goff1 + nb * res.img_elems()) if res is not None else None
+        ops.bn_act_apply(raw.imgs(nb, nb), sc[0, 1].data_ptr(), sc[1, 1].data_ptr(), nb, act, r1, y1)
 
 
 def base_conv(ctx: Ctx, m, x: View, y: View = None, res: View = None) -> View:
@@ -136,11 +148,8 @@ def base_conv(ctx: Ctx, m, x: View, y: View = None, res: View = None) -> View:
     if not ctx.train:
         scale, shift = _folded(m)
         ops.conv2d(x, wpk, y, k, s, ops.SY_CONV_FUSED, impl=ctx.impl, scale=scale, shift=shift, act=act, res=res)
-        _trace(m, y)
-        return y
-    raw = View.empty(x.n, ho, wo, cout, ctx.device)
-    sc = conv_bn_stats(ctx, (m,), x, wpk, raw, k, s)
-    ops.bn_act_apply(raw, sc[0].data_ptr(), sc[1].data_ptr(), ctx.split if ctx.groups == 2 else x.n, act, res, y)
+    else:
+        conv_bn_act(ctx, (m,), x, wpk, k, s, y, res, act)
     _trace(m, y)
     return y
 
@@ -176,9 +185,7 @@ def csp_layer(ctx: Ctx, m, x: View, out: View = None) -> View:
         scale, shift = _folded_pair(m.conv1, m.conv2)
         ops.conv2d(x, wpk, u, 1, 1, ops.SY_CONV_FUSED, impl=ctx.impl, scale=scale, shift=shift, act=1)
     else:
-        raw = View.empty(x.n, x.h, x.w, 2 * hid, ctx.device)
-        sc = conv_bn_stats(ctx, (m.conv1, m.conv2), x, wpk, raw, 1, 1)
-        ops.bn_act_apply(raw, sc[0].data_ptr(), sc[1].data_ptr(), ctx.split if ctx.groups == 2 else x.n, 1, None, u)
+        conv_bn_act(ctx, (m.conv1, m.conv2), x, wpk, 1, 1, u)
     _trace(m.conv1, a)
     _trace(m.conv2, u.ch(hid, hid))
     for blk in m.m:
@@ -211,9 +218,7 @@ def focus_stem(ctx: Ctx, m, x, frames) -> View:
         scale, shift = _folded(bc)
         ops.conv2d(xin, wpk, y, ops.STEM_K, 1, ops.SY_CONV_FUSED, impl=ctx.impl, scale=scale, shift=shift, act=1)
     else:
-        raw = View.empty(n, h // 2, w // 2, cout, ctx.device)
-        sc = conv_bn_stats(ctx, (bc,), xin, wpk, raw, ops.STEM_K, 1)
-        ops.bn_act_apply(raw, sc[0].data_ptr(), sc[1].data_ptr(), ctx.split if ctx.groups == 2 else n, 1, None, y)
+        conv_bn_act(ctx, (bc,), xin, wpk, ops.STEM_K, 1, y)
     _trace(bc, y)
     return y
 
@@ -281,23 +286,20 @@ def dfp_fuse(ctx: Ctx, net, cur, sup):
                        shift=shift, act=1, res=c.ch(half, half))
         else:
             # the reference runs jian(cur) then jian(sup): two BN batches, two running-stat updates.
-            # Batched here when cur/sup are the two halves of one buffer, else two launches.
-            same = (c.buf is s.buf) and s.n0 == c.n0 + nb and c.c0 == s.c0
+            # Batched here (grouped statistics) when cur/sup are the two halves of one buffer.
+            same = (c.buf is s.buf) and s.n0 == c.n0 + nb and c.c0 == s.c0 and c.c == s.c
             if same:
                 both = View(c.buf, c.c0, c.c, c.n0, 2 * nb)
-                raw = View.empty(2 * nb, c.h, c.w, half, ctx.device)
                 sub = Ctx(True, 2 * nb, nb, ctx.device)
-                sc = conv_bn_stats(sub, (m,), both, wpk, raw, 1, 1)
-                ops.bn_act_apply(raw.imgs(0, nb), sc[0, 0].data_ptr(), sc[1, 0].data_ptr(), nb, 1, c.ch(0, half),
-                                 out.ch(0, half))
-                ops.bn_act_apply(raw.imgs(nb, nb), sc[0, 1].data_ptr(), sc[1, 1].data_ptr(), nb, 1,
-                                 c.ch(half, half), out.ch(half, half))
+                # group 1 (support frames, images nb..2nb-1) lands in channels [half, 2*half) of image n - nb
+                yv = View(out.buf, 0, half, 0, 2 * nb)
+                rv = View(c.buf, c.c0, half, c.n0, 2 * nb)
+                conv_bn_act(sub, (m,), both, wpk, 1, 1, yv, rv, 1,
+                            y_goff1=half - nb * yv.img_elems(), res_goff1=half - nb * rv.img_elems())
             else:
                 sub = Ctx(True, nb, nb, ctx.device)
                 for src, dst, r in ((c, out.ch(0, half), c.ch(0, half)), (s, out.ch(half, half), c.ch(half, half))):
-                    raw = View.empty(nb, c.h, c.w, half, ctx.device)
-                    sc = conv_bn_stats(sub, (m,), src, wpk, raw, 1, 1)
-                    ops.bn_act_apply(raw, sc[0, 0].data_ptr(), sc[1, 0].data_ptr(), nb, 1, r, dst)
+                    conv_bn_act(sub, (m,), src, wpk, 1, 1, dst, r, 1)
         outs.append(out)
     return tuple(outs)
 

@@ -28,8 +28,7 @@ class SyConvDesc(C.Structure):
     _fields_ = [("x", SyTensor), ("y", SyTensor), ("w", C.c_void_p), ("kh", C.c_int32), ("kw", C.c_int32),
                 ("stride", C.c_int32), ("mode", C.c_int32), ("act", C.c_int32), ("scale", C.c_void_p),
                 ("shift", C.c_void_p), ("res", SyTensor), ("split_n", C.c_int32), ("stat_partials", C.c_void_p),
-                ("n_partials", C.c_int32), ("bn", SyBnSegment * 2), ("momentum", C.c_float), ("eps", C.c_float),
-                ("scale_out", C.c_void_p), ("shift_out", C.c_void_p), ("ticket", C.c_void_p)]
+                ("n_partials", C.c_int32), ("rows_written", C.POINTER(C.c_int32))]
 
 
 class SyHeadPredDesc(C.Structure):
@@ -67,6 +66,9 @@ _SIG = {
     "sy_bn_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
+    "sy_bn_train_apply": (C.c_int, [SyTensor, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(SyBnSegment), C.c_float,
+                                    C.c_float, C.c_void_p, C.c_void_p, C.c_int32, SyTensor, SyTensor, C.c_int64,
+                                    C.c_int64, C.c_void_p]),
     "sy_bn_act_apply": (C.c_int, [SyTensor, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, SyTensor, SyTensor,
                                   C.c_void_p]),
     "sy_upsample_nearest": (C.c_int, [SyTensor, SyTensor, C.c_void_p]),
@@ -128,11 +130,11 @@ NULL_T = SyTensor(None, 0, 0, 0, 0, 0)
 
 class View:
     """Channel-slice / image-slice view of an NHWC bf16 buffer ``buf[N,H,W,Ctot]``."""
-    __slots__ = ("buf", "n0", "n", "c0", "c")
+    __slots__ = ("buf", "n0", "n", "c0", "c", "off")
 
     def __init__(self, buf, c0=0, c=None, n0=0, n=None):
         assert buf.dtype == torch.bfloat16 and buf.dim() == 4 and buf.is_contiguous()
-        self.buf, self.c0, self.n0 = buf, c0, n0
+        self.buf, self.c0, self.n0, self.off = buf, c0, n0, 0
         self.c = buf.shape[3] - c0 if c is None else c
         self.n = buf.shape[0] - n0 if n is None else n
 
@@ -154,9 +156,19 @@ class View:
     def imgs(self, n0, n):
         return View(self.buf, self.c0, self.c, self.n0 + n0, n)
 
+    def img_elems(self):
+        b = self.buf
+        return b.shape[1] * b.shape[2] * b.shape[3]
+
+    def shifted(self, elems):
+        """Same shape, base address moved by ``elems`` elements (used for group-offset destinations)."""
+        v = View(self.buf, self.c0, self.c, self.n0, self.n)
+        v.off = getattr(self, "off", 0) + elems
+        return v
+
     def st(self):
         b = self.buf
-        ptr = b.data_ptr() + 2 * (self.n0 * b.shape[1] * b.shape[2] * b.shape[3] + self.c0)
+        ptr = b.data_ptr() + 2 * (self.n0 * b.shape[1] * b.shape[2] * b.shape[3] + self.c0 + self.off)
         return SyTensor(ptr, self.n, b.shape[1], b.shape[2], self.c, b.shape[3])
 
     def torch(self):
@@ -188,9 +200,9 @@ def conv_stat_rows():
 
 
 def conv2d(x: View, wpk, y: View, k, s, mode, impl="tc", scale=None, shift=None, act=1, res: View = None,
-           partials=None, split_n=0, bn=None, momentum=0.03, eps=1e-3, scale_out=None, shift_out=None, ticket=None):
-    """``k`` is an int (square) or (kh, kw).  ``bn``: list of up to two
-    (gamma, beta, running_mean, running_var, num_batches_tracked, c_begin) tuples -> BatchNorm finalize in-kernel."""
+           partials=None, split_n=0):
+    """``k`` is an int (square) or (kh, kw).  With ``partials`` (RAW mode, tensor-core path) returns the number
+    of per-CTA statistic rows the launch writes."""
     d = SyConvDesc()
     d.x, d.y = x.st(), y.st()
     d.w = wpk.data_ptr()
@@ -200,20 +212,28 @@ def conv2d(x: View, wpk, y: View, k, s, mode, impl="tc", scale=None, shift=None,
     d.shift = shift.data_ptr() if shift is not None else None
     d.res = res.st() if res is not None else NULL_T
     d.split_n = split_n
+    rows = C.c_int32(0)
     if partials is not None:
         d.stat_partials, d.n_partials = partials.data_ptr(), partials.shape[0]
-    if bn:
-        for i, (g, b_, rm, rv, nbt, c0) in enumerate(bn):
-            seg = d.bn[i]
-            seg.gamma, seg.beta = g.data_ptr(), b_.data_ptr()
-            seg.running_mean = rm.data_ptr() if rm is not None else None
-            seg.running_var = rv.data_ptr() if rv is not None else None
-            seg.num_batches_tracked = nbt.data_ptr() if nbt is not None else None
-            seg.c_begin = c0
-        d.momentum, d.eps = momentum, eps
-        d.scale_out, d.shift_out, d.ticket = scale_out.data_ptr(), shift_out.data_ptr(), ticket.data_ptr()
+        d.rows_written = C.pointer(rows)
     fn = lib().sy_conv2d_tc if impl == "tc" else lib().sy_conv2d_simt
     _check(fn(C.byref(d), _stream()))
+    return rows.value
+
+
+def bn_train_apply(x: View, partials, rows, split_n, bn, momentum, eps, scale_shift, sync, act, res, y: View,
+                   y_goff1=0, res_goff1=0):
+    """``bn``: list of 1-2 (gamma, beta, running_mean, running_var, num_batches_tracked, c_begin)."""
+    segs = (SyBnSegment * 2)()
+    for i, (g, b_, rm, rv, nbt, c0) in enumerate(bn):
+        segs[i].gamma, segs[i].beta = g.data_ptr(), b_.data_ptr()
+        segs[i].running_mean = rm.data_ptr() if rm is not None else None
+        segs[i].running_var = rv.data_ptr() if rv is not None else None
+        segs[i].num_batches_tracked = nbt.data_ptr() if nbt is not None else None
+        segs[i].c_begin = c0
+    _check(lib().sy_bn_train_apply(x.st(), partials.data_ptr(), rows, split_n, segs, momentum, eps,
+                                   scale_shift.data_ptr(), sync.data_ptr(), act,
+                                   res.st() if res is not None else NULL_T, y.st(), y_goff1, res_goff1, _stream()))
 
 
 def focus_pack(x, frames, y: View):

@@ -98,9 +98,10 @@ def test_conv_raw(case, impl):
             assert torch.allclose(pr[g, 1], part.pow(2).sum((0, 2, 3)), rtol=2e-3, atol=1e-3), "sumsq"
 
 
-def test_conv_tc_bn_finalize_in_kernel():
-    """RAW conv + statistics + BatchNorm finalize (two groups, two parameter segments) in one launch,
-    against F.batch_norm on the stored conv output; the ticket must come back to zero."""
+def test_conv_tc_stats_then_bn_train_apply():
+    """RAW conv with per-CTA statistic rows, then ONE normalise launch that reduces them (two groups, two
+    parameter segments), updates running statistics and applies SiLU + residual; against F.batch_norm on the
+    stored conv output.  The sync counters must come back to zero (re-launch / graph replay safe)."""
     n, ci, co, h, w = 4, 64, 128, 19, 30
     x, wt = rand_act(n, ci, h, w, 61), rand_w(co, ci, 1, 62)
     g = torch.Generator().manual_seed(63)
@@ -111,22 +112,25 @@ def test_conv_tc_bn_finalize_in_kernel():
     nbt = [torch.zeros((), dtype=torch.long, device=DEV) for _ in range(2)]
     segs = [(gamma[:half].contiguous(), beta[:half].contiguous(), rm[:half], rv[:half], nbt[0], 0),
             (gamma[half:].contiguous(), beta[half:].contiguous(), rm[half:], rv[half:], nbt[1], half)]
+    raw = View.empty(n, h, w, co, DEV)
     y = View.empty(n, h, w, co, DEV)
-    rows = ops.conv_stat_rows()
-    partials = torch.empty((rows, 4 * co), device=DEV)
-    sc = torch.empty((2, 2, co), device=DEV)
-    ticket = torch.zeros(1, dtype=torch.int32, device=DEV)
-    for rep in range(2):      # twice: the self-cleaning ticket must allow re-launch (graph replay)
-        ops.conv2d(ops.from_nchw(x), ops.pack_conv_weight(wt), y, 1, 1, ops.SY_CONV_RAW, partials=partials, split_n=2,
-                   bn=segs, momentum=0.03, eps=1e-3, scale_out=sc[0], shift_out=sc[1], ticket=ticket)
+    resid = rand_act(n, co, h, w, 64)
+    partials = torch.empty((ops.conv_stat_rows(), 4 * co), device=DEV)
+    ss = torch.empty((2, 2, co), device=DEV)
+    sync = torch.zeros(2, dtype=torch.int32, device=DEV)
+    for rep in range(2):
+        rows = ops.conv2d(ops.from_nchw(x), ops.pack_conv_weight(wt), raw, 1, 1, ops.SY_CONV_RAW, partials=partials,
+                          split_n=2)
+        assert 1 <= rows <= ops.conv_stat_rows()
+        ops.bn_train_apply(raw, partials, rows, 2, segs, 0.03, 1e-3, ss, sync, 1, ops.from_nchw(resid), y)
         torch.cuda.synchronize()
-        assert int(ticket) == 0
-        raw = y.nchw_float()
+        assert sync.tolist() == [0, 0]
+        rawf = raw.nchw_float()
+        refs = []
         for gi in range(2):
-            xs = raw[gi * 2:(gi + 1) * 2]
-            ref = F.batch_norm(xs, rm_ref, rv_ref, gamma, beta, True, 0.03, 1e-3)
-            got = xs * sc[0, gi][None, :, None, None] + sc[1, gi][None, :, None, None]
-            assert torch.allclose(got, ref, rtol=1e-3, atol=1e-3)
+            refs.append(F.batch_norm(rawf[gi * 2:(gi + 1) * 2], rm_ref, rv_ref, gamma, beta, True, 0.03, 1e-3))
+        ref = F.silu(torch.cat(refs, 0)) + resid
+        check_close(y.nchw_float(), ref, "bn_train_apply")
         assert torch.allclose(rm, rm_ref, rtol=1e-4, atol=1e-5) and torch.allclose(rv, rv_ref, rtol=1e-4, atol=1e-5)
         assert int(nbt[0]) == 2 * (rep + 1) and int(nbt[1]) == 2 * (rep + 1)
 

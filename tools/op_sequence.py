@@ -33,9 +33,14 @@ def install_mocks():
         fl = 2.0 * y.n * y.h * y.w * y.c * x.c * kh * kw_
         by = 2.0 * (x.n * x.h * x.w * x.c + y.n * y.h * y.w * y.c) + (2.0 * y.n * y.h * y.w * y.c if res is not None else 0)
         record("conv", "conv_tc_kernel", cur["name"], fl, by, f"{x.n}x{x.h}x{x.w} {x.c}->{y.c} k{k}s{s}")
+        return 148
 
     def bn_finalize(partials, *a, **k):
         record("finalize", "bn_finalize_kernel", cur["name"], 0, partials.numel() * 4.0, f"P={partials.shape[0]} C={partials.shape[2]}")
+
+    def bn_train_apply(x, partials, rows, split, bn, mom, eps, ss, sync, act, res, y, *a):
+        by = 2.0 * x.n * x.h * x.w * x.c * (3 if res is not None else 2)
+        record("apply", "bn_train_apply_kernel", cur["name"], 0, by, f"{x.n}x{x.h}x{x.w}x{x.c}")
 
     def bn_act_apply(x, sc, sh, split, act, res, y):
         by = 2.0 * x.n * x.h * x.w * x.c * (3 if res is not None else 2)
@@ -58,7 +63,7 @@ def install_mocks():
         for kn in ("k_labels", "k_anchor_prep", "k_pair", "k_dynk", "k_resolve_loss", "k_final"):
             record("loss", kn, "loss", 0, 0, "")
 
-    ops.conv2d, ops.bn_finalize, ops.bn_act_apply = conv2d, bn_finalize, bn_act_apply
+    ops.conv2d, ops.bn_finalize, ops.bn_act_apply, ops.bn_train_apply = conv2d, bn_finalize, bn_act_apply, bn_train_apply
     ops.upsample_nearest, ops.spp_maxpool, ops.copy = simple("upsample_nearest_kernel"), simple("spp_maxpool_kernel"), simple("copy_kernel")
     ops.focus_pack, ops.head_pred_decode, ops.tal_loss = focus_pack, head_pred, tal_loss
     ops.channel_stats = simple("channel_stats_kernel")
@@ -69,12 +74,12 @@ def install_mocks():
         cur["name"] = getattr(m, "_sy_name", "?")
         return orig_base(ctx, m, x, y, res)
     engine.base_conv = named_base
-    orig_cbs = engine.conv_bn_stats
+    orig_cba = engine.conv_bn_act
 
-    def named_cbs(ctx, mods, x, wpk, raw, k, s):
+    def named_cba(ctx, mods, *a, **k):
         cur["name"] = "|".join(getattr(m, "_sy_name", "?") for m in mods)
-        return orig_cbs(ctx, mods, x, wpk, raw, k, s)
-    engine.conv_bn_stats = named_cbs
+        return orig_cba(ctx, mods, *a, **k)
+    engine.conv_bn_act = named_cba
     orig_stem = engine.focus_stem
 
     def named_stem(ctx, m, x, frames):
