@@ -83,6 +83,9 @@ typedef struct {
   float* stat_partials;  /* [n_partials][2 groups][2 (sum, sumsq)][Cout] floats, one row per CTA, or NULL */
   int32_t n_partials;    /* >= sy_conv_stat_rows(); rows of CTAs that did not run are NOT written */
   int32_t* rows_written; /* out (host int, may be NULL): number of partial rows this launch writes */
+  /* ---- debugging only: CTA 0 records (event, clock64) int64 pairs of its three pipeline roles ---- */
+  void* debug_timeline;  /* device buffer of 2*debug_timeline_events int64, or NULL */
+  int32_t debug_timeline_events;
 } SyConvDesc;
 
 /* Rows of the statistics workspace (= SM count: one row per persistent CTA). */

@@ -173,8 +173,15 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const f
     while (ld_acquire_u32(&sync[0]) < (unsigned int)nred) __nanosleep(64);
   }
   __syncthreads();
-  const float* scale = ss;
-  const float* shift = ss + 2 * C;
+  // scale/shift were written by other SMs during this launch: pull them from L2 once into shared memory
+  extern __shared__ float s_ss[];     // [2 (scale|shift)][2 groups][C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(ss) + i);
+    reinterpret_cast<float4*>(s_ss)[i] = v;
+  }
+  __syncthreads();
+  const float* scale = s_ss;
+  const float* shift = s_ss + 2 * C;
   const int G = C / 8;
   const long long total = npix * G;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -184,10 +191,10 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const f
     const int grp = pix >= split_pix ? 1 : 0;
     float f[8], r[8];
     unpack8(*reinterpret_cast<const uint4*>(x + pix * xp + g * 8), f);
-    const float4 s0 = __ldcg(reinterpret_cast<const float4*>(scale + grp * C + g * 8));
-    const float4 s1 = __ldcg(reinterpret_cast<const float4*>(scale + grp * C + g * 8 + 4));
-    const float4 h0 = __ldcg(reinterpret_cast<const float4*>(shift + grp * C + g * 8));
-    const float4 h1 = __ldcg(reinterpret_cast<const float4*>(shift + grp * C + g * 8 + 4));
+    const float4 s0 = *reinterpret_cast<const float4*>(scale + grp * C + g * 8);
+    const float4 s1 = *reinterpret_cast<const float4*>(scale + grp * C + g * 8 + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(shift + grp * C + g * 8);
+    const float4 h1 = *reinterpret_cast<const float4*>(shift + grp * C + g * 8 + 4);
     const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
     const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
@@ -367,7 +374,8 @@ extern "C" int sy_bn_train_apply(SyTensor x, const float* partials, int32_t rows
   int grid = grid_for(npix * (x.c / 8), 256);
   const int nred = cdiv(x.c, 32);
   if (grid < nred) grid = nred;
-  bn_train_apply_kernel<<<grid, 256, 0, stream>>>(CBF(x.ptr), x.pitch, partials, rows, (long long)sn * hw, (double)sn * hw,
+  SY_REQUIRE(x.c <= 2048, SY_EINVAL, "bn_train_apply: c=%d > 2048", x.c);
+  bn_train_apply_kernel<<<grid, 256, (size_t)16 * x.c, stream>>>(CBF(x.ptr), x.pitch, partials, rows, (long long)sn * hw, (double)sn * hw,
                                                   (double)(x.n - sn) * hw, groups, s0, s1, n_seg, momentum, eps,
                                                   scale_shift, sync, act, rp, rpitch, BF(y.ptr), y.pitch, npix, x.c,
                                                   (long long)y_goff1, (long long)r_goff1);

@@ -14,9 +14,11 @@
 //
 // Warp roles (384 threads, persistent CTA, one per SM):
 //   warp 0   TMA producer          warp 1   MMA issuer       warp 2   TMEM alloc/free
-//   warps 4-11 epilogue (two warpgroups, each owns half of the columns of a staged slab):
-//             TMEM -> registers -> (raw | folded BN + SiLU + residual) -> bf16 -> shared staging
-//             -> per-channel statistics + coalesced 16B global stores
+//   warps 4-11 epilogue, per 64-column slab of the accumulator: TMEM -> registers -> (raw | folded BN +
+//             SiLU + residual) -> bf16 -> 128B-swizzled shared staging tile -> ONE 4-D TMA store (the
+//             tensor map clips the patch to the image and the channel slice) while the eight warps
+//             reduce the slab's per-channel (sum, sum of squares) from shared memory with 16-byte loads
+//             and a recursive-halving shuffle (16 shuffles for 16 values)
 //
 // Train-mode BatchNorm is folded into this kernel as far as the grid-wide dependency allows:
 // every CTA accumulates per-channel (sum, sum of squares) of the values it stored, per
@@ -57,7 +59,18 @@ struct Params {
   // statistics / BatchNorm finalize (RAW mode)
   int split_n;              // images >= split_n form statistics group 1
   float* partials;          // [gridDim][2 groups][2][Cout] or nullptr (no statistics)
+  long long* timeline;      // debug: CTA 0 records (event id, clock) pairs; nullptr in production
+  int timeline_cap;
 };
+
+// debug timeline: event = role<<28 | phase<<24 | tile<<8 | kb ; written by CTA 0 only
+__device__ __forceinline__ void tl_rec(const Params& p, int& n, int role, int phase, int tile, int kb) {
+  if (p.timeline != nullptr && blockIdx.x == 0 && n + 1 < p.timeline_cap) {
+    p.timeline[2 * n] = ((long long)role << 28) | ((long long)phase << 24) | ((long long)(tile & 0xffff) << 8) | (kb & 0xff);
+    p.timeline[2 * n + 1] = clock64();
+    ++n;
+  }
+}
 
 // ----------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -108,6 +121,23 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -163,33 +193,33 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 }
 
+constexpr int kSlabCols = 64;                  // epilogue slab: 64 bf16 columns = one 128-byte swizzled row
+constexpr int kSlabBytes = kBlockM * 128;      // 16 KiB staging tile
+
 template <int BN>
 struct Cfg {
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageCols = (BN < 128) ? BN : 128;          // epilogue staging width (SC)
-  static constexpr int kStagePitch = kStageCols * 2 + 16;           // bytes, +16 breaks bank conflicts
   static constexpr int kTmemCols = 2 * BN;                          // double-buffered accumulator (power of two)
   // fixed part of dynamic smem (everything but the A/B ring and the per-CTA statistic accumulators)
-  static constexpr int kFixedBytes = 1024 /*align slack*/ + kBlockM * kStagePitch + 2 * 256 * 4 /*scale,shift*/ +
-                                     kBlockM * 8 /*row offsets*/ + 4 * kStageCols * 4 * 2 /*stat scratch*/ + 256 /*barriers*/;
+  static constexpr int kFixedBytes = 1024 /*align slack*/ + kSlabBytes + 2 * 256 * 4 /*scale,shift*/ + 256 /*barriers*/;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmY, const Params p) {
   using C = Cfg<BN>;
   const int S = p.stages;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the 128B swizzle atoms; plain pointer arithmetic keeps the shared address space
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = sA + S * kABytes;
-  uint8_t* sStage = sB + S * C::kBBytes;
-  float* sScale = reinterpret_cast<float*>(sStage + kBlockM * C::kStagePitch);
+  uint8_t* sStage = sB + S * C::kBBytes;                                 // 1024-aligned: the rings are multiples of 1 KiB
+  float* sScale = reinterpret_cast<float*>(sStage + kSlabBytes);
   float* sShift = sScale + 256;
-  long long* sRowOff = reinterpret_cast<long long*>(sShift + 256);
-  float* sScratch = reinterpret_cast<float*>(sRowOff + kBlockM);        // [2][4][SC]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sScratch + 8 * C::kStageCols);
-  // bars: [0,8) full, [8,16) empty, [16,18) tmem_full, [18,20) tmem_empty, then tmem base slot + flag
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sShift + 256);
+  // bars: [0,8) full, [8,16) empty, [16,18) tmem_full, [18,20) tmem_empty, then the tmem base slot
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
   float* sAcc = reinterpret_cast<float*>(bars + 32);                     // [2 groups][2][Cout]
 
@@ -204,6 +234,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    prefetch_tmap(&tmY);
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -228,6 +259,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int tl_n = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
         const int img = m_tile / per_img, rem = m_tile % per_img;
@@ -236,6 +268,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int tap = kb / p.cblocks, cb = kb % p.cblocks;
           const int r = tap / p.kw, s = tap % p.kw;
           mbar_wait(empty_bar(stage), phase ^ 1u);
+          tl_rec(p, tl_n, 0, 0, tile, kb);
           mbar_expect_tx(full_bar(stage), a_bytes + (uint32_t)C::kBBytes);
           tma_load_4d(smem_u32(sA + stage * kABytes), &tmA, full_bar(stage), cb * kBlockK,
                       x0 * p.stride + s - p.pad_w, y0 * p.stride + r - p.pad_h, img);
@@ -251,14 +284,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      int tl_n = p.timeline_cap / 4;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tl_rec(p, tl_n, 1, 0, tile, 0);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
+          tl_rec(p, tl_n, 1, 1, tile, kb);
           tcgen05_fence_after();
           const uint64_t da = make_smem_desc(smem_u32(sA + stage * kABytes));
           const uint64_t db = make_smem_desc(smem_u32(sB + stage * C::kBBytes));
@@ -275,130 +311,160 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
-    constexpr int SC = C::kStageCols;
-    constexpr int CH = SC / 8;                 // 16-byte chunks per staged row
-    constexpr int HC = SC / 2;                 // columns per epilogue warpgroup
-    constexpr int RH = kEpiThreads / SC;       // row groups of the statistics pass (2 or 4)
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;          // which half of the staged columns this warpgroup owns
+    const int half = (warp - 4) >> 2;          // which 32 columns of a 64-column slab this warpgroup converts
+    const int ew = warp - 4;                   // 0..7: the 8-column group this warp reduces in the statistics pass
     const int row = q * 32 + lane;             // tile row == TMEM lane
     const int et = threadIdx.x - 128;          // 0..255
     const int ty = row / p.tw, tx = row - ty * p.tw;
+    const bool in_patch = row < p.th * p.tw;
+    const uint32_t stage_base = smem_u32(sStage);
+    const uint32_t my_row = stage_base + (uint32_t)row * 128u;
+    const uint32_t rsw = (uint32_t)(row & 7);
     const bool do_stats = (p.mode == SY_CONV_RAW) && (p.partials != nullptr);
     if (do_stats) {
       for (int i = et; i < 4 * p.Cout; i += kEpiThreads) sAcc[i] = 0.f;
     }
     int it = 0;
+    int tl_n = (et == 0) ? p.timeline_cap / 2 : p.timeline_cap;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
-      const int img = m_tile / per_img, rem = m_tile % per_img;
-      const int oy = (rem / p.tiles_x) * p.th + ty, ox = (rem % p.tiles_x) * p.tw + tx;
-      const bool valid = (row < p.th * p.tw) && (oy < p.Ho) && (ox < p.Wo);
+      const int n_tile = tile / p.m_tiles, m_tile = tile - n_tile * p.m_tiles;
+      const int img = m_tile / per_img, rem = m_tile - img * per_img;
+      const int py = rem / p.tiles_x, px = rem - py * p.tiles_x;
+      const int y0 = py * p.th, x0 = px * p.tw;
+      const int oy = y0 + ty, ox = x0 + tx;
+      const bool valid = in_patch && (oy < p.Ho) && (ox < p.Wo);
       const long long pix = ((long long)img * p.Ho + oy) * p.Wo + ox;
       const int n0 = n_tile * BN;
       const int grp = img >= p.split_n ? 1 : 0;
-      if (half == 0) sRowOff[row] = valid ? pix : -1;
+      tl_rec(p, tl_n, 2, 0, tile, 0);
       if (p.mode == SY_CONV_FUSED) {
+        epi_bar();                               // previous tile's readers of sScale/sShift are done
         for (int c = et; c < BN; c += kEpiThreads) {
           const int cg = n0 + c;
           sScale[c] = (cg < p.Cout && p.scale) ? p.scale[cg] : 1.0f;
           sShift[c] = (cg < p.Cout && p.shift) ? p.shift[cg] : 0.0f;
         }
+        epi_bar();
       }
       mbar_wait(tfull_bar(acc), acc_phase);
+      tl_rec(p, tl_n, 2, 1, tile, 0);
       tcgen05_fence_after();
-      epi_bar();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int h0 = 0; h0 < BN; h0 += SC) {
-#pragma unroll 1
-        for (int j = 0; j < HC / 32; ++j) {
-          const int cl = half * HC + j * 32;          // column inside the staged slab
-          uint32_t v[32];
-          tmem_ld32(taddr + (uint32_t)(h0 + cl), v);
-          tmem_ld_wait();
-          uint32_t packed[16];
-          if (p.mode == SY_CONV_RAW) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              packed[i] = valid ? pack_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) : 0u;
-          } else {
-            float f[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int c = h0 + cl + i;
-              float t = __uint_as_float(v[i]) * sScale[c] + sShift[c];
-              f[i] = p.act ? silu_f(t) : t;
-            }
-            if (p.res != nullptr && valid) {
-              const __nv_bfloat16* rp = p.res + pix * p.res_pitch + n0 + h0 + cl;
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if (n0 + h0 + cl + g * 8 < p.Cout) {
-                  const uint4 rv = *reinterpret_cast<const uint4*>(rp + g * 8);
-                  f[g * 8 + 0] += bf16_lo(rv.x); f[g * 8 + 1] += bf16_hi(rv.x);
-                  f[g * 8 + 2] += bf16_lo(rv.y); f[g * 8 + 3] += bf16_hi(rv.y);
-                  f[g * 8 + 4] += bf16_lo(rv.z); f[g * 8 + 5] += bf16_hi(rv.z);
-                  f[g * 8 + 6] += bf16_lo(rv.w); f[g * 8 + 7] += bf16_hi(rv.w);
-                }
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) packed[i] = valid ? pack_bf16(f[2 * i], f[2 * i + 1]) : 0u;
-          }
-          uint4* dst = reinterpret_cast<uint4*>(sStage + row * C::kStagePitch + cl * 2);
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            dst[g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
-        }
-        if (h0 + SC >= BN) {
+      for (int slab = 0; slab < BN / kSlabCols; ++slab) {
+        const int cl = slab * kSlabCols + half * 32;     // first of this thread's 32 accumulator columns
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)cl, v);
+        tmem_ld_wait();
+        if (slab == BN / kSlabCols - 1) {
           // every TMEM read of this accumulator is complete: hand it back to the MMA warp
           tcgen05_fence_before();
           mbar_arrive(tempty_bar(acc));
         }
-        epi_bar();
-        // ---- per-channel statistics of the STORED (bf16-rounded) values: column sums over row groups
-        if (do_stats) {
-          const int col = et % SC, rh = et / SC;
-          float s1 = 0.f, s2 = 0.f;
-          const uint8_t* cp = sStage + col * 2 + (rh * (kBlockM / RH)) * C::kStagePitch;
-#pragma unroll 8
-          for (int r = 0; r < kBlockM / RH; ++r) {
-            const float x = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(cp + r * C::kStagePitch)) << 16);
-            s1 += x;
-            s2 += x * x;
-          }
-          sScratch[rh * SC + col] = s1;
-          sScratch[(4 + rh) * SC + col] = s2;
-        }
-        // ---- coalesced stores: consecutive threads write consecutive 16-byte chunks of a pixel row
-        for (int qd = et; qd < kBlockM * CH; qd += kEpiThreads) {
-          const int r = qd / CH, cc = qd - r * CH;
-          const long long po = sRowOff[r];
-          const int cg = n0 + h0 + cc * 8;
-          if (po >= 0 && cg < p.Cout) {
-            const uint4 val = *reinterpret_cast<const uint4*>(sStage + r * C::kStagePitch + cc * 16);
-            *reinterpret_cast<uint4*>(p.y + po * p.y_pitch + cg) = val;
-          }
-        }
-        epi_bar();
-        if (do_stats && et < SC) {
-          const int cg = n0 + h0 + et;
-          if (cg < p.Cout) {
-            float s1 = 0.f, s2 = 0.f;
+        uint32_t packed[16];
+        if (p.mode == SY_CONV_RAW) {
 #pragma unroll
-            for (int rh = 0; rh < RH; ++rh) { s1 += sScratch[rh * SC + et]; s2 += sScratch[(4 + rh) * SC + et]; }
-            sAcc[(grp * 2 + 0) * p.Cout + cg] += s1;      // single owner per column: fixed order, deterministic
-            sAcc[(grp * 2 + 1) * p.Cout + cg] += s2;
+          for (int i = 0; i < 16; ++i)
+            packed[i] = valid ? pack_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) : 0u;
+        } else {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float t = __uint_as_float(v[i]) * sScale[cl + i] + sShift[cl + i];
+            f[i] = p.act ? silu_f(t) : t;
+          }
+          if (p.res != nullptr && valid) {
+            const __nv_bfloat16* rp = p.res + pix * p.res_pitch + n0 + cl;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (n0 + cl + g * 8 < p.Cout) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(rp + g * 8);
+                f[g * 8 + 0] += bf16_lo(rv.x); f[g * 8 + 1] += bf16_hi(rv.x);
+                f[g * 8 + 2] += bf16_lo(rv.y); f[g * 8 + 3] += bf16_hi(rv.y);
+                f[g * 8 + 4] += bf16_lo(rv.z); f[g * 8 + 5] += bf16_hi(rv.z);
+                f[g * 8 + 6] += bf16_lo(rv.w); f[g * 8 + 7] += bf16_hi(rv.w);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) packed[i] = valid ? pack_bf16(f[2 * i], f[2 * i + 1]) : 0u;
+        }
+        tl_rec(p, tl_n, 2, 2, tile, slab);
+        if (et == 0) bulk_wait_read();           // the previous slab's TMA store has finished reading the staging tile
+        epi_bar();                               // (A) staging tile free: store drained, statistics readers done
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {            // 16-byte chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4)
+          const uint32_t j = (uint32_t)(half * 4 + g);
+          sts128(my_row + ((j ^ rsw) << 4), packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+        }
+        fence_proxy_async();                     // generic-proxy writes -> visible to the TMA (async proxy)
+        epi_bar();                               // (B) staging tile complete
+        tl_rec(p, tl_n, 2, 3, tile, slab);
+        if (et == 0) {
+          tma_store_4d(&tmY, stage_base, n0 + slab * kSlabCols, x0, y0, img);
+          bulk_commit();
+        }
+        if (do_stats) {
+          // warp ew reduces columns [8*ew, 8*ew+8) of the slab: lane l reads rows l, l+32, l+64, l+96
+          float a[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) a[i] = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const uint32_t r = (uint32_t)(lane + 32 * rr);
+            const uint4 u = lds128(stage_base + r * 128u + ((((uint32_t)ew) ^ (r & 7u)) << 4));
+            const float x[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                                bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a[i] += x[i]; a[8 + i] += x[i] * x[i]; }
+          }
+          // recursive halving over the 32 lanes: 8 + 4 + 2 + 1 + 1 shuffles, fixed order (deterministic)
+          float b8[8], c4[4], d2[2], e1;
+          {
+            const bool up = (lane & 16) != 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float send = up ? a[i] : a[8 + i], keep = up ? a[8 + i] : a[i];
+              b8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+          }
+          {
+            const bool up = (lane & 8) != 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float send = up ? b8[i] : b8[4 + i], keep = up ? b8[4 + i] : b8[i];
+              c4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+          }
+          {
+            const bool up = (lane & 4) != 0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float send = up ? c4[i] : c4[2 + i], keep = up ? c4[2 + i] : c4[i];
+              d2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+          }
+          {
+            const bool up = (lane & 2) != 0;
+            const float send = up ? d2[0] : d2[1], keep = up ? d2[1] : d2[0];
+            e1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+          e1 += __shfl_xor_sync(0xffffffffu, e1, 1);
+          if ((lane & 1) == 0) {                 // 16 owner lanes: bit4 = sum | sumsq, bits 3..1 = column in the group
+            const int col = n0 + slab * kSlabCols + ew * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            if (col < p.Cout) sAcc[(grp * 2 + (lane >> 4)) * p.Cout + col] += e1;
           }
         }
+        tl_rec(p, tl_n, 2, 4, tile, slab);
       }
     }
+    if (et == 0) bulk_wait_all();                // the last TMA store must be complete before the CTA exits
     // ---------------------------------------------- per-CTA partial row (reduced by the normalise pass)
     if (do_stats) {
-      epi_bar();
+      epi_bar();                                 // every warp's sAcc updates are done
       float* mine = p.partials + (size_t)blockIdx.x * 4 * p.Cout;
       for (int i = et; i < 4 * p.Cout; i += kEpiThreads) mine[i] = sAcc[i];
     }
@@ -485,7 +551,7 @@ static int pick_bn(int cout, int m_tiles, int kblocks) {
 static const int kSmemLimit = 232448;   // 227 KiB opt-in maximum per CTA
 
 template <int BN>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params& p, cudaStream_t stream) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, Params& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
@@ -495,12 +561,11 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params& p, cudaS
   const int stage_bytes = kABytes + Cfg<BN>::kBBytes;
   int stages = (kSmemLimit - Cfg<BN>::kFixedBytes - acc_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > p.kblocks * 2 && p.kblocks * 2 >= 2) stages = p.kblocks * 2 > kMaxStages ? kMaxStages : p.kblocks * 2;
   SY_REQUIRE(stages >= 2, SY_EINVAL, "conv2d_tc: Cout=%d leaves no room for the operand ring", p.Cout);
   p.stages = stages;
   const int smem = Cfg<BN>::kFixedBytes + acc_bytes + stages * stage_bytes;
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_tc_kernel<BN><<<grid, kThreads, smem, stream>>>(ta, tb, p);
+  conv_tc_kernel<BN><<<grid, kThreads, smem, stream>>>(ta, tb, ty, p);
   return launch_status("conv_tc_kernel");
 }
 
@@ -554,10 +619,12 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
     SY_REQUIRE(d->n_partials >= tc::num_sms(), SY_EWORKSPACE, "conv2d_tc: %d statistic rows, need %d (sy_conv_stat_rows)",
                d->n_partials, tc::num_sms());
   }
+  p.timeline = reinterpret_cast<long long*>(d->debug_timeline);
+  p.timeline_cap = d->debug_timeline ? d->debug_timeline_events : 0;
   if (d->rows_written) *d->rows_written = p.total_tiles < tc::num_sms() ? p.total_tiles : tc::num_sms();
 
   // A: input view as (C, W, H, N), box (64, TW*s, TH*s, 1) traversed with element strides (1, s, s, 1)
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, ty;
   {
     cuuint64_t dims[4] = {(cuuint64_t)x.c, (cuuint64_t)x.w, (cuuint64_t)x.h, (cuuint64_t)x.n};
     cuuint64_t strides[3] = {(cuuint64_t)x.pitch * 2, (cuuint64_t)x.pitch * 2 * x.w, (cuuint64_t)x.pitch * 2 * x.w * x.h};
@@ -580,9 +647,20 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SY_REQUIRE(r == CUDA_SUCCESS, SY_ELAUNCH, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
   }
+  {
+    // Y: output view as (C, W, H, N), box (64, TW, TH, 1): the TMA store clips the patch to the image / slice
+    cuuint64_t dims[4] = {(cuuint64_t)y.c, (cuuint64_t)y.w, (cuuint64_t)y.h, (cuuint64_t)y.n};
+    cuuint64_t strides[3] = {(cuuint64_t)y.pitch * 2, (cuuint64_t)y.pitch * 2 * y.w, (cuuint64_t)y.pitch * 2 * y.w * y.h};
+    cuuint32_t box[4] = {(cuuint32_t)tc::kSlabCols, (cuuint32_t)p.tw, (cuuint32_t)p.th, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&ty, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y.ptr, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SY_REQUIRE(r == CUDA_SUCCESS, SY_ELAUNCH, "cuTensorMapEncodeTiled(Y) failed: %d", (int)r);
+  }
   switch (bn) {
-    case 64: return tc::launch<64>(ta, tb, p, stream);
-    case 128: return tc::launch<128>(ta, tb, p, stream);
-    default: return tc::launch<256>(ta, tb, p, stream);
+    case 64: return tc::launch<64>(ta, tb, ty, p, stream);
+    case 128: return tc::launch<128>(ta, tb, ty, p, stream);
+    default: return tc::launch<256>(ta, tb, ty, p, stream);
   }
 }

@@ -1,0 +1,44 @@
+"""Pipeline timeline of CTA 0 of the tcgen05 conv kernel (debug instrumentation) + event timing.
+usage: python tools/conv_timeline.py n cin cout h w k s [reps]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from streamyolo_b200 import ops
+from streamyolo_b200.ops import View
+
+n, ci, co, h, w, k, s = map(int, sys.argv[1:8])
+x = View(torch.randn((n, h, w, ci), device="cuda").to(torch.bfloat16))
+wt = ops.pack_conv_weight(torch.randn((co, ci, k, k), device="cuda") * 0.05)
+ho, wo = ops.conv_out_hw(h, w, k, s)
+y = View.empty(n, ho, wo, co, "cuda")
+part = torch.empty((ops.conv_stat_rows(), 4 * co), device="cuda")
+for _ in range(3):
+    ops.conv2d(x, wt, y, k, s, ops.SY_CONV_RAW, partials=part, split_n=n // 2)
+torch.cuda.synchronize()
+ts = []
+for _ in range(5):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ops.conv2d(x, wt, y, k, s, ops.SY_CONV_RAW, partials=part, split_n=n // 2)
+    e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1) * 1e3)
+fl = 2.0 * n * ho * wo * co * ci * k * k
+print(f"shape {sys.argv[1:8]}: {min(ts):.1f} us best, {fl / min(ts) / 1e6:.0f} TFLOP/s, {(x.buf.numel() + y.buf.numel()) * 2 / min(ts) / 1e3:.0f} GB/s")
+cap = 8192
+tl = torch.zeros(2 * cap, dtype=torch.int64, device="cuda")
+ops.conv2d(x, wt, y, k, s, ops.SY_CONV_RAW, partials=part, split_n=n // 2, timeline=tl)
+torch.cuda.synchronize()
+t = tl.view(cap, 2).cpu().numpy()
+ev = [(int(c), int(e) >> 28, (int(e) >> 24) & 15, (int(e) >> 8) & 0xffff, int(e) & 255) for e, c in t if c != 0]
+ev.sort()
+t0 = ev[0][0]
+names = {(0, 0): "P slot-free", (1, 0): "M acc-free", (1, 1): "M data-landed", (2, 0): "E tile-start", (2, 1): "E acc-ready",
+         (2, 2): "E converted", (2, 3): "E staged", (2, 4): "E slab-done"}
+tiles = sorted({e[3] for e in ev})
+print("events", len(ev), "tiles of CTA0", len(tiles), "span cycles", ev[-1][0] - t0)
+for c, role, ph, tile, kb in ev[:400]:
+    print(f"{c - t0:9d}  tile {tile:5d} kb {kb:3d}  {names.get((role, ph), (role, ph))}")
