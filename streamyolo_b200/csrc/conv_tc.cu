@@ -178,6 +178,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// staging-tile hand-off between the 8 epilogue warps and the store warp (warp 3): 256 + 32 threads
+__device__ __forceinline__ void bar_free() { asm volatile("bar.sync 2, 288;" ::: "memory"); }    // (A) staging tile free
+__device__ __forceinline__ void bar_staged() { asm volatile("bar.sync 3, 288;" ::: "memory"); }  // (B) staging tile complete
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -309,6 +312,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------- store warp
+    // One 4-D TMA store per 64-column slab; the tensor map clips the patch to the image and to the
+    // channel slice.  Issuing it here keeps its issue + drain latency off the epilogue warps' path.
+    const uint32_t stage_base = smem_u32(smem + S * (kABytes + C::kBBytes));
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_tile = tile / p.m_tiles, m_tile = tile - n_tile * p.m_tiles;
+      const int img = m_tile / per_img, rem = m_tile - img * per_img;
+      const int py = rem / p.tiles_x, px = rem - py * p.tiles_x;
+      for (int slab = 0; slab < BN / kSlabCols; ++slab) {
+        bar_free();
+        bar_staged();
+        if (lane == 0) {
+          tma_store_4d(&tmY, stage_base, n_tile * BN + slab * kSlabCols, px * p.tw, py * p.th, img);
+          bulk_commit();
+          bulk_wait_read();                      // staging tile may be overwritten once the TMA has read it
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) bulk_wait_all();              // all stores complete before the CTA exits
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
@@ -393,20 +417,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 16; ++i) packed[i] = valid ? pack_bf16(f[2 * i], f[2 * i + 1]) : 0u;
         }
         tl_rec(p, tl_n, 2, 2, tile, slab);
-        if (et == 0) bulk_wait_read();           // the previous slab's TMA store has finished reading the staging tile
-        epi_bar();                               // (A) staging tile free: store drained, statistics readers done
+        bar_free();                              // (A) staging tile free: store drained, statistics readers done
 #pragma unroll
         for (int g = 0; g < 4; ++g) {            // 16-byte chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4)
           const uint32_t j = (uint32_t)(half * 4 + g);
           sts128(my_row + ((j ^ rsw) << 4), packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
         }
         fence_proxy_async();                     // generic-proxy writes -> visible to the TMA (async proxy)
-        epi_bar();                               // (B) staging tile complete
+        bar_staged();                            // (B) staging tile complete: the store warp takes it from here
         tl_rec(p, tl_n, 2, 3, tile, slab);
-        if (et == 0) {
-          tma_store_4d(&tmY, stage_base, n0 + slab * kSlabCols, x0, y0, img);
-          bulk_commit();
-        }
         if (do_stats) {
           // warp ew reduces columns [8*ew, 8*ew+8) of the slab: lane l reads rows l, l+32, l+64, l+96
           float a[16];
@@ -461,7 +480,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tl_rec(p, tl_n, 2, 4, tile, slab);
       }
     }
-    if (et == 0) bulk_wait_all();                // the last TMA store must be complete before the CTA exits
     // ---------------------------------------------- per-CTA partial row (reduced by the normalise pass)
     if (do_stats) {
       epi_bar();                                 // every warp's sAcc updates are done
