@@ -86,6 +86,7 @@ typedef struct {
   /* ---- debugging only: CTA 0 records (event, clock64) int64 pairs of its three pipeline roles ---- */
   void* debug_timeline;  /* device buffer of 2*debug_timeline_events int64, or NULL */
   int32_t debug_timeline_events;
+  int32_t debug_flags;   /* 0 in production; 1 = skip MMAs, 2 = skip TMA loads (pipeline dissection, results invalid) */
 } SyConvDesc;
 
 /* Rows of the statistics workspace (= SM count: one row per persistent CTA). */

@@ -12,8 +12,12 @@
 // with both operands in shared memory and the fp32 accumulator in TMEM (double
 // buffered), so the epilogue of tile i overlaps the main loop of tile i+1.
 //
-// Warp roles (384 threads, persistent CTA, one per SM):
-//   warp 0   TMA producer          warp 1   MMA issuer       warp 2   TMEM alloc/free
+// Warp roles (384 threads, persistent CTA, one per SM).  The warp scheduler favours HIGHER warp ids, so the
+// latency-critical single-thread roles take the highest ids and the eight throughput-bound epilogue warps
+// the lowest (with the roles the other way round the MMA issuer starves behind the epilogue warps of its
+// own scheduler: measured ~440 cycles of pure hand-shake per K block):
+//   warps 0-7 epilogue   warp 8 TMA store   warp 9 TMEM alloc + weight (B) loads   warp 10 activation (A) loads
+//   warp 11 MMA issuer
 //   warps 4-11 epilogue, per 64-column slab of the accumulator: TMEM -> registers -> (raw | folded BN +
 //             SiLU + residual) -> bf16 -> 128B-swizzled shared staging tile -> ONE 4-D TMA store (the
 //             tensor map clips the patch to the image and the channel slice) while the eight warps
@@ -61,6 +65,7 @@ struct Params {
   float* partials;          // [gridDim][2 groups][2][Cout] or nullptr (no statistics)
   long long* timeline;      // debug: CTA 0 records (event id, clock) pairs; nullptr in production
   int timeline_cap;
+  int debug_flags;          // debug: 1 = skip the MMAs, 2 = skip the TMA loads (barriers still cycle), 4 = skip epilogue work
 };
 
 // debug timeline: event = role<<28 | phase<<24 | tile<<8 | kb ; written by CTA 0 only
@@ -104,6 +109,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       else if ((unsigned long long)(now - t0) > kSpinLimit) __trap();
     }
   }
+}
+// one lane of a fully converged warp; keeps the surrounding control flow warp-uniform so that the
+// compiler holds descriptors / addresses in uniform registers (no per-lane serialisation loops)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -228,18 +244,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  int tl_k = 3 * (p.timeline_cap / 4);
+  if (threadIdx.x == 8 * 32) tl_rec(p, tl_k, 4, 0, 0, 0);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + 2 + a); };
 
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 11 * 32) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmY);
     for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), 2);     // A producer + B producer
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -248,71 +266,92 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
+  if (warp == 9) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 8 * 32) tl_rec(p, tl_k, 4, 1, 0, 0);
 
   const uint32_t a_bytes = (uint32_t)(p.th * p.tw) * 128u;
   const int per_img = p.tiles_x * p.tiles_y;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+  if (warp == 10 || warp == 9) {
+    // ----------------------------------------------- TMA producers: warp 10 loads A (activations), warp 9 loads B (weights)
+    // Two issuing threads because a single thread needs ~350 cycles per cp.async.bulk.tensor: the pair keeps a
+    // K block's issue time below its MMA time.  Both arrive (with their byte counts) on the same full barrier.
+    {
+      const bool is_a = (warp == 10);
       int stage = 0;
       uint32_t phase = 0;
-      int tl_n = 0;
+      int tl_n = is_a ? 0 : p.timeline_cap / 8;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
-        const int img = m_tile / per_img, rem = m_tile % per_img;
-        const int y0 = (rem / p.tiles_x) * p.th, x0 = (rem % p.tiles_x) * p.tw;
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          const int tap = kb / p.cblocks, cb = kb % p.cblocks;
-          const int r = tap / p.kw, s = tap % p.kw;
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          tl_rec(p, tl_n, 0, 0, tile, kb);
-          mbar_expect_tx(full_bar(stage), a_bytes + (uint32_t)C::kBBytes);
-          tma_load_4d(smem_u32(sA + stage * kABytes), &tmA, full_bar(stage), cb * kBlockK,
-                      x0 * p.stride + s - p.pad_w, y0 * p.stride + r - p.pad_h, img);
-          tma_load_3d(smem_u32(sB + stage * C::kBBytes), &tmB, full_bar(stage), cb * kBlockK, tap, n_tile * BN);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
+        const int n_tile = tile / p.m_tiles, m_tile = tile - n_tile * p.m_tiles;
+        const int img = m_tile / per_img, rem = m_tile - img * per_img;
+        const int py = rem / p.tiles_x, px = rem - py * p.tiles_x;
+        const int y0 = py * p.th * p.stride - p.pad_h, x0 = px * p.tw * p.stride - p.pad_w;
+        int kb = 0;
+        for (int r = 0; r < p.kh; ++r) {
+          for (int sx = 0; sx < p.kw; ++sx) {
+            const int tap = r * p.kw + sx;
+            for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);          // whole warp waits: control flow stays uniform
+              if (elect_one()) {
+                tl_rec(p, tl_n, is_a ? 0 : 3, 0, tile, kb);
+                if (p.debug_flags & 2) {
+                  mbar_arrive(full_bar(stage));
+                } else if (is_a) {
+                  mbar_expect_tx(full_bar(stage), a_bytes);
+                  tma_load_4d(smem_u32(sA + stage * kABytes), &tmA, full_bar(stage), cb * kBlockK, x0 + sx, y0 + r, img);
+                } else {
+                  mbar_expect_tx(full_bar(stage), (uint32_t)C::kBBytes);
+                  tma_load_3d(smem_u32(sB + stage * C::kBBytes), &tmB, full_bar(stage), cb * kBlockK, tap, n_tile * BN);
+                }
+              }
+              __syncwarp();
+              if (++stage == S) { stage = 0; phase ^= 1u; }
+            }
+          }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 11) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      int tl_n = p.timeline_cap / 4;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-        tl_rec(p, tl_n, 1, 0, tile, 0);
+    // The whole warp walks the pipeline (uniform control flow, operands in uniform registers); one elected
+    // lane issues the tcgen05 instructions.
+    constexpr uint32_t idesc = make_idesc(BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    int tl_n = p.timeline_cap / 4;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+        if (elect_one()) {
           tl_rec(p, tl_n, 1, 1, tile, kb);
-          tcgen05_fence_after();
           const uint64_t da = make_smem_desc(smem_u32(sA + stage * kABytes));
           const uint64_t db = make_smem_desc(smem_u32(sB + stage * C::kBBytes));
+          if (!(p.debug_flags & 1)) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+              umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            }
           }
           umma_commit(empty_bar(stage));            // frees the smem slot when these MMAs retire
           if (kb == p.kblocks - 1) umma_commit(tfull_bar(acc));
-          if (++stage == S) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 3) {
+  } else if (warp == 8) {
     // ------------------------------------------------------------- store warp
     // One 4-D TMA store per 64-column slab; the tensor map clips the patch to the image and to the
     // channel slice.  Issuing it here keeps its issue + drain latency off the epilogue warps' path.
@@ -324,7 +363,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int slab = 0; slab < BN / kSlabCols; ++slab) {
         bar_free();
         bar_staged();
-        if (lane == 0) {
+        if (elect_one()) {
           tma_store_4d(&tmY, stage_base, n_tile * BN + slab * kSlabCols, px * p.tw, py * p.th, img);
           bulk_commit();
           bulk_wait_read();                      // staging tile may be overwritten once the TMA has read it
@@ -333,13 +372,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (lane == 0) bulk_wait_all();              // all stores complete before the CTA exits
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;          // which 32 columns of a 64-column slab this warpgroup converts
-    const int ew = warp - 4;                   // 0..7: the 8-column group this warp reduces in the statistics pass
+    const int half = warp >> 2;                // which 32 columns of a 64-column slab this warpgroup converts
+    const int ew = warp;                       // 0..7: the 8-column group this warp reduces in the statistics pass
     const int row = q * 32 + lane;             // tile row == TMEM lane
-    const int et = threadIdx.x - 128;          // 0..255
+    const int et = threadIdx.x;                // 0..255
     const int ty = row / p.tw, tx = row - ty * p.tw;
     const bool in_patch = row < p.th * p.tw;
     const uint32_t stage_base = smem_u32(sStage);
@@ -481,6 +520,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     // ---------------------------------------------- per-CTA partial row (reduced by the normalise pass)
+    if (et == 0) tl_rec(p, tl_n, 4, 2, 0, 0);
     if (do_stats) {
       epi_bar();                                 // every warp's sAcc updates are done
       float* mine = p.partials + (size_t)blockIdx.x * 4 * p.Cout;
@@ -489,10 +529,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (threadIdx.x == 8 * 32) tl_rec(p, tl_k, 4, 3, 0, 0);
+  if (warp == 9) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
   }
+  if (threadIdx.x == 9 * 32) { int k2 = tl_k + 8; tl_rec(p, k2, 4, 4, 0, 0); }
 }
 
 // ------------------------------------------------------------------ host side
@@ -637,6 +679,7 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
     SY_REQUIRE(d->n_partials >= tc::num_sms(), SY_EWORKSPACE, "conv2d_tc: %d statistic rows, need %d (sy_conv_stat_rows)",
                d->n_partials, tc::num_sms());
   }
+  p.debug_flags = d->debug_flags;
   p.timeline = reinterpret_cast<long long*>(d->debug_timeline);
   p.timeline_cap = d->debug_timeline ? d->debug_timeline_events : 0;
   if (d->rows_written) *d->rows_written = p.total_tiles < tc::num_sms() ? p.total_tiles : tc::num_sms();

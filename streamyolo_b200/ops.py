@@ -29,7 +29,7 @@ class SyConvDesc(C.Structure):
                 ("stride", C.c_int32), ("mode", C.c_int32), ("act", C.c_int32), ("scale", C.c_void_p),
                 ("shift", C.c_void_p), ("res", SyTensor), ("split_n", C.c_int32), ("stat_partials", C.c_void_p),
                 ("n_partials", C.c_int32), ("rows_written", C.POINTER(C.c_int32)), ("debug_timeline", C.c_void_p),
-                ("debug_timeline_events", C.c_int32)]
+                ("debug_timeline_events", C.c_int32), ("debug_flags", C.c_int32)]
 
 
 class SyHeadPredDesc(C.Structure):
@@ -201,7 +201,7 @@ def conv_stat_rows():
 
 
 def conv2d(x: View, wpk, y: View, k, s, mode, impl="tc", scale=None, shift=None, act=1, res: View = None,
-           partials=None, split_n=0, timeline=None):
+           partials=None, split_n=0, timeline=None, debug_flags=0):
     """``k`` is an int (square) or (kh, kw).  With ``partials`` (RAW mode, tensor-core path) returns the number
     of per-CTA statistic rows the launch writes."""
     d = SyConvDesc()
@@ -217,6 +217,7 @@ def conv2d(x: View, wpk, y: View, k, s, mode, impl="tc", scale=None, shift=None,
     if partials is not None:
         d.stat_partials, d.n_partials = partials.data_ptr(), partials.shape[0]
         d.rows_written = C.pointer(rows)
+    d.debug_flags = debug_flags
     if timeline is not None:
         d.debug_timeline, d.debug_timeline_events = timeline.data_ptr(), timeline.numel() // 2
     fn = lib().sy_conv2d_tc if impl == "tc" else lib().sy_conv2d_simt

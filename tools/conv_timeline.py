@@ -10,6 +10,7 @@ from streamyolo_b200 import ops
 from streamyolo_b200.ops import View
 
 n, ci, co, h, w, k, s = map(int, sys.argv[1:8])
+FLAGS = int(sys.argv[8]) if len(sys.argv) > 8 else 0
 x = View(torch.randn((n, h, w, ci), device="cuda").to(torch.bfloat16))
 wt = ops.pack_conv_weight(torch.randn((co, ci, k, k), device="cuda") * 0.05)
 ho, wo = ops.conv_out_hw(h, w, k, s)
@@ -30,15 +31,28 @@ fl = 2.0 * n * ho * wo * co * ci * k * k
 print(f"shape {sys.argv[1:8]}: {min(ts):.1f} us best, {fl / min(ts) / 1e6:.0f} TFLOP/s, {(x.buf.numel() + y.buf.numel()) * 2 / min(ts) / 1e3:.0f} GB/s")
 cap = 8192
 tl = torch.zeros(2 * cap, dtype=torch.int64, device="cuda")
-ops.conv2d(x, wt, y, k, s, ops.SY_CONV_RAW, partials=part, split_n=n // 2, timeline=tl)
+ops.conv2d(x, wt, y, k, s, ops.SY_CONV_RAW, partials=part, split_n=n // 2, timeline=tl, debug_flags=FLAGS)
 torch.cuda.synchronize()
 t = tl.view(cap, 2).cpu().numpy()
 ev = [(int(c), int(e) >> 28, (int(e) >> 24) & 15, (int(e) >> 8) & 0xffff, int(e) & 255) for e, c in t if c != 0]
 ev.sort()
 t0 = ev[0][0]
-names = {(0, 0): "P slot-free", (1, 0): "M acc-free", (1, 1): "M data-landed", (2, 0): "E tile-start", (2, 1): "E acc-ready",
+names = {(0, 0): "PA slot-free", (3, 0): "PB slot-free", (1, 0): "M acc-free", (1, 1): "M data-landed", (1, 2): "M issued", (1, 3): "M committed", (4, 0): "K entry", (4, 1): "K setup-done", (4, 2): "K tiles-done", (4, 3): "K all-synced", (4, 4): "K tmem-freed", (2, 0): "E tile-start", (2, 1): "E acc-ready",
          (2, 2): "E converted", (2, 3): "E staged", (2, 4): "E slab-done"}
 tiles = sorted({e[3] for e in ev})
 print("events", len(ev), "tiles of CTA0", len(tiles), "span cycles", ev[-1][0] - t0)
+import time
+for _ in range(3):
+    t_0 = time.perf_counter(); ops.conv2d(x, wt, y, k, s, ops.SY_CONV_RAW, partials=part, split_n=n // 2); torch.cuda.synchronize(); print("wall us", (time.perf_counter() - t_0) * 1e6)
+g = torch.cuda.CUDAGraph()
+st = torch.cuda.Stream()
+with torch.cuda.stream(st):
+    with torch.cuda.graph(g):
+        for _ in range(20):
+            ops.conv2d(x, wt, y, k, s, ops.SY_CONV_RAW, partials=part, split_n=n // 2)
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+    print("graph of 20 back-to-back launches: us per launch", e0.elapsed_time(e1) * 1e3 / 20)
 for c, role, ph, tile, kb in ev[:400]:
     print(f"{c - t0:9d}  tile {tile:5d} kb {kb:3d}  {names.get((role, ph), (role, ph))}")
