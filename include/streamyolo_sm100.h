@@ -83,6 +83,10 @@ typedef struct {
   float* stat_partials;  /* [n_partials][2 groups][2 (sum, sumsq)][Cout] floats, one row per CTA, or NULL */
   int32_t n_partials;    /* >= sy_conv_stat_rows(); rows of CTAs that did not run are NOT written */
   int32_t* rows_written; /* out (host int, may be NULL): number of partial rows this launch writes */
+  SyBnSegment bn[2];     /* bn[0].gamma != NULL: finalize BatchNorm in the kernel tail (1-2 parameter segments) */
+  float momentum, eps;
+  float* scale_shift;    /* [2 (scale|shift)][2 groups][Cout]: y = x*scale + shift, ready when the kernel ends */
+  uint32_t* sync;        /* two zero-initialised counters (grid barrier); the kernel leaves them at zero */
   /* ---- debugging only: CTA 0 records (event, clock64) int64 pairs of its three pipeline roles ---- */
   void* debug_timeline;  /* device buffer of 2*debug_timeline_events int64, or NULL */
   int32_t debug_timeline_events;
@@ -93,7 +97,10 @@ typedef struct {
 int sy_conv_stat_rows(void);
 /* tcgen05 implicit-GEMM kernel (TMA -> smem -> UMMA -> TMEM -> epilogue).  In RAW mode with
  * stat_partials it also accumulates per-channel (sum, sum of squares) of the stored values per
- * statistics group, one partial row per CTA (deterministic); sy_bn_train_apply reduces them. */
+ * statistics group, one partial row per CTA; with bn[] the persistent grid (all CTAs co-resident)
+ * ends with a grid barrier and finalizes BatchNorm in parallel: batch statistics -> scale/shift,
+ * running statistics (group 0 then group 1, unbiased variance, momentum).  Deterministic.  Do not
+ * run two such launches concurrently on one GPU (the barrier needs every SM). */
 int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream);
 /* plain CUDA-core direct convolution with the same x/y/w/FUSED contract (no statistics):
  * device-side cross-check of the tensor-core kernel. */
@@ -124,23 +131,13 @@ int sy_bn_finalize(const float* partials, int32_t n_partials, int32_t p_split, i
                    const float* gamma, const float* beta, float* running_mean, float* running_var,
                    int64_t* num_batches_tracked, float momentum, float eps,
                    float* scale_out, float* shift_out, sy_stream_t stream);
-/* Train-mode BatchNorm + activation in ONE launch on the tensor-core path: the first blocks reduce the
- * conv kernel's partial rows [rows][2][2][c] in a fixed order (fp64), update the running statistics
- * (group 0 then group 1, unbiased variance, momentum) and publish scale/shift [2 groups][c]; every block
- * then waits for them and computes y = act(x*scale[g]+shift[g]) (+ res), g = (image >= split_n).
- * ``bn`` has 1 or 2 parameter segments (bn[1].gamma NULL = one).  ``sync`` points at two zero-initialised
- * uint32 (one pair per concurrently running launch); the kernel leaves them at zero (graph replay safe).
- * scale_shift: workspace [2 (scale|shift)][2 groups][c] floats.
+/* y = act(x*scale[g]+shift[g]) (+ res), g = (image >= split_n); single bf16 rounding.
  * y_group1_offset / res_group1_offset: element offsets added to the y / res addresses of the images of
  * statistics group 1 (0 = plain views).  The DFP fusion (exps/model/dfp_pafpn.py:168-170) uses them to
  * write jian(support frame n) into channels [c, 2c) of output image n - split_n, next to jian(current). */
-int sy_bn_train_apply(SyTensor x, const float* partials, int32_t rows, int32_t split_n,
-                      const SyBnSegment* bn, float momentum, float eps, float* scale_shift, uint32_t* sync,
-                      int32_t act, SyTensor res, SyTensor y, int64_t y_group1_offset, int64_t res_group1_offset,
-                      sy_stream_t stream);
-/* y = act(x*scale[g]+shift[g]) (+ res), g = (image >= split_n); single bf16 rounding. */
 int sy_bn_act_apply(SyTensor x, const float* scale, const float* shift, int32_t split_n, int32_t act,
-                    SyTensor res, SyTensor y, sy_stream_t stream);
+                    SyTensor res, SyTensor y, int64_t y_group1_offset, int64_t res_group1_offset,
+                    sy_stream_t stream);
 
 /* -------- glue ------------------------------------------------------------- */
 /* F.interpolate(mode="nearest", size=) of exps/model/dfp_pafpn.py:125,130 into a channel

@@ -66,122 +66,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 __global__ void bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const float* __restrict__ scale,
                                     const float* __restrict__ shift, long long split_pix, int act,
                                     const __nv_bfloat16* res, long long rp, __nv_bfloat16* y, long long yp,
-                                    long long npix, int C) {
-  const int G = C / 8;
-  const long long total = npix * G;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % G);
-    const long long pix = idx / G;
-    const int grp = pix >= split_pix ? 1 : 0;
-    float f[8], r[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + pix * xp + g * 8), f);
-    const float4 s0 = *reinterpret_cast<const float4*>(scale + grp * C + g * 8);
-    const float4 s1 = *reinterpret_cast<const float4*>(scale + grp * C + g * 8 + 4);
-    const float4 h0 = *reinterpret_cast<const float4*>(shift + grp * C + g * 8);
-    const float4 h1 = *reinterpret_cast<const float4*>(shift + grp * C + g * 8 + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float t = f[i] * sc[i] + sh[i];
-      f[i] = act ? silu_f(t) : t;
-    }
-    if (res != nullptr) {
-      unpack8(*reinterpret_cast<const uint4*>(res + pix * rp + g * 8), r);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] += r[i];
-    }
-    *reinterpret_cast<uint4*>(y + pix * yp + g * 8) = pack8(f);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Train-mode BatchNorm + activation in one launch (tensor-core path).  Blocks [0, ceil(C/32)) first reduce
-// the conv kernel's per-CTA partial rows for 32 channels each (fixed order, fp64), update the running
-// statistics and publish scale/shift; every block then waits on a global counter for those few blocks
-// (they have the lowest block ids, so they are always scheduled first: no deadlock) and runs the
-// vectorised normalise + SiLU (+ residual) pass.  The last block to leave re-zeroes the two counters.
-struct BnSegDev {
-  const float* gamma; const float* beta; float* rmean; float* rvar; long long* nbt; int c_begin;
-};
-
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__global__ void __launch_bounds__(256)
-bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const float* __restrict__ partials, int rows,
-                      long long split_pix, double count0, double count1, int groups, BnSegDev seg0, BnSegDev seg1,
-                      int n_seg, float momentum, float eps, float* ss, unsigned int* sync, int act,
-                      const __nv_bfloat16* res, long long rp, __nv_bfloat16* y, long long yp, long long npix, int C,
-                      long long y_goff1, long long r_goff1) {
-  __shared__ double red[2][8][33];
-  const int nred = (C + 31) / 32;
-  if ((int)blockIdx.x < nred) {
-    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cl;
-    const BnSegDev& sg = (n_seg > 1 && c >= seg1.c_begin) ? seg1 : seg0;
-    const int cs = c - sg.c_begin;
-    float rm = 0.f, rv = 1.f;
-    if (rl == 0 && c < C) {
-      rm = sg.rmean ? sg.rmean[cs] : 0.f;
-      rv = sg.rvar ? sg.rvar[cs] : 1.f;
-    }
-    for (int g = 0; g < groups; ++g) {
-      double s1 = 0.0, s2 = 0.0;
-      if (c < C) {
-        for (int r = rl; r < rows; r += 8) {
-          s1 += (double)partials[(size_t)r * 4 * C + (g * 2 + 0) * C + c];
-          s2 += (double)partials[(size_t)r * 4 * C + (g * 2 + 1) * C + c];
-        }
-      }
-      red[0][rl][cl] = s1;
-      red[1][rl][cl] = s2;
-      __syncthreads();
-      if (rl == 0 && c < C) {
-        s1 = 0.0; s2 = 0.0;
-        for (int r = 0; r < 8; ++r) { s1 += red[0][r][cl]; s2 += red[1][r][cl]; }
-        const double cnt = g == 0 ? count0 : count1;
-        const double mean = s1 / cnt;
-        double var = s2 / cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
-        const float sc = sg.gamma[cs] * (float)(1.0 / sqrt(var + (double)eps));
-        ss[(0 * 2 + g) * C + c] = sc;
-        ss[(1 * 2 + g) * C + c] = sg.beta[cs] - (float)mean * sc;
-        const double unbiased = cnt > 1.0 ? var * (cnt / (cnt - 1.0)) : var;
-        rm = (1.f - momentum) * rm + momentum * (float)mean;
-        rv = (1.f - momentum) * rv + momentum * (float)unbiased;
-      }
-      __syncthreads();
-    }
-    if (rl == 0 && c < C) {
-      if (sg.rmean) sg.rmean[cs] = rm;
-      if (sg.rvar) sg.rvar[cs] = rv;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      if (seg0.nbt) *seg0.nbt += groups;
-      if (n_seg > 1 && seg1.nbt) *seg1.nbt += groups;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(&sync[0], 1u);
-  }
-  if (threadIdx.x == 0) {
-    while (ld_acquire_u32(&sync[0]) < (unsigned int)nred) __nanosleep(64);
-  }
-  __syncthreads();
-  // scale/shift were written by other SMs during this launch: pull them from L2 once into shared memory
-  extern __shared__ float s_ss[];     // [2 (scale|shift)][2 groups][C]
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    const float4 v = __ldcg(reinterpret_cast<const float4*>(ss) + i);
-    reinterpret_cast<float4*>(s_ss)[i] = v;
-  }
-  __syncthreads();
-  const float* scale = s_ss;
-  const float* shift = s_ss + 2 * C;
+                                    long long npix, int C, long long y_goff1, long long r_goff1) {
   const int G = C / 8;
   const long long total = npix * G;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -208,15 +93,6 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const f
       for (int i = 0; i < 8; ++i) f[i] += r[i];
     }
     *reinterpret_cast<uint4*>(y + pix * yp + g * 8 + (grp ? y_goff1 : 0)) = pack8(f);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int old = atomicAdd(&sync[1], 1u);
-    if (old == gridDim.x - 1) {       // every other block has left: safe to re-arm for the next launch
-      sync[0] = 0u;
-      sync[1] = 0u;
-      __threadfence();
-    }
   }
 }
 
@@ -321,11 +197,12 @@ extern "C" int sy_bn_finalize(const float* partials, int32_t n_partials, int32_t
 }
 
 extern "C" int sy_bn_act_apply(SyTensor x, const float* scale, const float* shift, int32_t split_n, int32_t act,
-                               SyTensor res, SyTensor y, sy_stream_t stream_) {
+                               SyTensor res, SyTensor y, int64_t y_goff1, int64_t r_goff1, sy_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SY_REQUIRE(view_ok(x) && view_ok(y) && scale && shift, SY_EINVAL, "bn_act_apply: bad view");
   SY_REQUIRE(x.n == y.n && x.h == y.h && x.w == y.w && x.c == y.c, SY_EINVAL, "bn_act_apply: x/y shape mismatch");
   SY_REQUIRE(((uintptr_t)scale % 16) == 0 && ((uintptr_t)shift % 16) == 0, SY_EINVAL, "bn_act_apply: scale/shift alignment");
+  SY_REQUIRE((y_goff1 % 8) == 0 && (r_goff1 % 8) == 0, SY_EINVAL, "bn_act_apply: group offsets must be multiples of 8");
   const __nv_bfloat16* rp = nullptr;
   long long rpitch = 0;
   if (res.ptr) {
@@ -336,50 +213,9 @@ extern "C" int sy_bn_act_apply(SyTensor x, const float* scale, const float* shif
   const long long npix = (long long)x.n * x.h * x.w;
   const long long split_pix = (long long)split_n * x.h * x.w;
   bn_act_apply_kernel<<<grid_for(npix * (x.c / 8), 256), 256, 0, stream>>>(CBF(x.ptr), x.pitch, scale, shift, split_pix,
-                                                                           act, rp, rpitch, BF(y.ptr), y.pitch, npix, x.c);
+                                                                           act, rp, rpitch, BF(y.ptr), y.pitch, npix, x.c,
+                                                                           (long long)y_goff1, (long long)r_goff1);
   return launch_status("bn_act_apply_kernel");
-}
-
-extern "C" int sy_bn_train_apply(SyTensor x, const float* partials, int32_t rows, int32_t split_n,
-                                 const SyBnSegment* bn, float momentum, float eps, float* scale_shift, uint32_t* sync,
-                                 int32_t act, SyTensor res, SyTensor y, int64_t y_goff1, int64_t r_goff1,
-                                 sy_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  SY_REQUIRE(view_ok(x) && view_ok(y) && partials && bn && scale_shift && sync, SY_EINVAL, "bn_train_apply: bad argument");
-  SY_REQUIRE((y_goff1 % 8) == 0 && (r_goff1 % 8) == 0, SY_EINVAL, "bn_train_apply: group offsets must be multiples of 8");
-  SY_REQUIRE(x.n == y.n && x.h == y.h && x.w == y.w && x.c == y.c, SY_EINVAL, "bn_train_apply: x/y shape mismatch");
-  SY_REQUIRE(rows >= 1 && bn[0].gamma && bn[0].beta && bn[0].c_begin == 0, SY_EINVAL, "bn_train_apply: rows/segment 0");
-  SY_REQUIRE(((uintptr_t)scale_shift % 16) == 0, SY_EINVAL, "bn_train_apply: scale_shift alignment");
-  BnSegDev s0{bn[0].gamma, bn[0].beta, bn[0].running_mean, bn[0].running_var,
-              reinterpret_cast<long long*>(bn[0].num_batches_tracked), 0};
-  BnSegDev s1{};
-  int n_seg = 1;
-  if (bn[1].gamma != nullptr) {
-    SY_REQUIRE(bn[1].beta && bn[1].c_begin > 0 && bn[1].c_begin < x.c, SY_EINVAL, "bn_train_apply: bad segment 1");
-    s1 = BnSegDev{bn[1].gamma, bn[1].beta, bn[1].running_mean, bn[1].running_var,
-                  reinterpret_cast<long long*>(bn[1].num_batches_tracked), bn[1].c_begin};
-    n_seg = 2;
-  }
-  const __nv_bfloat16* rp = nullptr;
-  long long rpitch = 0;
-  if (res.ptr) {
-    SY_REQUIRE(view_ok(res) && res.n == x.n && res.h == x.h && res.w == x.w && res.c == x.c, SY_EINVAL,
-               "bn_train_apply: residual mismatch");
-    rp = CBF(res.ptr); rpitch = res.pitch;
-  }
-  const int groups = (split_n > 0 && split_n < x.n) ? 2 : 1;
-  const int sn = groups == 2 ? split_n : x.n;
-  const long long hw = (long long)x.h * x.w;
-  const long long npix = (long long)x.n * hw;
-  int grid = grid_for(npix * (x.c / 8), 256);
-  const int nred = cdiv(x.c, 32);
-  if (grid < nred) grid = nred;
-  SY_REQUIRE(x.c <= 2048, SY_EINVAL, "bn_train_apply: c=%d > 2048", x.c);
-  bn_train_apply_kernel<<<grid, 256, (size_t)16 * x.c, stream>>>(CBF(x.ptr), x.pitch, partials, rows, (long long)sn * hw, (double)sn * hw,
-                                                  (double)(x.n - sn) * hw, groups, s0, s1, n_seg, momentum, eps,
-                                                  scale_shift, sync, act, rp, rpitch, BF(y.ptr), y.pitch, npix, x.c,
-                                                  (long long)y_goff1, (long long)r_goff1);
-  return launch_status("bn_train_apply_kernel");
 }
 
 extern "C" int sy_upsample_nearest(SyTensor x, SyTensor y, sy_stream_t stream_) {

@@ -26,9 +26,11 @@
 //
 // Train-mode BatchNorm is folded into this kernel as far as the grid-wide dependency allows:
 // every CTA accumulates per-channel (sum, sum of squares) of the values it stored, per
-// statistics group (current / support frames), and writes ONE partial row; the <= 148 rows are
-// reduced in a fixed order (deterministic) by the first blocks of the normalise+SiLU pass
-// (bn_glue.cu), which also updates the running statistics.
+// statistics group (current / support frames), and writes ONE partial row.  All CTAs of the
+// persistent grid are co-resident (one per SM), so the kernel ends with a grid-wide barrier after
+// which every CTA reduces a slice of the channels over the <= 148 rows in a fixed order
+// (deterministic), updates the running statistics and publishes scale/shift for the normalise+SiLU
+// pass.  (Two such kernels must not run concurrently on one GPU: the barrier needs the whole grid.)
 //
 // Replaces the cuDNN conv + ATen BN/SiLU triplet behind [yolox] BaseConv
 // (/root/reference/exps/model/darknet.py:115-165, dfp_pafpn.py:33-105, tal_head.py:55-104).
@@ -47,6 +49,12 @@ constexpr int kABytes = kBlockM * 128;   // 16 KiB per stage
 constexpr int kMaxStages = 8;
 constexpr uint64_t kSpinLimit = 6000000000ull;  // ~3 s of SM clocks, then trap instead of hanging
 
+struct BnSeg {
+  const float* gamma; const float* beta;
+  float* rmean; float* rvar; long long* nbt;
+  int c_begin;
+};
+
 struct Params {
   int N, Ho, Wo, Cout, Cin;
   int kh, kw, stride, pad_h, pad_w;
@@ -63,6 +71,11 @@ struct Params {
   // statistics / BatchNorm finalize (RAW mode)
   int split_n;              // images >= split_n form statistics group 1
   float* partials;          // [gridDim][2 groups][2][Cout] or nullptr (no statistics)
+  int n_seg;                // > 0: finalize BatchNorm in the kernel tail (grid barrier + parallel reduce)
+  BnSeg seg[2];
+  float momentum, eps;
+  float* ss;                // [2 (scale|shift)][2 groups][Cout]
+  unsigned int* sync;       // two counters, zero between launches
   long long* timeline;      // debug: CTA 0 records (event id, clock) pairs; nullptr in production
   int timeline_cap;
   int debug_flags;          // debug: 1 = skip the MMAs, 2 = skip the TMA loads (barriers still cycle), 4 = skip epilogue work
@@ -153,6 +166,11 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -525,6 +543,73 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       epi_bar();                                 // every warp's sAcc updates are done
       float* mine = p.partials + (size_t)blockIdx.x * 4 * p.Cout;
       for (int i = et; i < 4 * p.Cout; i += kEpiThreads) mine[i] = sAcc[i];
+      if (p.n_seg > 0) {
+        // ---- grid barrier (all CTAs are resident), then every CTA finalizes its slice of the channels
+        __threadfence();
+        epi_bar();
+        if (et == 0) {
+          atomicAdd(&p.sync[0], 1u);
+          while (ld_acquire_u32(&p.sync[0]) < gridDim.x) __nanosleep(32);
+        }
+        epi_bar();
+        double* red = reinterpret_cast<double*>(sScale);        // unused in RAW mode: [8 warps][4]
+        const int groups = p.split_n < p.N ? 2 : 1;
+        const int cpc = (p.Cout + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int c_end = min(p.Cout, ((int)blockIdx.x + 1) * cpc);
+        for (int c = (int)blockIdx.x * cpc; c < c_end; ++c) {
+          double v[4] = {0.0, 0.0, 0.0, 0.0};
+          if (et < (int)gridDim.x) {                              // thread t owns partial row t
+            const float* rowp = p.partials + (size_t)et * 4 * p.Cout + c;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = (double)__ldcg(rowp + i * p.Cout);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], m);
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) red[warp * 4 + i] = v[i];
+          }
+          epi_bar();
+          if (et == 0) {
+            double t[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int w8 = 0; w8 < 8; ++w8)
+              for (int i = 0; i < 4; ++i) t[i] += red[w8 * 4 + i];
+            const BnSeg& sg = (p.n_seg > 1 && c >= p.seg[1].c_begin) ? p.seg[1] : p.seg[0];
+            const int cs = c - sg.c_begin;
+            float rm = sg.rmean ? sg.rmean[cs] : 0.f, rv = sg.rvar ? sg.rvar[cs] : 1.f;
+            for (int g = 0; g < groups; ++g) {
+              const double cnt = (double)(g == 0 ? (groups == 2 ? p.split_n : p.N) : p.N - p.split_n) * p.Ho * p.Wo;
+              const double mean = t[2 * g] / cnt;
+              double var = t[2 * g + 1] / cnt - mean * mean;
+              if (var < 0.0) var = 0.0;
+              const float sc = sg.gamma[cs] * (float)(1.0 / sqrt(var + (double)p.eps));
+              p.ss[(0 * 2 + g) * p.Cout + c] = sc;
+              p.ss[(1 * 2 + g) * p.Cout + c] = sg.beta[cs] - (float)mean * sc;
+              const double unbiased = cnt > 1.0 ? var * (cnt / (cnt - 1.0)) : var;
+              rm = (1.f - p.momentum) * rm + p.momentum * (float)mean;
+              rv = (1.f - p.momentum) * rv + p.momentum * (float)unbiased;
+            }
+            if (sg.rmean) sg.rmean[cs] = rm;
+            if (sg.rvar) sg.rvar[cs] = rv;
+          }
+          epi_bar();
+        }
+        if (et == 0) {
+          if (blockIdx.x == 0) {
+            for (int sgi = 0; sgi < p.n_seg; ++sgi)
+              if (p.seg[sgi].nbt) *p.seg[sgi].nbt += groups;
+          }
+          const unsigned int old = atomicAdd(&p.sync[1], 1u);
+          if (old == gridDim.x - 1) {               // every CTA is past the barrier: re-arm for the next launch
+            p.sync[0] = 0u;
+            p.sync[1] = 0u;
+            __threadfence();
+          }
+        }
+      }
     }
   }
   tcgen05_fence_before();
@@ -682,6 +767,24 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
   p.debug_flags = d->debug_flags;
   p.timeline = reinterpret_cast<long long*>(d->debug_timeline);
   p.timeline_cap = d->debug_timeline ? d->debug_timeline_events : 0;
+  p.n_seg = 0;
+  if (p.partials && d->bn[0].gamma != nullptr) {
+    SY_REQUIRE(d->sync && d->scale_shift, SY_EINVAL, "conv2d_tc: BN finalize needs sync counters and scale_shift");
+    for (int sgi = 0; sgi < 2; ++sgi) {
+      if (d->bn[sgi].gamma == nullptr) break;
+      SY_REQUIRE(d->bn[sgi].beta != nullptr && d->bn[sgi].c_begin >= 0 && d->bn[sgi].c_begin < y.c, SY_EINVAL,
+                 "conv2d_tc: bad BN segment %d", sgi);
+      p.seg[sgi].gamma = d->bn[sgi].gamma; p.seg[sgi].beta = d->bn[sgi].beta;
+      p.seg[sgi].rmean = d->bn[sgi].running_mean; p.seg[sgi].rvar = d->bn[sgi].running_var;
+      p.seg[sgi].nbt = reinterpret_cast<long long*>(d->bn[sgi].num_batches_tracked);
+      p.seg[sgi].c_begin = d->bn[sgi].c_begin;
+      p.n_seg = sgi + 1;
+    }
+    SY_REQUIRE(p.seg[0].c_begin == 0, SY_EINVAL, "conv2d_tc: first BN segment must start at channel 0");
+    p.momentum = d->momentum; p.eps = d->eps;
+    p.ss = d->scale_shift;
+    p.sync = d->sync;
+  }
   if (d->rows_written) *d->rows_written = p.total_tiles < tc::num_sms() ? p.total_tiles : tc::num_sms();
 
   // A: input view as (C, W, H, N), box (64, TW*s, TH*s, 1) traversed with element strides (1, s, s, 1)

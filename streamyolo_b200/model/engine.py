@@ -83,8 +83,8 @@ def _bn_seg(m, c_begin=0):
 
 def conv_bn_act(ctx: Ctx, mods, x: View, wpk, k, s, y: View, res: View = None, act=1, y_goff1=0, res_goff1=0):
     """Train mode: conv -> batch statistics -> BatchNorm (running-stat update) -> act (+res) into ``y``.
-    Tensor-core path = 2 launches: the conv writes the raw bf16 result + one statistics row per CTA, the
-    normalise pass reduces those rows in its first blocks and applies.  ``mods``: one BaseConv, or two whose
+    Tensor-core path = 2 launches: the conv writes the raw bf16 result, accumulates the statistics and
+    (grid barrier + parallel reduce in its tail) publishes scale/shift; then the normalise pass.  ``mods``: one BaseConv, or two whose
     outputs are concatenated along channels (CSPLayer conv1 | conv2)."""
     kh, kw = (k, k) if isinstance(k, int) else k
     ho = (x.h + 2 * ((kh - 1) // 2) - kh) // s + 1
@@ -99,14 +99,14 @@ def conv_bn_act(ctx: Ctx, mods, x: View, wpk, k, s, y: View, res: View = None, a
         m._stats_epoch = getattr(m, "_stats_epoch", 0) + 1
     if ctx.impl == "tc":
         partials = torch.empty((ops.conv_stat_rows(), 4 * cout), dtype=torch.float32, device=ctx.device)
-        rows = ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="tc", partials=partials, split_n=split)
         segs, c0 = [], 0
         for m in mods:
             segs.append(_bn_seg(m, c0))
             c0 += m.conv.out_channels
         ss = torch.empty((2, 2, cout), dtype=torch.float32, device=ctx.device)
-        ops.bn_train_apply(raw, partials, rows, split, segs, mom, float(bn0.eps), ss, _sync(mods[0], ctx.device), act,
-                           res, y, y_goff1, res_goff1)
+        ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="tc", partials=partials, split_n=split, bn=segs,
+                   momentum=mom, eps=float(bn0.eps), scale_shift=ss, sync=_sync(mods[0], ctx.device))
+        ops.bn_act_apply(raw, ss[0].data_ptr(), ss[1].data_ptr(), split if split else n, act, res, y, y_goff1, res_goff1)
         return
     # CUDA-core cross-check path: conv, separate statistics pass, separate finalize per module, apply
     ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="simt")

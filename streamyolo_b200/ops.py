@@ -28,7 +28,9 @@ class SyConvDesc(C.Structure):
     _fields_ = [("x", SyTensor), ("y", SyTensor), ("w", C.c_void_p), ("kh", C.c_int32), ("kw", C.c_int32),
                 ("stride", C.c_int32), ("mode", C.c_int32), ("act", C.c_int32), ("scale", C.c_void_p),
                 ("shift", C.c_void_p), ("res", SyTensor), ("split_n", C.c_int32), ("stat_partials", C.c_void_p),
-                ("n_partials", C.c_int32), ("rows_written", C.POINTER(C.c_int32)), ("debug_timeline", C.c_void_p),
+                ("n_partials", C.c_int32), ("rows_written", C.POINTER(C.c_int32)), ("bn", SyBnSegment * 2),
+                ("momentum", C.c_float), ("eps", C.c_float), ("scale_shift", C.c_void_p), ("sync", C.c_void_p),
+                ("debug_timeline", C.c_void_p),
                 ("debug_timeline_events", C.c_int32), ("debug_flags", C.c_int32)]
 
 
@@ -67,11 +69,8 @@ _SIG = {
     "sy_bn_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
-    "sy_bn_train_apply": (C.c_int, [SyTensor, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(SyBnSegment), C.c_float,
-                                    C.c_float, C.c_void_p, C.c_void_p, C.c_int32, SyTensor, SyTensor, C.c_int64,
-                                    C.c_int64, C.c_void_p]),
     "sy_bn_act_apply": (C.c_int, [SyTensor, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, SyTensor, SyTensor,
-                                  C.c_void_p]),
+                                  C.c_int64, C.c_int64, C.c_void_p]),
     "sy_upsample_nearest": (C.c_int, [SyTensor, SyTensor, C.c_void_p]),
     "sy_spp_maxpool": (C.c_int, [SyTensor, SyTensor, SyTensor, SyTensor, C.c_void_p]),
     "sy_copy": (C.c_int, [SyTensor, SyTensor, C.c_void_p]),
@@ -201,7 +200,8 @@ def conv_stat_rows():
 
 
 def conv2d(x: View, wpk, y: View, k, s, mode, impl="tc", scale=None, shift=None, act=1, res: View = None,
-           partials=None, split_n=0, timeline=None, debug_flags=0):
+           partials=None, split_n=0, timeline=None, debug_flags=0, bn=None, momentum=0.03, eps=1e-3, scale_shift=None,
+           sync=None):
     """``k`` is an int (square) or (kh, kw).  With ``partials`` (RAW mode, tensor-core path) returns the number
     of per-CTA statistic rows the launch writes."""
     d = SyConvDesc()
@@ -217,27 +217,22 @@ def conv2d(x: View, wpk, y: View, k, s, mode, impl="tc", scale=None, shift=None,
     if partials is not None:
         d.stat_partials, d.n_partials = partials.data_ptr(), partials.shape[0]
         d.rows_written = C.pointer(rows)
+    if bn:
+        for i, (g, b_, rm, rv, nbt, c0) in enumerate(bn):
+            seg = d.bn[i]
+            seg.gamma, seg.beta = g.data_ptr(), b_.data_ptr()
+            seg.running_mean = rm.data_ptr() if rm is not None else None
+            seg.running_var = rv.data_ptr() if rv is not None else None
+            seg.num_batches_tracked = nbt.data_ptr() if nbt is not None else None
+            seg.c_begin = c0
+        d.momentum, d.eps = momentum, eps
+        d.scale_shift, d.sync = scale_shift.data_ptr(), sync.data_ptr()
     d.debug_flags = debug_flags
     if timeline is not None:
         d.debug_timeline, d.debug_timeline_events = timeline.data_ptr(), timeline.numel() // 2
     fn = lib().sy_conv2d_tc if impl == "tc" else lib().sy_conv2d_simt
     _check(fn(C.byref(d), _stream()))
     return rows.value
-
-
-def bn_train_apply(x: View, partials, rows, split_n, bn, momentum, eps, scale_shift, sync, act, res, y: View,
-                   y_goff1=0, res_goff1=0):
-    """``bn``: list of 1-2 (gamma, beta, running_mean, running_var, num_batches_tracked, c_begin)."""
-    segs = (SyBnSegment * 2)()
-    for i, (g, b_, rm, rv, nbt, c0) in enumerate(bn):
-        segs[i].gamma, segs[i].beta = g.data_ptr(), b_.data_ptr()
-        segs[i].running_mean = rm.data_ptr() if rm is not None else None
-        segs[i].running_var = rv.data_ptr() if rv is not None else None
-        segs[i].num_batches_tracked = nbt.data_ptr() if nbt is not None else None
-        segs[i].c_begin = c0
-    _check(lib().sy_bn_train_apply(x.st(), partials.data_ptr(), rows, split_n, segs, momentum, eps,
-                                   scale_shift.data_ptr(), sync.data_ptr(), act,
-                                   res.st() if res is not None else NULL_T, y.st(), y_goff1, res_goff1, _stream()))
 
 
 def focus_pack(x, frames, y: View):
@@ -275,9 +270,9 @@ def bn_finalize(partials, p_split, groups, count, gamma, beta, rmean, rvar, nbt,
                                 momentum, eps, scale.data_ptr(), shift.data_ptr(), _stream()))
 
 
-def bn_act_apply(x: View, scale_ptr, shift_ptr, split_n, act, res, y: View):
+def bn_act_apply(x: View, scale_ptr, shift_ptr, split_n, act, res, y: View, y_goff1=0, res_goff1=0):
     _check(lib().sy_bn_act_apply(x.st(), scale_ptr, shift_ptr, split_n, act,
-                                 res.st() if res is not None else NULL_T, y.st(), _stream()))
+                                 res.st() if res is not None else NULL_T, y.st(), y_goff1, res_goff1, _stream()))
 
 
 def upsample_nearest(x: View, y: View):

@@ -98,10 +98,10 @@ def test_conv_raw(case, impl):
             assert torch.allclose(pr[g, 1], part.pow(2).sum((0, 2, 3)), rtol=2e-3, atol=1e-3), "sumsq"
 
 
-def test_conv_tc_stats_then_bn_train_apply():
-    """RAW conv with per-CTA statistic rows, then ONE normalise launch that reduces them (two groups, two
-    parameter segments), updates running statistics and applies SiLU + residual; against F.batch_norm on the
-    stored conv output.  The sync counters must come back to zero (re-launch / graph replay safe)."""
+def test_conv_tc_bn_finalize_then_apply():
+    """RAW conv that also finalizes BatchNorm in its tail (grid barrier + parallel reduce; two groups, two
+    parameter segments, running statistics), then the normalise pass with SiLU + residual; against
+    F.batch_norm on the stored conv output.  The sync counters must come back to zero (graph replay safe)."""
     n, ci, co, h, w = 4, 64, 128, 19, 30
     x, wt = rand_act(n, ci, h, w, 61), rand_w(co, ci, 1, 62)
     g = torch.Generator().manual_seed(63)
@@ -120,9 +120,9 @@ def test_conv_tc_stats_then_bn_train_apply():
     sync = torch.zeros(2, dtype=torch.int32, device=DEV)
     for rep in range(2):
         rows = ops.conv2d(ops.from_nchw(x), ops.pack_conv_weight(wt), raw, 1, 1, ops.SY_CONV_RAW, partials=partials,
-                          split_n=2)
+                          split_n=2, bn=segs, momentum=0.03, eps=1e-3, scale_shift=ss, sync=sync)
         assert 1 <= rows <= ops.conv_stat_rows()
-        ops.bn_train_apply(raw, partials, rows, 2, segs, 0.03, 1e-3, ss, sync, 1, ops.from_nchw(resid), y)
+        ops.bn_act_apply(raw, ss[0].data_ptr(), ss[1].data_ptr(), 2, 1, ops.from_nchw(resid), y)
         torch.cuda.synchronize()
         assert sync.tolist() == [0, 0]
         rawf = raw.nchw_float()

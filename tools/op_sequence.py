@@ -42,7 +42,7 @@ def install_mocks():
         by = 2.0 * x.n * x.h * x.w * x.c * (3 if res is not None else 2)
         record("apply", "bn_train_apply_kernel", cur["name"], 0, by, f"{x.n}x{x.h}x{x.w}x{x.c}")
 
-    def bn_act_apply(x, sc, sh, split, act, res, y):
+    def bn_act_apply(x, sc, sh, split, act, res, y, *a):
         by = 2.0 * x.n * x.h * x.w * x.c * (3 if res is not None else 2)
         record("apply", "bn_act_apply_kernel", cur["name"], 0, by, f"{x.n}x{x.h}x{x.w}x{x.c}")
 
