@@ -115,15 +115,62 @@ __global__ void upsample_nearest_kernel(const __nv_bfloat16* __restrict__ x, lon
   }
 }
 
-__device__ __forceinline__ void max8(float* m, const float* f) {
+__device__ __forceinline__ uint4 bmax(const uint4 a, const uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], f[i]);
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
 }
 
-// stride-1 same-padded max pools k=5,9,13 (-inf padding): nested windows, one pass
-__global__ void spp_maxpool_kernel(const __nv_bfloat16* __restrict__ x, long long xp, int N, int H, int W, int C,
-                                   __nv_bfloat16* y5, long long p5, __nv_bfloat16* y9, long long p9,
-                                   __nv_bfloat16* y13, long long p13) {
+// stride-1 same-padded max pools k = 5, 9, 13 (-inf padding) as a cascade of separable 5-wide pools
+// (5 o 5 = 9, 5 o 5 o 5 = 13 for max with -inf padding).  One block = one (image, 8-channel group) plane
+// held in shared memory; every pass is a 5-tap row or column max on packed bf16 (exact).
+constexpr int kSppMaxPix = 1024;
+__global__ void __launch_bounds__(256)
+spp_maxpool_kernel(const __nv_bfloat16* __restrict__ x, long long xp, int H, int W, int C,
+                   __nv_bfloat16* y5, long long p5, __nv_bfloat16* y9, long long p9,
+                   __nv_bfloat16* y13, long long p13) {
+  __shared__ uint4 bufA[kSppMaxPix], bufB[kSppMaxPix];
+  const int G = C / 8;
+  const int n = blockIdx.x / G, g = blockIdx.x % G;
+  const int HW = H * W;
+  const long long base = (long long)n * HW;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x)
+    bufA[i] = *reinterpret_cast<const uint4*>(x + (base + i) * xp + g * 8);
+  __syncthreads();
+  __nv_bfloat16* outs[3] = {y5, y9, y13};
+  const long long pitches[3] = {p5, p9, p13};
+#pragma unroll 1
+  for (int lvl = 0; lvl < 3; ++lvl) {
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {      // row pass
+      const int yy = i / W, xx = i - yy * W;
+      uint4 m = bufA[i];
+#pragma unroll
+      for (int d = -2; d <= 2; ++d)
+        if (d != 0 && xx + d >= 0 && xx + d < W) m = bmax(m, bufA[i + d]);
+      bufB[i] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {      // column pass
+      const int yy = i / W;
+      uint4 m = bufB[i];
+#pragma unroll
+      for (int d = -2; d <= 2; ++d)
+        if (d != 0 && yy + d >= 0 && yy + d < H) m = bmax(m, bufB[i + d * W]);
+      bufA[i] = m;
+      *reinterpret_cast<uint4*>(outs[lvl] + (base + i) * pitches[lvl] + g * 8) = m;
+    }
+    __syncthreads();
+  }
+}
+
+// large planes (not used by the 600x960 configs): direct nested-window version
+__global__ void spp_maxpool_direct_kernel(const __nv_bfloat16* __restrict__ x, long long xp, int N, int H, int W, int C,
+                                          __nv_bfloat16* y5, long long p5, __nv_bfloat16* y9, long long p9,
+                                          __nv_bfloat16* y13, long long p13) {
   const int G = C / 8;
   const long long total = (long long)N * H * W * G;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -132,26 +179,23 @@ __global__ void spp_maxpool_kernel(const __nv_bfloat16* __restrict__ x, long lon
     const long long pix = idx / G;
     const int ox = (int)(pix % W), oy = (int)((pix / W) % H);
     const int n = (int)(pix / ((long long)W * H));
-    float m5[8], m9[8], m13[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m5[i] = m9[i] = m13[i] = -INFINITY;
+    uint4 m5 = *reinterpret_cast<const uint4*>(x + pix * xp + g * 8), m9 = m5, m13 = m5;
     for (int dy = -6; dy <= 6; ++dy) {
       const int iy = oy + dy;
       if (iy < 0 || iy >= H) continue;
       for (int dx = -6; dx <= 6; ++dx) {
         const int ix = ox + dx;
         if (ix < 0 || ix >= W) continue;
-        float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(x + (((long long)n * H + iy) * W + ix) * xp + g * 8), f);
-        max8(m13, f);
+        const uint4 v = *reinterpret_cast<const uint4*>(x + (((long long)n * H + iy) * W + ix) * xp + g * 8);
+        m13 = bmax(m13, v);
         const int ad = max(abs(dy), abs(dx));
-        if (ad <= 4) max8(m9, f);
-        if (ad <= 2) max8(m5, f);
+        if (ad <= 4) m9 = bmax(m9, v);
+        if (ad <= 2) m5 = bmax(m5, v);
       }
     }
-    *reinterpret_cast<uint4*>(y5 + pix * p5 + g * 8) = pack8(m5);
-    *reinterpret_cast<uint4*>(y9 + pix * p9 + g * 8) = pack8(m9);
-    *reinterpret_cast<uint4*>(y13 + pix * p13 + g * 8) = pack8(m13);
+    *reinterpret_cast<uint4*>(y5 + pix * p5 + g * 8) = m5;
+    *reinterpret_cast<uint4*>(y9 + pix * p9 + g * 8) = m9;
+    *reinterpret_cast<uint4*>(y13 + pix * p13 + g * 8) = m13;
   }
 }
 
@@ -232,9 +276,15 @@ extern "C" int sy_spp_maxpool(SyTensor x, SyTensor y5, SyTensor y9, SyTensor y13
   SY_REQUIRE(view_ok(x) && view_ok(y5) && view_ok(y9) && view_ok(y13), SY_EINVAL, "spp: bad views");
   SY_REQUIRE(y5.c == x.c && y9.c == x.c && y13.c == x.c && y5.h == x.h && y5.w == x.w && y5.n == x.n, SY_EINVAL,
              "spp: shape mismatch");
-  const long long total = (long long)x.n * x.h * x.w * (x.c / 8);
-  spp_maxpool_kernel<<<grid_for(total, 128), 128, 0, stream>>>(CBF(x.ptr), x.pitch, x.n, x.h, x.w, x.c, BF(y5.ptr),
-                                                               y5.pitch, BF(y9.ptr), y9.pitch, BF(y13.ptr), y13.pitch);
+  if (x.h * x.w <= kSppMaxPix) {
+    spp_maxpool_kernel<<<x.n * (x.c / 8), 256, 0, stream>>>(CBF(x.ptr), x.pitch, x.h, x.w, x.c, BF(y5.ptr), y5.pitch,
+                                                            BF(y9.ptr), y9.pitch, BF(y13.ptr), y13.pitch);
+  } else {
+    const long long total = (long long)x.n * x.h * x.w * (x.c / 8);
+    spp_maxpool_direct_kernel<<<grid_for(total, 128), 128, 0, stream>>>(CBF(x.ptr), x.pitch, x.n, x.h, x.w, x.c,
+                                                                        BF(y5.ptr), y5.pitch, BF(y9.ptr), y9.pitch,
+                                                                        BF(y13.ptr), y13.pitch);
+  }
   return launch_status("spp_maxpool_kernel");
 }
 

@@ -10,52 +10,60 @@
 namespace sy {
 
 // ================================================================ prediction + decode
-// one warp per pixel; lanes split the channels (16-byte loads), 5+ncls dot products reduced by shuffles.
+// Four threads per pixel: thread ks takes the 16-byte channel chunks ks, ks+4, ks+8, ... of both feature
+// maps (the four threads read 64 contiguous bytes), keeps 5+ncls partial dot products, and two shuffles per
+// output combine them.  Weights live in shared memory as fp32 (conflict-free: the four threads of a pixel
+// read neighbouring 32-byte segments, the eight pixels of a warp broadcast).
 // Output row layout [reg4, obj1, cls*] (tal_head.py:174,197-199); anchors row-major y then x (:236-239).
 constexpr int kMaxPred = 5 + 32;
 
-__global__ void head_pred_kernel(const SyHeadPredDesc d, int B, int H, int W, int C) {
-  extern __shared__ float wsm[];   // [(5+ncls)][C] : reg(4), obj(1), cls(ncls)
-  const int NO = 5 + d.num_classes;
+template <int NO>
+__global__ void __launch_bounds__(256)
+head_pred_kernel(const SyHeadPredDesc d, int B, int H, int W, int C) {
+  extern __shared__ float wsm[];   // [NO][C] : reg(4), obj(1), cls(NO-5)
   for (int i = threadIdx.x; i < NO * C; i += blockDim.x) {
     const int o = i / C, c = i % C;
     wsm[i] = (o < 4) ? d.w_reg[o * C + c] : (o == 4 ? d.w_obj[c] : d.w_cls[(o - 5) * C + c]);
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int ks = threadIdx.x & 3;
   const long long npix = (long long)B * H * W;
   const __nv_bfloat16* cf = reinterpret_cast<const __nv_bfloat16*>(d.cls_feat.ptr);
   const __nv_bfloat16* rf = reinterpret_cast<const __nv_bfloat16*>(d.reg_feat.ptr);
-  for (long long pix = (long long)blockIdx.x * wpb + warp; pix < npix; pix += (long long)gridDim.x * wpb) {
-    float acc[kMaxPred];
+  const int chunks = C / 8;
+  for (long long pix0 = (long long)blockIdx.x * 64; pix0 < npix; pix0 += (long long)gridDim.x * 64) {
+    const long long pix = pix0 + (threadIdx.x >> 2);
+    const bool live = pix < npix;
+    float acc[NO];
 #pragma unroll
-    for (int o = 0; o < kMaxPred; ++o) acc[o] = 0.f;
-    for (int g = lane; g < C / 8; g += 32) {
-      const uint4 rv = *reinterpret_cast<const uint4*>(rf + pix * d.reg_feat.pitch + g * 8);
-      const uint4 cv = *reinterpret_cast<const uint4*>(cf + pix * d.cls_feat.pitch + g * 8);
-      const float r[8] = {bf16_lo(rv.x), bf16_hi(rv.x), bf16_lo(rv.y), bf16_hi(rv.y),
-                          bf16_lo(rv.z), bf16_hi(rv.z), bf16_lo(rv.w), bf16_hi(rv.w)};
-      const float c[8] = {bf16_lo(cv.x), bf16_hi(cv.x), bf16_lo(cv.y), bf16_hi(cv.y),
-                          bf16_lo(cv.z), bf16_hi(cv.z), bf16_lo(cv.w), bf16_hi(cv.w)};
+    for (int o = 0; o < NO; ++o) acc[o] = 0.f;
+    if (live) {
+      for (int ch = ks; ch < chunks; ch += 4) {
+        const uint4 rv = *reinterpret_cast<const uint4*>(rf + pix * d.reg_feat.pitch + ch * 8);
+        const uint4 cv = *reinterpret_cast<const uint4*>(cf + pix * d.cls_feat.pitch + ch * 8);
+        const float r[8] = {bf16_lo(rv.x), bf16_hi(rv.x), bf16_lo(rv.y), bf16_hi(rv.y),
+                            bf16_lo(rv.z), bf16_hi(rv.z), bf16_lo(rv.w), bf16_hi(rv.w)};
+        const float c[8] = {bf16_lo(cv.x), bf16_hi(cv.x), bf16_lo(cv.y), bf16_hi(cv.y),
+                            bf16_lo(cv.z), bf16_hi(cv.z), bf16_lo(cv.w), bf16_hi(cv.w)};
 #pragma unroll
-      for (int o = 0; o < kMaxPred; ++o) {
-        if (o < NO) {
-          const float* wp = wsm + o * C + g * 8;
-          float s = 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) s += (o < 5 ? r[i] : c[i]) * wp[i];
+        for (int o = 0; o < NO; ++o) {
+          const float4 w0 = *reinterpret_cast<const float4*>(wsm + o * C + ch * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(wsm + o * C + ch * 8 + 4);
+          const float* v = (o < 5) ? r : c;
+          float s = v[0] * w0.x;          // explicit FMAs: this unit is compiled with -fmad=false for the loss
+          s = __fmaf_rn(v[1], w0.y, s); s = __fmaf_rn(v[2], w0.z, s); s = __fmaf_rn(v[3], w0.w, s);
+          s = __fmaf_rn(v[4], w1.x, s); s = __fmaf_rn(v[5], w1.y, s); s = __fmaf_rn(v[6], w1.z, s);
+          s = __fmaf_rn(v[7], w1.w, s);
           acc[o] += s;
         }
       }
     }
 #pragma unroll
-    for (int o = 0; o < kMaxPred; ++o) {
-      if (o < NO) {
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], m);
-      }
+    for (int o = 0; o < NO; ++o) {
+      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
+      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
     }
-    if (lane == 0) {
+    if (live && ks == 0) {
       const int x = (int)(pix % W), y = (int)((pix / W) % H);
       const int b = (int)(pix / ((long long)W * H));
       const long long a = (long long)b * d.a_total + d.anchor_offset + (long long)y * W + x;
@@ -79,14 +87,23 @@ __global__ void head_pred_kernel(const SyHeadPredDesc d, int B, int H, int W, in
       const float obj = acc[4] + d.b_obj[0];
       out[4] = d.sigmoid ? 1.0f / (1.0f + expf(-obj)) : obj;
 #pragma unroll
-      for (int o = 5; o < kMaxPred; ++o) {
-        if (o < NO) {
-          const float v = acc[o] + d.b_cls[o - 5];
-          out[o] = d.sigmoid ? 1.0f / (1.0f + expf(-v)) : v;
-        }
+      for (int o = 5; o < NO; ++o) {
+        const float v = acc[o] + d.b_cls[o - 5];
+        out[o] = d.sigmoid ? 1.0f / (1.0f + expf(-v)) : v;
       }
     }
   }
+}
+
+template <int NO>
+static int launch_head_pred(const SyHeadPredDesc* d, const SyTensor& f, cudaStream_t stream) {
+  const size_t smem = sizeof(float) * NO * f.c;
+  if (smem > 48 * 1024) SY_CUDA(cudaFuncSetAttribute(head_pred_kernel<NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long npix = (long long)f.n * f.h * f.w;
+  int blocks = (int)((npix + 63) / 64);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  head_pred_kernel<NO><<<blocks, 256, smem, stream>>>(*d, f.n, f.h, f.w, f.c);
+  return launch_status("head_pred_kernel");
 }
 
 // ======================================================================= loss
@@ -458,14 +475,15 @@ extern "C" int sy_head_pred_decode(const SyHeadPredDesc* d, sy_stream_t stream_)
                  d->b_obj && d->b_cls,
              SY_EINVAL, "head_pred: null weights or num_classes out of range");
   SY_REQUIRE(d->anchor_offset >= 0 && d->anchor_offset + f.h * f.w <= d->a_total, SY_EINVAL, "head_pred: anchor range");
-  const size_t smem = sizeof(float) * (5 + d->num_classes) * f.c;
-  SY_REQUIRE(smem <= 160 * 1024, SY_EINVAL, "head_pred: too many channels (%d)", f.c);
-  if (smem > 48 * 1024) SY_CUDA(cudaFuncSetAttribute(head_pred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long npix = (long long)f.n * f.h * f.w;
-  int blocks = (int)((npix + 7) / 8);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  head_pred_kernel<<<blocks, 256, smem, stream>>>(*d, f.n, f.h, f.w, f.c);
-  return launch_status("head_pred_kernel");
+  SY_REQUIRE(sizeof(float) * (5 + d->num_classes) * f.c <= 160 * 1024, SY_EINVAL, "head_pred: too many channels (%d)", f.c);
+  switch (d->num_classes) {           // compile-time output counts for the class counts in use (Argoverse-HD: 8; COCO: 80 -> generic)
+    case 8: return launch_head_pred<13>(d, f, stream);
+    case 1: return launch_head_pred<6>(d, f, stream);
+    case 20: return launch_head_pred<25>(d, f, stream);
+    default: break;
+  }
+  SY_REQUIRE(false, SY_EINVAL, "head_pred: num_classes=%d not instantiated (8, 1, 20)", d->num_classes);
+  return SY_EINVAL;
 }
 
 extern "C" size_t sy_tal_loss_workspace_bytes(int32_t b, int32_t a_total, int32_t max_labels, int32_t num_classes) {
