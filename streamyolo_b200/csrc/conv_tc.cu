@@ -47,6 +47,7 @@ constexpr int kThreads = 384;
 constexpr int kEpiThreads = 256;
 constexpr int kABytes = kBlockM * 128;   // 16 KiB per stage
 constexpr int kMaxStages = 8;
+constexpr int kSub = 2;                  // 64-deep K sub-blocks per pipeline stage (one barrier round = K 128)
 constexpr uint64_t kSpinLimit = 6000000000ull;  // ~3 s of SM clocks, then trap instead of hanging
 
 struct BnSeg {
@@ -82,8 +83,9 @@ struct Params {
 };
 
 // debug timeline: event = role<<28 | phase<<24 | tile<<8 | kb ; written by CTA 0 only
+template <bool TL>
 __device__ __forceinline__ void tl_rec(const Params& p, int& n, int role, int phase, int tile, int kb) {
-  if (p.timeline != nullptr && blockIdx.x == 0 && n + 1 < p.timeline_cap) {
+  if (TL && p.timeline != nullptr && blockIdx.x == 0 && n + 1 < p.timeline_cap) {
     p.timeline[2 * n] = ((long long)role << 28) | ((long long)phase << 24) | ((long long)(tile & 0xffff) << 8) | (kb & 0xff);
     p.timeline[2 * n + 1] = clock64();
     ++n;
@@ -241,7 +243,7 @@ struct Cfg {
   static constexpr int kFixedBytes = 1024 /*align slack*/ + kSlabBytes + 2 * 256 * 4 /*scale,shift*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+template <int BN, bool TL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const Params p) {
@@ -251,8 +253,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // 1024-byte alignment for the 128B swizzle atoms; plain pointer arithmetic keeps the shared address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
-  uint8_t* sB = sA + S * kABytes;
-  uint8_t* sStage = sB + S * C::kBBytes;                                 // 1024-aligned: the rings are multiples of 1 KiB
+  uint8_t* sB = sA + S * kSub * kABytes;
+  uint8_t* sStage = sB + S * kSub * C::kBBytes;                                 // 1024-aligned: the rings are multiples of 1 KiB
   float* sScale = reinterpret_cast<float*>(sStage + kSlabBytes);
   float* sShift = sScale + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sShift + 256);
@@ -263,7 +265,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   int tl_k = 3 * (p.timeline_cap / 4);
-  if (threadIdx.x == 8 * 32) tl_rec(p, tl_k, 4, 0, 0, 0);
+  if (threadIdx.x == 8 * 32) tl_rec<TL>(p, tl_k, 4, 0, 0, 0);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
@@ -289,7 +291,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 8 * 32) tl_rec(p, tl_k, 4, 1, 0, 0);
+  if (threadIdx.x == 8 * 32) tl_rec<TL>(p, tl_k, 4, 1, 0, 0);
 
   const uint32_t a_bytes = (uint32_t)(p.th * p.tw) * 128u;
   const int per_img = p.tiles_x * p.tiles_y;
@@ -308,28 +310,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int img = m_tile / per_img, rem = m_tile - img * per_img;
         const int py = rem / p.tiles_x, px = rem - py * p.tiles_x;
         const int y0 = py * p.th * p.stride - p.pad_h, x0 = px * p.tw * p.stride - p.pad_w;
-        int kb = 0;
-        for (int r = 0; r < p.kh; ++r) {
-          for (int sx = 0; sx < p.kw; ++sx) {
-            const int tap = r * p.kw + sx;
-            for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);          // whole warp waits: control flow stays uniform
-              if (elect_one()) {
-                tl_rec(p, tl_n, is_a ? 0 : 3, 0, tile, kb);
-                if (p.debug_flags & 2) {
-                  mbar_arrive(full_bar(stage));
-                } else if (is_a) {
-                  mbar_expect_tx(full_bar(stage), a_bytes);
-                  tma_load_4d(smem_u32(sA + stage * kABytes), &tmA, full_bar(stage), cb * kBlockK, x0 + sx, y0 + r, img);
-                } else {
-                  mbar_expect_tx(full_bar(stage), (uint32_t)C::kBBytes);
-                  tma_load_3d(smem_u32(sB + stage * C::kBBytes), &tmB, full_bar(stage), cb * kBlockK, tap, n_tile * BN);
-                }
-              }
-              __syncwarp();
-              if (++stage == S) { stage = 0; phase ^= 1u; }
+        // walk the (tap, channel block) sub-blocks kSub at a time: one barrier round per stage
+        int r = 0, sx = 0, cb = 0;
+        for (int sb0 = 0; sb0 < p.kblocks; sb0 += kSub) {
+          const int nsub = min(kSub, p.kblocks - sb0);
+          mbar_wait(empty_bar(stage), phase ^ 1u);          // whole warp waits: control flow stays uniform
+          if (elect_one()) {
+            tl_rec<TL>(p, tl_n, is_a ? 0 : 3, 0, tile, sb0);
+            if (p.debug_flags & 2) {
+              mbar_arrive(full_bar(stage));
+            } else if (is_a) {
+              mbar_expect_tx(full_bar(stage), a_bytes * (uint32_t)nsub);
+            } else {
+              mbar_expect_tx(full_bar(stage), (uint32_t)(C::kBBytes * nsub));
             }
           }
+          for (int j = 0; j < nsub; ++j) {
+            if (!(p.debug_flags & 2) && elect_one()) {
+              if (is_a)
+                tma_load_4d(smem_u32(sA + (stage * kSub + j) * kABytes), &tmA, full_bar(stage), cb * kBlockK, x0 + sx,
+                            y0 + r, img);
+              else
+                tma_load_3d(smem_u32(sB + (stage * kSub + j) * C::kBBytes), &tmB, full_bar(stage), cb * kBlockK,
+                            r * p.kw + sx, n_tile * BN);
+            }
+            if (++cb == p.cblocks) { cb = 0; if (++sx == p.kw) { sx = 0; ++r; } }
+          }
+          __syncwarp();
+          if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -348,22 +356,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-      for (int kb = 0; kb < p.kblocks; ++kb) {
+      for (int sb0 = 0; sb0 < p.kblocks; sb0 += kSub) {
+        const int nsub = min(kSub, p.kblocks - sb0);
         mbar_wait(full_bar(stage), phase);
         tcgen05_fence_after();
         if (elect_one()) {
-          tl_rec(p, tl_n, 1, 1, tile, kb);
-          const uint64_t da = make_smem_desc(smem_u32(sA + stage * kABytes));
-          const uint64_t db = make_smem_desc(smem_u32(sB + stage * C::kBBytes));
+          tl_rec<TL>(p, tl_n, 1, 1, tile, sb0);
           if (!(p.debug_flags & 1)) {
+            for (int j = 0; j < nsub; ++j) {
+              const uint64_t da = make_smem_desc(smem_u32(sA + (stage * kSub + j) * kABytes));
+              const uint64_t db = make_smem_desc(smem_u32(sB + (stage * kSub + j) * C::kBBytes));
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-              umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+                umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (sb0 | j | k) != 0);
+              }
             }
           }
           umma_commit(empty_bar(stage));            // frees the smem slot when these MMAs retire
-          if (kb == p.kblocks - 1) umma_commit(tfull_bar(acc));
+          if (sb0 + kSub >= p.kblocks) umma_commit(tfull_bar(acc));
         }
         __syncwarp();
         if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -373,7 +384,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------- store warp
     // One 4-D TMA store per 64-column slab; the tensor map clips the patch to the image and to the
     // channel slice.  Issuing it here keeps its issue + drain latency off the epilogue warps' path.
-    const uint32_t stage_base = smem_u32(smem + S * (kABytes + C::kBBytes));
+    const uint32_t stage_base = smem_u32(smem + S * kSub * (kABytes + C::kBBytes));
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = tile / p.m_tiles, m_tile = tile - n_tile * p.m_tiles;
       const int img = m_tile / per_img, rem = m_tile - img * per_img;
@@ -420,7 +431,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long pix = ((long long)img * p.Ho + oy) * p.Wo + ox;
       const int n0 = n_tile * BN;
       const int grp = img >= p.split_n ? 1 : 0;
-      tl_rec(p, tl_n, 2, 0, tile, 0);
+      tl_rec<TL>(p, tl_n, 2, 0, tile, 0);
       if (p.mode == SY_CONV_FUSED) {
         epi_bar();                               // previous tile's readers of sScale/sShift are done
         for (int c = et; c < BN; c += kEpiThreads) {
@@ -431,7 +442,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         epi_bar();
       }
       mbar_wait(tfull_bar(acc), acc_phase);
-      tl_rec(p, tl_n, 2, 1, tile, 0);
+      tl_rec<TL>(p, tl_n, 2, 1, tile, 0);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
@@ -473,7 +484,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 16; ++i) packed[i] = valid ? pack_bf16(f[2 * i], f[2 * i + 1]) : 0u;
         }
-        tl_rec(p, tl_n, 2, 2, tile, slab);
+        tl_rec<TL>(p, tl_n, 2, 2, tile, slab);
         bar_free();                              // (A) staging tile free: store drained, statistics readers done
 #pragma unroll
         for (int g = 0; g < 4; ++g) {            // 16-byte chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4)
@@ -482,7 +493,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         fence_proxy_async();                     // generic-proxy writes -> visible to the TMA (async proxy)
         bar_staged();                            // (B) staging tile complete: the store warp takes it from here
-        tl_rec(p, tl_n, 2, 3, tile, slab);
+        tl_rec<TL>(p, tl_n, 2, 3, tile, slab);
         if (do_stats) {
           // warp ew reduces columns [8*ew, 8*ew+8) of the slab: lane l reads rows l, l+32, l+64, l+96
           float a[16];
@@ -534,11 +545,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (col < p.Cout) sAcc[(grp * 2 + (lane >> 4)) * p.Cout + col] += e1;
           }
         }
-        tl_rec(p, tl_n, 2, 4, tile, slab);
+        tl_rec<TL>(p, tl_n, 2, 4, tile, slab);
       }
     }
     // ---------------------------------------------- per-CTA partial row (reduced by the normalise pass)
-    if (et == 0) tl_rec(p, tl_n, 4, 2, 0, 0);
+    if (et == 0) tl_rec<TL>(p, tl_n, 4, 2, 0, 0);
     if (do_stats) {
       epi_bar();                                 // every warp's sAcc updates are done
       float* mine = p.partials + (size_t)blockIdx.x * 4 * p.Cout;
@@ -614,12 +625,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (threadIdx.x == 8 * 32) tl_rec(p, tl_k, 4, 3, 0, 0);
+  if (threadIdx.x == 8 * 32) tl_rec<TL>(p, tl_k, 4, 3, 0, 0);
   if (warp == 9) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
   }
-  if (threadIdx.x == 9 * 32) { int k2 = tl_k + 8; tl_rec(p, k2, 4, 4, 0, 0); }
+  if (threadIdx.x == 9 * 32) { int k2 = tl_k + 8; tl_rec<TL>(p, k2, 4, 4, 0, 0); }
 }
 
 // ------------------------------------------------------------------ host side
@@ -699,18 +710,23 @@ template <int BN>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, Params& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
   const int acc_bytes = (p.mode == SY_CONV_RAW && p.partials) ? 16 * p.Cout : 0;
-  const int stage_bytes = kABytes + Cfg<BN>::kBBytes;
+  const int stage_bytes = kSub * (kABytes + Cfg<BN>::kBBytes);
   int stages = (kSmemLimit - Cfg<BN>::kFixedBytes - acc_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  if ((p.debug_flags >> 8) & 15) stages = min(stages, (p.debug_flags >> 8) & 15);   // debug: cap the ring depth
   SY_REQUIRE(stages >= 2, SY_EINVAL, "conv2d_tc: Cout=%d leaves no room for the operand ring", p.Cout);
   p.stages = stages;
   const int smem = Cfg<BN>::kFixedBytes + acc_bytes + stages * stage_bytes;
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_tc_kernel<BN><<<grid, kThreads, smem, stream>>>(ta, tb, ty, p);
+  if (p.timeline != nullptr)
+    conv_tc_kernel<BN, true><<<grid, kThreads, smem, stream>>>(ta, tb, ty, p);
+  else
+    conv_tc_kernel<BN, false><<<grid, kThreads, smem, stream>>>(ta, tb, ty, p);
   return launch_status("conv_tc_kernel");
 }
 
@@ -739,6 +755,7 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
   SY_REQUIRE(enc != nullptr, SY_EARCH, "cuTensorMapEncodeTiled not available from the driver");
 
   tc::Params p{};
+  p.debug_flags = d->debug_flags;
   p.N = x.n; p.Ho = ho; p.Wo = wo; p.Cout = y.c; p.Cin = x.c;
   p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_h = ph; p.pad_w = pw;
   tc::pick_patch(ho, wo, &p.th, &p.tw);
@@ -764,7 +781,6 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
     SY_REQUIRE(d->n_partials >= tc::num_sms(), SY_EWORKSPACE, "conv2d_tc: %d statistic rows, need %d (sy_conv_stat_rows)",
                d->n_partials, tc::num_sms());
   }
-  p.debug_flags = d->debug_flags;
   p.timeline = reinterpret_cast<long long*>(d->debug_timeline);
   p.timeline_cap = d->debug_timeline ? d->debug_timeline_events : 0;
   p.n_seg = 0;
