@@ -240,7 +240,8 @@ struct Cfg {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kTmemCols = 2 * BN;                          // double-buffered accumulator (power of two)
   // fixed part of dynamic smem (everything but the A/B ring and the per-CTA statistic accumulators)
-  static constexpr int kFixedBytes = 1024 /*align slack*/ + kSlabBytes + 2 * 256 * 4 /*scale,shift*/ + 256 /*barriers*/;
+  // plus, after the barriers, ONE region that is scale/shift (FUSED, 2 KiB) or the statistic accumulators (RAW)
+  static constexpr int kFixedBytes = 1024 /*align slack*/ + kSlabBytes + 256 /*barriers*/;
 };
 
 template <int BN, bool TL>
@@ -255,12 +256,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sA = smem;
   uint8_t* sB = sA + S * kSub * kABytes;
   uint8_t* sStage = sB + S * kSub * C::kBBytes;                                 // 1024-aligned: the rings are multiples of 1 KiB
-  float* sScale = reinterpret_cast<float*>(sStage + kSlabBytes);
-  float* sShift = sScale + 256;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sShift + 256);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + kSlabBytes);
   // bars: [0,8) full, [8,16) empty, [16,18) tmem_full, [18,20) tmem_empty, then the tmem base slot
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
-  float* sAcc = reinterpret_cast<float*>(bars + 32);                     // [2 groups][2][Cout]
+  float* sAcc = reinterpret_cast<float*>(bars + 32);                     // RAW:   [2 groups][2][Cout]
+  float* sScale = sAcc;                                                  // FUSED: [256] scale, [256] shift
+  float* sShift = sScale + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -563,7 +564,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           while (ld_acquire_u32(&p.sync[0]) < gridDim.x) __nanosleep(32);
         }
         epi_bar();
-        double* red = reinterpret_cast<double*>(sScale);        // unused in RAW mode: [8 warps][4]
+        double* red = reinterpret_cast<double*>(sA);            // operand ring is idle now: [8 warps][4]
         const int groups = p.split_n < p.N ? 2 : 1;
         const int cpc = (p.Cout + (int)gridDim.x - 1) / (int)gridDim.x;
         const int c_end = min(p.Cout, ((int)blockIdx.x + 1) * cpc);
@@ -714,7 +715,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
-  const int acc_bytes = (p.mode == SY_CONV_RAW && p.partials) ? 16 * p.Cout : 0;
+  const int acc_bytes = (p.mode == SY_CONV_RAW && p.partials) ? 16 * p.Cout : 2048;
   const int stage_bytes = kSub * (kABytes + Cfg<BN>::kBBytes);
   int stages = (kSmemLimit - Cfg<BN>::kFixedBytes - acc_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
