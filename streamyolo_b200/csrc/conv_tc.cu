@@ -47,7 +47,8 @@ constexpr int kThreads = 384;
 constexpr int kEpiThreads = 256;
 constexpr int kABytes = kBlockM * 128;   // 16 KiB per stage
 constexpr int kMaxStages = 8;
-constexpr int kSub = 2;                  // 64-deep K sub-blocks per pipeline stage (one barrier round = K 128)
+// 64-deep K sub-blocks per pipeline stage: two (one barrier round per K = 128) halve the per-round hand-shake
+// cost, which dominates narrow tiles; BN = 256 keeps one so that four 48 KiB stages fit (ring depth matters more)
 constexpr uint64_t kSpinLimit = 6000000000ull;  // ~3 s of SM clocks, then trap instead of hanging
 
 struct BnSeg {
@@ -238,6 +239,7 @@ constexpr int kSlabBytes = kBlockM * 128;      // 16 KiB staging tile
 template <int BN>
 struct Cfg {
   static constexpr int kBBytes = BN * 128;
+  static constexpr int kSub = (BN == 256) ? 1 : 2;
   static constexpr int kTmemCols = 2 * BN;                          // double-buffered accumulator (power of two)
   // fixed part of dynamic smem (everything but the A/B ring and the per-CTA statistic accumulators)
   // plus, after the barriers, ONE region that is scale/shift (FUSED, 2 KiB) or the statistic accumulators (RAW)
@@ -250,6 +252,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmY, const Params p) {
   using C = Cfg<BN>;
   const int S = p.stages;
+  constexpr int kSub = C::kSub;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms; plain pointer arithmetic keeps the shared address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -681,12 +684,13 @@ static int num_sms() {
   return n;
 }
 
-// Tile width heuristic.  Per 64-deep K block one SM needs the larger of the MMA time, 2*BN cycles
-// (128 x BN x 64 MACs at 4096 MAC/clk), and the time to pull the A+B operand bytes out of L2,
-// (16 KiB + BN*128 B) / ~44 B/clk/SM (measured: the chip-wide L2->SM path, not the tensor pipe, bounds a
-// 128-row tile), so wide tiles win unless they leave SMs idle: rounds of the persistent grid quantise.
+// Tile width heuristic from measured costs (B200, 1.965 GHz): one 64-deep K block of a 128-row tile costs about
+// 665 / 515 / 560 cycles at BN = 256 / 128 / 64 (MMA issue + barrier hand-shake + operand supply; the MMA itself
+// would need 512 / 256 / 128), the epilogue about 1900 cycles per 64-column slab and overlaps the next tile's main
+// loop, and the persistent grid runs ceil(tiles / SMs) rounds -- so wide tiles win unless they add a round.
 static int pick_bn(int cout, int m_tiles, int kblocks) {
   const int cands[3] = {256, 128, 64};
+  const double kbc[3] = {665.0, 515.0, 560.0};
   int best_bn = 64;
   double best = 1e30;
   for (int i = 0; i < 3; ++i) {
@@ -694,12 +698,9 @@ static int pick_bn(int cout, int m_tiles, int kblocks) {
     if (bn > 64 && bn / 2 >= cout) continue;          // a narrower tile already covers every channel
     const int tiles = m_tiles * cdiv(cout, bn);
     const int rounds = cdiv(tiles, num_sms());
-    const double l2 = (16384.0 + 128.0 * bn) / 44.0;
-    const double kb = (2.0 * bn > l2) ? 2.0 * bn : l2;
-    const double epi = 1200.0 + 10.0 * bn;
-    const double main_c = kblocks * kb;
-    const double per_tile = (main_c > epi ? main_c : epi) + 300.0;
-    const double t = rounds * per_tile + (main_c < epi ? main_c : epi);
+    const double main_c = kblocks * kbc[i];
+    const double epi = 1900.0 * (bn / 64);
+    const double t = rounds * ((main_c > epi ? main_c : epi) + 400.0) + (main_c < epi ? main_c : epi);
     if (t < best) { best = t; best_bn = bn; }
   }
   return best_bn;
@@ -716,7 +717,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     attr_set = true;
   }
   const int acc_bytes = (p.mode == SY_CONV_RAW && p.partials) ? 16 * p.Cout : 2048;
-  const int stage_bytes = kSub * (kABytes + Cfg<BN>::kBBytes);
+  const int stage_bytes = Cfg<BN>::kSub * (kABytes + Cfg<BN>::kBBytes);
   int stages = (kSmemLimit - Cfg<BN>::kFixedBytes - acc_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if ((p.debug_flags >> 8) & 15) stages = min(stages, (p.debug_flags >> 8) & 15);   // debug: cap the ring depth
