@@ -100,3 +100,13 @@ def test_gloo_world2(tmp_path):
                                       stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_dropin_aliases():
+    """cfgs/*.py: `from exps.model.yolox import YOLOX` etc. must resolve to the B200 classes after install()."""
+    code = ("import streamyolo_b200.dropin as d; d.install();"
+            "from exps.model.yolox import YOLOX; from exps.model.dfp_pafpn import DFPPAFPN;"
+            "from exps.model.tal_head import TALHead; from exps.model.darknet import CSPDarknet;"
+            "import streamyolo_b200.model as m; assert YOLOX is m.YOLOX and TALHead is m.TALHead; print('ok')")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr
