@@ -86,7 +86,13 @@ typedef struct {
   SyBnSegment bn[2];     /* bn[0].gamma != NULL: finalize BatchNorm in the kernel tail (1-2 parameter segments) */
   float momentum, eps;
   float* scale_shift;    /* [2 (scale|shift)][2 groups][Cout]: y = x*scale + shift, ready when the kernel ends */
-  uint32_t* sync;        /* two zero-initialised counters (grid barrier); the kernel leaves them at zero */
+  uint32_t* sync;        /* four zero-initialised counters (grid barriers); the kernel leaves them at zero */
+  /* With bn[]: optional normalise + act (+ residual) pass INSIDE the same launch (after a second grid barrier
+   * every CTA re-reads the raw tiles it stored -- L2 resident -- and writes apply_y = act(y*scale+shift) (+ apply_res)).
+   * apply_y.ptr == NULL: leave it to sy_bn_act_apply.  The *_group1_offset are element offsets added to the
+   * addresses of statistics-group-1 images (DFP fusion, see sy_bn_act_apply). */
+  SyTensor apply_y, apply_res;
+  int64_t apply_y_group1_offset, apply_res_group1_offset;
   /* ---- debugging only: CTA 0 records (event, clock64) int64 pairs of its three pipeline roles ---- */
   void* debug_timeline;  /* device buffer of 2*debug_timeline_events int64, or NULL */
   int32_t debug_timeline_events;

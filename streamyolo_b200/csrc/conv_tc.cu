@@ -77,7 +77,12 @@ struct Params {
   BnSeg seg[2];
   float momentum, eps;
   float* ss;                // [2 (scale|shift)][2 groups][Cout]
-  unsigned int* sync;       // two counters, zero between launches
+  unsigned int* sync;       // three counters (two grid barriers + exit ticket), zero between launches
+  // normalise + act (+ residual) pass done by this kernel after the statistics are final (nullptr: separate launch)
+  __nv_bfloat16* ap_y; long long ap_y_pitch;
+  const __nv_bfloat16* ap_res; long long ap_res_pitch;
+  long long ap_y_goff1, ap_res_goff1;
+  int ap_act;
   long long* timeline;      // debug: CTA 0 records (event id, clock) pairs; nullptr in production
   int timeline_cap;
   int debug_flags;          // debug: 1 = skip the MMAs, 2 = skip the TMA loads (barriers still cycle), 4 = skip epilogue work
@@ -404,7 +409,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
       }
     }
-    if (lane == 0) bulk_wait_all();              // all stores complete before the CTA exits
+    if (lane == 0) {
+      bulk_wait_all();                           // every store of this CTA has been performed
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("bar.sync 4, 288;" ::: "memory");   // the epilogue warps may now re-read this CTA's own raw tiles
   } else if (warp < 8) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
@@ -552,21 +562,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tl_rec<TL>(p, tl_n, 2, 4, tile, slab);
       }
     }
-    // ---------------------------------------------- per-CTA partial row (reduced by the normalise pass)
+    // ---------------------------------------------- per-CTA partial row, grid barrier, BatchNorm finalize, apply
     if (et == 0) tl_rec<TL>(p, tl_n, 4, 2, 0, 0);
+    asm volatile("bar.sync 4, 288;" ::: "memory");   // store warp: all TMA stores of this CTA are complete
     if (do_stats) {
-      epi_bar();                                 // every warp's sAcc updates are done
       float* mine = p.partials + (size_t)blockIdx.x * 4 * p.Cout;
       for (int i = et; i < 4 * p.Cout; i += kEpiThreads) mine[i] = sAcc[i];
       if (p.n_seg > 0) {
-        // ---- grid barrier (all CTAs are resident), then every CTA finalizes its slice of the channels
-        __threadfence();
-        epi_bar();
-        if (et == 0) {
-          atomicAdd(&p.sync[0], 1u);
-          while (ld_acquire_u32(&p.sync[0]) < gridDim.x) __nanosleep(32);
-        }
-        epi_bar();
+        auto grid_barrier = [&](unsigned int* ctr) {    // all CTAs of the persistent grid are resident (1 per SM)
+          __threadfence();
+          epi_bar();
+          if (et == 0) {
+            atomicAdd(ctr, 1u);
+            while (ld_acquire_u32(ctr) < gridDim.x) __nanosleep(32);
+          }
+          epi_bar();
+        };
+        grid_barrier(&p.sync[0]);
         double* red = reinterpret_cast<double*>(sA);            // operand ring is idle now: [8 warps][4]
         const int groups = p.split_n < p.N ? 2 : 1;
         const int cpc = (p.Cout + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -612,15 +624,64 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           epi_bar();
         }
-        if (et == 0) {
-          if (blockIdx.x == 0) {
-            for (int sgi = 0; sgi < p.n_seg; ++sgi)
-              if (p.seg[sgi].nbt) *p.seg[sgi].nbt += groups;
+        if (et == 0 && blockIdx.x == 0) {
+          for (int sgi = 0; sgi < p.n_seg; ++sgi)
+            if (p.seg[sgi].nbt) *p.seg[sgi].nbt += groups;
+        }
+        if (p.ap_y != nullptr) {
+          // ---- second grid barrier: scale/shift of every channel are published; normalise this CTA's own tiles,
+          //      re-reading the raw bf16 values it just stored (L2 resident for all but the largest layers)
+          grid_barrier(&p.sync[1]);
+          for (int i = et; i < p.Cout; i += kEpiThreads)          // [2 (scale|shift)][2 groups][Cout] -> smem (over sAcc)
+            reinterpret_cast<float4*>(sAcc)[i] = __ldcg(reinterpret_cast<const float4*>(p.ss) + i);
+          epi_bar();
+          constexpr int CPR = BN / 8;                              // 16-byte chunks per pixel row of a tile
+          constexpr int RPP = kEpiThreads / CPR;                   // tile rows handled per pass of the 256 threads
+          const int chunk = et % CPR, r0 = et / CPR;
+          for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int n_tile = tile / p.m_tiles, m_tile = tile - n_tile * p.m_tiles;
+            const int img = m_tile / per_img, rem = m_tile - img * per_img;
+            const int py = rem / p.tiles_x, px = rem - py * p.tiles_x;
+            const int cg = n_tile * BN + chunk * 8;
+            if (cg >= p.Cout) continue;
+            const int grp = img >= p.split_n ? 1 : 0;
+            const float* sc = sAcc + grp * p.Cout + cg;
+            const float* sh = sAcc + (2 + grp) * p.Cout + cg;
+            const float4 s0 = *reinterpret_cast<const float4*>(sc), s1 = *reinterpret_cast<const float4*>(sc + 4);
+            const float4 h0 = *reinterpret_cast<const float4*>(sh), h1 = *reinterpret_cast<const float4*>(sh + 4);
+            const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float shv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            const long long yoff = grp ? p.ap_y_goff1 : 0, roff = grp ? p.ap_res_goff1 : 0;
+#pragma unroll 4
+            for (int rr = r0; rr < p.th * p.tw; rr += RPP) {
+              const int tyy = rr / p.tw, txx = rr - tyy * p.tw;
+              const int oy = py * p.th + tyy, ox = px * p.tw + txx;
+              if (oy >= p.Ho || ox >= p.Wo) continue;
+              const long long pix = ((long long)img * p.Ho + oy) * p.Wo + ox;
+              const uint4 u = __ldcg(reinterpret_cast<const uint4*>(p.y + pix * p.y_pitch + cg));
+              float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                            bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float t = f[i] * scv[i] + shv[i];
+                f[i] = p.ap_act ? silu_f(t) : t;
+              }
+              if (p.ap_res != nullptr) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(p.ap_res + pix * p.ap_res_pitch + cg + roff);
+                f[0] += bf16_lo(rv.x); f[1] += bf16_hi(rv.x); f[2] += bf16_lo(rv.y); f[3] += bf16_hi(rv.y);
+                f[4] += bf16_lo(rv.z); f[5] += bf16_hi(rv.z); f[6] += bf16_lo(rv.w); f[7] += bf16_hi(rv.w);
+              }
+              *reinterpret_cast<uint4*>(p.ap_y + pix * p.ap_y_pitch + cg + yoff) =
+                  make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            }
           }
-          const unsigned int old = atomicAdd(&p.sync[1], 1u);
-          if (old == gridDim.x - 1) {               // every CTA is past the barrier: re-arm for the next launch
+        }
+        if (et == 0) {
+          const unsigned int old = atomicAdd(&p.sync[2], 1u);
+          if (old == gridDim.x - 1) {               // every CTA is past both barriers: re-arm for the next launch
             p.sync[0] = 0u;
             p.sync[1] = 0u;
+            p.sync[2] = 0u;
             __threadfence();
           }
         }
@@ -802,6 +863,20 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
     p.momentum = d->momentum; p.eps = d->eps;
     p.ss = d->scale_shift;
     p.sync = d->sync;
+    if (d->apply_y.ptr != nullptr) {
+      const SyTensor& ay = d->apply_y;
+      SY_REQUIRE(view_ok(ay) && ay.h == ho && ay.w == wo && ay.c == y.c, SY_EINVAL, "conv2d_tc: apply_y view mismatch");
+      SY_REQUIRE((d->apply_y_group1_offset % 8) == 0 && (d->apply_res_group1_offset % 8) == 0, SY_EINVAL,
+                 "conv2d_tc: group offsets must be multiples of 8");
+      p.ap_y = reinterpret_cast<__nv_bfloat16*>(ay.ptr); p.ap_y_pitch = ay.pitch;
+      p.ap_act = d->act;
+      p.ap_y_goff1 = d->apply_y_group1_offset; p.ap_res_goff1 = d->apply_res_group1_offset;
+      if (d->apply_res.ptr != nullptr) {
+        SY_REQUIRE(view_ok(d->apply_res) && d->apply_res.h == ho && d->apply_res.w == wo && d->apply_res.c == y.c, SY_EINVAL,
+                   "conv2d_tc: apply_res view mismatch");
+        p.ap_res = reinterpret_cast<const __nv_bfloat16*>(d->apply_res.ptr); p.ap_res_pitch = d->apply_res.pitch;
+      }
+    }
   }
   if (d->rows_written) *d->rows_written = p.total_tiles < tc::num_sms() ? p.total_tiles : tc::num_sms();
 

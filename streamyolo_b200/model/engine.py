@@ -19,6 +19,7 @@ from .. import ops
 from ..ops import View
 
 
+FUSE_APPLY = os.environ.get("SY_FUSE_APPLY", "1") != "0"   # normalise pass inside the conv launch (1 launch / BaseConv)
 TRACE = None      # debugging: set to a dict to capture every BaseConv's stored output by module name
 
 
@@ -71,7 +72,7 @@ def _sync(m, device):
     """Two persistent zero-initialised counters per module (bn_train_apply leaves them at zero)."""
     t = getattr(m, "_sy_sync", None)
     if t is None or t.device != device:
-        t = torch.zeros(2, dtype=torch.int32, device=device)
+        t = torch.zeros(4, dtype=torch.int32, device=device)
         m._sy_sync = t
     return t
 
@@ -104,9 +105,15 @@ def conv_bn_act(ctx: Ctx, mods, x: View, wpk, k, s, y: View, res: View = None, a
             segs.append(_bn_seg(m, c0))
             c0 += m.conv.out_channels
         ss = torch.empty((2, 2, cout), dtype=torch.float32, device=ctx.device)
-        ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="tc", partials=partials, split_n=split, bn=segs,
-                   momentum=mom, eps=float(bn0.eps), scale_shift=ss, sync=_sync(mods[0], ctx.device))
-        ops.bn_act_apply(raw, ss[0].data_ptr(), ss[1].data_ptr(), split if split else n, act, res, y, y_goff1, res_goff1)
+        if FUSE_APPLY:
+            ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="tc", partials=partials, split_n=split, bn=segs,
+                       momentum=mom, eps=float(bn0.eps), scale_shift=ss, sync=_sync(mods[0], ctx.device), act=act,
+                       apply_y=y, apply_res=res, y_goff1=y_goff1, res_goff1=res_goff1)
+        else:
+            ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="tc", partials=partials, split_n=split, bn=segs,
+                       momentum=mom, eps=float(bn0.eps), scale_shift=ss, sync=_sync(mods[0], ctx.device))
+            ops.bn_act_apply(raw, ss[0].data_ptr(), ss[1].data_ptr(), split if split else n, act, res, y, y_goff1,
+                             res_goff1)
         return
     # CUDA-core cross-check path: conv, separate statistics pass, separate finalize per module, apply
     ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="simt")

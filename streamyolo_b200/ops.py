@@ -30,6 +30,8 @@ class SyConvDesc(C.Structure):
                 ("shift", C.c_void_p), ("res", SyTensor), ("split_n", C.c_int32), ("stat_partials", C.c_void_p),
                 ("n_partials", C.c_int32), ("rows_written", C.POINTER(C.c_int32)), ("bn", SyBnSegment * 2),
                 ("momentum", C.c_float), ("eps", C.c_float), ("scale_shift", C.c_void_p), ("sync", C.c_void_p),
+                ("apply_y", SyTensor), ("apply_res", SyTensor), ("apply_y_group1_offset", C.c_int64),
+                ("apply_res_group1_offset", C.c_int64),
                 ("debug_timeline", C.c_void_p),
                 ("debug_timeline_events", C.c_int32), ("debug_flags", C.c_int32)]
 
@@ -201,7 +203,7 @@ def conv_stat_rows():
 
 def conv2d(x: View, wpk, y: View, k, s, mode, impl="tc", scale=None, shift=None, act=1, res: View = None,
            partials=None, split_n=0, timeline=None, debug_flags=0, bn=None, momentum=0.03, eps=1e-3, scale_shift=None,
-           sync=None):
+           sync=None, apply_y: View = None, apply_res: View = None, y_goff1=0, res_goff1=0):
     """``k`` is an int (square) or (kh, kw).  With ``partials`` (RAW mode, tensor-core path) returns the number
     of per-CTA statistic rows the launch writes."""
     d = SyConvDesc()
@@ -227,6 +229,10 @@ def conv2d(x: View, wpk, y: View, k, s, mode, impl="tc", scale=None, shift=None,
             seg.c_begin = c0
         d.momentum, d.eps = momentum, eps
         d.scale_shift, d.sync = scale_shift.data_ptr(), sync.data_ptr()
+        if apply_y is not None:
+            d.apply_y = apply_y.st()
+            d.apply_res = apply_res.st() if apply_res is not None else NULL_T
+            d.apply_y_group1_offset, d.apply_res_group1_offset = y_goff1, res_goff1
     d.debug_flags = debug_flags
     if timeline is not None:
         d.debug_timeline, d.debug_timeline_events = timeline.data_ptr(), timeline.numel() // 2

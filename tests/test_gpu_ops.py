@@ -117,14 +117,19 @@ def test_conv_tc_bn_finalize_then_apply():
     resid = rand_act(n, co, h, w, 64)
     partials = torch.empty((ops.conv_stat_rows(), 4 * co), device=DEV)
     ss = torch.empty((2, 2, co), device=DEV)
-    sync = torch.zeros(2, dtype=torch.int32, device=DEV)
-    for rep in range(2):
-        rows = ops.conv2d(ops.from_nchw(x), ops.pack_conv_weight(wt), raw, 1, 1, ops.SY_CONV_RAW, partials=partials,
-                          split_n=2, bn=segs, momentum=0.03, eps=1e-3, scale_shift=ss, sync=sync)
+    sync = torch.zeros(4, dtype=torch.int32, device=DEV)
+    resid_v, x_v = ops.from_nchw(resid), ops.from_nchw(x)
+    for rep in range(3):
+        fused = rep == 2        # last repetition: normalise pass inside the conv launch
+        y.buf.fill_(float("nan"))
+        rows = ops.conv2d(x_v, ops.pack_conv_weight(wt), raw, 1, 1, ops.SY_CONV_RAW, partials=partials,
+                          split_n=2, bn=segs, momentum=0.03, eps=1e-3, scale_shift=ss, sync=sync, act=1,
+                          apply_y=y if fused else None, apply_res=resid_v if fused else None)
         assert 1 <= rows <= ops.conv_stat_rows()
-        ops.bn_act_apply(raw, ss[0].data_ptr(), ss[1].data_ptr(), 2, 1, ops.from_nchw(resid), y)
+        if not fused:
+            ops.bn_act_apply(raw, ss[0].data_ptr(), ss[1].data_ptr(), 2, 1, resid_v, y)
         torch.cuda.synchronize()
-        assert sync.tolist() == [0, 0]
+        assert sync.tolist() == [0, 0, 0, 0]
         rawf = raw.nchw_float()
         refs = []
         for gi in range(2):
