@@ -652,27 +652,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
             const float shv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
             const long long yoff = grp ? p.ap_y_goff1 : 0, roff = grp ? p.ap_res_goff1 : 0;
-#pragma unroll 4
-            for (int rr = r0; rr < p.th * p.tw; rr += RPP) {
-              const int tyy = rr / p.tw, txx = rr - tyy * p.tw;
-              const int oy = py * p.th + tyy, ox = px * p.tw + txx;
-              if (oy >= p.Ho || ox >= p.Wo) continue;
-              const long long pix = ((long long)img * p.Ho + oy) * p.Wo + ox;
-              const uint4 u = __ldcg(reinterpret_cast<const uint4*>(p.y + pix * p.y_pitch + cg));
-              float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
-                            bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+            // batches of kAB rows: all loads first (the stores may alias the loads, so the compiler cannot hoist them)
+            constexpr int kAB = 4;
+            const int rows_in_patch = p.th * p.tw;
+            for (int rb = r0; rb < rows_in_patch; rb += RPP * kAB) {
+              long long pixv[kAB];
+              uint4 u[kAB], rv[kAB];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float t = f[i] * scv[i] + shv[i];
-                f[i] = p.ap_act ? silu_f(t) : t;
+              for (int j = 0; j < kAB; ++j) {
+                const int rr = rb + j * RPP;
+                const int tyy = rr / p.tw, txx = rr - tyy * p.tw;
+                const int oy = py * p.th + tyy, ox = px * p.tw + txx;
+                pixv[j] = (rr < rows_in_patch && oy < p.Ho && ox < p.Wo) ? ((long long)img * p.Ho + oy) * p.Wo + ox : -1;
               }
+#pragma unroll
+              for (int j = 0; j < kAB; ++j)
+                if (pixv[j] >= 0) u[j] = __ldcg(reinterpret_cast<const uint4*>(p.y + pixv[j] * p.y_pitch + cg));
               if (p.ap_res != nullptr) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(p.ap_res + pix * p.ap_res_pitch + cg + roff);
-                f[0] += bf16_lo(rv.x); f[1] += bf16_hi(rv.x); f[2] += bf16_lo(rv.y); f[3] += bf16_hi(rv.y);
-                f[4] += bf16_lo(rv.z); f[5] += bf16_hi(rv.z); f[6] += bf16_lo(rv.w); f[7] += bf16_hi(rv.w);
+#pragma unroll
+                for (int j = 0; j < kAB; ++j)
+                  if (pixv[j] >= 0) rv[j] = *reinterpret_cast<const uint4*>(p.ap_res + pixv[j] * p.ap_res_pitch + cg + roff);
               }
-              *reinterpret_cast<uint4*>(p.ap_y + pix * p.ap_y_pitch + cg + yoff) =
-                  make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+#pragma unroll
+              for (int j = 0; j < kAB; ++j) {
+                if (pixv[j] < 0) continue;
+                float f[8] = {bf16_lo(u[j].x), bf16_hi(u[j].x), bf16_lo(u[j].y), bf16_hi(u[j].y),
+                              bf16_lo(u[j].z), bf16_hi(u[j].z), bf16_lo(u[j].w), bf16_hi(u[j].w)};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float t = f[i] * scv[i] + shv[i];
+                  f[i] = p.ap_act ? silu_f(t) : t;
+                }
+                if (p.ap_res != nullptr) {
+                  f[0] += bf16_lo(rv[j].x); f[1] += bf16_hi(rv[j].x); f[2] += bf16_lo(rv[j].y); f[3] += bf16_hi(rv[j].y);
+                  f[4] += bf16_lo(rv[j].z); f[5] += bf16_hi(rv[j].z); f[6] += bf16_lo(rv[j].w); f[7] += bf16_hi(rv[j].w);
+                }
+                *reinterpret_cast<uint4*>(p.ap_y + pixv[j] * p.ap_y_pitch + cg + yoff) =
+                    make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+              }
             }
           }
         }

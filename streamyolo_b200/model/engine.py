@@ -19,7 +19,9 @@ from .. import ops
 from ..ops import View
 
 
-FUSE_APPLY = os.environ.get("SY_FUSE_APPLY", "1") != "0"   # normalise pass inside the conv launch (1 launch / BaseConv)
+# normalise pass inside the conv launch (1 launch / BaseConv): correct but measured SLOWER on B200 (11.7 vs 8.2 ms/step:
+# 256 threads per SM cannot keep enough bytes in flight), so off by default
+FUSE_APPLY = os.environ.get("SY_FUSE_APPLY", "0") != "0"
 TRACE = None      # debugging: set to a dict to capture every BaseConv's stored output by module name
 
 
