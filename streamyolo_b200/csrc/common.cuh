@@ -55,6 +55,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 __device__ __forceinline__ float round_bf16(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+// SiLU with the approximate divide (MUFU.RCP + FMUL, ~2 ulp fp32 -- far below the bf16 output rounding): the
+// normalise pass is otherwise ALU-bound (a correctly rounded fp32 divide costs ~10 instructions per element).
+// For v << 0 the denominator overflows to +inf and the quotient is -0, the correct limit.
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 }  // namespace sy

@@ -579,16 +579,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           epi_bar();
         };
         grid_barrier(&p.sync[0]);
-        double* red = reinterpret_cast<double*>(sA);            // operand ring is idle now: [8 warps][4]
+        // This CTA finalizes channels [b*cpc, (b+1)*cpc): one WARP per channel (no block barriers): lane l sums the
+        // partial rows l, l+32, ... in order, a fixed shuffle tree combines the lanes (deterministic), lane 0 finalizes.
         const int groups = p.split_n < p.N ? 2 : 1;
         const int cpc = (p.Cout + (int)gridDim.x - 1) / (int)gridDim.x;
         const int c_end = min(p.Cout, ((int)blockIdx.x + 1) * cpc);
-        for (int c = (int)blockIdx.x * cpc; c < c_end; ++c) {
+        for (int c = (int)blockIdx.x * cpc + warp; c < c_end; c += 8) {
           double v[4] = {0.0, 0.0, 0.0, 0.0};
-          if (et < (int)gridDim.x) {                              // thread t owns partial row t
-            const float* rowp = p.partials + (size_t)et * 4 * p.Cout + c;
+          for (int r = lane; r < (int)gridDim.x; r += 32) {
+            const float* rowp = p.partials + (size_t)r * 4 * p.Cout + c;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = (double)__ldcg(rowp + i * p.Cout);
+            for (int i = 0; i < 4; ++i) v[i] += (double)__ldcg(rowp + i * p.Cout);
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -596,21 +597,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int m = 16; m >= 1; m >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], m);
           }
           if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) red[warp * 4 + i] = v[i];
-          }
-          epi_bar();
-          if (et == 0) {
-            double t[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int w8 = 0; w8 < 8; ++w8)
-              for (int i = 0; i < 4; ++i) t[i] += red[w8 * 4 + i];
             const BnSeg& sg = (p.n_seg > 1 && c >= p.seg[1].c_begin) ? p.seg[1] : p.seg[0];
             const int cs = c - sg.c_begin;
             float rm = sg.rmean ? sg.rmean[cs] : 0.f, rv = sg.rvar ? sg.rvar[cs] : 1.f;
             for (int g = 0; g < groups; ++g) {
               const double cnt = (double)(g == 0 ? (groups == 2 ? p.split_n : p.N) : p.N - p.split_n) * p.Ho * p.Wo;
-              const double mean = t[2 * g] / cnt;
-              double var = t[2 * g + 1] / cnt - mean * mean;
+              const double mean = v[2 * g] / cnt;
+              double var = v[2 * g + 1] / cnt - mean * mean;
               if (var < 0.0) var = 0.0;
               const float sc = sg.gamma[cs] * (float)(1.0 / sqrt(var + (double)p.eps));
               p.ss[(0 * 2 + g) * p.Cout + c] = sc;
@@ -622,7 +615,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (sg.rmean) sg.rmean[cs] = rm;
             if (sg.rvar) sg.rvar[cs] = rv;
           }
-          epi_bar();
         }
         if (et == 0 && blockIdx.x == 0) {
           for (int sgi = 0; sgi < p.n_seg; ++sgi)
