@@ -227,8 +227,11 @@ def test_eval_and_on_pipe_vs_oracle(impl):
     r2, _ = o.forward(x[1:2, 0:3], buffer=rbuf, mode="on_pipe")
     torch.cuda.synchronize()
     assert rel(o1[..., :4], r1[..., :4]) < 3e-2 and rel(o2[..., :4], r2[..., :4]) < 3e-2
-    for a, b in zip(buf, rbuf):
-        assert rel(a, b) < 7e-2      # eval mode, ~70 bf16 layers deep (layer trace: ~1e-2 and flat)
+    # un-fused PAN buffers (~70 bf16 layers deep, down to a 4x5 map): judged against the rounding-noise floor,
+    # i.e. the same oracle code on inputs nudged by 1e-6
+    _, pbuf = o.forward(x[:1, 0:3] * (1 + 1e-6), mode="on_pipe")
+    for a, b, pb in zip(buf, rbuf, pbuf):
+        assert rel(a, b) <= 1.5 * rel(pb, b) + 2e-2
 
 
 def test_s_model_full_resolution_golden():
