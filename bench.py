@@ -113,35 +113,50 @@ def build_model(tag, device):
 
 
 def time_dominant_kernel(tag, batch, peaks):
-    """The heaviest conv of the net (head tower 3x3 at stride 8), alone, CUDA events, warm."""
+    """The heaviest conv of the net (head tower 3x3 at stride 8) alone: a CUDA graph of 16 launches that rotate
+    over 8 input/output buffer sets (8 x 74 MB > the 126 MB L2, so every launch reads its operands from HBM and
+    no host launch overhead is inside the timed region), CUDA events around the replay, best of 5."""
     from streamyolo_b200 import ops
     from streamyolo_b200.ops import View
     width = MODELS[tag][1]
     c = int(256 * width)
     n, h, w = batch, 75, 120
-    x = View(torch.randn((n, h, w, c), device="cuda").to(torch.bfloat16))
+    sets = 8
+    xs = [View(torch.randn((n, h, w, c), device="cuda").to(torch.bfloat16)) for _ in range(sets)]
+    ys = [View.empty(n, h, w, c, "cuda") for _ in range(sets)]
     wt = ops.pack_conv_weight(torch.randn((c, c, 3, 3), device="cuda") * 0.02)
-    y = View.empty(n, h, w, c, "cuda")
     part = torch.empty((ops.conv_stat_rows(), 4 * c), device="cuda")
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    for _ in range(3):
-        ops.conv2d(x, wt, y, 3, 1, ops.SY_CONV_RAW, partials=part)
-    times = []
-    for _ in range(10):
-        flush.zero_()                                           # evict L2 between timed launches
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ops.conv2d(x, wt, y, 3, 1, ops.SY_CONV_RAW, partials=part)
-        e1.record()
+    launches = 16
+
+    def go(i):
+        ops.conv2d(xs[i % sets], wt, ys[i % sets], 3, 1, ops.SY_CONV_RAW, partials=part)
+    for i in range(3):
+        go(i)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        with torch.cuda.graph(g):
+            for i in range(launches):
+                go(i)
+        g.replay()
         torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
-    ms = sum(times) / len(times)
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            g.replay()
+            e1.record(st)
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / launches)
+    ms = best
     flops = 2.0 * n * h * w * c * c * 9
     ach = flops / (ms * 1e-3) / 1e12
     return {"bound": "tensor", "kernel": f"conv_tc_kernel<{min(256, c)}> 3x3 s1 {c}->{c} @{n}x{h}x{w}",
             "achieved": round(ach, 1), "peak": peaks["burst"], "unit": "TFLOP/s", "frac": round(ach / peaks["burst"], 4),
             "peak_source": peaks["source"] + " cuBLAS bf16 burst", "ms_per_launch": round(ms, 4),
-            "algorithmic_flop_per_launch": flops, "traffic": None}
+            "algorithmic_flop_per_launch": flops, "traffic": None,
+            "how": "graph of 16 launches over 8 rotating buffer sets (operands > L2), CUDA events, best of 5"}
 
 
 def host_threads():
@@ -215,6 +230,7 @@ def main():
         raise SystemExit("bench.py --impl ours needs a B200 (no CPU path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    os.environ["NCCL_DEBUG"] = os.environ.get("SY_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
     sydist.init("nccl")
     from streamyolo_b200 import ops, synth
     from streamyolo_b200.build import build
@@ -332,6 +348,7 @@ def main():
         h2d = x_host.numel() * 4 + fut_host.numel() * 4 + cur_host.numel() * 4
         loss_e2e = float(res_host[0])
 
+    sydist.shutdown()
     if rank != 0:
         return
     gf = GFLOP_PER_PAIR.get(args.model)

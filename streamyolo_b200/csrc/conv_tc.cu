@@ -12,12 +12,10 @@
 // with both operands in shared memory and the fp32 accumulator in TMEM (double
 // buffered), so the epilogue of tile i overlaps the main loop of tile i+1.
 //
-// Warp roles (384 threads, persistent CTA, one per SM).  The warp scheduler favours HIGHER warp ids, so the
-// latency-critical single-thread roles take the highest ids and the eight throughput-bound epilogue warps
-// the lowest (with the roles the other way round the MMA issuer starves behind the epilogue warps of its
-// own scheduler: measured ~440 cycles of pure hand-shake per K block):
-//   warps 0-7 epilogue   warp 8 TMA store   warp 9 TMEM alloc + weight (B) loads   warp 10 activation (A) loads
-//   warp 11 MMA issuer
+// Warp roles (640 threads, persistent CTA, one per SM):
+//   warps 0-7   convert: TMEM -> registers -> epilogue math -> bf16 -> swizzled smem staging tile
+//   warps 8-15  statistics: per-channel (sum, sum of squares) of the staged tile (overlaps the next slab's conversion)
+//   warp 16 TMA store   warp 17 TMEM alloc + weight (B) loads   warp 18 activation (A) loads   warp 19 MMA issuer
 //   warps 4-11 epilogue, per 64-column slab of the accumulator: TMEM -> registers -> (raw | folded BN +
 //             SiLU + residual) -> bf16 -> 128B-swizzled shared staging tile -> ONE 4-D TMA store (the
 //             tensor map clips the patch to the image and the channel slice) while the eight warps
@@ -43,7 +41,7 @@ namespace tc {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;              // bf16 elements = one 128-byte swizzle row
-constexpr int kThreads = 384;
+constexpr int kThreads = 640;
 constexpr int kEpiThreads = 256;
 constexpr int kABytes = kBlockM * 128;   // 16 KiB per stage
 constexpr int kMaxStages = 8;
@@ -221,8 +219,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 // staging-tile hand-off between the 8 epilogue warps and the store warp (warp 3): 256 + 32 threads
-__device__ __forceinline__ void bar_free() { asm volatile("bar.sync 2, 288;" ::: "memory"); }    // (A) staging tile free
-__device__ __forceinline__ void bar_staged() { asm volatile("bar.sync 3, 288;" ::: "memory"); }  // (B) staging tile complete
+// staging-tile hand-off between the 8 convert warps, the 8 statistics warps and the store warp: 256 + 256 + 32 threads
+__device__ __forceinline__ void bar_free() { asm volatile("bar.sync 2, 544;" ::: "memory"); }    // (A) staging tile free
+__device__ __forceinline__ void bar_staged() { asm volatile("bar.sync 3, 544;" ::: "memory"); }  // (B) staging tile complete
+__device__ __forceinline__ void bar_stats_done() { asm volatile("bar.sync 5, 512;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -274,14 +274,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   int tl_k = 3 * (p.timeline_cap / 4);
-  if (threadIdx.x == 8 * 32) tl_rec<TL>(p, tl_k, 4, 0, 0, 0);
+  if (threadIdx.x == 16 * 32) tl_rec<TL>(p, tl_k, 4, 0, 0, 0);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + 2 + a); };
 
-  if (threadIdx.x == 11 * 32) {
+  if (threadIdx.x == 19 * 32) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmY);
@@ -295,22 +295,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
+  if (warp == 17) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 8 * 32) tl_rec<TL>(p, tl_k, 4, 1, 0, 0);
+  if (threadIdx.x == 16 * 32) tl_rec<TL>(p, tl_k, 4, 1, 0, 0);
 
   const uint32_t a_bytes = (uint32_t)(p.th * p.tw) * 128u;
   const int per_img = p.tiles_x * p.tiles_y;
 
-  if (warp == 10 || warp == 9) {
-    // ----------------------------------------------- TMA producers: warp 10 loads A (activations), warp 9 loads B (weights)
+  if (warp == 18 || warp == 17) {
+    // ----------------------------------------------- TMA producers: warp 18 loads A (activations), warp 17 loads B (weights)
     // Two issuing threads because a single thread needs ~350 cycles per cp.async.bulk.tensor: the pair keeps a
     // K block's issue time below its MMA time.  Both arrive (with their byte counts) on the same full barrier.
     {
-      const bool is_a = (warp == 10);
+      const bool is_a = (warp == 18);
       int stage = 0;
       uint32_t phase = 0;
       int tl_n = is_a ? 0 : p.timeline_cap / 8;
@@ -350,7 +350,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 11) {
+  } else if (warp == 19) {
     // -------------------------------------------------------------- MMA issuer
     // The whole warp walks the pipeline (uniform control flow, operands in uniform registers); one elected
     // lane issues the tcgen05 instructions.
@@ -389,7 +389,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 16) {
     // ------------------------------------------------------------- store warp
     // One 4-D TMA store per 64-column slab; the tensor map clips the patch to the image and to the
     // channel slice.  Issuing it here keeps its issue + drain latency off the epilogue warps' path.
@@ -415,11 +415,83 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
     asm volatile("bar.sync 4, 288;" ::: "memory");   // the epilogue warps may now re-read this CTA's own raw tiles
+  } else if (warp >= 8 && warp < 16) {
+    // ------------------------------------------------------------ statistics warps
+    // Warp ew reduces columns [8*ew, 8*ew+8) of every staged 64-column slab while the convert warps already
+    // pull the next slab out of TMEM; one owner lane per (column, sum|sumsq) accumulates in fixed order.
+    const int ew = warp - 8;
+    const int st = threadIdx.x - 256;            // 0..255
+    const uint32_t stage_base = smem_u32(sStage);
+    const bool do_stats = (p.mode == SY_CONV_RAW) && (p.partials != nullptr);
+    if (do_stats) {
+      for (int i = st; i < 4 * p.Cout; i += 256) sAcc[i] = 0.f;
+    }
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_tile = tile / p.m_tiles, m_tile = tile - n_tile * p.m_tiles;
+      const int img = m_tile / per_img;
+      const int n0 = n_tile * BN;
+      const int grp = img >= p.split_n ? 1 : 0;
+      for (int slab = 0; slab < BN / kSlabCols; ++slab) {
+        bar_free();
+        bar_staged();
+        if (do_stats) {
+          // warp ew reduces columns [8*ew, 8*ew+8) of the slab: lane l reads rows l, l+32, l+64, l+96
+          float a[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) a[i] = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const uint32_t r = (uint32_t)(lane + 32 * rr);
+            const uint4 u = lds128(stage_base + r * 128u + ((((uint32_t)ew) ^ (r & 7u)) << 4));
+            const float x[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                                bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a[i] += x[i]; a[8 + i] += x[i] * x[i]; }
+          }
+          // recursive halving over the 32 lanes: 8 + 4 + 2 + 1 + 1 shuffles, fixed order (deterministic)
+          float b8[8], c4[4], d2[2], e1;
+          {
+            const bool up = (lane & 16) != 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float send = up ? a[i] : a[8 + i], keep = up ? a[8 + i] : a[i];
+              b8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+          }
+          {
+            const bool up = (lane & 8) != 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float send = up ? b8[i] : b8[4 + i], keep = up ? b8[4 + i] : b8[i];
+              c4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+          }
+          {
+            const bool up = (lane & 4) != 0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float send = up ? c4[i] : c4[2 + i], keep = up ? c4[2 + i] : c4[i];
+              d2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+          }
+          {
+            const bool up = (lane & 2) != 0;
+            const float send = up ? d2[0] : d2[1], keep = up ? d2[1] : d2[0];
+            e1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+          e1 += __shfl_xor_sync(0xffffffffu, e1, 1);
+          if ((lane & 1) == 0) {                 // 16 owner lanes: bit4 = sum | sumsq, bits 3..1 = column in the group
+            const int col = n0 + slab * kSlabCols + ew * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            if (col < p.Cout) sAcc[(grp * 2 + (lane >> 4)) * p.Cout + col] += e1;
+          }
+        }
+      }
+    }
+    bar_stats_done();
   } else if (warp < 8) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
     const int half = warp >> 2;                // which 32 columns of a 64-column slab this warpgroup converts
-    const int ew = warp;                       // 0..7: the 8-column group this warp reduces in the statistics pass
     const int row = q * 32 + lane;             // tile row == TMEM lane
     const int et = threadIdx.x;                // 0..255
     const int ty = row / p.tw, tx = row - ty * p.tw;
@@ -428,9 +500,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t my_row = stage_base + (uint32_t)row * 128u;
     const uint32_t rsw = (uint32_t)(row & 7);
     const bool do_stats = (p.mode == SY_CONV_RAW) && (p.partials != nullptr);
-    if (do_stats) {
-      for (int i = et; i < 4 * p.Cout; i += kEpiThreads) sAcc[i] = 0.f;
-    }
     int it = 0;
     int tl_n = (et == 0) ? p.timeline_cap / 2 : p.timeline_cap;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -508,63 +577,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_proxy_async();                     // generic-proxy writes -> visible to the TMA (async proxy)
         bar_staged();                            // (B) staging tile complete: the store warp takes it from here
         tl_rec<TL>(p, tl_n, 2, 3, tile, slab);
-        if (do_stats) {
-          // warp ew reduces columns [8*ew, 8*ew+8) of the slab: lane l reads rows l, l+32, l+64, l+96
-          float a[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) a[i] = 0.f;
-#pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
-            const uint32_t r = (uint32_t)(lane + 32 * rr);
-            const uint4 u = lds128(stage_base + r * 128u + ((((uint32_t)ew) ^ (r & 7u)) << 4));
-            const float x[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
-                                bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { a[i] += x[i]; a[8 + i] += x[i] * x[i]; }
-          }
-          // recursive halving over the 32 lanes: 8 + 4 + 2 + 1 + 1 shuffles, fixed order (deterministic)
-          float b8[8], c4[4], d2[2], e1;
-          {
-            const bool up = (lane & 16) != 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float send = up ? a[i] : a[8 + i], keep = up ? a[8 + i] : a[i];
-              b8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
-          }
-          {
-            const bool up = (lane & 8) != 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float send = up ? b8[i] : b8[4 + i], keep = up ? b8[4 + i] : b8[i];
-              c4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-          }
-          {
-            const bool up = (lane & 4) != 0;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float send = up ? c4[i] : c4[2 + i], keep = up ? c4[2 + i] : c4[i];
-              d2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-          }
-          {
-            const bool up = (lane & 2) != 0;
-            const float send = up ? d2[0] : d2[1], keep = up ? d2[1] : d2[0];
-            e1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-          }
-          e1 += __shfl_xor_sync(0xffffffffu, e1, 1);
-          if ((lane & 1) == 0) {                 // 16 owner lanes: bit4 = sum | sumsq, bits 3..1 = column in the group
-            const int col = n0 + slab * kSlabCols + ew * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            if (col < p.Cout) sAcc[(grp * 2 + (lane >> 4)) * p.Cout + col] += e1;
-          }
-        }
         tl_rec<TL>(p, tl_n, 2, 4, tile, slab);
       }
     }
     // ---------------------------------------------- per-CTA partial row, grid barrier, BatchNorm finalize, apply
     if (et == 0) tl_rec<TL>(p, tl_n, 4, 2, 0, 0);
     asm volatile("bar.sync 4, 288;" ::: "memory");   // store warp: all TMA stores of this CTA are complete
+    bar_stats_done();                                // statistics warps: every sAcc update is done
     if (do_stats) {
       float* mine = p.partials + (size_t)blockIdx.x * 4 * p.Cout;
       for (int i = et; i < 4 * p.Cout; i += kEpiThreads) mine[i] = sAcc[i];
@@ -699,12 +718,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (threadIdx.x == 8 * 32) tl_rec<TL>(p, tl_k, 4, 3, 0, 0);
-  if (warp == 9) {
+  if (threadIdx.x == 16 * 32) tl_rec<TL>(p, tl_k, 4, 3, 0, 0);
+  if (warp == 17) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
   }
-  if (threadIdx.x == 9 * 32) { int k2 = tl_k + 8; tl_rec<TL>(p, k2, 4, 4, 0, 0); }
+  if (threadIdx.x == 17 * 32) { int k2 = tl_k + 8; tl_rec<TL>(p, k2, 4, 4, 0, 0); }
 }
 
 // ------------------------------------------------------------------ host side
