@@ -163,7 +163,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -220,10 +220,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 // staging-tile hand-off between the 8 epilogue warps and the store warp (warp 3): 256 + 32 threads
 // staging-tile hand-off between the 8 convert warps, the 8 statistics warps and the store warp: 256 + 256 + 32 threads
-// Two staging tiles (slab j uses tile j & 1) so that the TMA store / statistics of one slab overlap the conversion
-// of the next; named barriers 2,3 belong to tile 0 and 6,7 to tile 1.
-__device__ __forceinline__ void bar_free(int b) { asm volatile("bar.sync %0, 544;" ::"r"(2 + 4 * b) : "memory"); }    // tile b may be overwritten
-__device__ __forceinline__ void bar_staged(int b) { asm volatile("bar.sync %0, 544;" ::"r"(3 + 4 * b) : "memory"); }  // tile b is complete
+__device__ __forceinline__ void bar_free() { asm volatile("bar.sync 2, 544;" ::: "memory"); }    // (A) staging tile free
+__device__ __forceinline__ void bar_staged() { asm volatile("bar.sync 3, 544;" ::: "memory"); }  // (B) staging tile complete
 __device__ __forceinline__ void bar_stats_done() { asm volatile("bar.sync 5, 512;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
@@ -250,7 +248,7 @@ struct Cfg {
   static constexpr int kTmemCols = 2 * BN;                          // double-buffered accumulator (power of two)
   // fixed part of dynamic smem (everything but the A/B ring and the per-CTA statistic accumulators)
   // plus, after the barriers, ONE region that is scale/shift (FUSED, 2 KiB) or the statistic accumulators (RAW)
-  static constexpr int kFixedBytes = 1024 /*align slack*/ + 2 * kSlabBytes + 256 /*barriers*/;
+  static constexpr int kFixedBytes = 1024 /*align slack*/ + kSlabBytes + 256 /*barriers*/;
 };
 
 template <int BN, bool TL>
@@ -266,7 +264,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sA = smem;
   uint8_t* sB = sA + S * kSub * kABytes;
   uint8_t* sStage = sB + S * kSub * C::kBBytes;                                 // 1024-aligned: the rings are multiples of 1 KiB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 2 * kSlabBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + kSlabBytes);
   // bars: [0,8) full, [8,16) empty, [16,18) tmem_full, [18,20) tmem_empty, then the tmem base slot
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
   float* sAcc = reinterpret_cast<float*>(bars + 32);                     // RAW:   [2 groups][2][Cout]
@@ -396,19 +394,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // One 4-D TMA store per 64-column slab; the tensor map clips the patch to the image and to the
     // channel slice.  Issuing it here keeps its issue + drain latency off the epilogue warps' path.
     const uint32_t stage_base = smem_u32(smem + S * kSub * (kABytes + C::kBBytes));
-    int sbuf = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = tile / p.m_tiles, m_tile = tile - n_tile * p.m_tiles;
       const int img = m_tile / per_img, rem = m_tile - img * per_img;
       const int py = rem / p.tiles_x, px = rem - py * p.tiles_x;
-      for (int slab = 0; slab < BN / kSlabCols; ++slab, sbuf ^= 1) {
-        if (elect_one()) bulk_wait_read1();      // the store that last used THIS tile (two slabs ago) has read it
-        __syncwarp();
-        bar_free(sbuf);
-        bar_staged(sbuf);
+      for (int slab = 0; slab < BN / kSlabCols; ++slab) {
+        bar_free();
+        bar_staged();
         if (elect_one()) {
-          tma_store_4d(&tmY, stage_base + (uint32_t)(sbuf * kSlabBytes), n_tile * BN + slab * kSlabCols, px * p.tw, py * p.th, img);
+          tma_store_4d(&tmY, stage_base, n_tile * BN + slab * kSlabCols, px * p.tw, py * p.th, img);
           bulk_commit();
+          bulk_wait_read();                      // staging tile may be overwritten once the TMA has read it
         }
         __syncwarp();
       }
@@ -430,16 +426,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (do_stats) {
       for (int i = st; i < 4 * p.Cout; i += 256) sAcc[i] = 0.f;
     }
-    int sbuf = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = tile / p.m_tiles, m_tile = tile - n_tile * p.m_tiles;
       const int img = m_tile / per_img;
       const int n0 = n_tile * BN;
       const int grp = img >= p.split_n ? 1 : 0;
-      for (int slab = 0; slab < BN / kSlabCols; ++slab, sbuf ^= 1) {
-        bar_free(sbuf);
-        bar_staged(sbuf);
-        const uint32_t tile_base = stage_base + (uint32_t)(sbuf * kSlabBytes);
+      for (int slab = 0; slab < BN / kSlabCols; ++slab) {
+        bar_free();
+        bar_staged();
         if (do_stats) {
           // warp ew reduces columns [8*ew, 8*ew+8) of the slab: lane l reads rows l, l+32, l+64, l+96
           float a[16];
@@ -448,7 +442,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int rr = 0; rr < 4; ++rr) {
             const uint32_t r = (uint32_t)(lane + 32 * rr);
-            const uint4 u = lds128(tile_base + r * 128u + ((((uint32_t)ew) ^ (r & 7u)) << 4));
+            const uint4 u = lds128(stage_base + r * 128u + ((((uint32_t)ew) ^ (r & 7u)) << 4));
             const float x[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
                                 bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
 #pragma unroll
@@ -502,8 +496,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int et = threadIdx.x;                // 0..255
     const int ty = row / p.tw, tx = row - ty * p.tw;
     const bool in_patch = row < p.th * p.tw;
-    const uint32_t my_row = smem_u32(sStage) + (uint32_t)row * 128u;
-    int sbuf = 0;
+    const uint32_t stage_base = smem_u32(sStage);
+    const uint32_t my_row = stage_base + (uint32_t)row * 128u;
     const uint32_t rsw = (uint32_t)(row & 7);
     const bool do_stats = (p.mode == SY_CONV_RAW) && (p.partials != nullptr);
     int it = 0;
@@ -535,7 +529,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int slab = 0; slab < BN / kSlabCols; ++slab, sbuf ^= 1) {
+      for (int slab = 0; slab < BN / kSlabCols; ++slab) {
         const int cl = slab * kSlabCols + half * 32;     // first of this thread's 32 accumulator columns
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)cl, v);
@@ -574,15 +568,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 16; ++i) packed[i] = valid ? pack_bf16(f[2 * i], f[2 * i + 1]) : 0u;
         }
         tl_rec<TL>(p, tl_n, 2, 2, tile, slab);
-        bar_free(sbuf);                          // (A) staging tile free: its store drained, its statistics readers done
-        const uint32_t my_tile_row = my_row + (uint32_t)(sbuf * kSlabBytes);
+        bar_free();                              // (A) staging tile free: store drained, statistics readers done
 #pragma unroll
         for (int g = 0; g < 4; ++g) {            // 16-byte chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4)
           const uint32_t j = (uint32_t)(half * 4 + g);
-          sts128(my_tile_row + ((j ^ rsw) << 4), packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+          sts128(my_row + ((j ^ rsw) << 4), packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
         }
         fence_proxy_async();                     // generic-proxy writes -> visible to the TMA (async proxy)
-        bar_staged(sbuf);                        // (B) staging tile complete: store + statistics warps take it from here
+        bar_staged();                            // (B) staging tile complete: the store warp takes it from here
         tl_rec<TL>(p, tl_n, 2, 3, tile, slab);
         tl_rec<TL>(p, tl_n, 2, 4, tile, slab);
       }
