@@ -49,6 +49,27 @@ constexpr int kMaxStages = 8;
 // cost, which dominates narrow tiles; BN = 256 keeps one so that four 48 KiB stages fit (ring depth matters more)
 constexpr uint64_t kSpinLimit = 6000000000ull;  // ~3 s of SM clocks, then trap instead of hanging
 
+// division by a runtime constant without the ~40-cycle integer divide (libdivide's branch-free u32 scheme);
+// the per-tile coordinate decode sits on the critical path of every warp role
+struct FastDiv {
+  uint32_t mul, shr, d;
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{0u, 0u, d};
+  if (d > 1) {
+    uint32_t s = 0;
+    while ((1ull << s) < d) ++s;
+    f.mul = (uint32_t)((((1ull << 32) * ((1ull << s) - d)) / d) + 1);
+    f.shr = s - 1;
+  }
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+  if (f.d == 1) return n;
+  const uint32_t t = __umulhi((uint32_t)n, f.mul);
+  return (int)((t + (((uint32_t)n - t) >> 1)) >> f.shr);
+}
+
 struct BnSeg {
   const float* gamma; const float* beta;
   float* rmean; float* rvar; long long* nbt;
@@ -60,6 +81,7 @@ struct Params {
   int kh, kw, stride, pad_h, pad_w;
   int th, tw, tiles_x, tiles_y;
   int m_tiles, n_tiles, total_tiles;
+  FastDiv fd_m_tiles, fd_per_img, fd_tiles_x, fd_tw;
   int cblocks, kblocks, stages;
   int mode, act;
   __nv_bfloat16* y;
@@ -315,9 +337,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int tl_n = is_a ? 0 : p.timeline_cap / 8;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n_tile = tile / p.m_tiles, m_tile = tile - n_tile * p.m_tiles;
-        const int img = m_tile / per_img, rem = m_tile - img * per_img;
-        const int py = rem / p.tiles_x, px = rem - py * p.tiles_x;
+        const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
+        const int img = fdiv(m_tile, p.fd_per_img), rem = m_tile - img * per_img;
+        const int py = fdiv(rem, p.fd_tiles_x), px = rem - py * p.tiles_x;
         const int y0 = py * p.th * p.stride - p.pad_h, x0 = px * p.tw * p.stride - p.pad_w;
         // walk the (tap, channel block) sub-blocks kSub at a time: one barrier round per stage
         int r = 0, sx = 0, cb = 0;
@@ -395,9 +417,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // channel slice.  Issuing it here keeps its issue + drain latency off the epilogue warps' path.
     const uint32_t stage_base = smem_u32(smem + S * kSub * (kABytes + C::kBBytes));
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int n_tile = tile / p.m_tiles, m_tile = tile - n_tile * p.m_tiles;
-      const int img = m_tile / per_img, rem = m_tile - img * per_img;
-      const int py = rem / p.tiles_x, px = rem - py * p.tiles_x;
+      const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
+      const int img = fdiv(m_tile, p.fd_per_img), rem = m_tile - img * per_img;
+      const int py = fdiv(rem, p.fd_tiles_x), px = rem - py * p.tiles_x;
       for (int slab = 0; slab < BN / kSlabCols; ++slab) {
         bar_free();
         bar_staged();
@@ -427,8 +449,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int i = st; i < 4 * p.Cout; i += 256) sAcc[i] = 0.f;
     }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int n_tile = tile / p.m_tiles, m_tile = tile - n_tile * p.m_tiles;
-      const int img = m_tile / per_img;
+      const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
+      const int img = fdiv(m_tile, p.fd_per_img);
       const int n0 = n_tile * BN;
       const int grp = img >= p.split_n ? 1 : 0;
       for (int slab = 0; slab < BN / kSlabCols; ++slab) {
@@ -494,7 +516,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = warp >> 2;                // which 32 columns of a 64-column slab this warpgroup converts
     const int row = q * 32 + lane;             // tile row == TMEM lane
     const int et = threadIdx.x;                // 0..255
-    const int ty = row / p.tw, tx = row - ty * p.tw;
+    const int ty = fdiv(row, p.fd_tw), tx = row - ty * p.tw;
     const bool in_patch = row < p.th * p.tw;
     const uint32_t stage_base = smem_u32(sStage);
     const uint32_t my_row = stage_base + (uint32_t)row * 128u;
@@ -505,9 +527,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const int n_tile = tile / p.m_tiles, m_tile = tile - n_tile * p.m_tiles;
-      const int img = m_tile / per_img, rem = m_tile - img * per_img;
-      const int py = rem / p.tiles_x, px = rem - py * p.tiles_x;
+      const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
+      const int img = fdiv(m_tile, p.fd_per_img), rem = m_tile - img * per_img;
+      const int py = fdiv(rem, p.fd_tiles_x), px = rem - py * p.tiles_x;
       const int y0 = py * p.th, x0 = px * p.tw;
       const int oy = y0 + ty, ox = x0 + tx;
       const bool valid = in_patch && (oy < p.Ho) && (ox < p.Wo);
@@ -650,9 +672,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           constexpr int RPP = kEpiThreads / CPR;                   // tile rows handled per pass of the 256 threads
           const int chunk = et % CPR, r0 = et / CPR;
           for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int n_tile = tile / p.m_tiles, m_tile = tile - n_tile * p.m_tiles;
-            const int img = m_tile / per_img, rem = m_tile - img * per_img;
-            const int py = rem / p.tiles_x, px = rem - py * p.tiles_x;
+            const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
+            const int img = fdiv(m_tile, p.fd_per_img), rem = m_tile - img * per_img;
+            const int py = fdiv(rem, p.fd_tiles_x), px = rem - py * p.tiles_x;
             const int cg = n_tile * BN + chunk * 8;
             if (cg >= p.Cout) continue;
             const int grp = img >= p.split_n ? 1 : 0;
@@ -857,6 +879,10 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
   const int bn = tc::pick_bn(y.c, p.m_tiles, p.kblocks);
   p.n_tiles = cdiv(y.c, bn);
   p.total_tiles = p.m_tiles * p.n_tiles;
+  p.fd_m_tiles = tc::make_fastdiv((uint32_t)p.m_tiles);
+  p.fd_per_img = tc::make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y));
+  p.fd_tiles_x = tc::make_fastdiv((uint32_t)p.tiles_x);
+  p.fd_tw = tc::make_fastdiv((uint32_t)p.tw);
   p.mode = d->mode; p.act = d->act;
   p.y = reinterpret_cast<__nv_bfloat16*>(y.ptr); p.y_pitch = y.pitch;
   p.res = nullptr; p.res_pitch = 0;
