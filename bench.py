@@ -155,7 +155,12 @@ def time_dominant_kernel(tag, batch, peaks):
     return {"bound": "tensor", "kernel": f"conv_tc_kernel<{min(256, c)}> 3x3 s1 {c}->{c} @{n}x{h}x{w}",
             "achieved": round(ach, 1), "peak": peaks["burst"], "unit": "TFLOP/s", "frac": round(ach / peaks["burst"], 4),
             "peak_source": peaks["source"] + " cuBLAS bf16 burst", "ms_per_launch": round(ms, 4),
-            "algorithmic_flop_per_launch": flops, "traffic": None,
+            "algorithmic_flop_per_launch": flops,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch shape (8x75x120, 256->256) from the ncu --set full
+            # capture summarised in profiles/r01_ncu_full_summary.txt (38.12 MB read + 1.80 MB written; the 36.9 MB
+            # output is still L2-resident when the kernel ends).  Only meaningful for that shape.
+            "traffic": (39.91e6 if (n, c) == (8, 256) else None), "traffic_unit": "bytes/launch (ncu, r01)",
+            "algorithmic_bytes_per_launch": 2 * n * h * w * c * 2 + 9 * c * c * 2,
             "how": "graph of 16 launches over 8 rotating buffer sets (operands > L2), CUDA events, best of 5"}
 
 
