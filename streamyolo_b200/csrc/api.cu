@@ -1,5 +1,6 @@
 // Runtime entry points: error text, version, device check.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -10,6 +11,11 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+// read on every launch (a getenv is ~100 ns) so that a process can switch it between two measurements
+bool pdl_enabled() {
+  const char* e = getenv("SY_PDL");
+  return !(e != nullptr && e[0] == '0');
 }
 }  // namespace sy
 

@@ -63,36 +63,73 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
 
-__global__ void bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const float* __restrict__ scale,
-                                    const float* __restrict__ shift, long long split_pix, int act,
-                                    const __nv_bfloat16* res, long long rp, __nv_bfloat16* y, long long yp,
-                                    long long npix, int C, long long y_goff1, long long r_goff1) {
-  const int G = C / 8;
-  const long long total = npix * G;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % G);
-    const long long pix = idx / G;
-    const int grp = pix >= split_pix ? 1 : 0;
-    float f[8], r[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + pix * xp + g * 8), f);
-    const float4 s0 = *reinterpret_cast<const float4*>(scale + grp * C + g * 8);
-    const float4 s1 = *reinterpret_cast<const float4*>(scale + grp * C + g * 8 + 4);
-    const float4 h0 = *reinterpret_cast<const float4*>(shift + grp * C + g * 8);
-    const float4 h1 = *reinterpret_cast<const float4*>(shift + grp * C + g * 8 + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+// y = act(x * scale[grp] + shift[grp]) (+ res), 16 bytes (8 channels) per thread and pixel.
+// A thread keeps ONE channel chunk for its whole life (scale/shift of both statistics groups live in registers, no
+// per-element index division) and walks the pixels with kApplyUnroll independent 16-byte loads in flight.
+constexpr int kApplyThreads = 256;
+constexpr int kApplyUnroll = 4;
+__global__ void __launch_bounds__(kApplyThreads, 3)
+bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const float* __restrict__ scale,
+                    const float* __restrict__ shift, long long split_pix, int act,
+                    const __nv_bfloat16* res, long long rp, __nv_bfloat16* y, long long yp,
+                    long long npix, int C, long long y_goff1, long long r_goff1) {
+  pdl_launch_dependents();
+  const int G = C >> 3;                           // 16-byte chunks per pixel (<= 256)
+  const int ppb = kApplyThreads / G;              // pixels per block pass
+  const int prow = (int)threadIdx.x / G, g = (int)threadIdx.x - prow * G;
+  if (prow >= ppb) return;
+  pdl_wait();                                     // x, scale, shift (and res) come from the preceding kernels
+  // scale/shift of the statistics group the thread is currently in (pixels are ordered group 0 then group 1, so a
+  // thread switches at most once)
+  float sc[8], sh[8];
+  int cur = -1;
+  auto load_group = [&](int grp) {
+    const float4* a = reinterpret_cast<const float4*>(scale + (long long)grp * C + g * 8);
+    const float4* b = reinterpret_cast<const float4*>(shift + (long long)grp * C + g * 8);
+    const float4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+    sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+    sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+    cur = grp;
+  };
+  const long long step = (long long)gridDim.x * ppb;
+  const __nv_bfloat16* xg = x + g * 8;
+  const __nv_bfloat16* rg = res ? res + g * 8 : nullptr;
+  __nv_bfloat16* yg = y + g * 8;
+  for (long long pix0 = (long long)blockIdx.x * ppb + prow; pix0 < npix; pix0 += step * kApplyUnroll) {
+    uint4 v[kApplyUnroll], rv[kApplyUnroll];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float t = f[i] * sc[i] + sh[i];
-      f[i] = act ? silu_f(t) : t;
+    for (int j = 0; j < kApplyUnroll; ++j) {
+      const long long pix = pix0 + j * step;
+      if (pix < npix) v[j] = *reinterpret_cast<const uint4*>(xg + pix * xp);
     }
-    if (res != nullptr) {
-      unpack8(*reinterpret_cast<const uint4*>(res + pix * rp + g * 8 + (grp ? r_goff1 : 0)), r);
+    if (rg != nullptr) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] += r[i];
+      for (int j = 0; j < kApplyUnroll; ++j) {
+        const long long pix = pix0 + j * step;
+        if (pix < npix) rv[j] = *reinterpret_cast<const uint4*>(rg + pix * rp + (pix >= split_pix ? r_goff1 : 0));
+      }
     }
-    *reinterpret_cast<uint4*>(y + pix * yp + g * 8 + (grp ? y_goff1 : 0)) = pack8(f);
+#pragma unroll
+    for (int j = 0; j < kApplyUnroll; ++j) {
+      const long long pix = pix0 + j * step;
+      if (pix >= npix) continue;
+      const bool g1 = pix >= split_pix;
+      if ((int)g1 != cur) load_group((int)g1);
+      float f[8];
+      unpack8(v[j], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float t = f[i] * sc[i] + sh[i];
+        f[i] = act ? silu_f(t) : t;
+      }
+      if (rg != nullptr) {
+        float r[8];
+        unpack8(rv[j], r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] += r[i];
+      }
+      *reinterpret_cast<uint4*>(yg + pix * yp + (g1 ? y_goff1 : 0)) = pack8(f);
+    }
   }
 }
 
@@ -256,9 +293,14 @@ extern "C" int sy_bn_act_apply(SyTensor x, const float* scale, const float* shif
   }
   const long long npix = (long long)x.n * x.h * x.w;
   const long long split_pix = (long long)split_n * x.h * x.w;
-  bn_act_apply_kernel<<<grid_for(npix * (x.c / 8), 256), 256, 0, stream>>>(CBF(x.ptr), x.pitch, scale, shift, split_pix,
-                                                                           act, rp, rpitch, BF(y.ptr), y.pitch, npix, x.c,
-                                                                           (long long)y_goff1, (long long)r_goff1);
+  SY_REQUIRE(x.c <= 8 * kApplyThreads, SY_EINVAL, "bn_act_apply: C=%d > %d", x.c, 8 * kApplyThreads);
+  const int ppb = kApplyThreads / (x.c / 8);
+  // enough blocks for one pass of kApplyUnroll pixels per thread, capped at two waves of 3 resident blocks per SM
+  const long long want = (npix + (long long)ppb * kApplyUnroll - 1) / ((long long)ppb * kApplyUnroll);
+  const int grid = (int)(want < 1 ? 1 : (want < 148LL * 6 ? want : 148LL * 6));
+  SY_CUDA(launch_pdl(bn_act_apply_kernel, dim3(grid), dim3(kApplyThreads), 0, stream, CBF(x.ptr), (long long)x.pitch, scale,
+                     shift, split_pix, act, rp, rpitch, BF(y.ptr), (long long)y.pitch, npix, x.c, (long long)y_goff1,
+                     (long long)r_goff1));
   return launch_status("bn_act_apply_kernel");
 }
 

@@ -42,7 +42,8 @@ namespace tc {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;              // bf16 elements = one 128-byte swizzle row
 constexpr int kThreads = 640;
-constexpr int kEpiThreads = 256;
+constexpr int kEpiThreads = 256;    // convert warps 0-7
+constexpr int kTailThreads = 512;   // convert + statistics warps run the kernel tail (partials, grid barrier, finalize, apply)
 constexpr int kABytes = kBlockM * 128;   // 16 KiB per stage
 constexpr int kMaxStages = 8;
 // 64-deep K sub-blocks per pipeline stage: two (one barrier round per K = 128) halve the per-round hand-shake
@@ -82,6 +83,10 @@ struct Params {
   int th, tw, tiles_x, tiles_y;
   int m_tiles, n_tiles, total_tiles;
   FastDiv fd_m_tiles, fd_per_img, fd_tiles_x, fd_tw;
+  // linear tiles (LIN): an M tile is 128 consecutive output pixels of the flattened (n, oh, ow) space
+  int P_total;              // N * Ho * Wo
+  int gp;                   // first output pixel of statistics group 1 (== P_total: single group)
+  FastDiv fd_hw, fd_wo;
   int cblocks, kblocks, stages;
   int mode, act;
   __nv_bfloat16* y;
@@ -170,6 +175,15 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// im2col-mode load: 128 consecutive output pixels' worth of input pixels (base pixel (w, h, n) in INPUT coordinates =
+// -pad + out * stride, walked along w, then h, then n inside the tensor map's bounding box) shifted by the filter tap
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int w,
+                                                   int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
@@ -273,7 +287,7 @@ struct Cfg {
   static constexpr int kFixedBytes = 1024 /*align slack*/ + kSlabBytes + 256 /*barriers*/;
 };
 
-template <int BN, bool TL>
+template <int BN, bool TL, bool LIN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const Params p) {
@@ -295,6 +309,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();               // the next kernel on the stream may start its own prologue
   int tl_k = 3 * (p.timeline_cap / 4);
   if (threadIdx.x == 16 * 32) tl_rec<TL>(p, tl_k, 4, 0, 0, 0);
   const uint32_t bar0 = smem_u32(bars);
@@ -322,10 +337,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only smem / TMEM / kernel parameters; from here on we read what the previous kernels wrote
+  pdl_wait();
   if (threadIdx.x == 16 * 32) tl_rec<TL>(p, tl_k, 4, 1, 0, 0);
 
-  const uint32_t a_bytes = (uint32_t)(p.th * p.tw) * 128u;
+  const uint32_t a_bytes = LIN ? (uint32_t)kABytes : (uint32_t)(p.th * p.tw) * 128u;
   const int per_img = p.tiles_x * p.tiles_y;
+  const int hw = p.Ho * p.Wo;
+  int tl_epi = p.timeline_cap;           // debug-timeline cursor of thread 0, carried from the convert loop into the tail
 
   if (warp == 18 || warp == 17) {
     // ----------------------------------------------- TMA producers: warp 18 loads A (activations), warp 17 loads B (weights)
@@ -338,9 +357,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int tl_n = is_a ? 0 : p.timeline_cap / 8;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
-        const int img = fdiv(m_tile, p.fd_per_img), rem = m_tile - img * per_img;
-        const int py = fdiv(rem, p.fd_tiles_x), px = rem - py * p.tiles_x;
-        const int y0 = py * p.th * p.stride - p.pad_h, x0 = px * p.tw * p.stride - p.pad_w;
+        int img, y0, x0;
+        if constexpr (LIN) {
+          const int p0 = m_tile * kBlockM;
+          img = fdiv(p0, p.fd_hw);
+          const int rem = p0 - img * hw;
+          const int oh = fdiv(rem, p.fd_wo), ow = rem - oh * p.Wo;
+          y0 = oh * p.stride - p.pad_h; x0 = ow * p.stride - p.pad_w;
+        } else {
+          img = fdiv(m_tile, p.fd_per_img);
+          const int rem = m_tile - img * per_img;
+          const int py = fdiv(rem, p.fd_tiles_x), px = rem - py * p.tiles_x;
+          y0 = py * p.th * p.stride - p.pad_h; x0 = px * p.tw * p.stride - p.pad_w;
+        }
         // walk the (tap, channel block) sub-blocks kSub at a time: one barrier round per stage
         int r = 0, sx = 0, cb = 0;
         for (int sb0 = 0; sb0 < p.kblocks; sb0 += kSub) {
@@ -358,10 +387,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           for (int j = 0; j < nsub; ++j) {
             if (!(p.debug_flags & 2) && elect_one()) {
-              if (is_a)
-                tma_load_4d(smem_u32(sA + (stage * kSub + j) * kABytes), &tmA, full_bar(stage), cb * kBlockK, x0 + sx,
-                            y0 + r, img);
-              else
+              if (is_a) {
+                if constexpr (LIN)
+                  tma_load_im2col_4d(smem_u32(sA + (stage * kSub + j) * kABytes), &tmA, full_bar(stage), cb * kBlockK, x0,
+                                     y0, img, (uint16_t)sx, (uint16_t)r);
+                else
+                  tma_load_4d(smem_u32(sA + (stage * kSub + j) * kABytes), &tmA, full_bar(stage), cb * kBlockK, x0 + sx,
+                              y0 + r, img);
+              } else
                 tma_load_3d(smem_u32(sB + (stage * kSub + j) * C::kBBytes), &tmB, full_bar(stage), cb * kBlockK,
                             r * p.kw + sx, n_tile * BN);
             }
@@ -418,13 +451,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t stage_base = smem_u32(smem + S * kSub * (kABytes + C::kBBytes));
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
-      const int img = fdiv(m_tile, p.fd_per_img), rem = m_tile - img * per_img;
-      const int py = fdiv(rem, p.fd_tiles_x), px = rem - py * p.tiles_x;
+      int c1, c2, c3;                            // store coordinates below the channel: (x, y, image) | (pixel, 0, 0)
+      if constexpr (LIN) {
+        c1 = m_tile * kBlockM; c2 = 0; c3 = 0;
+      } else {
+        const int img = fdiv(m_tile, p.fd_per_img), rem = m_tile - img * per_img;
+        const int py = fdiv(rem, p.fd_tiles_x), px = rem - py * p.tiles_x;
+        c1 = px * p.tw; c2 = py * p.th; c3 = img;
+      }
       for (int slab = 0; slab < BN / kSlabCols; ++slab) {
         bar_free();
         bar_staged();
         if (elect_one()) {
-          tma_store_4d(&tmY, stage_base, n_tile * BN + slab * kSlabCols, px * p.tw, py * p.th, img);
+          tma_store_4d(&tmY, stage_base, n_tile * BN + slab * kSlabCols, c1, c2, c3);
           bulk_commit();
           bulk_wait_read();                      // staging tile may be overwritten once the TMA has read it
         }
@@ -450,74 +489,86 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
-      const int img = fdiv(m_tile, p.fd_per_img);
       const int n0 = n_tile * BN;
-      const int grp = img >= p.split_n ? 1 : 0;
+      // rows [0, cut) of the tile belong to statistics group 0, rows [cut, 128) to group 1 (a patch tile lies in one
+      // image = one group; a linear tile can straddle the boundary; rows past the end of the tensor were staged as zeros)
+      int cut;
+      if constexpr (LIN) {
+        cut = min(max(p.gp - m_tile * kBlockM, 0), kBlockM);
+      } else {
+        cut = fdiv(m_tile, p.fd_per_img) >= p.split_n ? 0 : kBlockM;
+      }
       for (int slab = 0; slab < BN / kSlabCols; ++slab) {
         bar_free();
         bar_staged();
         if (do_stats) {
-          // warp ew reduces columns [8*ew, 8*ew+8) of the slab: lane l reads rows l, l+32, l+64, l+96
-          float a[16];
+#pragma unroll 1
+          for (int grp = 0; grp < 2; ++grp) {
+            const int lo = grp ? cut : 0, hi = grp ? kBlockM : cut;
+            if (lo >= hi) continue;              // warp-uniform
+            // warp ew reduces columns [8*ew, 8*ew+8) of the slab: lane l reads rows l, l+32, l+64, l+96
+            float a[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) a[i] = 0.f;
+            for (int i = 0; i < 16; ++i) a[i] = 0.f;
 #pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
-            const uint32_t r = (uint32_t)(lane + 32 * rr);
-            const uint4 u = lds128(stage_base + r * 128u + ((((uint32_t)ew) ^ (r & 7u)) << 4));
-            const float x[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
-                                bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+            for (int rr = 0; rr < 4; ++rr) {
+              const uint32_t r = (uint32_t)(lane + 32 * rr);
+              if ((int)r >= lo && (int)r < hi) {
+                const uint4 u = lds128(stage_base + r * 128u + ((((uint32_t)ew) ^ (r & 7u)) << 4));
+                const float x[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                                    bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { a[i] += x[i]; a[8 + i] += x[i] * x[i]; }
-          }
-          // recursive halving over the 32 lanes: 8 + 4 + 2 + 1 + 1 shuffles, fixed order (deterministic)
-          float b8[8], c4[4], d2[2], e1;
-          {
-            const bool up = (lane & 16) != 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float send = up ? a[i] : a[8 + i], keep = up ? a[8 + i] : a[i];
-              b8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                for (int i = 0; i < 8; ++i) { a[i] += x[i]; a[8 + i] += x[i] * x[i]; }
+              }
             }
-          }
-          {
-            const bool up = (lane & 8) != 0;
+            // recursive halving over the 32 lanes: 8 + 4 + 2 + 1 + 1 shuffles, fixed order (deterministic)
+            float b8[8], c4[4], d2[2], e1;
+            {
+              const bool up = (lane & 16) != 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float send = up ? b8[i] : b8[4 + i], keep = up ? b8[4 + i] : b8[i];
-              c4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              for (int i = 0; i < 8; ++i) {
+                const float send = up ? a[i] : a[8 + i], keep = up ? a[8 + i] : a[i];
+                b8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+              }
             }
-          }
-          {
-            const bool up = (lane & 4) != 0;
+            {
+              const bool up = (lane & 8) != 0;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float send = up ? c4[i] : c4[2 + i], keep = up ? c4[2 + i] : c4[i];
-              d2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              for (int i = 0; i < 4; ++i) {
+                const float send = up ? b8[i] : b8[4 + i], keep = up ? b8[4 + i] : b8[i];
+                c4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
             }
-          }
-          {
-            const bool up = (lane & 2) != 0;
-            const float send = up ? d2[0] : d2[1], keep = up ? d2[1] : d2[0];
-            e1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-          }
-          e1 += __shfl_xor_sync(0xffffffffu, e1, 1);
-          if ((lane & 1) == 0) {                 // 16 owner lanes: bit4 = sum | sumsq, bits 3..1 = column in the group
-            const int col = n0 + slab * kSlabCols + ew * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            if (col < p.Cout) sAcc[(grp * 2 + (lane >> 4)) * p.Cout + col] += e1;
+            {
+              const bool up = (lane & 4) != 0;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const float send = up ? c4[i] : c4[2 + i], keep = up ? c4[2 + i] : c4[i];
+                d2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              }
+            }
+            {
+              const bool up = (lane & 2) != 0;
+              const float send = up ? d2[0] : d2[1], keep = up ? d2[1] : d2[0];
+              e1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            e1 += __shfl_xor_sync(0xffffffffu, e1, 1);
+            if ((lane & 1) == 0) {               // 16 owner lanes: bit4 = sum | sumsq, bits 3..1 = column in the group
+              const int col = n0 + slab * kSlabCols + ew * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+              if (col < p.Cout) sAcc[(grp * 2 + (lane >> 4)) * p.Cout + col] += e1;
+            }
           }
         }
       }
     }
-    bar_stats_done();
   } else if (warp < 8) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
     const int half = warp >> 2;                // which 32 columns of a 64-column slab this warpgroup converts
     const int row = q * 32 + lane;             // tile row == TMEM lane
     const int et = threadIdx.x;                // 0..255
-    const int ty = fdiv(row, p.fd_tw), tx = row - ty * p.tw;
-    const bool in_patch = row < p.th * p.tw;
+    const int ty = LIN ? 0 : fdiv(row, p.fd_tw), tx = LIN ? 0 : row - ty * p.tw;
+    const bool in_patch = LIN ? true : row < p.th * p.tw;
     const uint32_t stage_base = smem_u32(sStage);
     const uint32_t my_row = stage_base + (uint32_t)row * 128u;
     const uint32_t rsw = (uint32_t)(row & 7);
@@ -528,14 +579,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
-      const int img = fdiv(m_tile, p.fd_per_img), rem = m_tile - img * per_img;
-      const int py = fdiv(rem, p.fd_tiles_x), px = rem - py * p.tiles_x;
-      const int y0 = py * p.th, x0 = px * p.tw;
-      const int oy = y0 + ty, ox = x0 + tx;
-      const bool valid = in_patch && (oy < p.Ho) && (ox < p.Wo);
-      const long long pix = ((long long)img * p.Ho + oy) * p.Wo + ox;
+      bool valid;
+      long long pix;                             // this thread's output pixel in the flattened (n, oh, ow) space
+      if constexpr (LIN) {
+        pix = (long long)m_tile * kBlockM + row;
+        valid = pix < p.P_total;
+      } else {
+        const int img = fdiv(m_tile, p.fd_per_img), rem = m_tile - img * per_img;
+        const int py = fdiv(rem, p.fd_tiles_x), px = rem - py * p.tiles_x;
+        const int oy = py * p.th + ty, ox = px * p.tw + tx;
+        valid = in_patch && (oy < p.Ho) && (ox < p.Wo);
+        pix = ((long long)img * p.Ho + oy) * p.Wo + ox;
+      }
       const int n0 = n_tile * BN;
-      const int grp = img >= p.split_n ? 1 : 0;
       tl_rec<TL>(p, tl_n, 2, 0, tile, 0);
       if (p.mode == SY_CONV_FUSED) {
         epi_bar();                               // previous tile's readers of sScale/sShift are done
@@ -602,22 +658,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tl_rec<TL>(p, tl_n, 2, 4, tile, slab);
       }
     }
-    // ---------------------------------------------- per-CTA partial row, grid barrier, BatchNorm finalize, apply
-    if (et == 0) tl_rec<TL>(p, tl_n, 4, 2, 0, 0);
+    tl_epi = tl_n;
     asm volatile("bar.sync 4, 288;" ::: "memory");   // store warp: all TMA stores of this CTA are complete
-    bar_stats_done();                                // statistics warps: every sAcc update is done
+  }
+  if (warp < 16) {
+    // ---------------------------------------------- per-CTA partial row, grid barrier, BatchNorm finalize, apply
+    // run by the 16 convert + statistics warps (512 threads)
+    const int et = threadIdx.x;                        // 0..511
+    const bool do_stats = (p.mode == SY_CONV_RAW) && (p.partials != nullptr);
+    if (et == 0) tl_rec<TL>(p, tl_epi, 4, 2, 0, 0);
+    bar_stats_done();                                // every sAcc update is done; convert warps have seen the stores drain
     if (do_stats) {
       float* mine = p.partials + (size_t)blockIdx.x * 4 * p.Cout;
-      for (int i = et; i < 4 * p.Cout; i += kEpiThreads) mine[i] = sAcc[i];
+      for (int i = et; i < 4 * p.Cout; i += kTailThreads) mine[i] = sAcc[i];
       if (p.n_seg > 0) {
         auto grid_barrier = [&](unsigned int* ctr) {    // all CTAs of the persistent grid are resident (1 per SM)
           __threadfence();
-          epi_bar();
+          bar_stats_done();
           if (et == 0) {
             atomicAdd(ctr, 1u);
             while (ld_acquire_u32(ctr) < gridDim.x) __nanosleep(32);
           }
-          epi_bar();
+          bar_stats_done();
         };
         grid_barrier(&p.sync[0]);
         // This CTA finalizes channels [b*cpc, (b+1)*cpc): one WARP per channel (no block barriers): lane l sums the
@@ -625,7 +687,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int groups = p.split_n < p.N ? 2 : 1;
         const int cpc = (p.Cout + (int)gridDim.x - 1) / (int)gridDim.x;
         const int c_end = min(p.Cout, ((int)blockIdx.x + 1) * cpc);
-        for (int c = (int)blockIdx.x * cpc + warp; c < c_end; c += 8) {
+        for (int c = (int)blockIdx.x * cpc + warp; c < c_end; c += kTailThreads / 32) {
           double v[4] = {0.0, 0.0, 0.0, 0.0};
           for (int r = lane; r < (int)gridDim.x; r += 32) {
             const float* rowp = p.partials + (size_t)r * 4 * p.Cout + c;
@@ -665,38 +727,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // ---- second grid barrier: scale/shift of every channel are published; normalise this CTA's own tiles,
           //      re-reading the raw bf16 values it just stored (L2 resident for all but the largest layers)
           grid_barrier(&p.sync[1]);
-          for (int i = et; i < p.Cout; i += kEpiThreads)          // [2 (scale|shift)][2 groups][Cout] -> smem (over sAcc)
+          for (int i = et; i < p.Cout; i += kTailThreads)          // [2 (scale|shift)][2 groups][Cout] -> smem (over sAcc)
             reinterpret_cast<float4*>(sAcc)[i] = __ldcg(reinterpret_cast<const float4*>(p.ss) + i);
-          epi_bar();
+          bar_stats_done();
           constexpr int CPR = BN / 8;                              // 16-byte chunks per pixel row of a tile
-          constexpr int RPP = kEpiThreads / CPR;                   // tile rows handled per pass of the 256 threads
+          constexpr int RPP = kTailThreads / CPR;                  // tile rows handled per pass of the 512 threads
           const int chunk = et % CPR, r0 = et / CPR;
           for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
-            const int img = fdiv(m_tile, p.fd_per_img), rem = m_tile - img * per_img;
-            const int py = fdiv(rem, p.fd_tiles_x), px = rem - py * p.tiles_x;
             const int cg = n_tile * BN + chunk * 8;
             if (cg >= p.Cout) continue;
-            const int grp = img >= p.split_n ? 1 : 0;
-            const float* sc = sAcc + grp * p.Cout + cg;
-            const float* sh = sAcc + (2 + grp) * p.Cout + cg;
-            const float4 s0 = *reinterpret_cast<const float4*>(sc), s1 = *reinterpret_cast<const float4*>(sc + 4);
-            const float4 h0 = *reinterpret_cast<const float4*>(sh), h1 = *reinterpret_cast<const float4*>(sh + 4);
-            const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-            const float shv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-            const long long yoff = grp ? p.ap_y_goff1 : 0, roff = grp ? p.ap_res_goff1 : 0;
+            int img = 0, py = 0, px = 0;
+            if constexpr (!LIN) {
+              img = fdiv(m_tile, p.fd_per_img);
+              const int rem = m_tile - img * per_img;
+              py = fdiv(rem, p.fd_tiles_x); px = rem - py * p.tiles_x;
+            }
             // batches of kAB rows: all loads first (the stores may alias the loads, so the compiler cannot hoist them)
             constexpr int kAB = 4;
-            const int rows_in_patch = p.th * p.tw;
+            const int rows_in_patch = LIN ? kBlockM : p.th * p.tw;
             for (int rb = r0; rb < rows_in_patch; rb += RPP * kAB) {
               long long pixv[kAB];
               uint4 u[kAB], rv[kAB];
 #pragma unroll
               for (int j = 0; j < kAB; ++j) {
                 const int rr = rb + j * RPP;
-                const int tyy = rr / p.tw, txx = rr - tyy * p.tw;
-                const int oy = py * p.th + tyy, ox = px * p.tw + txx;
-                pixv[j] = (rr < rows_in_patch && oy < p.Ho && ox < p.Wo) ? ((long long)img * p.Ho + oy) * p.Wo + ox : -1;
+                if constexpr (LIN) {
+                  const long long pp = (long long)m_tile * kBlockM + rr;
+                  pixv[j] = (rr < kBlockM && pp < p.P_total) ? pp : -1;
+                } else {
+                  const int tyy = fdiv(rr, p.fd_tw), txx = rr - tyy * p.tw;
+                  const int oy = py * p.th + tyy, ox = px * p.tw + txx;
+                  pixv[j] = (rr < rows_in_patch && oy < p.Ho && ox < p.Wo) ? ((long long)img * p.Ho + oy) * p.Wo + ox : -1;
+                }
               }
 #pragma unroll
               for (int j = 0; j < kAB; ++j)
@@ -704,11 +767,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (p.ap_res != nullptr) {
 #pragma unroll
                 for (int j = 0; j < kAB; ++j)
-                  if (pixv[j] >= 0) rv[j] = *reinterpret_cast<const uint4*>(p.ap_res + pixv[j] * p.ap_res_pitch + cg + roff);
+                  if (pixv[j] >= 0)
+                    rv[j] = *reinterpret_cast<const uint4*>(p.ap_res + pixv[j] * p.ap_res_pitch + cg +
+                                                            (pixv[j] >= p.gp ? p.ap_res_goff1 : 0));
               }
 #pragma unroll
               for (int j = 0; j < kAB; ++j) {
                 if (pixv[j] < 0) continue;
+                const int grp = pixv[j] >= p.gp ? 1 : 0;
+                const float* sc = sAcc + grp * p.Cout + cg;
+                const float* sh = sAcc + (2 + grp) * p.Cout + cg;
+                const float4 s0 = *reinterpret_cast<const float4*>(sc), s1 = *reinterpret_cast<const float4*>(sc + 4);
+                const float4 h0 = *reinterpret_cast<const float4*>(sh), h1 = *reinterpret_cast<const float4*>(sh + 4);
+                const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const float shv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
                 float f[8] = {bf16_lo(u[j].x), bf16_hi(u[j].x), bf16_lo(u[j].y), bf16_hi(u[j].y),
                               bf16_lo(u[j].z), bf16_hi(u[j].z), bf16_lo(u[j].w), bf16_hi(u[j].w)};
 #pragma unroll
@@ -720,7 +792,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   f[0] += bf16_lo(rv[j].x); f[1] += bf16_hi(rv[j].x); f[2] += bf16_lo(rv[j].y); f[3] += bf16_hi(rv[j].y);
                   f[4] += bf16_lo(rv[j].z); f[5] += bf16_hi(rv[j].z); f[6] += bf16_lo(rv[j].w); f[7] += bf16_hi(rv[j].w);
                 }
-                *reinterpret_cast<uint4*>(p.ap_y + pixv[j] * p.ap_y_pitch + cg + yoff) =
+                *reinterpret_cast<uint4*>(p.ap_y + pixv[j] * p.ap_y_pitch + cg + (grp ? p.ap_y_goff1 : 0)) =
                     make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
               }
             }
@@ -765,6 +837,33 @@ static EncodeTiledFn get_encode() {
       fn = reinterpret_cast<EncodeTiledFn>(ptr);
   }
   return fn;
+}
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+static EncodeIm2colFn get_encode_im2col() {
+  static EncodeIm2colFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(ptr);
+  }
+  return fn;
+}
+
+// M tiling: "linear" = 128 consecutive output pixels of the flattened (n, oh, ow) space, fetched with im2col-mode TMA
+// (no partial tiles except the very last: 10-20 % fewer tiles than rectangular patches on 38x60 / 19x30 maps, which is
+// often a whole round of the persistent grid); SY_CONV_TILES=patch selects the rectangular TH x TW patches.
+static bool linear_tiles() {
+  const char* e = getenv("SY_CONV_TILES");
+  return !(e != nullptr && e[0] == 'p');
 }
 
 // choose the TH x TW output patch (<= 128 pixels) that needs the fewest tiles
@@ -819,12 +918,12 @@ static int pick_bn(int cout, int m_tiles, int kblocks) {
 
 static const int kSmemLimit = 232448;   // 227 KiB opt-in maximum per CTA
 
-template <int BN>
+template <int BN, bool LIN>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, Params& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, false, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, true, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
   const int acc_bytes = (p.mode == SY_CONV_RAW && p.partials) ? 16 * p.Cout : 2048;
@@ -837,9 +936,9 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   const int smem = Cfg<BN>::kFixedBytes + acc_bytes + stages * stage_bytes;
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   if (p.timeline != nullptr)
-    conv_tc_kernel<BN, true><<<grid, kThreads, smem, stream>>>(ta, tb, ty, p);
+    SY_CUDA(launch_pdl(conv_tc_kernel<BN, true, LIN>, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
   else
-    conv_tc_kernel<BN, false><<<grid, kThreads, smem, stream>>>(ta, tb, ty, p);
+    SY_CUDA(launch_pdl(conv_tc_kernel<BN, false, LIN>, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
   return launch_status("conv_tc_kernel");
 }
 
@@ -871,9 +970,14 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
   p.debug_flags = d->debug_flags;
   p.N = x.n; p.Ho = ho; p.Wo = wo; p.Cout = y.c; p.Cin = x.c;
   p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_h = ph; p.pad_w = pw;
+  const bool lin = tc::linear_tiles();
+  SY_REQUIRE((long long)x.n * ho * wo < (1ll << 31) - 256, SY_EINVAL, "conv2d_tc: too many output pixels");
+  p.P_total = x.n * ho * wo;
   tc::pick_patch(ho, wo, &p.th, &p.tw);
   p.tiles_y = cdiv(ho, p.th); p.tiles_x = cdiv(wo, p.tw);
-  p.m_tiles = x.n * p.tiles_y * p.tiles_x;
+  p.m_tiles = lin ? cdiv(p.P_total, tc::kBlockM) : x.n * p.tiles_y * p.tiles_x;
+  p.fd_hw = tc::make_fastdiv((uint32_t)(ho * wo));
+  p.fd_wo = tc::make_fastdiv((uint32_t)wo);
   p.cblocks = cdiv(x.c, tc::kBlockK);
   p.kblocks = d->kh * d->kw * p.cblocks;
   const int bn = tc::pick_bn(y.c, p.m_tiles, p.kblocks);
@@ -893,6 +997,7 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
   }
   p.scale = d->scale; p.shift = d->shift;
   p.split_n = (d->split_n > 0 && d->split_n < x.n) ? d->split_n : x.n;
+  p.gp = p.split_n * ho * wo;
   p.partials = (d->mode == SY_CONV_RAW) ? d->stat_partials : nullptr;
   if (p.partials) {
     SY_REQUIRE(d->n_partials >= tc::num_sms(), SY_EWORKSPACE, "conv2d_tc: %d statistic rows, need %d (sy_conv_stat_rows)",
@@ -936,7 +1041,26 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
 
   // A: input view as (C, W, H, N), box (64, TW*s, TH*s, 1) traversed with element strides (1, s, s, 1)
   CUtensorMap ta, tb, ty;
-  {
+  if (lin) {
+    // A, im2col mode: tensor (C, W, H, N); the bounding box of base pixels is [-pad, dim + pad - (k - 1)) per spatial
+    // dim, walked with the conv stride; one load = 128 consecutive base pixels x 64 channels, shifted by the tap offset
+    tc::EncodeIm2colFn enc2 = tc::get_encode_im2col();
+    SY_REQUIRE(enc2 != nullptr, SY_EARCH, "cuTensorMapEncodeIm2col not available from the driver");
+    cuuint64_t dims[4] = {(cuuint64_t)x.c, (cuuint64_t)x.w, (cuuint64_t)x.h, (cuuint64_t)x.n};
+    cuuint64_t strides[3] = {(cuuint64_t)x.pitch * 2, (cuuint64_t)x.pitch * 2 * x.w, (cuuint64_t)x.pitch * 2 * x.w * x.h};
+    int lower[2] = {-pw, -ph};                                   // {W, H}
+    int upper[2] = {pw - (d->kw - 1), ph - (d->kh - 1)};
+    if (getenv("SY_IM2COL_HW") != nullptr) {                     // bring-up switch: corners in {H, W} order
+      int t = lower[0]; lower[0] = lower[1]; lower[1] = t;
+      t = upper[0]; upper[0] = upper[1]; upper[1] = t;
+    }
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    CUresult r = enc2(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x.ptr, dims, strides, lower, upper, (cuuint32_t)tc::kBlockK,
+                      (cuuint32_t)tc::kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SY_REQUIRE(r == CUDA_SUCCESS, SY_ELAUNCH, "cuTensorMapEncodeIm2col(A) failed: %d (c=%d w=%d h=%d n=%d pitch=%lld k=%dx%d s=%d)",
+               (int)r, x.c, x.w, x.h, x.n, (long long)x.pitch, d->kh, d->kw, d->stride);
+  } else {
     cuuint64_t dims[4] = {(cuuint64_t)x.c, (cuuint64_t)x.w, (cuuint64_t)x.h, (cuuint64_t)x.n};
     cuuint64_t strides[3] = {(cuuint64_t)x.pitch * 2, (cuuint64_t)x.pitch * 2 * x.w, (cuuint64_t)x.pitch * 2 * x.w * x.h};
     cuuint32_t box[4] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)(p.tw * d->stride), (cuuint32_t)(p.th * d->stride), 1};
@@ -958,7 +1082,17 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SY_REQUIRE(r == CUDA_SUCCESS, SY_ELAUNCH, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
   }
-  {
+  if (lin) {
+    // Y: output view as (C, pixels, 1, 1), box (64, 128, 1, 1): the TMA store clips the last tile / the channel slice
+    cuuint64_t dims[4] = {(cuuint64_t)y.c, (cuuint64_t)p.P_total, 1, 1};
+    cuuint64_t strides[3] = {(cuuint64_t)y.pitch * 2, (cuuint64_t)y.pitch * 2 * p.P_total, (cuuint64_t)y.pitch * 2 * p.P_total};
+    cuuint32_t box[4] = {(cuuint32_t)tc::kSlabCols, (cuuint32_t)tc::kBlockM, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&ty, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y.ptr, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SY_REQUIRE(r == CUDA_SUCCESS, SY_ELAUNCH, "cuTensorMapEncodeTiled(Y linear) failed: %d", (int)r);
+  } else {
     // Y: output view as (C, W, H, N), box (64, TW, TH, 1): the TMA store clips the patch to the image / slice
     cuuint64_t dims[4] = {(cuuint64_t)y.c, (cuuint64_t)y.w, (cuuint64_t)y.h, (cuuint64_t)y.n};
     cuuint64_t strides[3] = {(cuuint64_t)y.pitch * 2, (cuuint64_t)y.pitch * 2 * y.w, (cuuint64_t)y.pitch * 2 * y.w * y.h};
@@ -969,9 +1103,16 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SY_REQUIRE(r == CUDA_SUCCESS, SY_ELAUNCH, "cuTensorMapEncodeTiled(Y) failed: %d", (int)r);
   }
+  if (lin) {
+    switch (bn) {
+      case 64: return tc::launch<64, true>(ta, tb, ty, p, stream);
+      case 128: return tc::launch<128, true>(ta, tb, ty, p, stream);
+      default: return tc::launch<256, true>(ta, tb, ty, p, stream);
+    }
+  }
   switch (bn) {
-    case 64: return tc::launch<64>(ta, tb, ty, p, stream);
-    case 128: return tc::launch<128>(ta, tb, ty, p, stream);
-    default: return tc::launch<256>(ta, tb, ty, p, stream);
+    case 64: return tc::launch<64, false>(ta, tb, ty, p, stream);
+    case 128: return tc::launch<128, false>(ta, tb, ty, p, stream);
+    default: return tc::launch<256, false>(ta, tb, ty, p, stream);
   }
 }

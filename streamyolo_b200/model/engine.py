@@ -19,9 +19,11 @@ from .. import ops
 from ..ops import View
 
 
-# normalise pass inside the conv launch (1 launch / BaseConv): correct but measured SLOWER on B200 (11.7 vs 8.2 ms/step:
-# 256 threads per SM cannot keep enough bytes in flight), so off by default
+# normalise pass inside the conv launch (1 launch / BaseConv).  For every layer it was measured SLOWER on B200 (11.7 vs
+# 8.2 ms/step: one CTA per SM cannot keep enough bytes in flight on the big tensors), so SY_FUSE_APPLY=1 is a debug
+# switch; SY_FUSE_APPLY_MAX_MB fuses only the layers whose raw output is at most that many MB (L2 resident, launch-bound)
 FUSE_APPLY = os.environ.get("SY_FUSE_APPLY", "0") != "0"
+FUSE_APPLY_MAX_BYTES = float(os.environ.get("SY_FUSE_APPLY_MAX_MB", "0")) * 1e6
 TRACE = None      # debugging: set to a dict to capture every BaseConv's stored output by module name
 
 
@@ -107,7 +109,7 @@ def conv_bn_act(ctx: Ctx, mods, x: View, wpk, k, s, y: View, res: View = None, a
             segs.append(_bn_seg(m, c0))
             c0 += m.conv.out_channels
         ss = torch.empty((2, 2, cout), dtype=torch.float32, device=ctx.device)
-        if FUSE_APPLY:
+        if FUSE_APPLY or n * ho * wo * cout * 2 <= FUSE_APPLY_MAX_BYTES:
             ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="tc", partials=partials, split_n=split, bn=segs,
                        momentum=mom, eps=float(bn0.eps), scale_shift=ss, sync=_sync(mods[0], ctx.device), act=act,
                        apply_y=y, apply_res=res, y_goff1=y_goff1, res_goff1=res_goff1)

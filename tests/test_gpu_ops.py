@@ -48,6 +48,19 @@ def check_close(got, ref, what, ulp=2.0 ** -7):
     return rel
 
 
+# SY_TEST_TILES=linear|patch restricts the tensor-core variants under test (bring-up aid); default: both
+_T = os.environ.get("SY_TEST_TILES", "both")
+TC_IMPLS = [i for i in ("tc", "tc_patch") if _T == "both" or (_T == "linear") == (i == "tc")]
+
+
+def tc_impl(impl, monkeypatch):
+    """'tc' = linear M tiles (im2col-mode TMA, the default), 'tc_patch' = rectangular patch tiles; both are product paths."""
+    if impl.startswith("tc"):
+        monkeypatch.setenv("SY_CONV_TILES", "patch" if impl == "tc_patch" else "linear")
+        return "tc"
+    return impl
+
+
 CONV_CASES = [
     # n, cin, cout, h, w, k, s
     (2, 64, 64, 8, 16, 1, 1),
@@ -62,13 +75,16 @@ CONV_CASES = [
     (2, 96, 96, 19, 30, 3, 1),
     (1, 1024, 512, 19, 30, 1, 1),
     (2, 256, 256, 75, 120, 3, 1),      # head tower conv (largest single conv of l)
+    (3, 64, 64, 13, 17, 3, 1),         # 221 pixels per image: every linear tile straddles an image boundary
+    (5, 32, 64, 9, 7, 3, 2),           # stride 2 on odd sizes, images much smaller than a tile
 ]
 
 
-@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("impl", ["simt"] + TC_IMPLS)
 @pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
-def test_conv_raw(case, impl):
+def test_conv_raw(case, impl, monkeypatch):
     n, ci, co, h, w, k, s = case
+    impl = tc_impl(impl, monkeypatch)
     if impl == "simt" and ci * co * h * w * k * k * n > 3e10:
         pytest.skip("too slow on the CUDA-core cross-check kernel")
     x = rand_act(n, ci, h, w, 1)
@@ -98,7 +114,13 @@ def test_conv_raw(case, impl):
             assert torch.allclose(pr[g, 1], part.pow(2).sum((0, 2, 3)), rtol=2e-3, atol=1e-3), "sumsq"
 
 
-def test_conv_tc_bn_finalize_then_apply():
+@pytest.mark.parametrize("tiles", TC_IMPLS)
+def test_conv_tc_bn_finalize_then_apply(tiles, monkeypatch):
+    tc_impl(tiles, monkeypatch)
+    _bn_finalize_then_apply()
+
+
+def _bn_finalize_then_apply():
     """RAW conv that also finalizes BatchNorm in its tail (grid barrier + parallel reduce; two groups, two
     parameter segments, running statistics), then the normalise pass with SiLU + residual; against
     F.batch_norm on the stored conv output.  The sync counters must come back to zero (graph replay safe)."""
@@ -140,9 +162,10 @@ def test_conv_tc_bn_finalize_then_apply():
         assert int(nbt[0]) == 2 * (rep + 1) and int(nbt[1]) == 2 * (rep + 1)
 
 
-@pytest.mark.parametrize("impl", ["simt", "tc"])
-def test_conv_fused_residual_slices(impl):
+@pytest.mark.parametrize("impl", ["simt"] + TC_IMPLS)
+def test_conv_fused_residual_slices(impl, monkeypatch):
     """FUSED epilogue (scale, shift, SiLU, residual) reading and writing channel slices, in place."""
+    impl = tc_impl(impl, monkeypatch)
     n, ci, co, h, w = 2, 64, 64, 19, 30
     x = rand_act(n, ci, h, w, 3)
     wt = rand_w(co, ci, 3, 4)
@@ -180,8 +203,9 @@ def test_conv_tc_matches_simt_bitwise_mostly():
     check_close(a.torch().float(), b.torch().float(), "tc vs simt")
 
 
-@pytest.mark.parametrize("impl", ["simt", "tc"])
-def test_stem_focus(impl):
+@pytest.mark.parametrize("impl", ["simt"] + TC_IMPLS)
+def test_stem_focus(impl, monkeypatch):
+    impl = tc_impl(impl, monkeypatch)
     b, h, w, co = 2, 120, 160, 16
     g = torch.Generator().manual_seed(0)
     x = (torch.rand(b, 6, h, w, generator=g) * 255).to(DEV)

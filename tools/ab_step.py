@@ -1,0 +1,77 @@
+"""A/B the whole training-forward step under different kernel switches in ONE process: for every setting the step is
+re-captured as a CUDA graph (the switches are read at launch / capture time) and replayed.
+Prints one line per setting: ms/step, pairs/s, loss (must agree across settings up to bf16 noise).
+
+usage: python tools/ab_step.py [model] [pairs]    settings are listed in SETTINGS below"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import bench
+from streamyolo_b200 import ops, synth
+from streamyolo_b200.model import engine
+
+tag = sys.argv[1] if len(sys.argv) > 1 else "l"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(dev)
+model = bench.build_model(tag, dev)
+x = synth.synth_frames(B, 600, 960, seed=1234).to(dev)
+fut, cur = synth.synth_labels(B, 600, 960, seed=1)
+fut, cur = fut.to(dev), cur.to(dev)
+
+SETTINGS = [
+    # (label, SY_CONV_TILES, SY_PDL, fuse-apply threshold MB)
+    ("patch  pdl0", "patch", "0", 0),
+    ("patch  pdl1", "patch", "1", 0),
+    ("linear pdl0", "linear", "0", 0),
+    ("linear pdl1", "linear", "1", 0),
+    ("linear pdl1 fuse<=5MB", "linear", "1", 5),
+    ("linear pdl1 fuse<=10MB", "linear", "1", 10),
+    ("linear pdl1 fuse<=20MB", "linear", "1", 20),
+    ("linear pdl1 fuse<=40MB", "linear", "1", 40),
+]
+if len(sys.argv) > 3:
+    SETTINGS = [s for s in SETTINGS if any(k in s[0] for k in sys.argv[3].split(","))]
+
+
+def measure(label, tiles, pdl, fuse_mb, steps=20, warmup=4):
+    os.environ["SY_CONV_TILES"] = tiles
+    os.environ["SY_PDL"] = pdl
+    engine.FUSE_APPLY_MAX_BYTES = fuse_mb * 1e6
+    with torch.no_grad():
+        ops.LAUNCHES = 0
+        out = model(x, (fut, cur))
+        launches = ops.LAUNCHES
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            model(x, (fut, cur))
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            o = model(x, (fut, cur))
+            loss = o["total_loss"]
+        for _ in range(warmup):
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    print(f"{label:26s} {ms:8.3f} ms/step {B / ms * 1e3:8.1f} pairs/s  loss {float(loss):.5f}  launches {launches}", flush=True)
+    del g
+
+
+for s in SETTINGS:
+    try:
+        measure(*s)
+    except Exception as e:  # keep going: a failing switch must not hide the others
+        print(f"{s[0]:26s} FAILED: {type(e).__name__}: {str(e)[:300]}", flush=True)
+        torch.cuda.synchronize()
