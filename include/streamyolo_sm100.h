@@ -115,10 +115,11 @@ int sy_conv2d_simt(const SyConvDesc* d, sy_stream_t stream);
 /* Focus stem, part 1: [yolox] Focus space-to-depth (TL/BL/TR/BR channel order), used at
  * exps/model/darknet.py:115.  x is the NCHW float32 frame-pair batch [b, in_ch, h, w]
  * (exps/model/dfp_pafpn.py:120,145 split it); image n of y takes frame n / b (0 = current,
- * 1 = support; channels 3*frame .. 3*frame+2) of batch element n % b.  y = [frames*b, h/2, w/2, 48]
+ * 1 = support; channels 3*frame .. 3*frame+2) of batch element n % b.  y = [frames*b, h/2, w/2, 64]
  * bf16: for each focus pixel its three horizontal taps (x-1, x, x+1; zero outside the image), each
- * 12 focus channels + 4 zero channels.  The stem's 3x3 conv then runs on sy_conv2d_tc as a 3x1 conv
- * over 48 channels with weights packed [cout][3][48]. */
+ * 12 focus channels + 4 zero channels, then 16 zero channels (one aligned 128-byte row per pixel).
+ * The stem's 3x3 conv then runs on sy_conv2d_tc as a 3x1 conv over 64 channels with weights packed
+ * [cout][3][64]. */
 int sy_focus_pack(const float* x, int32_t b, int32_t in_ch, int32_t h, int32_t w_px, int32_t frames,
                   SyTensor y, sy_stream_t stream);
 

@@ -69,22 +69,24 @@ __global__ void conv_simt_kernel(const SimtConvParams p) {
 
 // Focus space-to-depth (TL, BL, TR, BR order) from the NCHW fp32 frame-pair batch into NHWC bf16, already
 // gathered along W for the 3x3 stem conv: pixel (y, x) holds taps x-1, x, x+1 (zero outside the image), each
-// 12 focus channels + 4 zero channels = 48 channels, so that the stem is a 3x1 conv with three 64-deep K
-// blocks for the tensor-core kernel.  thread = (pixel, tap).  Input pixels are rounded to bf16.
+// 12 focus channels + 4 zero channels, plus 16 zero channels = 64 channels = one 128-byte row per pixel (TMA boxes
+// whose inner extent runs past a 96-byte pixel were measured 2.6x slower: 354 vs 133 us for the stem conv), so that
+// the stem is a 3x1 conv with three 64-deep K blocks for the tensor-core kernel.  thread = (pixel, tap | pad).
+// Input pixels are rounded to bf16.
 __global__ void focus_pack_kernel(const float* __restrict__ x, int B, int in_ch, int H, int W, int frames,
                                   __nv_bfloat16* y, long long y_pitch) {
   const int Ho = H / 2, Wo = W / 2;
-  const long long total = (long long)frames * B * Ho * Wo * 3;
+  const long long total = (long long)frames * B * Ho * Wo * 4;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int s = (int)(idx % 3);
-    const long long pix = idx / 3;
+    const int s = (int)(idx & 3);
+    const long long pix = idx >> 2;
     const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho);
     const int n = (int)(pix / ((long long)Wo * Ho));
     const int frame = n / B, b = n % B;
     const int fx = ox + s - 1;
     float v[12];
-    if (fx >= 0 && fx < Wo) {
+    if (s < 3 && fx >= 0 && fx < Wo) {
       const float* xb = x + ((long long)b * in_ch + frame * 3) * H * W;
 #pragma unroll
       for (int fc = 0; fc < 12; ++fc) {
@@ -181,9 +183,9 @@ extern "C" int sy_focus_pack(const float* x, int32_t b, int32_t in_ch, int32_t h
   SY_REQUIRE(x && view_ok(y), SY_EINVAL, "focus_pack: null input or bad output view");
   SY_REQUIRE(h % 2 == 0 && w_px % 2 == 0 && frames >= 1 && frames * 3 <= in_ch, SY_EINVAL,
              "focus_pack: h=%d w=%d must be even, frames=%d in_ch=%d", h, w_px, frames, in_ch);
-  SY_REQUIRE(y.n == frames * b && y.h == h / 2 && y.w == w_px / 2 && y.c == 48, SY_EINVAL,
-             "focus_pack: output view must be [frames*b, h/2, w/2, 48]");
-  const long long total = (long long)y.n * y.h * y.w * 3;
+  SY_REQUIRE(y.n == frames * b && y.h == h / 2 && y.w == w_px / 2 && y.c == 64, SY_EINVAL,
+             "focus_pack: output view must be [frames*b, h/2, w/2, 64]");
+  const long long total = (long long)y.n * y.h * y.w * 4;
   const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
   focus_pack_kernel<<<blocks, 256, 0, stream>>>(x, b, in_ch, h, w_px, frames, reinterpret_cast<__nv_bfloat16*>(y.ptr),
                                                 y.pitch);

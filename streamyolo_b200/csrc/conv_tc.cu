@@ -88,6 +88,7 @@ struct Params {
   int gp;                   // first output pixel of statistics group 1 (== P_total: single group)
   FastDiv fd_hw, fd_wo;
   int cblocks, kblocks, stages;
+  int stage_tiles;          // 1 or 2 epilogue staging tiles
   int mode, act;
   __nv_bfloat16* y;
   long long y_pitch;
@@ -200,6 +201,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -256,8 +258,18 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 // staging-tile hand-off between the 8 epilogue warps and the store warp (warp 3): 256 + 32 threads
 // staging-tile hand-off between the 8 convert warps, the 8 statistics warps and the store warp: 256 + 256 + 32 threads
-__device__ __forceinline__ void bar_free() { asm volatile("bar.sync 2, 544;" ::: "memory"); }    // (A) staging tile free
-__device__ __forceinline__ void bar_staged() { asm volatile("bar.sync 3, 544;" ::: "memory"); }  // (B) staging tile complete
+// One or two staging tiles (Params::stage_tiles; slab j uses tile j & 1 when there are two, so that the TMA store /
+// statistics of one slab overlap the conversion of the next -- worth an operand stage only for epilogue-bound layers);
+// named barriers 2,3 belong to tile 0 and 6,7 to tile 1.
+// Producer/consumer protocol (PTX bar.arrive / bar.sync pairs, 256 + 256 + 32 = 544 threads per barrier):
+//   free(b)   : store warp arrives when its TMA store has read tile b, statistics warps arrive when their loads of
+//               tile b are done; the convert warps WAIT on it before overwriting the tile
+//   staged(b) : convert warps arrive after writing tile b (+ proxy fence); store and statistics warps WAIT on it
+// so the convert warps never wait for the statistics arithmetic or the store issue, only for the tile to be read.
+__device__ __forceinline__ void bar_free_wait(int b) { asm volatile("bar.sync %0, 544;" ::"r"(2 + 4 * b) : "memory"); }
+__device__ __forceinline__ void bar_free_arrive(int b) { asm volatile("bar.arrive %0, 544;" ::"r"(2 + 4 * b) : "memory"); }
+__device__ __forceinline__ void bar_staged_wait(int b) { asm volatile("bar.sync %0, 544;" ::"r"(3 + 4 * b) : "memory"); }
+__device__ __forceinline__ void bar_staged_arrive(int b) { asm volatile("bar.arrive %0, 544;" ::"r"(3 + 4 * b) : "memory"); }
 __device__ __forceinline__ void bar_stats_done() { asm volatile("bar.sync 5, 512;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
@@ -300,7 +312,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sA = smem;
   uint8_t* sB = sA + S * kSub * kABytes;
   uint8_t* sStage = sB + S * kSub * C::kBBytes;                                 // 1024-aligned: the rings are multiples of 1 KiB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + kSlabBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + p.stage_tiles * kSlabBytes);
+  const int sflip = p.stage_tiles - 1;                                          // slab parity toggles the tile iff there are two
   // bars: [0,8) full, [8,16) empty, [16,18) tmem_full, [18,20) tmem_empty, then the tmem base slot
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
   float* sAcc = reinterpret_cast<float*>(bars + 32);                     // RAW:   [2 groups][2][Cout]
@@ -449,6 +462,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // One 4-D TMA store per 64-column slab; the tensor map clips the patch to the image and to the
     // channel slice.  Issuing it here keeps its issue + drain latency off the epilogue warps' path.
     const uint32_t stage_base = smem_u32(smem + S * kSub * (kABytes + C::kBBytes));
+    int sbuf = 0, prev = -1;
+    bar_free_arrive(0);                          // both tiles start out free
+    if (sflip) bar_free_arrive(1);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
       int c1, c2, c3;                            // store coordinates below the channel: (x, y, image) | (pixel, 0, 0)
@@ -459,16 +475,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int py = fdiv(rem, p.fd_tiles_x), px = rem - py * p.tiles_x;
         c1 = px * p.tw; c2 = py * p.th; c3 = img;
       }
-      for (int slab = 0; slab < BN / kSlabCols; ++slab) {
-        bar_free();
-        bar_staged();
+      for (int slab = 0; slab < BN / kSlabCols; ++slab, sbuf ^= sflip) {
+        bar_staged_wait(sbuf);
         if (elect_one()) {
-          tma_store_4d(&tmY, stage_base, n_tile * BN + slab * kSlabCols, c1, c2, c3);
+          tma_store_4d(&tmY, stage_base + (uint32_t)(sbuf * kSlabBytes), n_tile * BN + slab * kSlabCols, c1, c2, c3);
           bulk_commit();
-          bulk_wait_read();                      // staging tile may be overwritten once the TMA has read it
+          if (sflip) {
+            if (prev >= 0) bulk_wait_read1();    // two tiles: the previous slab's store has read ITS tile
+          } else {
+            bulk_wait_read();                    // one tile: wait until this store has read it
+          }
         }
         __syncwarp();
+        if (sflip) {
+          if (prev >= 0) bar_free_arrive(prev);
+          prev = sbuf;
+        } else {
+          bar_free_arrive(0);
+        }
       }
+    }
+    if (sflip && prev >= 0) {
+      if (elect_one()) bulk_wait_read();
+      __syncwarp();
+      bar_free_arrive(prev);
     }
     if (lane == 0) {
       bulk_wait_all();                           // every store of this CTA has been performed
@@ -487,6 +517,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (do_stats) {
       for (int i = st; i < 4 * p.Cout; i += 256) sAcc[i] = 0.f;
     }
+    int sbuf = 0;
+    bar_free_arrive(0);                          // both tiles start out free
+    if (sflip) bar_free_arrive(1);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
       const int n0 = n_tile * BN;
@@ -498,27 +531,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else {
         cut = fdiv(m_tile, p.fd_per_img) >= p.split_n ? 0 : kBlockM;
       }
-      for (int slab = 0; slab < BN / kSlabCols; ++slab) {
-        bar_free();
-        bar_staged();
+      for (int slab = 0; slab < BN / kSlabCols; ++slab, sbuf ^= sflip) {
+        bar_staged_wait(sbuf);
+        const uint32_t tile_base = stage_base + (uint32_t)(sbuf * kSlabBytes);
+        // warp ew reduces columns [8*ew, 8*ew+8) of the slab: lane l reads rows l, l+32, l+64, l+96
+        float x[4][8];
+        if (do_stats) {
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const uint32_t r = (uint32_t)(lane + 32 * rr);
+            const uint4 u = lds128(tile_base + r * 128u + ((((uint32_t)ew) ^ (r & 7u)) << 4));
+            x[rr][0] = bf16_lo(u.x); x[rr][1] = bf16_hi(u.x); x[rr][2] = bf16_lo(u.y); x[rr][3] = bf16_hi(u.y);
+            x[rr][4] = bf16_lo(u.z); x[rr][5] = bf16_hi(u.z); x[rr][6] = bf16_lo(u.w); x[rr][7] = bf16_hi(u.w);
+          }
+        }
+        bar_free_arrive(sbuf);                   // the values are in registers: the tile may be overwritten
         if (do_stats) {
 #pragma unroll 1
           for (int grp = 0; grp < 2; ++grp) {
             const int lo = grp ? cut : 0, hi = grp ? kBlockM : cut;
             if (lo >= hi) continue;              // warp-uniform
-            // warp ew reduces columns [8*ew, 8*ew+8) of the slab: lane l reads rows l, l+32, l+64, l+96
             float a[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) a[i] = 0.f;
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
-              const uint32_t r = (uint32_t)(lane + 32 * rr);
-              if ((int)r >= lo && (int)r < hi) {
-                const uint4 u = lds128(stage_base + r * 128u + ((((uint32_t)ew) ^ (r & 7u)) << 4));
-                const float x[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
-                                    bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+              const int r = lane + 32 * rr;
+              if (r >= lo && r < hi) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { a[i] += x[i]; a[8 + i] += x[i] * x[i]; }
+                for (int i = 0; i < 8; ++i) { a[i] += x[rr][i]; a[8 + i] += x[rr][i] * x[rr][i]; }
               }
             }
             // recursive halving over the 32 lanes: 8 + 4 + 2 + 1 + 1 shuffles, fixed order (deterministic)
@@ -574,6 +615,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t rsw = (uint32_t)(row & 7);
     const bool do_stats = (p.mode == SY_CONV_RAW) && (p.partials != nullptr);
     int it = 0;
+    int sbuf = 0;
     int tl_n = (et == 0) ? p.timeline_cap / 2 : p.timeline_cap;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -607,7 +649,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int slab = 0; slab < BN / kSlabCols; ++slab) {
+      for (int slab = 0; slab < BN / kSlabCols; ++slab, sbuf ^= sflip) {
         const int cl = slab * kSlabCols + half * 32;     // first of this thread's 32 accumulator columns
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)cl, v);
@@ -646,19 +688,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 16; ++i) packed[i] = valid ? pack_bf16(f[2 * i], f[2 * i + 1]) : 0u;
         }
         tl_rec<TL>(p, tl_n, 2, 2, tile, slab);
-        bar_free();                              // (A) staging tile free: store drained, statistics readers done
+        bar_free_wait(sbuf);                     // (A) staging tile free: its store has read it, the statistics loads are done
+        const uint32_t my_tile_row = my_row + (uint32_t)(sbuf * kSlabBytes);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {            // 16-byte chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4)
           const uint32_t j = (uint32_t)(half * 4 + g);
-          sts128(my_row + ((j ^ rsw) << 4), packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+          sts128(my_tile_row + ((j ^ rsw) << 4), packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
         }
         fence_proxy_async();                     // generic-proxy writes -> visible to the TMA (async proxy)
-        bar_staged();                            // (B) staging tile complete: the store warp takes it from here
+        bar_staged_arrive(sbuf);                 // (B) staging tile complete: store + statistics warps take it from here
         tl_rec<TL>(p, tl_n, 2, 3, tile, slab);
         tl_rec<TL>(p, tl_n, 2, 4, tile, slab);
       }
     }
     tl_epi = tl_n;
+    bar_free_wait(0);                                // drain the last arrivals (balanced barriers at exit)
+    if (sflip) bar_free_wait(1);
     asm volatile("bar.sync 4, 288;" ::: "memory");   // store warp: all TMA stores of this CTA are complete
   }
   if (warp < 16) {
@@ -928,12 +973,20 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   }
   const int acc_bytes = (p.mode == SY_CONV_RAW && p.partials) ? 16 * p.Cout : 2048;
   const int stage_bytes = Cfg<BN>::kSub * (kABytes + Cfg<BN>::kBBytes);
-  int stages = (kSmemLimit - Cfg<BN>::kFixedBytes - acc_bytes) / stage_bytes;
+  // epilogue-bound layers (main loop of a tile shorter than its epilogue: 1x1 convs with few input channels, the
+  // stem) get a second staging tile: the store + statistics of a slab then overlap the conversion of the next
+  {
+    const double kbc = BN == 256 ? 665.0 : (BN == 128 ? 515.0 : 560.0);
+    p.stage_tiles = (p.kblocks * kbc < 1900.0 * (BN / 64)) ? 2 : 1;
+    if (const char* e = getenv("SY_STAGE_TILES")) p.stage_tiles = (e[0] == '2') ? 2 : 1;   // tuning aid
+  }
+  const int fixed_bytes = Cfg<BN>::kFixedBytes + (p.stage_tiles - 1) * kSlabBytes;
+  int stages = (kSmemLimit - fixed_bytes - acc_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if ((p.debug_flags >> 8) & 15) stages = min(stages, (p.debug_flags >> 8) & 15);   // debug: cap the ring depth
   SY_REQUIRE(stages >= 2, SY_EINVAL, "conv2d_tc: Cout=%d leaves no room for the operand ring", p.Cout);
   p.stages = stages;
-  const int smem = Cfg<BN>::kFixedBytes + acc_bytes + stages * stage_bytes;
+  const int smem = fixed_bytes + acc_bytes + stages * stage_bytes;
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   if (p.timeline != nullptr)
     SY_CUDA(launch_pdl(conv_tc_kernel<BN, true, LIN>, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));

@@ -216,12 +216,12 @@ def _packed_stem(bc):
 
 def focus_stem(ctx: Ctx, m, x, frames) -> View:
     """[yolox] Focus + BaseConv straight from the NCHW float frame-pair batch: space-to-depth + W-gather into
-    a 48-channel NHWC tensor, then the tensor-core kernel runs the 3x3 stem as a 3x1 conv (3 K blocks)."""
+    a 64-channel NHWC tensor, then the tensor-core kernel runs the 3x3 stem as a 3x1 conv (3 K blocks)."""
     b, ch, h, w = x.shape
     bc = m.conv
     cout = bc.conv.out_channels
     n = frames * b
-    xin = View.empty(n, h // 2, w // 2, 48, ctx.device)
+    xin = View.empty(n, h // 2, w // 2, 64, ctx.device)
     ops.focus_pack(x, frames, xin)
     wpk = _packed_stem(bc)
     y = View.empty(n, h // 2, w // 2, cout, ctx.device)

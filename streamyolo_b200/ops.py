@@ -247,15 +247,15 @@ def focus_pack(x, frames, y: View):
     _check(lib().sy_focus_pack(x.data_ptr(), b, ch, h, w, frames, y.st(), _stream()))
 
 
-STEM_K = (3, 1)      # the stem runs as a 3x1 conv over the W-gathered 48-channel focus tensor
+STEM_K = (3, 1)      # the stem runs as a 3x1 conv over the W-gathered 64-channel focus tensor
 
 
 def pack_stem_weight(w):
-    """[O,12,3,3] float -> bf16 [O][3 (row)][48 = 3 taps x (12 focus + 4 zero)]."""
+    """[O,12,3,3] float -> bf16 [O][3 (row)][64 = 3 taps x (12 focus + 4 zero) + 16 zero]."""
     o = w.shape[0]
-    p = torch.zeros((o, 3, 3, 16), dtype=torch.bfloat16, device=w.device)
-    p[..., :12] = w.detach().permute(0, 2, 3, 1).to(torch.bfloat16)       # [O, r, s, fc]
-    return p.reshape(o, 3, 48).contiguous()
+    p = torch.zeros((o, 3, 4, 16), dtype=torch.bfloat16, device=w.device)
+    p[:, :, :3, :12] = w.detach().permute(0, 2, 3, 1).to(torch.bfloat16)  # [O, r, s, fc]
+    return p.reshape(o, 3, 64).contiguous()
 
 
 def stats_num_partials(n, hw):

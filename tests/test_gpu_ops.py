@@ -210,7 +210,7 @@ def test_stem_focus(impl, monkeypatch):
     g = torch.Generator().manual_seed(0)
     x = (torch.rand(b, 6, h, w, generator=g) * 255).to(DEV)
     wt = rand_w(co, 12, 3, 7)
-    xin = View.empty(2 * b, h // 2, w // 2, 48, DEV)
+    xin = View.empty(2 * b, h // 2, w // 2, 64, DEV)
     ops.focus_pack(x, 2, xin)
     y = View.empty(2 * b, h // 2, w // 2, co, DEV)
     ops.conv2d(xin, ops.pack_stem_weight(wt), y, ops.STEM_K, 1, ops.SY_CONV_RAW, impl=impl)
@@ -219,6 +219,7 @@ def test_stem_focus(impl, monkeypatch):
     foc = torch.cat([xs[..., ::2, ::2], xs[..., 1::2, ::2], xs[..., ::2, 1::2], xs[..., 1::2, 1::2]], 1)
     packed = xin.nchw_float()
     assert torch.equal(packed[:, 16:28], foc) and (packed[:, 28:32] == 0).all()            # centre tap: exact
+    assert (packed[:, 44:64] == 0).all()                                                    # tap padding + row padding
     assert torch.equal(packed[:, 0:12, :, 1:], foc[..., :-1]) and (packed[:, 0:12, :, 0] == 0).all()
     assert torch.equal(packed[:, 32:44, :, :-1], foc[..., 1:]) and (packed[:, 32:44, :, -1] == 0).all()
     ref = F.conv2d(foc, wt, None, 1, 1)

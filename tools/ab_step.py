@@ -23,23 +23,24 @@ fut, cur = synth.synth_labels(B, 600, 960, seed=1)
 fut, cur = fut.to(dev), cur.to(dev)
 
 SETTINGS = [
-    # (label, SY_CONV_TILES, SY_PDL, fuse-apply threshold MB)
-    ("patch  pdl0", "patch", "0", 0),
-    ("patch  pdl1", "patch", "1", 0),
-    ("linear pdl0", "linear", "0", 0),
-    ("linear pdl1", "linear", "1", 0),
-    ("linear pdl1 fuse<=5MB", "linear", "1", 5),
-    ("linear pdl1 fuse<=10MB", "linear", "1", 10),
-    ("linear pdl1 fuse<=20MB", "linear", "1", 20),
-    ("linear pdl1 fuse<=40MB", "linear", "1", 40),
+    # (label, environment switches, fuse-apply threshold MB)
+    ("base", {}, 0),
+    ("one staging tile", {"SY_STAGE_TILES": "1"}, 0),
+    ("two staging tiles", {"SY_STAGE_TILES": "2"}, 0),
+    ("apply v1", {"SY_APPLY": "v1"}, 0),
+    ("apply cap 3/SM", {"SY_APPLY_CAP": "3"}, 0),
+    ("patch tiles", {"SY_CONV_TILES": "patch"}, 0),
+    ("no pdl", {"SY_PDL": "0"}, 0),
 ]
 if len(sys.argv) > 3:
     SETTINGS = [s for s in SETTINGS if any(k in s[0] for k in sys.argv[3].split(","))]
+SWITCHES = ("SY_CONV_TILES", "SY_PDL", "SY_APPLY", "SY_APPLY_CAP", "SY_STAGE_TILES")
 
 
-def measure(label, tiles, pdl, fuse_mb, steps=20, warmup=4):
-    os.environ["SY_CONV_TILES"] = tiles
-    os.environ["SY_PDL"] = pdl
+def measure(label, env, fuse_mb, steps=20, warmup=4):
+    for k in SWITCHES:
+        os.environ.pop(k, None)
+    os.environ.update(env)
     engine.FUSE_APPLY_MAX_BYTES = fuse_mb * 1e6
     with torch.no_grad():
         ops.LAUNCHES = 0
@@ -65,7 +66,7 @@ def measure(label, tiles, pdl, fuse_mb, steps=20, warmup=4):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-    print(f"{label:26s} {ms:8.3f} ms/step {B / ms * 1e3:8.1f} pairs/s  loss {float(loss):.5f}  launches {launches}", flush=True)
+    print(f"{label:30s} {ms:8.3f} ms/step {B / ms * 1e3:8.1f} pairs/s  loss {float(loss):.5f}  launches {launches}", flush=True)
     del g
 
 
@@ -73,5 +74,5 @@ for s in SETTINGS:
     try:
         measure(*s)
     except Exception as e:  # keep going: a failing switch must not hide the others
-        print(f"{s[0]:26s} FAILED: {type(e).__name__}: {str(e)[:300]}", flush=True)
+        print(f"{s[0]:30s} FAILED: {type(e).__name__}: {str(e)[:300]}", flush=True)
         torch.cuda.synchronize()

@@ -9,11 +9,14 @@ import torch
 from streamyolo_b200 import ops
 from streamyolo_b200.ops import View
 
-n, ci, co, h, w, k, s = map(int, sys.argv[1:8])
+n, ci, co, h, w = map(int, sys.argv[1:6])
+kh, kw = (map(int, sys.argv[6].split("x")) if "x" in sys.argv[6] else (int(sys.argv[6]),) * 2)
+s = int(sys.argv[7])
+k = (kh, kw)
 FLAGS = int(sys.argv[8]) if len(sys.argv) > 8 else 0
 x = View(torch.randn((n, h, w, ci), device="cuda").to(torch.bfloat16))
-wt = ops.pack_conv_weight(torch.randn((co, ci, k, k), device="cuda") * 0.05)
-ho, wo = ops.conv_out_hw(h, w, k, s)
+wt = ops.pack_conv_weight(torch.randn((co, ci, kh, kw), device="cuda") * 0.05)
+ho, wo = (h + 2 * ((kh - 1) // 2) - kh) // s + 1, (w + 2 * ((kw - 1) // 2) - kw) // s + 1
 y = View.empty(n, ho, wo, co, "cuda")
 part = torch.empty((ops.conv_stat_rows(), 4 * co), device="cuda")
 for _ in range(3):
@@ -27,7 +30,7 @@ for _ in range(5):
     e1.record()
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1) * 1e3)
-fl = 2.0 * n * ho * wo * co * ci * k * k
+fl = 2.0 * n * ho * wo * co * ci * kh * kw
 print(f"shape {sys.argv[1:8]}: {min(ts):.1f} us best, {fl / min(ts) / 1e6:.0f} TFLOP/s, {(x.buf.numel() + y.buf.numel()) * 2 / min(ts) / 1e3:.0f} GB/s")
 cap = 8192
 tl = torch.zeros(2 * cap, dtype=torch.int64, device="cuda")
