@@ -103,6 +103,7 @@ __global__ void bn_act_apply_v1_kernel(const __nv_bfloat16* __restrict__ x, long
 // per-element index division) and walks the pixels with kApplyUnroll independent 16-byte loads in flight.
 constexpr int kApplyThreads = 256;
 constexpr int kApplyUnroll = 4;
+template <bool ACT, bool RES>
 __global__ void __launch_bounds__(kApplyThreads, 3)
 bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const float* __restrict__ scale,
                     const float* __restrict__ shift, long long split_pix, int act,
@@ -128,7 +129,7 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const flo
   };
   const long long step = (long long)gridDim.x * ppb;
   const __nv_bfloat16* xg = x + g * 8;
-  const __nv_bfloat16* rg = res ? res + g * 8 : nullptr;
+  const __nv_bfloat16* rg = RES ? res + g * 8 : nullptr;
   __nv_bfloat16* yg = y + g * 8;
   for (long long pix0 = (long long)blockIdx.x * ppb + prow; pix0 < npix; pix0 += step * kApplyUnroll) {
     uint4 v[kApplyUnroll], rv[kApplyUnroll];
@@ -137,7 +138,7 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const flo
       const long long pix = pix0 + j * step;
       if (pix < npix) v[j] = *reinterpret_cast<const uint4*>(xg + pix * xp);
     }
-    if (rg != nullptr) {
+    if (RES) {
 #pragma unroll
       for (int j = 0; j < kApplyUnroll; ++j) {
         const long long pix = pix0 + j * step;
@@ -155,9 +156,9 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const flo
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float t = f[i] * sc[i] + sh[i];
-        f[i] = act ? silu_f(t) : t;
+        f[i] = ACT ? silu_f(t) : t;
       }
-      if (rg != nullptr) {
+      if (RES) {
         float r[8];
         unpack8(rv[j], r);
 #pragma unroll
@@ -339,14 +340,25 @@ extern "C" int sy_bn_act_apply(SyTensor x, const float* scale, const float* shif
   }
   SY_REQUIRE(x.c <= 8 * kApplyThreads, SY_EINVAL, "bn_act_apply: C=%d > %d", x.c, 8 * kApplyThreads);
   const int ppb = kApplyThreads / (x.c / 8);
-  // enough blocks for one pass of kApplyUnroll pixels per thread, capped at two waves of 3 resident blocks per SM
+  // enough blocks for one pass of kApplyUnroll pixels per thread, capped at one wave of 3 resident blocks per SM
   const long long want = (npix + (long long)ppb * kApplyUnroll - 1) / ((long long)ppb * kApplyUnroll);
-  long long cap = 148LL * 6;
-  if (const char* e = getenv("SY_APPLY_CAP")) cap = 148LL * (atoi(e) > 0 ? atoi(e) : 6);   // tuning aid: blocks per SM
+  long long cap = 148LL * 3;   // one wave of 3 resident blocks per SM (measured best: 6.188 vs 6.198 ms/step at 6 per SM)
+  if (const char* e = getenv("SY_APPLY_CAP")) cap = 148LL * (atoi(e) > 0 ? atoi(e) : 3);   // tuning aid: blocks per SM
   const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
-  SY_CUDA(launch_pdl(bn_act_apply_kernel, dim3(grid), dim3(kApplyThreads), 0, stream, CBF(x.ptr), (long long)x.pitch, scale,
-                     shift, split_pix, act, rp, rpitch, BF(y.ptr), (long long)y.pitch, npix, x.c, (long long)y_goff1,
-                     (long long)r_goff1));
+  const bool has_res = rp != nullptr;
+  auto launch = [&](auto kernel) -> int {
+    // L1/shared split: measured on the whole step (StreamYOLO-l, 8 pairs): carveout 0 (all L1) 6.40 ms, default and
+    // 100 (all shared, the conv kernels' split) 6.51 ms.
+    SY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+    SY_CUDA(launch_pdl(kernel, dim3(grid), dim3(kApplyThreads), 0, stream, CBF(x.ptr), (long long)x.pitch, scale, shift,
+                       split_pix, act, rp, rpitch, BF(y.ptr), (long long)y.pitch, npix, x.c, (long long)y_goff1,
+                       (long long)r_goff1));
+    return SY_OK;
+  };
+  int rc;
+  if (act) rc = has_res ? launch(bn_act_apply_kernel<true, true>) : launch(bn_act_apply_kernel<true, false>);
+  else rc = has_res ? launch(bn_act_apply_kernel<false, true>) : launch(bn_act_apply_kernel<false, false>);
+  if (rc != SY_OK) return rc;
   return launch_status("bn_act_apply_kernel");
 }
 

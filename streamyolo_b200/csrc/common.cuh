@@ -80,9 +80,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 __device__ __forceinline__ float round_bf16(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
 
-// SiLU with the approximate divide (MUFU.RCP + FMUL, ~2 ulp fp32 -- far below the bf16 output rounding): the
-// normalise pass is otherwise ALU-bound (a correctly rounded fp32 divide costs ~10 instructions per element).
-// For v << 0 the denominator overflows to +inf and the quotient is -0, the correct limit.
-__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// SiLU = v * rcp(1 + 2^(-v * log2 e)) on the two approximate SFU ops (ex2.approx, rcp.approx: ~2 ulp fp32, far below
+// the bf16 output rounding) = 5 instructions per value; the normalise pass is issue-bound otherwise (a correctly
+// rounded divide costs ~10 instructions, div.approx adds range fix-ups).  v << 0: 2^x overflows to +inf, rcp(inf) = 0,
+// the product is -0, the correct limit.
+__device__ __forceinline__ float silu_f(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return v * r;
+}
 
 }  // namespace sy

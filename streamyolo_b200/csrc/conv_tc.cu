@@ -501,8 +501,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       bar_free_arrive(prev);
     }
     if (lane == 0) {
-      bulk_wait_all();                           // every store of this CTA has been performed
-      asm volatile("fence.proxy.async;" ::: "memory");
+      if (p.ap_y != nullptr) {
+        bulk_wait_all();                         // the fused normalise pass re-reads this CTA's raw tiles from global
+        asm volatile("fence.proxy.async;" ::: "memory");
+      } else {
+        bulk_wait_read();                        // smem has been read; the writes complete with the grid
+      }
     }
     __syncwarp();
     asm volatile("bar.sync 4, 288;" ::: "memory");   // the epilogue warps may now re-read this CTA's own raw tiles
@@ -648,11 +652,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tl_rec<TL>(p, tl_n, 2, 1, tile, 0);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+      // software pipeline: the TMEM load of slab s+1 is in flight while slab s is staged (debug flag 32: off)
+      const bool pf = !(p.debug_flags & 32);
+      uint32_t v[32];
+      tmem_ld32(taddr + (uint32_t)(half * 32), v);
 #pragma unroll 1
       for (int slab = 0; slab < BN / kSlabCols; ++slab, sbuf ^= sflip) {
         const int cl = slab * kSlabCols + half * 32;     // first of this thread's 32 accumulator columns
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)cl, v);
+        if (!pf && slab > 0) tmem_ld32(taddr + (uint32_t)cl, v);
         tmem_ld_wait();
         if (slab == BN / kSlabCols - 1) {
           // every TMEM read of this accumulator is complete: hand it back to the MMA warp
@@ -687,6 +694,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 16; ++i) packed[i] = valid ? pack_bf16(f[2 * i], f[2 * i + 1]) : 0u;
         }
+        if (pf && slab + 1 < BN / kSlabCols) tmem_ld32(taddr + (uint32_t)(cl + kSlabCols), v);   // v is dead: prefetch the next slab
         tl_rec<TL>(p, tl_n, 2, 2, tile, slab);
         bar_free_wait(sbuf);                     // (A) staging tile free: its store has read it, the statistics loads are done
         const uint32_t my_tile_row = my_row + (uint32_t)(sbuf * kSlabBytes);
@@ -1021,6 +1029,7 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
 
   tc::Params p{};
   p.debug_flags = d->debug_flags;
+  if (const char* e = getenv("SY_CONV_DEBUG")) p.debug_flags |= atoi(e);    // tuning aid (see Params::debug_flags)
   p.N = x.n; p.Ho = ho; p.Wo = wo; p.Cout = y.c; p.Cin = x.c;
   p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_h = ph; p.pad_w = pw;
   const bool lin = tc::linear_tiles();
