@@ -89,6 +89,11 @@ struct Params {
   FastDiv fd_hw, fd_wo;
   int cblocks, kblocks, stages;
   int stage_tiles;          // 1 or 2 epilogue staging tiles
+  // halo mode (AM == 2)
+  int stagesA;              // halo ring depth
+  int halo_pitch;           // pixels per halo row in shared memory (16, or 10 with debug flag 128)
+  int halo_bytes;           // stage stride (multiple of 1 KiB)
+  int halo_tx;              // bytes one halo load delivers
   int mode, act;
   __nv_bfloat16* y;
   long long y_pitch;
@@ -281,6 +286,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                     // SWIZZLE_128B
   return d;
 }
+// general form: stride between 8-row atoms and the swizzle phase ("matrix base offset") of a start address that is not
+// 1024-byte aligned
+__device__ __forceinline__ uint64_t make_smem_desc_ex(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_offset & 7u) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128.
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
@@ -299,18 +315,28 @@ struct Cfg {
   static constexpr int kFixedBytes = 1024 /*align slack*/ + kSlabBytes + 256 /*barriers*/;
 };
 
-template <int BN, bool TL, bool LIN>
+// AM = how the A operand (activations) reaches shared memory:
+//   0 patch  : TH x TW patch tiles, one tiled 4-D TMA load per (tap, channel block)
+//   1 linear : 128 consecutive output pixels, one im2col-mode TMA load per (tap, channel block)
+//   2 halo   : 16 x 8 patch tiles, ONE tiled load per channel block of the 18 x (8+2) input halo; the nine taps are nine
+//              shared-memory descriptors into that halo (row pitch 16 pixels = 2 KiB, so every 8-pixel swizzle atom of a
+//              tap view keeps the phase of its first row).  3x3 stride-1 only.  Each input pixel crosses L2 -> SM once
+//              per tile instead of nine times: the tap re-reads are what bounds the 3x3 layers otherwise.
+template <int BN, bool TL, int AM>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const Params p) {
   using C = Cfg<BN>;
-  const int S = p.stages;
-  constexpr int kSub = C::kSub;
+  constexpr bool LIN = (AM == 1);
+  constexpr bool HALO = (AM == 2);
+  const int S = p.stages;                                  // patch/linear: A+B ring depth; halo: B ring depth
+  // 64-deep K sub-blocks per ring stage; halo mode: filter taps per weight-ring stage (one barrier round per filter row)
+  constexpr int kSub = HALO ? (BN == 256 ? 1 : 3) : C::kSub;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms; plain pointer arithmetic keeps the shared address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
-  uint8_t* sB = sA + S * kSub * kABytes;
+  uint8_t* sB = sA + (HALO ? p.stagesA * p.halo_bytes : S * kSub * kABytes);
   uint8_t* sStage = sB + S * kSub * C::kBBytes;                                 // 1024-aligned: the rings are multiples of 1 KiB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + p.stage_tiles * kSlabBytes);
   const int sflip = p.stage_tiles - 1;                                          // slab parity toggles the tile iff there are two
@@ -330,14 +356,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + 2 + a); };
+  auto fullA_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 6 + s); };      // halo ring (<= 3 stages)
+  auto emptyA_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 9 + s); };
 
   if (threadIdx.x == 19 * 32) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmY);
     for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 2);     // A producer + B producer
+      mbar_init(full_bar(s), HALO ? 1 : 2);     // A producer + B producer (halo: B only)
       mbar_init(empty_bar(s), 1);
+    }
+    if (HALO) {
+      for (int s = 0; s < p.stagesA; ++s) {
+        mbar_init(fullA_bar(s), 1);
+        mbar_init(emptyA_bar(s), 1);
+      }
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -359,7 +393,89 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int hw = p.Ho * p.Wo;
   int tl_epi = p.timeline_cap;           // debug-timeline cursor of thread 0, carried from the convert loop into the tail
 
-  if (warp == 18 || warp == 17) {
+  if (HALO && (warp == 18 || warp == 17)) {
+    // ----------------------------------------------- halo mode producers
+    if (warp == 18) {                            // A: one halo box [18 rows][pitch px][64 ch] per (tile, channel block)
+      int sa = 0;
+      uint32_t pha = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
+        const int img = fdiv(m_tile, p.fd_per_img), rem = m_tile - img * per_img;
+        const int py = fdiv(rem, p.fd_tiles_x), px = rem - py * p.tiles_x;
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          mbar_wait(emptyA_bar(sa), pha ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(fullA_bar(sa), (uint32_t)p.halo_tx);
+            tma_load_4d(smem_u32(sA + sa * p.halo_bytes), &tmA, fullA_bar(sa), cb * kBlockK, px * p.tw - 1, py * p.th - 1, img);
+          }
+          __syncwarp();
+          if (++sa == p.stagesA) { sa = 0; pha ^= 1u; }
+        }
+      }
+    } else {                                     // B: one [BN][64] weight slab per (channel block, tap)
+      int sb = 0;
+      uint32_t phb = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_tile = fdiv(tile, p.fd_m_tiles);
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          for (int t0 = 0; t0 < 9; t0 += kSub) {
+            mbar_wait(empty_bar(sb), phb ^ 1u);
+            if (elect_one()) mbar_expect_tx(full_bar(sb), (uint32_t)(kSub * C::kBBytes));
+#pragma unroll
+            for (int j = 0; j < kSub; ++j) {
+              if (elect_one())
+                tma_load_3d(smem_u32(sB + (sb * kSub + j) * C::kBBytes), &tmB, full_bar(sb), cb * kBlockK, t0 + j, n_tile * BN);
+            }
+            __syncwarp();
+            if (++sb == S) { sb = 0; phb ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (HALO && warp == 19) {
+    // ----------------------------------------------- halo mode MMA issuer: K order = (channel block, tap)
+    constexpr uint32_t idesc = make_idesc(BN);
+    int sa = 0, sb = 0, it = 0;
+    uint32_t pha = 0, phb = 0;
+    const uint32_t row_bytes = (uint32_t)p.halo_pitch * 128u;            // one halo row; also the stride between 8-pixel atoms
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      for (int cb = 0; cb < p.cblocks; ++cb) {
+        mbar_wait(fullA_bar(sa), pha);
+        const uint32_t halo = smem_u32(sA + sa * p.halo_bytes);
+        for (int t0 = 0; t0 < 9; t0 += kSub) {
+          mbar_wait(full_bar(sb), phb);
+          tcgen05_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int j = 0; j < kSub; ++j) {
+              const int tap = t0 + j;
+              const int r = tap / 3, sx = tap - 3 * r;
+              const uint32_t a_addr = halo + (uint32_t)r * row_bytes + (uint32_t)sx * 128u;
+              const uint32_t boff = (p.debug_flags & 64) ? ((a_addr >> 7) & 7u) : 0u;
+              const uint64_t da = make_smem_desc_ex(a_addr, row_bytes, boff);
+              const uint64_t db = make_smem_desc(smem_u32(sB + (sb * kSub + j) * C::kBBytes));
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cb | tap | k) != 0);
+            }
+            umma_commit(empty_bar(sb));                       // the weight slabs are free when these MMAs retire
+            if (t0 + kSub >= 9) {
+              umma_commit(emptyA_bar(sa));                    // ... and so is the halo after its ninth tap
+              if (cb == p.cblocks - 1) umma_commit(tfull_bar(acc));
+            }
+          }
+          __syncwarp();
+          if (++sb == S) { sb = 0; phb ^= 1u; }
+        }
+        if (++sa == p.stagesA) { sa = 0; pha ^= 1u; }
+      }
+    }
+  } else if (warp == 18 || warp == 17) {
     // ----------------------------------------------- TMA producers: warp 18 loads A (activations), warp 17 loads B (weights)
     // Two issuing threads because a single thread needs ~350 cycles per cp.async.bulk.tensor: the pair keeps a
     // K block's issue time below its MMA time.  Both arrive (with their byte counts) on the same full barrier.
@@ -461,7 +577,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------- store warp
     // One 4-D TMA store per 64-column slab; the tensor map clips the patch to the image and to the
     // channel slice.  Issuing it here keeps its issue + drain latency off the epilogue warps' path.
-    const uint32_t stage_base = smem_u32(smem + S * kSub * (kABytes + C::kBBytes));
+    const uint32_t stage_base = smem_u32(sStage);
     int sbuf = 0, prev = -1;
     bar_free_arrive(0);                          // both tiles start out free
     if (sflip) bar_free_arrive(1);
@@ -971,16 +1087,15 @@ static int pick_bn(int cout, int m_tiles, int kblocks) {
 
 static const int kSmemLimit = 232448;   // 227 KiB opt-in maximum per CTA
 
-template <int BN, bool LIN>
+template <int BN, int AM>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, Params& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, false, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, true, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, false, AM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, true, AM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
   const int acc_bytes = (p.mode == SY_CONV_RAW && p.partials) ? 16 * p.Cout : 2048;
-  const int stage_bytes = Cfg<BN>::kSub * (kABytes + Cfg<BN>::kBBytes);
   // epilogue-bound layers (main loop of a tile shorter than its epilogue: 1x1 convs with few input channels, the
   // stem) get a second staging tile: the store + statistics of a slab then overlap the conversion of the next
   {
@@ -989,18 +1104,56 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     if (const char* e = getenv("SY_STAGE_TILES")) p.stage_tiles = (e[0] == '2') ? 2 : 1;   // tuning aid
   }
   const int fixed_bytes = Cfg<BN>::kFixedBytes + (p.stage_tiles - 1) * kSlabBytes;
-  int stages = (kSmemLimit - fixed_bytes - acc_bytes) / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  if ((p.debug_flags >> 8) & 15) stages = min(stages, (p.debug_flags >> 8) & 15);   // debug: cap the ring depth
-  SY_REQUIRE(stages >= 2, SY_EINVAL, "conv2d_tc: Cout=%d leaves no room for the operand ring", p.Cout);
-  p.stages = stages;
-  const int smem = fixed_bytes + acc_bytes + stages * stage_bytes;
+  int smem;
+  if (AM == 2) {
+    // halo ring (2-3 stages of 36 KiB) + weight-slab ring (the rest, one [BN][64] slab per stage)
+    const int taps = (BN == 256) ? 1 : 3;                        // filter taps per weight-ring stage (kernel: kSub)
+    p.stagesA = (BN == 64 && p.cblocks > 1) ? 3 : 2;
+    int stages = (kSmemLimit - fixed_bytes - acc_bytes - p.stagesA * p.halo_bytes) / (taps * Cfg<BN>::kBBytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    SY_REQUIRE(stages >= 2, SY_EINVAL, "conv2d_tc(halo): Cout=%d leaves no room for the weight ring", p.Cout);
+    p.stages = stages;
+    smem = fixed_bytes + acc_bytes + p.stagesA * p.halo_bytes + stages * taps * Cfg<BN>::kBBytes;
+  } else {
+    const int stage_bytes = Cfg<BN>::kSub * (kABytes + Cfg<BN>::kBBytes);
+    int stages = (kSmemLimit - fixed_bytes - acc_bytes) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if ((p.debug_flags >> 8) & 15) stages = min(stages, (p.debug_flags >> 8) & 15);   // debug: cap the ring depth
+    SY_REQUIRE(stages >= 2, SY_EINVAL, "conv2d_tc: Cout=%d leaves no room for the operand ring", p.Cout);
+    p.stages = stages;
+    smem = fixed_bytes + acc_bytes + stages * stage_bytes;
+  }
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   if (p.timeline != nullptr)
-    SY_CUDA(launch_pdl(conv_tc_kernel<BN, true, LIN>, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
+    SY_CUDA(launch_pdl(conv_tc_kernel<BN, true, AM>, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
   else
-    SY_CUDA(launch_pdl(conv_tc_kernel<BN, false, LIN>, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
+    SY_CUDA(launch_pdl(conv_tc_kernel<BN, false, AM>, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
   return launch_status("conv_tc_kernel");
+}
+
+template <int AM>
+static int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, Params& p, cudaStream_t stream) {
+  switch (bn) {
+    case 64: return launch<64, AM>(ta, tb, ty, p, stream);
+    case 128: return launch<128, AM>(ta, tb, ty, p, stream);
+    default: return launch<256, AM>(ta, tb, ty, p, stream);
+  }
+}
+
+// Halo mode (conv_tc_kernel, AM = 2) for a 3x3 stride-1 convolution?  It needs 16 x 8 patch tiles (more tiles than the
+// linear tiling on small feature maps) and pays off where the tap re-reads bound the main loop, i.e. at BN <= 128.
+// Measured per-K-block costs on B200 (cycles): linear 515 / 560, halo 430 / 370 at BN = 128 / 64; equal at BN = 256.
+// SY_CONV_A=halo forces it (every eligible conv), SY_CONV_A=off disables it.
+static bool use_halo(int n, int ho, int wo, int cout, int kblocks) {
+  const char* e = getenv("SY_CONV_A");
+  if (e != nullptr && e[0] == 'h') return true;
+  if (e != nullptr && e[0] == 'o') return false;
+  const int tiles_l = cdiv(n * ho * wo, kBlockM), tiles_h = n * cdiv(ho, 16) * cdiv(wo, 8);
+  const int bn = pick_bn(cout, tiles_l, kblocks);
+  if (bn > 128) return false;
+  const double lin_c = bn == 128 ? 515.0 : 560.0, halo_c = bn == 128 ? 430.0 : 370.0;
+  const int nt = cdiv(cout, bn);
+  return cdiv(tiles_h * nt, num_sms()) * halo_c < cdiv(tiles_l * nt, num_sms()) * lin_c;
 }
 
 }  // namespace tc
@@ -1032,17 +1185,30 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
   if (const char* e = getenv("SY_CONV_DEBUG")) p.debug_flags |= atoi(e);    // tuning aid (see Params::debug_flags)
   p.N = x.n; p.Ho = ho; p.Wo = wo; p.Cout = y.c; p.Cin = x.c;
   p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_h = ph; p.pad_w = pw;
-  const bool lin = tc::linear_tiles();
+  const bool halo = d->kh == 3 && d->kw == 3 && d->stride == 1 && tc::linear_tiles() &&
+                    tc::use_halo(x.n, ho, wo, y.c, 9 * cdiv(x.c, tc::kBlockK));
+  const bool lin = !halo && tc::linear_tiles();
   SY_REQUIRE((long long)x.n * ho * wo < (1ll << 31) - 256, SY_EINVAL, "conv2d_tc: too many output pixels");
   p.P_total = x.n * ho * wo;
   tc::pick_patch(ho, wo, &p.th, &p.tw);
+  if (halo) {
+    p.th = 16; p.tw = 8;                                          // one 8-pixel swizzle atom per patch row
+    // halo rows are stored densely (TW + 2 pixels = 1280 bytes apart): the MMA's swizzle follows the absolute shared
+    // address bits, exactly like the TMA that wrote the tile, so neither the atoms' stride nor their start need 1 KiB
+    // alignment (verified on B200; debug flag 128 selects a 2 KiB row pitch instead, flag 64 sets the descriptor's
+    // base-offset field -- which breaks the result, i.e. the field must stay 0).
+    p.halo_pitch = (p.debug_flags & 128) ? 16 : p.tw + 2;
+    p.halo_tx = (p.th + 2) * p.halo_pitch * 128;
+    p.halo_bytes = (p.halo_tx + 1023) / 1024 * 1024;
+  }
   p.tiles_y = cdiv(ho, p.th); p.tiles_x = cdiv(wo, p.tw);
   p.m_tiles = lin ? cdiv(p.P_total, tc::kBlockM) : x.n * p.tiles_y * p.tiles_x;
   p.fd_hw = tc::make_fastdiv((uint32_t)(ho * wo));
   p.fd_wo = tc::make_fastdiv((uint32_t)wo);
   p.cblocks = cdiv(x.c, tc::kBlockK);
   p.kblocks = d->kh * d->kw * p.cblocks;
-  const int bn = tc::pick_bn(y.c, p.m_tiles, p.kblocks);
+  // tile width: chosen on the linear tiling (the halo decision above assumed that width)
+  const int bn = tc::pick_bn(y.c, halo ? cdiv(p.P_total, tc::kBlockM) : p.m_tiles, p.kblocks);
   p.n_tiles = cdiv(y.c, bn);
   p.total_tiles = p.m_tiles * p.n_tiles;
   p.fd_m_tiles = tc::make_fastdiv((uint32_t)p.m_tiles);
@@ -1103,7 +1269,17 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
 
   // A: input view as (C, W, H, N), box (64, TW*s, TH*s, 1) traversed with element strides (1, s, s, 1)
   CUtensorMap ta, tb, ty;
-  if (lin) {
+  if (halo) {
+    // A, halo mode: box (64 ch, pitch px, TH + 2 rows, 1 image) at (x0 - 1, y0 - 1): out of bounds = zero padding
+    cuuint64_t dims[4] = {(cuuint64_t)x.c, (cuuint64_t)x.w, (cuuint64_t)x.h, (cuuint64_t)x.n};
+    cuuint64_t strides[3] = {(cuuint64_t)x.pitch * 2, (cuuint64_t)x.pitch * 2 * x.w, (cuuint64_t)x.pitch * 2 * x.w * x.h};
+    cuuint32_t box[4] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)p.halo_pitch, (cuuint32_t)(p.th + 2), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x.ptr, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SY_REQUIRE(r == CUDA_SUCCESS, SY_ELAUNCH, "cuTensorMapEncodeTiled(A halo) failed: %d", (int)r);
+  } else if (lin) {
     // A, im2col mode: tensor (C, W, H, N); the bounding box of base pixels is [-pad, dim + pad - (k - 1)) per spatial
     // dim, walked with the conv stride; one load = 128 consecutive base pixels x 64 channels, shifted by the tap offset
     tc::EncodeIm2colFn enc2 = tc::get_encode_im2col();
@@ -1165,16 +1341,7 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SY_REQUIRE(r == CUDA_SUCCESS, SY_ELAUNCH, "cuTensorMapEncodeTiled(Y) failed: %d", (int)r);
   }
-  if (lin) {
-    switch (bn) {
-      case 64: return tc::launch<64, true>(ta, tb, ty, p, stream);
-      case 128: return tc::launch<128, true>(ta, tb, ty, p, stream);
-      default: return tc::launch<256, true>(ta, tb, ty, p, stream);
-    }
-  }
-  switch (bn) {
-    case 64: return tc::launch<64, false>(ta, tb, ty, p, stream);
-    case 128: return tc::launch<128, false>(ta, tb, ty, p, stream);
-    default: return tc::launch<256, false>(ta, tb, ty, p, stream);
-  }
+  if (halo) return tc::launch_bn<2>(bn, ta, tb, ty, p, stream);
+  if (lin) return tc::launch_bn<1>(bn, ta, tb, ty, p, stream);
+  return tc::launch_bn<0>(bn, ta, tb, ty, p, stream);
 }

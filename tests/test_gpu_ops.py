@@ -48,15 +48,18 @@ def check_close(got, ref, what, ulp=2.0 ** -7):
     return rel
 
 
-# SY_TEST_TILES=linear|patch restricts the tensor-core variants under test (bring-up aid); default: both
-_T = os.environ.get("SY_TEST_TILES", "both")
-TC_IMPLS = [i for i in ("tc", "tc_patch") if _T == "both" or (_T == "linear") == (i == "tc")]
+# SY_TEST_TILES=linear|patch|halo restricts the tensor-core variants under test (bring-up aid); default: all
+_T = os.environ.get("SY_TEST_TILES", "all")
+_ALL = {"tc": "linear", "tc_patch": "patch", "tc_halo": "halo"}
+TC_IMPLS = [i for i, t in _ALL.items() if _T in ("all", "both", t)]
 
 
 def tc_impl(impl, monkeypatch):
-    """'tc' = linear M tiles (im2col-mode TMA, the default), 'tc_patch' = rectangular patch tiles; both are product paths."""
+    """'tc' = linear M tiles (im2col-mode TMA, the default), 'tc_patch' = rectangular patch tiles, 'tc_halo' = one halo
+    load per tile and channel block for the 3x3 stride-1 convs (linear tiles elsewhere); all are product paths."""
     if impl.startswith("tc"):
         monkeypatch.setenv("SY_CONV_TILES", "patch" if impl == "tc_patch" else "linear")
+        monkeypatch.setenv("SY_CONV_A", "halo" if impl == "tc_halo" else "off")
         return "tc"
     return impl
 

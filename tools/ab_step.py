@@ -25,6 +25,8 @@ fut, cur = fut.to(dev), cur.to(dev)
 SETTINGS = [
     # (label, environment switches, fuse-apply threshold MB)
     ("base", {}, 0),
+    ("halo off", {"SY_CONV_A": "off"}, 0),
+    ("halo forced", {"SY_CONV_A": "halo"}, 0),
     ("apply carveout default", {"SY_APPLY_CARVEOUT": "-1"}, 0),
     ("apply carveout 0", {"SY_APPLY_CARVEOUT": "0"}, 0),
     ("no tmem prefetch", {"SY_CONV_DEBUG": "32"}, 0),
@@ -38,7 +40,7 @@ SETTINGS = [
 ]
 if len(sys.argv) > 3:
     SETTINGS = [s for s in SETTINGS if any(k in s[0] for k in sys.argv[3].split(","))]
-SWITCHES = ("SY_CONV_TILES", "SY_PDL", "SY_APPLY", "SY_APPLY_CAP", "SY_STAGE_TILES", "SY_APPLY_CARVEOUT", "SY_CONV_DEBUG")
+SWITCHES = ("SY_CONV_TILES", "SY_PDL", "SY_APPLY", "SY_APPLY_CAP", "SY_STAGE_TILES", "SY_APPLY_CARVEOUT", "SY_CONV_DEBUG", "SY_CONV_A")
 
 
 def measure(label, env, fuse_mb, steps=20, warmup=4):
