@@ -48,15 +48,31 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML polled every 2 ms
+    from a thread (the timed region can be shorter than nvidia-smi's start-up), `nvidia-smi -lms` as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml = index, [], None, None
+        self.sm, self.mx, self.reasons, self._stop = [], None, set(), False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -66,11 +82,33 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                mask = int(get_reasons(self.h))
+                for name, bit in self.BITS:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop = True
+            self.t.join(timeout=1.0)
+            sm = sorted(self.sm)
+            load = [v for v in sm if v >= 0.5 * sm[-1]] if sm else []
+            return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml, 2 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -92,7 +130,7 @@ class ClockSampler:
         # "under load": ignore idle samples well below the maximum seen
         load = [v for v in sm if v >= 0.5 * sm[-1]] if sm else []
         med = load[len(load) // 2] if load else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def build_model(tag, device):
@@ -157,9 +195,9 @@ def time_dominant_kernel(tag, batch, peaks):
             "peak_source": peaks["source"] + " cuBLAS bf16 burst", "ms_per_launch": round(ms, 4),
             "algorithmic_flop_per_launch": flops,
             # dram__bytes_read.sum + dram__bytes_write.sum of this launch shape (8x75x120, 256->256) from the ncu --set full
-            # capture summarised in profiles/r01_ncu_full_summary.txt (38.12 MB read + 1.80 MB written; the 36.9 MB
+            # capture summarised in profiles/r01_ncu_full_summary.txt (38.12 MB read + 2.96 MB written; the 36.9 MB
             # output is still L2-resident when the kernel ends).  Only meaningful for that shape.
-            "traffic": (39.91e6 if (n, c) == (8, 256) else None), "traffic_unit": "bytes/launch (ncu, r01)",
+            "traffic": (41.07e6 if (n, c) == (8, 256) else None), "traffic_unit": "bytes/launch (ncu, r01)",
             "algorithmic_bytes_per_launch": 2 * n * h * w * c * 2 + 9 * c * c * 2,
             "how": "graph of 16 launches over 8 rotating buffer sets (operands > L2), CUDA events, best of 5"}
 
