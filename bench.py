@@ -273,7 +273,9 @@ def main():
         raise SystemExit("bench.py --impl ours needs a B200 (no CPU path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    os.environ["NCCL_DEBUG"] = os.environ.get("SY_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
+    # keep stdout to the one JSON line: whatever NCCL_DEBUG level the launcher asked for goes to a file (even WARN prints
+    # the "NCCL version" banner on stdout otherwise)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/sy_nccl.%h.%p.log")
     sydist.init("nccl")
     from streamyolo_b200 import ops, synth
     from streamyolo_b200.build import build
