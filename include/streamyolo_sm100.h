@@ -195,6 +195,30 @@ typedef struct {
 size_t sy_tal_loss_workspace_bytes(int32_t b, int32_t a_total, int32_t max_labels, int32_t num_classes);
 int sy_tal_loss(const SyTalLossDesc* d, sy_stream_t stream);
 
+/* Backward of the loss: what autograd computes for loss.backward() (exps/train_utils/double_trainer.py:114)
+ * through TALHead.get_losses (exps/model/tal_head.py:426-461): the SimOTA assignment, the class targets and the
+ * normalised TAL weights are constants (tal_head.py:479 @torch.no_grad, weights detached), so the gradient is
+ * per anchor.  Must run after sy_tal_loss on the SAME workspace (assignment and loss sums are read from it).
+ * grad_outputs: d/d outputs[b, a, :] (decoded boxes, obj / cls logits); grad_origin: d/d origin_preds;
+ * grad_raw: d/d the raw head-conv outputs, i.e. the decode of tal_head.py:237-241 folded in and the L1 path added
+ * (what the prediction convs' backward consumes).  Any of the three may be NULL. */
+typedef struct SyTalLossBwdDesc {
+  const float* outputs;    /* [b, a_total, 5 + num_classes] as given to sy_tal_loss */
+  const float* origin;     /* [b, a_total, 4] or NULL when !use_l1 */
+  const float* labels_fut; /* [b, max_labels, 5] */
+  int32_t b, a_total, max_labels, num_classes, n_levels;
+  int32_t level_h[4], level_w[4], level_stride[4];
+  float gamma;
+  int32_t use_l1;
+  void* workspace;         /* the workspace sy_tal_loss ran on */
+  size_t workspace_bytes;
+  float grad_scale;        /* d objective / d total_loss (1, or the AMP loss scale) */
+  float* grad_outputs;     /* [b, a_total, 5 + num_classes] or NULL */
+  float* grad_origin;      /* [b, a_total, 4] or NULL */
+  float* grad_raw;         /* [b, a_total, 5 + num_classes] or NULL */
+} SyTalLossBwdDesc;
+int sy_tal_loss_backward(const SyTalLossBwdDesc* d, sy_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

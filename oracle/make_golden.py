@@ -143,6 +143,32 @@ def run_case(name, c):
           "n_fg", len(out["fg_anchor"]))
 
 
+def run_grad_case(name, c):
+    """Backward of the reference (tools/train.py path: loss.backward(), exps/train_utils/double_trainer.py:114) on CPU
+    fp32: every parameter's gradient statistics, the head prediction-conv bias gradients in full (= per-channel sums
+    of d loss / d raw head output: the pin for the loss-backward kernel), and two small weight gradients in full."""
+    torch.manual_seed(0)
+    model, shapes = build_reference(c["depth"], c["width"], c["gamma"], c["thr"], c["val"])
+    x = synth.synth_frames(c["B"], c["H"], c["W"])
+    fut, cur = synth.synth_labels(c["B"], c["H"], c["W"], empty_image=c["empty"])
+    model.train()
+    loss = model(x, (fut, cur))
+    loss["total_loss"].backward()
+    out = {"total_loss": np.array(float(loss["total_loss"]), np.float64)}
+    keys = [k for k, p_ in model.named_parameters() if p_.grad is not None]
+    grads = dict((k, p_.grad) for k, p_ in model.named_parameters() if p_.grad is not None)
+    out["grad_keys"] = np.array(keys)
+    out["grad_stats"] = np.stack([stat3(grads[k]) for k in keys])
+    out["grad_l2"] = np.array([float(grads[k].norm()) for k in keys], np.float64)
+    for k in keys:
+        if k.startswith(("head.cls_preds", "head.reg_preds", "head.obj_preds")) or k in (
+                "backbone.backbone.stem.conv.bn.weight", "backbone.jian0.bn.bias", "head.stems.2.bn.weight"):
+            out["g:" + k] = grads[k].numpy().astype(np.float32)
+    path = os.path.join(ROOT, "tests", "golden", "grad_" + name + ".npz")
+    np.savez_compressed(path, **out)
+    print("grad", name, "->", path, os.path.getsize(path) // 1024, "KiB  loss", out["total_loss"], len(keys), "params")
+
+
 def shapes_fixture():
     """state_dict key/shape inventory for s/m/l straight from the reference constructors."""
     inv = {}
@@ -163,3 +189,6 @@ if __name__ == "__main__":
     for n, c in CASES.items():
         if not only or n in only:
             run_case(n, c)
+    for n in ("tiny_120x160", "tiny_empty_96x160"):
+        if not only or "grad" in only or "grad_" + n in only:
+            run_grad_case(n, CASES[n])

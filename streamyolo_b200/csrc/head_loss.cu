@@ -115,6 +115,8 @@ struct LossWs {
   float* iou; float* cost;      // [B][L][A]
   int* cnt; int* match;         // [B][A]
   double* part;                 // [nblk][8]
+  int* mres; float* piou;       // [B][A] resolved match (-1: background) and matched IoU: kept for the backward pass
+  double* tot;                  // [8] the seven sums of k_final: kept for the backward pass
   size_t bytes;
 };
 
@@ -136,12 +138,15 @@ static LossWs carve(void* base, int B, int A, int L, int NC) {
   const size_t o_match = take(sizeof(int) * (size_t)B * A);
   const int nblk = cdiv(A, kLossThreads) * B;
   const size_t o_part = take(sizeof(double) * (size_t)nblk * 8);
+  const size_t o_mres = take(sizeof(int) * (size_t)B * A), o_piou = take(sizeof(float) * (size_t)B * A);
+  const size_t o_tot = take(sizeof(double) * 8);
   w.bytes = off;
   if (p) {
     w.ngt = (int*)(p + o_ngt); w.nsup = (int*)(p + o_nsup); w.tal = (float*)(p + o_tal);
     w.cand = (int*)(p + o_cand); w.clsterm = (float*)(p + o_cls); w.iou = (float*)(p + o_iou);
     w.cost = (float*)(p + o_cost); w.cnt = (int*)(p + o_cnt); w.match = (int*)(p + o_match);
     w.part = (double*)(p + o_part);
+    w.mres = (int*)(p + o_mres); w.piou = (float*)(p + o_piou); w.tot = (double*)(p + o_tot);
   }
   return w;
 }
@@ -364,6 +369,7 @@ struct LossArgs {
   const int* ngt; const float* tal; const float* iou_m; const float* cost_m; const int* cnt; const int* match;
   Levels lv; int A, L, NC; float gamma; int use_l1;
   double* part; int* fg_out; int* matched_out; float* piou_out;
+  int* mres; float* piou_ws;
 };
 
 __global__ void k_resolve_loss(const LossArgs q) {
@@ -409,6 +415,8 @@ __global__ void k_resolve_loss(const LossArgs q) {
       }
       v[0] = li; v[1] = w * li; v[2] = l1; v[3] = w * l1; v[5] = lc; v[6] = 1.f;
     }
+    q.mres[ba] = mg;
+    q.piou_ws[ba] = piou;
     if (q.fg_out) q.fg_out[ba] = fg ? 1 : 0;
     if (q.matched_out) q.matched_out[ba] = mg;
     if (q.piou_out) q.piou_out[ba] = piou;
@@ -431,7 +439,7 @@ __global__ void k_resolve_loss(const LossArgs q) {
 }
 
 // ---- 6. final scalars (tal_head.py:441-470)
-__global__ void k_final(const double* part, int nblk, const int* ngt, int B, int use_l1, float* out) {
+__global__ void k_final(const double* part, int nblk, const int* ngt, int B, int use_l1, float* out, double* tot_out) {
   __shared__ double tot[7];
   if (threadIdx.x < 7) {
     double s = 0.0;
@@ -439,6 +447,7 @@ __global__ void k_final(const double* part, int nblk, const int* ngt, int B, int
     tot[threadIdx.x] = s;
   }
   __syncthreads();
+  if (threadIdx.x < 7) tot_out[threadIdx.x] = tot[threadIdx.x];
   if (threadIdx.x == 0) {
     int num_gts = 0;
     for (int b = 0; b < B; ++b) num_gts += ngt[b];
@@ -457,6 +466,104 @@ __global__ void k_final(const double* part, int nblk, const int* ngt, int B, int
     out[3] = (float)l_cls;
     out[4] = (float)l_l1;
     out[5] = (float)(num_fg / (double)(num_gts > 1 ? num_gts : 1));
+  }
+}
+
+// ---- 7. backward of the loss (autograd of tal_head.py:426-461 as run by double_trainer.py:114).
+// The assignment, the matched IoUs (class targets) and the TAL weights are constants of the backward pass
+// (tal_head.py:479 @no_grad, weights detached), so every anchor contributes independently:
+//   d 5*L_iou / d box   = 5 * (w_i * S / SW) / N * d(1 - IoU^2)/d box          (fg anchors)
+//   d L_obj  / d logit  = (sigmoid(x) - [fg]) / N                              (all anchors)
+//   d L_cls  / d logit  = (sigmoid(x) - onehot * IoU_matched) / N              (fg anchors)
+//   d L_l1   / d origin = (w_i * S1 / SW1) / N * sign(origin - target)         (fg anchors, use_l1)
+// with N = max(N_fg, 1) and the sums S, SW, S1, SW1 left in the workspace by sy_tal_loss.
+struct LossBwdArgs {
+  const float* outputs; const float* origin; const float* fut; const float* tal;
+  const int* mres; const float* piou; const double* tot;
+  Levels lv; int A, L, NC; float gamma; int use_l1; float gscale;
+  float* g_out; float* g_origin; float* g_raw;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// d max(a, b) / d a as torch.maximum differentiates it (ties split evenly)
+__device__ __forceinline__ float dmax_a(float a, float b) { return a > b ? 1.f : (a == b ? 0.5f : 0.f); }
+__device__ __forceinline__ float dmin_a(float a, float b) { return a < b ? 1.f : (a == b ? 0.5f : 0.f); }
+
+__global__ void k_loss_backward(const LossBwdArgs q) {
+  const int b = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= q.A) return;
+  const size_t ba = (size_t)b * q.A + a;
+  const int no = 5 + q.NC;
+  const float* o = q.outputs + ba * no;
+  const double nfg_raw = q.tot[6];
+  const float inv_n = (float)(1.0 / (nfg_raw > 1.0 ? nfg_raw : 1.0)) * q.gscale;
+  const int mg = q.mres[ba];
+  const bool fg = mg >= 0;
+  float gbox[4] = {0.f, 0.f, 0.f, 0.f}, gorg[4] = {0.f, 0.f, 0.f, 0.f};
+  const float gobj = (sigmoidf_(o[4]) - (fg ? 1.f : 0.f)) * inv_n;
+  float gs = 1.f, gx = 0.f, gy = 0.f;
+  anchor_geom(q.lv, a, &gx, &gy, &gs);
+  if (fg) {
+    const float* r = q.fut + ((size_t)b * q.L + mg) * 5;
+    const Box t{r[1], r[2], r[3], r[4]}, p{o[0], o[1], o[2], o[3]};
+    const float tt = q.tal[(size_t)b * q.L + mg];
+    const float w = 1.0f / (((q.gamma == 1.0f) ? tt : powf(tt, q.gamma)) + 1e-8f);
+    // IoU loss
+    {
+      const float wi = (float)((double)w * q.tot[0] / q.tot[1]);       // w * S / SW
+      const float pl = p.cx - p.w / 2.f, tl_ = t.cx - t.w / 2.f, pr = p.cx + p.w / 2.f, tr = t.cx + t.w / 2.f;
+      const float pt = p.cy - p.h / 2.f, tt_ = t.cy - t.h / 2.f, pb = p.cy + p.h / 2.f, tb = t.cy + t.h / 2.f;
+      const float tlx = fmaxf(pl, tl_), brx = fminf(pr, tr), tly = fmaxf(pt, tt_), bry = fminf(pb, tb);
+      const float en = (tlx < brx && tly < bry) ? 1.f : 0.f;
+      const float iw = brx - tlx, ih = bry - tly;
+      const float ai = iw * ih * en;
+      const float au = p.w * p.h + t.w * t.h - ai;
+      const float den = au + 1e-16f;
+      const float iou = ai / den;
+      const float dl_diou = -2.f * iou * 5.f * wi * inv_n;             // d(5 * wi * (1 - iou^2) / N) / d iou
+      const float diou_dai = 1.f / den + ai / (den * den);             // union depends on the intersection too
+      const float diou_dap = -ai / (den * den);                        // through the predicted box area
+      const float g_ai = dl_diou * diou_dai, g_ap = dl_diou * diou_dap;
+      const float g_tlx = -g_ai * ih * en, g_brx = g_ai * ih * en, g_tly = -g_ai * iw * en, g_bry = g_ai * iw * en;
+      const float a_tlx = g_tlx * dmax_a(pl, tl_), a_brx = g_brx * dmin_a(pr, tr);
+      const float a_tly = g_tly * dmax_a(pt, tt_), a_bry = g_bry * dmin_a(pb, tb);
+      gbox[0] = a_tlx + a_brx;
+      gbox[1] = a_tly + a_bry;
+      gbox[2] = 0.5f * (a_brx - a_tlx) + g_ap * p.h;
+      gbox[3] = 0.5f * (a_bry - a_tly) + g_ap * p.w;
+    }
+    if (q.use_l1) {
+      const float w1 = (float)((double)w * q.tot[2] / q.tot[3]) * inv_n;
+      const float* og = q.origin + ba * 4;
+      const float tg[4] = {t.cx / gs - gx, t.cy / gs - gy, logf(t.w / gs + 1e-8f), logf(t.h / gs + 1e-8f)};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float dlt = og[i] - tg[i];
+        gorg[i] = w1 * (dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f));
+      }
+    }
+  }
+  const int gcls = fg ? (int)q.fut[((size_t)b * q.L + mg) * 5] : -1;
+  const float piou = fg ? q.piou[ba] : 0.f;
+  if (q.g_out) {
+    float* g = q.g_out + ba * no;
+    g[0] = gbox[0]; g[1] = gbox[1]; g[2] = gbox[2]; g[3] = gbox[3]; g[4] = gobj;
+    for (int k = 0; k < q.NC; ++k) g[5 + k] = fg ? (sigmoidf_(o[5 + k]) - (k == gcls ? piou : 0.f)) * inv_n : 0.f;
+  }
+  if (q.g_origin) {
+    float* g = q.g_origin + ba * 4;
+    g[0] = gorg[0]; g[1] = gorg[1]; g[2] = gorg[2]; g[3] = gorg[3];
+  }
+  if (q.g_raw) {
+    // decode chain (tal_head.py:237-241): box_xy = (raw_xy + grid) * stride, box_wh = exp(raw_wh) * stride = o[2:4];
+    // origin_preds is the raw regression output itself (tal_head.py:185-194)
+    float* g = q.g_raw + ba * no;
+    g[0] = gbox[0] * gs + gorg[0];
+    g[1] = gbox[1] * gs + gorg[1];
+    g[2] = gbox[2] * o[2] + gorg[2];
+    g[3] = gbox[3] * o[3] + gorg[3];
+    g[4] = gobj;
+    for (int k = 0; k < q.NC; ++k) g[5 + k] = fg ? (sigmoidf_(o[5 + k]) - (k == gcls ? piou : 0.f)) * inv_n : 0.f;
   }
 }
 
@@ -524,7 +631,35 @@ extern "C" int sy_tal_loss(const SyTalLossDesc* d, sy_stream_t stream_) {
   q.iou_m = w.iou; q.cost_m = w.cost; q.cnt = w.cnt; q.match = w.match; q.lv = lv; q.A = A; q.L = L; q.NC = NC;
   q.gamma = d->gamma; q.use_l1 = d->use_l1; q.part = w.part;
   q.fg_out = d->fg_out; q.matched_out = d->matched_out; q.piou_out = d->pred_iou_out;
+  q.mres = w.mres; q.piou_ws = w.piou;
   k_resolve_loss<<<dim3(ab, B), kLossThreads, 0, stream>>>(q);
-  k_final<<<1, 32, 0, stream>>>(w.part, ab * B, w.ngt, B, d->use_l1, d->loss_out);
+  k_final<<<1, 32, 0, stream>>>(w.part, ab * B, w.ngt, B, d->use_l1, d->loss_out, w.tot);
   return launch_status("tal_loss kernels");
+}
+
+extern "C" int sy_tal_loss_backward(const SyTalLossBwdDesc* d, sy_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SY_REQUIRE(d != nullptr, SY_EINVAL, "null descriptor");
+  SY_REQUIRE(d->b > 0 && d->a_total > 0 && d->max_labels > 0 && d->num_classes > 0 && d->n_levels >= 1 && d->n_levels <= 4,
+             SY_EINVAL, "tal_loss_backward: bad sizes");
+  SY_REQUIRE(d->outputs && d->labels_fut && d->workspace, SY_EINVAL, "tal_loss_backward: null pointer");
+  SY_REQUIRE(!d->use_l1 || d->origin, SY_EINVAL, "tal_loss_backward: use_l1 needs origin preds");
+  SY_REQUIRE(d->grad_outputs || d->grad_origin || d->grad_raw, SY_EINVAL, "tal_loss_backward: no gradient requested");
+  Levels lv{};
+  lv.n = d->n_levels;
+  int asum = 0;
+  for (int l = 0; l < d->n_levels; ++l) {
+    lv.h[l] = d->level_h[l]; lv.w[l] = d->level_w[l]; lv.s[l] = d->level_stride[l];
+    asum += lv.h[l] * lv.w[l];
+  }
+  SY_REQUIRE(asum == d->a_total, SY_EINVAL, "tal_loss_backward: levels give %d anchors, a_total=%d", asum, d->a_total);
+  LossWs w = carve(d->workspace, d->b, d->a_total, d->max_labels, d->num_classes);
+  SY_REQUIRE(d->workspace_bytes >= w.bytes, SY_EWORKSPACE, "tal_loss_backward: workspace %zu < %zu", d->workspace_bytes, w.bytes);
+  LossBwdArgs q{};
+  q.outputs = d->outputs; q.origin = d->origin; q.fut = d->labels_fut; q.tal = w.tal;
+  q.mres = w.mres; q.piou = w.piou; q.tot = w.tot; q.lv = lv; q.A = d->a_total; q.L = d->max_labels; q.NC = d->num_classes;
+  q.gamma = d->gamma; q.use_l1 = d->use_l1; q.gscale = d->grad_scale;
+  q.g_out = d->grad_outputs; q.g_origin = d->grad_origin; q.g_raw = d->grad_raw;
+  k_loss_backward<<<dim3(cdiv(d->a_total, kLossThreads), d->b), kLossThreads, 0, stream>>>(q);
+  return launch_status("k_loss_backward");
 }

@@ -56,6 +56,15 @@ class SyTalLossDesc(C.Structure):
                 ("matched_out", C.c_void_p), ("pred_iou_out", C.c_void_p)]
 
 
+class SyTalLossBwdDesc(C.Structure):
+    _fields_ = [("outputs", C.c_void_p), ("origin", C.c_void_p), ("labels_fut", C.c_void_p),
+                ("b", C.c_int32), ("a_total", C.c_int32), ("max_labels", C.c_int32), ("num_classes", C.c_int32),
+                ("n_levels", C.c_int32), ("level_h", C.c_int32 * 4), ("level_w", C.c_int32 * 4),
+                ("level_stride", C.c_int32 * 4), ("gamma", C.c_float), ("use_l1", C.c_int32),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("grad_scale", C.c_float),
+                ("grad_outputs", C.c_void_p), ("grad_origin", C.c_void_p), ("grad_raw", C.c_void_p)]
+
+
 # every symbol include/streamyolo_sm100.h declares: (restype, argtypes)
 _SIG = {
     "sy_last_error_string": (C.c_char_p, []),
@@ -79,6 +88,7 @@ _SIG = {
     "sy_head_pred_decode": (C.c_int, [C.POINTER(SyHeadPredDesc), C.c_void_p]),
     "sy_tal_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "sy_tal_loss": (C.c_int, [C.POINTER(SyTalLossDesc), C.c_void_p]),
+    "sy_tal_loss_backward": (C.c_int, [C.POINTER(SyTalLossBwdDesc), C.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIG)
 
@@ -329,3 +339,24 @@ def tal_loss(outputs, origin, labels_fut, labels_cur, hw, strides, gamma, ignore
     d.matched_out = matched_out.data_ptr() if matched_out is not None else None
     d.pred_iou_out = pred_iou_out.data_ptr() if pred_iou_out is not None else None
     _check(lib().sy_tal_loss(C.byref(d), _stream()), kernels=6)
+
+
+def tal_loss_backward(outputs, origin, labels_fut, hw, strides, gamma, use_l1, workspace, grad_scale=1.0,
+                      grad_outputs=None, grad_origin=None, grad_raw=None):
+    """Gradient of total_loss w.r.t. the head outputs; run after tal_loss() on the same workspace."""
+    d = SyTalLossBwdDesc()
+    b, a, no = outputs.shape
+    d.outputs = outputs.data_ptr()
+    d.origin = origin.data_ptr() if origin is not None else None
+    d.labels_fut = labels_fut.data_ptr()
+    d.b, d.a_total, d.max_labels, d.num_classes = b, a, labels_fut.shape[1], no - 5
+    d.n_levels = len(hw)
+    for i, ((h, w), s) in enumerate(zip(hw, strides)):
+        d.level_h[i], d.level_w[i], d.level_stride[i] = h, w, s
+    d.gamma, d.use_l1 = gamma, int(use_l1)
+    d.workspace, d.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    d.grad_scale = grad_scale
+    d.grad_outputs = grad_outputs.data_ptr() if grad_outputs is not None else None
+    d.grad_origin = grad_origin.data_ptr() if grad_origin is not None else None
+    d.grad_raw = grad_raw.data_ptr() if grad_raw is not None else None
+    _check(lib().sy_tal_loss_backward(C.byref(d), _stream()), kernels=1)

@@ -254,3 +254,58 @@ def test_s_model_full_resolution_golden():
     fg = asg["fg_out"].bool()
     assert int(fg.sum()) >= 1 and (asg["matched_out"][fg] >= 0).all() and (asg["matched_out"][~fg] == -1).all()
     assert (asg["pred_iou_out"][fg] >= 0).all() and (asg["pred_iou_out"][fg] <= 1).all()
+
+
+def test_loss_backward_vs_oracle_autograd():
+    """sy_tal_loss_backward on the oracle's own fp32 head outputs against torch.autograd through the oracle's loss
+    (which tests/test_oracle_golden.py pins to the reference's loss.backward()): d loss / d outputs, d loss / d origin
+    and the folded d loss / d raw head outputs, element-wise; then the per-level channel sums of the raw gradient against
+    the reference's own head prediction-conv bias gradients (tests/golden/grad_*.npz).  Tolerance 2e-4 relative to the
+    largest gradient entry (fp32 kernels, different summation order of the normalisers)."""
+    c = CASES["tiny_120x160"]
+    x = synth.synth_frames(c["B"], c["H"], c["W"])
+    tg = synth.synth_labels(c["B"], c["H"], c["W"], empty_image=c["empty"])
+    o = build_oracle(c["depth"], c["width"], c["gamma"], c["thr"], c["val"], q=None)
+    with torch.no_grad():
+        feats = o.backbone_off(x)
+        levels = o.head_levels(feats)
+        outputs, origin, grid = o.flatten_decode(levels, sigmoid=False)
+    out_l = outputs.clone().requires_grad_(True)
+    org_l = origin.clone().requires_grad_(True)
+    ref = o.losses(out_l, org_l, grid, tg)
+    ref["total_loss"].backward()
+    b, a, no = outputs.shape
+    dev = "cuda"
+    ws = torch.empty(ops.tal_loss_workspace_bytes(b, a, 120, 8), dtype=torch.uint8, device=dev)
+    loss = torch.empty(6, device=dev)
+    od, gd = outputs.cuda().contiguous(), origin.cuda().contiguous()
+    fut = tg[0].cuda()
+    ops.tal_loss(od, gd, fut, tg[1].cuda(), o.hw, (8, 16, 32), c["gamma"], c["thr"], c["val"], True, ws, loss)
+    g_out, g_org, g_raw = torch.full_like(od, float("nan")), torch.full_like(gd, float("nan")), torch.full_like(od, float("nan"))
+    ops.tal_loss_backward(od, gd, fut, o.hw, (8, 16, 32), c["gamma"], True, ws, 1.0, g_out, g_org, g_raw)
+    torch.cuda.synchronize()
+    assert abs(float(loss[0]) - float(ref["total_loss"])) < 1e-4 * abs(float(ref["total_loss"]))
+
+    def close(got, want, what):
+        got, want = got.cpu(), want
+        scale = float(want.abs().max())
+        err = float((got - want).abs().max())
+        assert torch.isfinite(got).all() and err <= 2e-4 * scale + 1e-9, f"{what}: max err {err:.3e} vs scale {scale:.3e}"
+
+    close(g_out, out_l.grad, "d loss / d outputs")
+    close(g_org, org_l.grad, "d loss / d origin")
+    gx, gy, gs = grid
+    want_raw = out_l.grad.clone()
+    want_raw[..., 0:2] = out_l.grad[..., 0:2] * gs[None, :, None] + org_l.grad[..., 0:2]
+    want_raw[..., 2:4] = out_l.grad[..., 2:4] * outputs[..., 2:4] + org_l.grad[..., 2:4]
+    close(g_raw, want_raw, "d loss / d raw head outputs")
+    # the reference's own bias gradients = channel sums of the raw gradient per level ([reg4, obj1, cls8] order)
+    gold = np.load(os.path.join(GOLD, "grad_tiny_120x160.npz"))
+    off = 0
+    for k, (h, w) in enumerate(o.hw):
+        sums = g_raw[:, off:off + h * w].sum((0, 1)).cpu().double()
+        off += h * w
+        for name, sl in (("reg", slice(0, 4)), ("obj", slice(4, 5)), ("cls", slice(5, 13))):
+            want = torch.from_numpy(gold[f"g:head.{name}_preds.{k}.bias"]).double()
+            assert torch.allclose(sums[sl], want, rtol=2e-3, atol=2e-4 * float(want.abs().max()) + 1e-7), \
+                f"head.{name}_preds.{k}.bias: {sums[sl].tolist()} vs {want.tolist()}"

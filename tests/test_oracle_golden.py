@@ -108,3 +108,35 @@ def test_on_pipe_star_equals_buffer_on_same_frame():
     a, buf = o.forward(x, mode="on_pipe")
     b, _ = o.forward(x, buffer=buf, mode="on_pipe")
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["tiny_120x160", "tiny_empty_96x160"])
+def test_oracle_backward_matches_reference(name):
+    """Autograd through the oracle (fp32) against loss.backward() of the unmodified reference: every parameter's
+    gradient norm, and the head prediction-conv bias gradients element-wise (they are the per-channel sums of
+    d loss / d raw head output, the quantity the loss-backward kernel produces).  This pins the oracle as the gradient
+    reference for the backward path."""
+    c = CASES[name]
+    g = np.load(os.path.join(GOLD, "grad_" + name + ".npz"))
+    o = _oracle(c)
+    for k, t in o.P.items():
+        if t.dtype.is_floating_point and not k.endswith(("running_mean", "running_var")):
+            t.requires_grad_(True)
+    x = synth.synth_frames(c["B"], c["H"], c["W"])
+    tg = synth.synth_labels(c["B"], c["H"], c["W"], empty_image=c["empty"])
+    loss = o.forward(x, tg)["total_loss"]
+    assert abs(float(loss) - float(g["total_loss"])) <= 2e-4 * abs(float(g["total_loss"]))
+    loss.backward()
+    keys = g["grad_keys"].tolist()
+    assert set(keys) == {k for k, t in o.P.items() if t.grad is not None}
+    l2 = dict(zip(keys, g["grad_l2"].tolist()))
+    worst = 0.0
+    for k in keys:
+        got = float(o.P[k].grad.norm())
+        worst = max(worst, abs(got - l2[k]) / (l2[k] + 1e-6))
+    assert worst < 5e-3, f"worst relative gradient-norm error {worst:.2e}"
+    for f in g.files:
+        if f.startswith("g:"):
+            ref = torch.from_numpy(g[f])
+            got = o.P[f[2:]].grad
+            assert torch.allclose(got, ref, rtol=2e-3, atol=2e-5 * float(ref.abs().max()) + 1e-7), f
