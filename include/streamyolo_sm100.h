@@ -195,6 +195,24 @@ typedef struct {
 size_t sy_tal_loss_workspace_bytes(int32_t b, int32_t a_total, int32_t max_labels, int32_t num_classes);
 int sy_tal_loss(const SyTalLossDesc* d, sy_stream_t stream);
 
+/* Weight gradient of a convolution (the cuDNN backward-filter call behind loss.backward(),
+ * exps/train_utils/double_trainer.py:114, for every [yolox] BaseConv: exps/model/darknet.py:115-165,
+ * dfp_pafpn.py:33-105, tal_head.py:55-104):  dw[co][ci][r][s] (+)= sum_p dy[p][co] * x[p @ (r, s)][ci].
+ * x = the layer's input [n, h, w, cin] bf16, dy = gradient w.r.t. the conv output [n, ho, wo, cout] bf16 (same kernel
+ * size / stride / padding (k-1)/2 as the forward), dw = fp32 in PyTorch's OIHW parameter layout.  Split-K over the
+ * pixels on the tensor cores, then a fixed-order reduction (deterministic).  The workspace holds the fp32 partials. */
+typedef struct SyConvWgradDesc {
+  SyTensor x;
+  SyTensor dy;
+  int32_t kh, kw, stride;
+  float* dw;               /* [cout, cin, kh, kw] fp32 */
+  int32_t accumulate;      /* 0: dw = result, 1: dw += result */
+  void* workspace;         /* sy_conv2d_wgrad_workspace_bytes(desc) bytes, 16-byte aligned */
+  size_t workspace_bytes;
+} SyConvWgradDesc;
+size_t sy_conv2d_wgrad_workspace_bytes(const SyConvWgradDesc* d);
+int sy_conv2d_wgrad_tc(const SyConvWgradDesc* d, sy_stream_t stream);
+
 /* Backward of the loss: what autograd computes for loss.backward() (exps/train_utils/double_trainer.py:114)
  * through TALHead.get_losses (exps/model/tal_head.py:426-461): the SimOTA assignment, the class targets and the
  * normalised TAL weights are constants (tal_head.py:479 @torch.no_grad, weights detached), so the gradient is

@@ -20,6 +20,7 @@ COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-st
 SOURCES = {
     "api.cu": [],
     "conv_tc.cu": [],
+    "conv_wgrad.cu": [],
     "conv_simt.cu": [],
     "bn_glue.cu": [],
     "head_loss.cu": ["-fmad=false"],

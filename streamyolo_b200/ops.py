@@ -56,6 +56,12 @@ class SyTalLossDesc(C.Structure):
                 ("matched_out", C.c_void_p), ("pred_iou_out", C.c_void_p)]
 
 
+class SyConvWgradDesc(C.Structure):
+    _fields_ = [("x", SyTensor), ("dy", SyTensor), ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32),
+                ("dw", C.c_void_p), ("accumulate", C.c_int32), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_size_t)]
+
+
 class SyTalLossBwdDesc(C.Structure):
     _fields_ = [("outputs", C.c_void_p), ("origin", C.c_void_p), ("labels_fut", C.c_void_p),
                 ("b", C.c_int32), ("a_total", C.c_int32), ("max_labels", C.c_int32), ("num_classes", C.c_int32),
@@ -89,6 +95,8 @@ _SIG = {
     "sy_tal_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "sy_tal_loss": (C.c_int, [C.POINTER(SyTalLossDesc), C.c_void_p]),
     "sy_tal_loss_backward": (C.c_int, [C.POINTER(SyTalLossBwdDesc), C.c_void_p]),
+    "sy_conv2d_wgrad_workspace_bytes": (C.c_size_t, [C.POINTER(SyConvWgradDesc)]),
+    "sy_conv2d_wgrad_tc": (C.c_int, [C.POINTER(SyConvWgradDesc), C.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIG)
 
@@ -360,3 +368,27 @@ def tal_loss_backward(outputs, origin, labels_fut, hw, strides, gamma, use_l1, w
     d.grad_origin = grad_origin.data_ptr() if grad_origin is not None else None
     d.grad_raw = grad_raw.data_ptr() if grad_raw is not None else None
     _check(lib().sy_tal_loss_backward(C.byref(d), _stream()), kernels=1)
+
+
+def pack_conv_weight_dgrad(w):
+    """Weights for the data gradient of a stride-1 conv: dx = conv(dy, w') with w'[ci][kh-1-r][kw-1-s][co] = w[co][ci][r][s]
+    (same padding), i.e. the forward tensor-core kernel on the flipped, channel-transposed filter."""
+    return pack_conv_weight(w.detach().flip(2, 3).transpose(0, 1).contiguous())
+
+
+def conv2d_wgrad(x: View, dy: View, k, s, dw, accumulate=False, workspace=None):
+    """dw[cout, cin, kh, kw] (fp32) (+)= weight gradient of the conv that maps x to (the shape of) dy."""
+    kh, kw = (k, k) if isinstance(k, int) else k
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and tuple(dw.shape) == (dy.c, x.c, kh, kw)
+    d = SyConvWgradDesc()
+    d.x, d.dy = x.st(), dy.st()
+    d.kh, d.kw, d.stride = kh, kw, s
+    d.dw, d.accumulate = dw.data_ptr(), int(accumulate)
+    need = lib().sy_conv2d_wgrad_workspace_bytes(C.byref(d))
+    if need == 0:
+        raise RuntimeError("conv2d_wgrad: " + (lib().sy_last_error_string() or b"").decode())
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dw.device)
+    d.workspace, d.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    _check(lib().sy_conv2d_wgrad_tc(C.byref(d), _stream()), kernels=2)
+    return workspace

@@ -310,3 +310,56 @@ def test_head_pred_decode():
         if train:
             assert torch.allclose(origin[:, off:], raw[..., :4], rtol=1e-4, atol=1e-5)
         assert (out[:, :off] == 0).all()
+
+
+# ---------------------------------------------------------------------------------------------- backward bricks
+WGRAD_CASES = [
+    # n, cin, cout, h, w, k, s
+    (2, 64, 64, 19, 30, 1, 1),
+    (2, 128, 128, 38, 60, 3, 1),
+    (2, 64, 128, 40, 60, 3, 2),        # stride 2
+    (2, 128, 256, 75, 120, 3, 2),      # stride 2, odd height -> 38
+    (1, 256, 512, 19, 30, 3, 1),       # several M tiles, BN = 256
+    (3, 8, 16, 15, 20, 3, 1),          # tiny widths: channel boxes mostly out of bounds
+    (2, 96, 96, 19, 30, 3, 1),         # StreamYOLO-m width
+    (2, 512, 1024, 19, 30, 1, 1),
+    (5, 32, 64, 9, 7, 3, 2),           # fewer pixels than one K block per image
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_wgrad(case):
+    """Tensor-core weight gradient (split-K over pixels + fixed-order reduction) against autograd of F.conv2d on the same
+    bf16-rounded operands in fp32.  Tolerance: 2e-4 of the largest gradient entry (fp32 accumulation, other order)."""
+    n, ci, co, h, w, k, s = case
+    x = rand_act(n, ci, h, w, 21)
+    ho, wo = ops.conv_out_hw(h, w, k, s)
+    dy = rand_act(n, co, ho, wo, 22)
+    wt = torch.zeros(co, ci, k, k, device=DEV, requires_grad=True)
+    F.conv2d(x, wt, None, s, (k - 1) // 2).backward(dy)
+    ref = wt.grad
+    dw = torch.full((co, ci, k, k), float("nan"), device=DEV)
+    ops.conv2d_wgrad(ops.from_nchw(x), ops.from_nchw(dy), k, s, dw)
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    err = (dw - ref).abs().max().item()
+    assert torch.isfinite(dw).all() and err <= 2e-4 * scale, f"wgrad{case}: max err {err:.4g} vs max |ref| {scale:.4g}"
+    # accumulate mode adds to what is there
+    ops.conv2d_wgrad(ops.from_nchw(x), ops.from_nchw(dy), k, s, dw, accumulate=True)
+    torch.cuda.synchronize()
+    assert (dw - 2 * ref).abs().max().item() <= 4e-4 * scale
+
+
+@pytest.mark.parametrize("case", [(2, 64, 128, 19, 30, 3), (2, 128, 64, 38, 60, 1), (1, 256, 256, 38, 60, 3)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv_dgrad_stride1(case):
+    """Data gradient of a stride-1 conv = the forward tensor-core kernel on the flipped, channel-transposed filter."""
+    n, ci, co, h, w, k = case
+    x = rand_act(n, ci, h, w, 31).requires_grad_(True)
+    wt = rand_w(co, ci, k, 32)
+    dy = rand_act(n, co, h, w, 33)
+    F.conv2d(x, wt, None, 1, (k - 1) // 2).backward(dy)
+    dx = View.empty(n, h, w, ci, DEV)
+    ops.conv2d(ops.from_nchw(dy), ops.pack_conv_weight_dgrad(wt), dx, k, 1, ops.SY_CONV_RAW)
+    torch.cuda.synchronize()
+    check_close(dx.nchw_float(), x.grad, f"dgrad{case}")
