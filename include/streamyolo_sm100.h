@@ -237,6 +237,25 @@ typedef struct SyTalLossBwdDesc {
 } SyTalLossBwdDesc;
 int sy_tal_loss_backward(const SyTalLossBwdDesc* d, sy_stream_t stream);
 
+/* Detection post-processing = [yolox 0.3.0] yolox.utils.postprocess as called by the evaluators and the streaming
+ * driver (exps/evaluators/onex_stream_evaluator.py:148, sAP/streamyolo/streamyolo_det.py:62-83): cxcywh -> xyxy,
+ * class_conf / class_pred = max over the class scores, keep obj * class_conf >= conf_thre, class-aware greedy NMS
+ * (torchvision.ops.batched_nms semantics), rows [x1, y1, x2, y2, obj, class_conf, class_pred] in decreasing score order.
+ * pred = the eval-mode head output [b, a_total, 5 + num_classes] (decoded boxes, sigmoid scores).  One CTA per image;
+ * a_total <= 16384.  det_out [b, max_det, 7] (rows past count_out[i] are not written), count_out [b]. */
+typedef struct SyNmsDesc {
+  const float* pred;
+  int32_t b, a_total, num_classes, max_det;
+  float conf_thre, nms_thre;
+  int32_t class_agnostic;
+  void* workspace;         /* sy_postprocess_nms_workspace_bytes(b, a_total) bytes, 16-byte aligned */
+  size_t workspace_bytes;
+  float* det_out;
+  int32_t* count_out;
+} SyNmsDesc;
+size_t sy_postprocess_nms_workspace_bytes(int32_t b, int32_t a_total);
+int sy_postprocess_nms(const SyNmsDesc* d, sy_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

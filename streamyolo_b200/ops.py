@@ -62,6 +62,13 @@ class SyConvWgradDesc(C.Structure):
                 ("workspace_bytes", C.c_size_t)]
 
 
+class SyNmsDesc(C.Structure):
+    _fields_ = [("pred", C.c_void_p), ("b", C.c_int32), ("a_total", C.c_int32), ("num_classes", C.c_int32),
+                ("max_det", C.c_int32), ("conf_thre", C.c_float), ("nms_thre", C.c_float), ("class_agnostic", C.c_int32),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("det_out", C.c_void_p),
+                ("count_out", C.c_void_p)]
+
+
 class SyTalLossBwdDesc(C.Structure):
     _fields_ = [("outputs", C.c_void_p), ("origin", C.c_void_p), ("labels_fut", C.c_void_p),
                 ("b", C.c_int32), ("a_total", C.c_int32), ("max_labels", C.c_int32), ("num_classes", C.c_int32),
@@ -95,6 +102,8 @@ _SIG = {
     "sy_tal_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "sy_tal_loss": (C.c_int, [C.POINTER(SyTalLossDesc), C.c_void_p]),
     "sy_tal_loss_backward": (C.c_int, [C.POINTER(SyTalLossBwdDesc), C.c_void_p]),
+    "sy_postprocess_nms_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "sy_postprocess_nms": (C.c_int, [C.POINTER(SyNmsDesc), C.c_void_p]),
     "sy_conv2d_wgrad_workspace_bytes": (C.c_size_t, [C.POINTER(SyConvWgradDesc)]),
     "sy_conv2d_wgrad_tc": (C.c_int, [C.POINTER(SyConvWgradDesc), C.c_void_p]),
 }
@@ -392,3 +401,20 @@ def conv2d_wgrad(x: View, dy: View, k, s, dw, accumulate=False, workspace=None):
     d.workspace, d.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     _check(lib().sy_conv2d_wgrad_tc(C.byref(d), _stream()), kernels=2)
     return workspace
+
+
+def postprocess_nms(pred, num_classes, conf_thre, nms_thre, class_agnostic=False, max_det=None):
+    """-> (det [B, max_det, 7] fp32, count [B] int32) on the device; rows [x1, y1, x2, y2, obj, class_conf, class_pred]."""
+    assert pred.dtype == torch.float32 and pred.is_contiguous() and pred.shape[2] == 5 + num_classes
+    b, a, _ = pred.shape
+    max_det = a if max_det is None else max_det
+    det = torch.empty((b, max_det, 7), dtype=torch.float32, device=pred.device)
+    count = torch.empty((b,), dtype=torch.int32, device=pred.device)
+    ws = torch.empty(load_library().sy_postprocess_nms_workspace_bytes(b, a), dtype=torch.uint8, device=pred.device)
+    d = SyNmsDesc()
+    d.pred, d.b, d.a_total, d.num_classes, d.max_det = pred.data_ptr(), b, a, num_classes, max_det
+    d.conf_thre, d.nms_thre, d.class_agnostic = conf_thre, nms_thre, int(class_agnostic)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+    d.det_out, d.count_out = det.data_ptr(), count.data_ptr()
+    _check(lib().sy_postprocess_nms(C.byref(d), _stream()), kernels=1)
+    return det, count
