@@ -213,6 +213,25 @@ typedef struct SyConvWgradDesc {
 size_t sy_conv2d_wgrad_workspace_bytes(const SyConvWgradDesc* d);
 int sy_conv2d_wgrad_tc(const SyConvWgradDesc* d, sy_stream_t stream);
 
+/* Backward of BatchNorm(train) + SiLU behind a [yolox] BaseConv (autograd of nn.BatchNorm2d + nn.SiLU under
+ * loss.backward(), exps/train_utils/double_trainer.py:114).  raw = the conv output the forward stored, dy = gradient w.r.t.
+ * the BaseConv output; scale / shift / mean / invstd = [2 groups][c] as published by the forward (scale = gamma * invstd,
+ * shift = beta - mean * scale; images >= split_n form statistics group 1).  Writes draw (bf16, gradient w.r.t. the conv
+ * output, input of the conv data / weight gradient kernels), dgamma / dbeta (fp32, (+)=).  partials: sy_bn_act_bwd_rows(n,
+ * h*w) rows of 2*c floats; coef: 4*c floats of scratch. */
+typedef struct SyBnActBwdDesc {
+  SyTensor raw, dy, draw;
+  const float* scale; const float* shift; const float* mean; const float* invstd;
+  int32_t split_n;
+  int32_t act;             /* 1: SiLU, 0: identity */
+  float* dgamma; float* dbeta;
+  int32_t accumulate;
+  float* partials; int32_t n_partials;
+  float* coef;
+} SyBnActBwdDesc;
+int sy_bn_act_bwd_rows(int32_t n, int32_t hw);
+int sy_bn_act_backward(const SyBnActBwdDesc* d, sy_stream_t stream);
+
 /* Backward of the loss: what autograd computes for loss.backward() (exps/train_utils/double_trainer.py:114)
  * through TALHead.get_losses (exps/model/tal_head.py:426-461): the SimOTA assignment, the class targets and the
  * normalised TAL weights are constants (tal_head.py:479 @torch.no_grad, weights detached), so the gradient is

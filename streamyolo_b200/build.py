@@ -23,6 +23,7 @@ SOURCES = {
     "conv_wgrad.cu": [],
     "conv_simt.cu": [],
     "bn_glue.cu": [],
+    "bn_bwd.cu": [],
     "head_loss.cu": ["-fmad=false"],
     "postprocess.cu": ["-fmad=false"],
 }

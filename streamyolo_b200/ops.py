@@ -69,6 +69,13 @@ class SyNmsDesc(C.Structure):
                 ("count_out", C.c_void_p)]
 
 
+class SyBnActBwdDesc(C.Structure):
+    _fields_ = [("raw", SyTensor), ("dy", SyTensor), ("draw", SyTensor), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("mean", C.c_void_p), ("invstd", C.c_void_p), ("split_n", C.c_int32), ("act", C.c_int32),
+                ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("accumulate", C.c_int32), ("partials", C.c_void_p),
+                ("n_partials", C.c_int32), ("coef", C.c_void_p)]
+
+
 class SyTalLossBwdDesc(C.Structure):
     _fields_ = [("outputs", C.c_void_p), ("origin", C.c_void_p), ("labels_fut", C.c_void_p),
                 ("b", C.c_int32), ("a_total", C.c_int32), ("max_labels", C.c_int32), ("num_classes", C.c_int32),
@@ -102,6 +109,8 @@ _SIG = {
     "sy_tal_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "sy_tal_loss": (C.c_int, [C.POINTER(SyTalLossDesc), C.c_void_p]),
     "sy_tal_loss_backward": (C.c_int, [C.POINTER(SyTalLossBwdDesc), C.c_void_p]),
+    "sy_bn_act_bwd_rows": (C.c_int, [C.c_int32, C.c_int32]),
+    "sy_bn_act_backward": (C.c_int, [C.POINTER(SyBnActBwdDesc), C.c_void_p]),
     "sy_postprocess_nms_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "sy_postprocess_nms": (C.c_int, [C.POINTER(SyNmsDesc), C.c_void_p]),
     "sy_conv2d_wgrad_workspace_bytes": (C.c_size_t, [C.POINTER(SyConvWgradDesc)]),
@@ -418,3 +427,18 @@ def postprocess_nms(pred, num_classes, conf_thre, nms_thre, class_agnostic=False
     d.det_out, d.count_out = det.data_ptr(), count.data_ptr()
     _check(lib().sy_postprocess_nms(C.byref(d), _stream()), kernels=1)
     return det, count
+
+
+def bn_act_backward(raw: View, dy: View, draw: View, scale, shift, mean, invstd, split_n, act, dgamma, dbeta,
+                    accumulate=False):
+    """BatchNorm(train) + SiLU backward of one BaseConv; scale/shift/mean/invstd: fp32 [2, C] (group-major)."""
+    rows = load_library().sy_bn_act_bwd_rows(raw.n, raw.h * raw.w)
+    partials = torch.empty((rows, 2 * raw.c), dtype=torch.float32, device=dgamma.device)
+    coef = torch.empty((4 * raw.c,), dtype=torch.float32, device=dgamma.device)
+    d = SyBnActBwdDesc()
+    d.raw, d.dy, d.draw = raw.st(), dy.st(), draw.st()
+    d.scale, d.shift, d.mean, d.invstd = scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr()
+    d.split_n, d.act = split_n, int(act)
+    d.dgamma, d.dbeta, d.accumulate = dgamma.data_ptr(), dbeta.data_ptr(), int(accumulate)
+    d.partials, d.n_partials, d.coef = partials.data_ptr(), rows, coef.data_ptr()
+    _check(lib().sy_bn_act_backward(C.byref(d), _stream()), kernels=3)

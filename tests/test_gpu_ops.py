@@ -363,3 +363,54 @@ def test_conv_dgrad_stride1(case):
     ops.conv2d(ops.from_nchw(dy), ops.pack_conv_weight_dgrad(wt), dx, k, 1, ops.SY_CONV_RAW)
     torch.cuda.synchronize()
     check_close(dx.nchw_float(), x.grad, f"dgrad{case}")
+
+
+@pytest.mark.parametrize("case", [(4, 64, 128, 19, 30, 3, 2), (2, 128, 64, 38, 60, 1, 0), (4, 32, 32, 16, 20, 3, 2)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_baseconv_backward_chain(case):
+    """Backward of one whole BaseConv (conv -> train-mode BatchNorm with two statistics groups -> SiLU) through the
+    product's kernels: sy_bn_act_backward -> draw (bf16), then the data gradient (forward tensor-core kernel on the
+    flipped filter) and the tensor-core weight gradient; against torch autograd in fp32 on the same bf16-rounded operands
+    (the conv output is rounded to bf16 with a straight-through estimator, as the product stores it).
+    Tolerances: rel l2 1e-2 for dx / dW (draw is stored in bf16), 5e-3 for dgamma / dbeta."""
+    n, ci, co, h, w, k, split = case
+    eps = 1e-3
+    x = rand_act(n, ci, h, w, 41)
+    wt = rand_w(co, ci, k, 42)
+    g = torch.Generator().manual_seed(43)
+    gamma, beta = (torch.rand(co, generator=g) + 0.5).to(DEV), (torch.rand(co, generator=g) - 0.5).to(DEV)
+    dy = rand_act(n, co, h, w, 44, scale=0.1)
+    # ---- reference
+    xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    raw_ref = F.conv2d(xr, wr, None, 1, (k - 1) // 2)
+    raw_q = raw_ref + (bf(raw_ref) - raw_ref).detach()
+    groups = [(0, split), (split, n)] if split else [(0, n)]
+    z = torch.cat([F.batch_norm(raw_q[a:b], None, None, gr, br, True, 0.0, eps) for a, b in groups], 0)
+    F.silu(z).backward(dy)
+    # ---- product: forward statistics from the stored raw values, like the conv kernel's tail
+    xv = ops.from_nchw(x)
+    raw = View.empty(n, h, w, co, DEV)
+    ops.conv2d(xv, ops.pack_conv_weight(wt), raw, k, 1, ops.SY_CONV_RAW)
+    rawf = raw.nchw_float()
+    mean = torch.stack([rawf[a:b].mean((0, 2, 3)) for a, b in groups] + ([] if split else [torch.zeros(co, device=DEV)]))
+    var = torch.stack([rawf[a:b].var((0, 2, 3), unbiased=False) for a, b in groups] + ([] if split else [torch.ones(co, device=DEV)]))
+    invstd = (var + eps).rsqrt()
+    scale = (gamma[None] * invstd).contiguous()
+    shift = (beta[None] - mean * scale).contiguous()
+    draw = View.empty(n, h, w, co, DEV)
+    dgamma, dbeta = torch.full((co,), float("nan"), device=DEV), torch.full((co,), float("nan"), device=DEV)
+    ops.bn_act_backward(raw, ops.from_nchw(dy), draw, scale, shift, mean.contiguous(), invstd.contiguous(), split, 1,
+                        dgamma, dbeta)
+    dx = View.empty(n, h, w, ci, DEV)
+    ops.conv2d(draw, ops.pack_conv_weight_dgrad(wt), dx, k, 1, ops.SY_CONV_RAW)
+    dw = torch.empty((co, ci, k, k), device=DEV)
+    ops.conv2d_wgrad(xv, draw, k, 1, dw)
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+    assert rel(dgamma, gr.grad) < 5e-3 and rel(dbeta, br.grad) < 5e-3, (rel(dgamma, gr.grad), rel(dbeta, br.grad))
+    assert rel(dx.nchw_float(), xr.grad) < 1e-2, rel(dx.nchw_float(), xr.grad)
+    assert rel(dw, wr.grad) < 1e-2, rel(dw, wr.grad)
