@@ -232,6 +232,32 @@ typedef struct SyBnActBwdDesc {
 int sy_bn_act_bwd_rows(int32_t n, int32_t hw);
 int sy_bn_act_backward(const SyBnActBwdDesc* d, sy_stream_t stream);
 
+/* Zero-insertion D[n, 2i, 2j, :] = g[n, i, j, :] (D = [n, H, W, c], H in {2h-1, 2h}): the data gradient of a stride-2
+ * 3x3 conv (the first convs of dark2..dark5, bu_conv1/2: exps/model/darknet.py:118-160, dfp_pafpn.py:57-69) is then
+ * sy_conv2d_tc on D with the flipped, channel-transposed filter, stride 1. */
+int sy_dilate2(SyTensor g, SyTensor D, sy_stream_t stream);
+
+/* Backward of F.interpolate(mode="nearest") (exps/model/dfp_pafpn.py:126,131): dx[n, iy, ix] = sum of dy over the
+ * destination pixels whose source index (the forward's fp32 expression) is (iy, ix). */
+int sy_upsample_nearest_backward(SyTensor dy, SyTensor dx, sy_stream_t stream);
+
+/* Backward of the three 1x1 prediction convs of one head level (exps/model/tal_head.py:101-131, 163-171):
+ * grad_raw [b, a_total, 5 + nc] (d loss / d raw head outputs, sy_tal_loss_backward) -> gradients w.r.t. the cls / reg
+ * tower outputs (bf16 views), the conv weights ([4][c], [1][c], [nc][c]) and biases (fp32, (+)=).
+ * partials: sy_head_pred_bwd_rows(b, h, w) rows of (5 + nc) * (c + 1) floats. */
+typedef struct SyHeadPredBwdDesc {
+  const float* grad_raw;
+  SyTensor cls_feat, reg_feat;         /* the forward's inputs */
+  SyTensor d_cls_feat, d_reg_feat;     /* outputs */
+  const float* w_reg; const float* w_obj; const float* w_cls;
+  int32_t num_classes, a_total, anchor_offset;
+  float* dw_reg; float* dw_obj; float* dw_cls; float* db_reg; float* db_obj; float* db_cls;
+  int32_t accumulate;
+  float* partials; int32_t n_partials;
+} SyHeadPredBwdDesc;
+int sy_head_pred_bwd_rows(int32_t b, int32_t h, int32_t w);
+int sy_head_pred_backward(const SyHeadPredBwdDesc* d, sy_stream_t stream);
+
 /* Backward of the loss: what autograd computes for loss.backward() (exps/train_utils/double_trainer.py:114)
  * through TALHead.get_losses (exps/model/tal_head.py:426-461): the SimOTA assignment, the class targets and the
  * normalised TAL weights are constants (tal_head.py:479 @torch.no_grad, weights detached), so the gradient is

@@ -24,6 +24,7 @@ SOURCES = {
     "conv_simt.cu": [],
     "bn_glue.cu": [],
     "bn_bwd.cu": [],
+    "bwd_glue.cu": [],
     "head_loss.cu": ["-fmad=false"],
     "postprocess.cu": ["-fmad=false"],
 }

@@ -1,0 +1,215 @@
+// Small backward kernels around the convolutions (autograd of the reference's graph under loss.backward(),
+// /root/reference/exps/train_utils/double_trainer.py:114):
+//   * sy_dilate2            zero-insertion of a stride-2 conv's output gradient, so that its data gradient is the stride-1
+//                           forward kernel on the flipped filter (dark2..dark5 first convs, bu_conv1/2)
+//   * sy_upsample_nearest_backward   F.interpolate(mode="nearest") backward (dfp_pafpn.py:126,131): each source pixel sums
+//                           the destination pixels that read it (same fp32 index expression as the forward)
+//   * sy_head_pred_backward the three 1x1 prediction convs of a head level (tal_head.py:101-131): data gradient into the
+//                           cls / reg tower outputs, weight + bias gradients (two-stage, fixed-order reduction)
+#include <math.h>
+
+#include "common.cuh"
+
+namespace sy {
+
+__device__ __forceinline__ void unpack8g(const uint4& v, float* f) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+
+// D[n, 2i, 2j, :] = g[n, i, j, :], zero elsewhere; D is [n, H, W, c] with H in {2h-1, 2h}, W in {2w-1, 2w}
+__global__ void dilate2_kernel(const __nv_bfloat16* g, long long gp, int N, int h, int w, __nv_bfloat16* D, long long dp, int H,
+                               int W, int C) {
+  const int G = C / 8;
+  const long long total = (long long)N * H * W * G;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % G);
+    const long long pix = idx / G;
+    const int x = (int)(pix % W), y = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (((x | y) & 1) == 0 && (y >> 1) < h && (x >> 1) < w)
+      v = *reinterpret_cast<const uint4*>(g + (((long long)n * h + (y >> 1)) * w + (x >> 1)) * gp + cg * 8);
+    *reinterpret_cast<uint4*>(D + pix * dp + cg * 8) = v;
+  }
+}
+
+// dx[n, iy, ix] = sum of dy[n, oy, ox] over the destination pixels with src(oy) == iy, src(ox) == ix
+__global__ void upsample_nearest_bwd_kernel(const __nv_bfloat16* dy, long long dyp, int N, int Ho, int Wo, __nv_bfloat16* dx,
+                                            long long dxp, int Hi, int Wi, int C) {
+  const int G = C / 8;
+  const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+  const long long total = (long long)N * Hi * Wi * G;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % G);
+    const long long pix = idx / G;
+    const int ix = (int)(pix % Wi), iy = (int)((pix / Wi) % Hi);
+    const int n = (int)(pix / ((long long)Wi * Hi));
+    // candidate destination rows / columns: a window around iy / sh that certainly contains every match
+    const int oy0 = max(0, (int)floorf((float)iy / sh) - 2), oy1 = min(Ho - 1, (int)ceilf((float)(iy + 1) / sh) + 2);
+    const int ox0 = max(0, (int)floorf((float)ix / sw) - 2), ox1 = min(Wo - 1, (int)ceilf((float)(ix + 1) / sw) + 2);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int oy = oy0; oy <= oy1; ++oy) {
+      if (min((int)floorf(__fmul_rn((float)oy, sh)), Hi - 1) != iy) continue;
+      for (int ox = ox0; ox <= ox1; ++ox) {
+        if (min((int)floorf(__fmul_rn((float)ox, sw)), Wi - 1) != ix) continue;
+        float f[8];
+        unpack8g(*reinterpret_cast<const uint4*>(dy + (((long long)n * Ho + oy) * Wo + ox) * dyp + cg * 8), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += f[i];
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + pix * dxp + cg * 8) =
+        make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+  }
+}
+
+// ---- head prediction convs: out[a][o] = sum_c feat_o[a][c] * w[o][c] + b[o], o = reg(4) | obj(1) | cls(NC);
+//      reg and obj read the reg tower output, cls reads the cls tower output
+struct HeadBwdArgs {
+  const float* g;          // [B][a_total][NO] gradient w.r.t. the raw outputs
+  const __nv_bfloat16* cf; long long cfp;
+  const __nv_bfloat16* rf; long long rfp;
+  const float* w_reg; const float* w_obj; const float* w_cls;
+  int B, H, W, C, NO, a_total, anchor_offset;
+  __nv_bfloat16* dcf; long long dcfp;
+  __nv_bfloat16* drf; long long drfp;
+  float* partial;          // [nblk][NO][C + 1]  (last column: bias)
+};
+
+__global__ void head_pred_bwd_data_kernel(const HeadBwdArgs q) {
+  const int G = q.C / 8;
+  const long long npix = (long long)q.B * q.H * q.W;
+  const long long total = npix * G;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % G);
+    const long long pix = idx / G;
+    const int b = (int)(pix / ((long long)q.H * q.W));
+    const long long a = (long long)b * q.a_total + q.anchor_offset + (pix - (long long)b * q.H * q.W);
+    const float* g = q.g + a * q.NO;
+    float dr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int o = 0; o < q.NO; ++o) {
+      const float gv = g[o];
+      const float* wrow = (o < 4) ? q.w_reg + (size_t)o * q.C : (o == 4 ? q.w_obj : q.w_cls + (size_t)(o - 5) * q.C);
+      float* dst = (o < 5) ? dr : dc;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst[i] += gv * wrow[cg * 8 + i];
+    }
+    *reinterpret_cast<uint4*>(q.drf + pix * q.drfp + cg * 8) =
+        make_uint4(pack_bf16(dr[0], dr[1]), pack_bf16(dr[2], dr[3]), pack_bf16(dr[4], dr[5]), pack_bf16(dr[6], dr[7]));
+    *reinterpret_cast<uint4*>(q.dcf + pix * q.dcfp + cg * 8) =
+        make_uint4(pack_bf16(dc[0], dc[1]), pack_bf16(dc[2], dc[3]), pack_bf16(dc[4], dc[5]), pack_bf16(dc[6], dc[7]));
+  }
+}
+
+constexpr int kHeadBwdPix = 256;      // pixels per partial row
+// block = one chunk of pixels; thread t owns channels t, t + 256, ...; partial[blk][o][c] = sum_p g[p][o] * feat_o[p][c]
+__global__ void __launch_bounds__(256) head_pred_bwd_weight_kernel(const HeadBwdArgs q) {
+  extern __shared__ float gsm[];       // [kHeadBwdPix][NO]
+  const long long npix = (long long)q.B * q.H * q.W;
+  const long long p0 = (long long)blockIdx.x * kHeadBwdPix;
+  const int np = (int)min((long long)kHeadBwdPix, npix - p0);
+  for (int i = threadIdx.x; i < np * q.NO; i += blockDim.x) {
+    const long long pix = p0 + i / q.NO;
+    const int b = (int)(pix / ((long long)q.H * q.W));
+    const long long a = (long long)b * q.a_total + q.anchor_offset + (pix - (long long)b * q.H * q.W);
+    gsm[i] = q.g[a * q.NO + i % q.NO];
+  }
+  __syncthreads();
+  float* out = q.partial + (size_t)blockIdx.x * q.NO * (q.C + 1);
+  for (int c = threadIdx.x; c < q.C; c += blockDim.x) {
+    float acc[32];
+    for (int o = 0; o < q.NO; ++o) acc[o] = 0.f;
+    for (int pp = 0; pp < np; ++pp) {
+      const float r = __bfloat162float(q.rf[(p0 + pp) * q.rfp + c]), cv = __bfloat162float(q.cf[(p0 + pp) * q.cfp + c]);
+      const float* g = gsm + pp * q.NO;
+      for (int o = 0; o < q.NO; ++o) acc[o] += g[o] * (o < 5 ? r : cv);
+    }
+    for (int o = 0; o < q.NO; ++o) out[(size_t)o * (q.C + 1) + c] = acc[o];
+  }
+  if (threadIdx.x < q.NO) {              // bias gradient of this chunk
+    float s = 0.f;
+    for (int pp = 0; pp < np; ++pp) s += gsm[pp * q.NO + threadIdx.x];
+    out[(size_t)threadIdx.x * (q.C + 1) + q.C] = s;
+  }
+}
+
+// dW rows in the nn.Conv2d layouts: reg [4][C], obj [1][C], cls [NC][C]; biases [4], [1], [NC]
+__global__ void head_pred_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int NO, int C, float* dw_reg, float* dw_obj,
+                                              float* dw_cls, float* db_reg, float* db_obj, float* db_cls, int accumulate) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NO * (C + 1)) return;
+  const int o = idx / (C + 1), c = idx % (C + 1);
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * NO * (C + 1) + idx];
+  float* dst;
+  if (c < C) dst = (o < 4) ? dw_reg + (size_t)o * C + c : (o == 4 ? dw_obj + c : dw_cls + (size_t)(o - 5) * C + c);
+  else dst = (o < 4) ? db_reg + o : (o == 4 ? db_obj : db_cls + (o - 5));
+  *dst = accumulate ? *dst + s : s;
+}
+
+static inline int grid_cap(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  return (int)(b < 1 ? 1 : (b < 148LL * 16 ? b : 148LL * 16));
+}
+
+}  // namespace sy
+
+using namespace sy;
+
+extern "C" int sy_dilate2(SyTensor g, SyTensor D, sy_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SY_REQUIRE(view_ok(g) && view_ok(D) && g.n == D.n && g.c == D.c, SY_EINVAL, "dilate2: bad views");
+  SY_REQUIRE((D.h == 2 * g.h || D.h == 2 * g.h - 1) && (D.w == 2 * g.w || D.w == 2 * g.w - 1), SY_EINVAL,
+             "dilate2: output %dx%d does not match input %dx%d", D.h, D.w, g.h, g.w);
+  const long long total = (long long)D.n * D.h * D.w * (D.c / 8);
+  dilate2_kernel<<<grid_cap(total, 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(g.ptr), g.pitch, g.n, g.h, g.w,
+                                                           reinterpret_cast<__nv_bfloat16*>(D.ptr), D.pitch, D.h, D.w, D.c);
+  return launch_status("dilate2_kernel");
+}
+
+extern "C" int sy_upsample_nearest_backward(SyTensor dy, SyTensor dx, sy_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SY_REQUIRE(view_ok(dy) && view_ok(dx) && dy.n == dx.n && dy.c == dx.c, SY_EINVAL, "upsample_backward: bad views");
+  const long long total = (long long)dx.n * dx.h * dx.w * (dx.c / 8);
+  upsample_nearest_bwd_kernel<<<grid_cap(total, 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy.ptr), dy.pitch,
+                                                                        dy.n, dy.h, dy.w, reinterpret_cast<__nv_bfloat16*>(dx.ptr),
+                                                                        dx.pitch, dx.h, dx.w, dx.c);
+  return launch_status("upsample_nearest_bwd_kernel");
+}
+
+extern "C" int sy_head_pred_bwd_rows(int32_t b, int32_t h, int32_t w) { return cdiv(b * h * w, kHeadBwdPix); }
+
+extern "C" int sy_head_pred_backward(const SyHeadPredBwdDesc* d, sy_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SY_REQUIRE(d != nullptr, SY_EINVAL, "null descriptor");
+  const SyTensor& f = d->cls_feat;
+  SY_REQUIRE(view_ok(f) && view_ok(d->reg_feat) && view_ok(d->d_cls_feat) && view_ok(d->d_reg_feat), SY_EINVAL,
+             "head_pred_backward: bad views");
+  SY_REQUIRE(d->reg_feat.n == f.n && d->reg_feat.h == f.h && d->reg_feat.w == f.w && d->reg_feat.c == f.c &&
+                 d->d_cls_feat.c == f.c && d->d_reg_feat.c == f.c && d->d_cls_feat.h == f.h && d->d_reg_feat.w == f.w,
+             SY_EINVAL, "head_pred_backward: shape mismatch");
+  SY_REQUIRE(d->num_classes >= 1 && d->num_classes <= 27, SY_EINVAL, "head_pred_backward: num_classes out of range");
+  SY_REQUIRE(d->grad_raw && d->w_reg && d->w_obj && d->w_cls && d->dw_reg && d->dw_obj && d->dw_cls && d->db_reg && d->db_obj &&
+                 d->db_cls && d->partials,
+             SY_EINVAL, "head_pred_backward: null pointer");
+  SY_REQUIRE(d->anchor_offset >= 0 && d->anchor_offset + f.h * f.w <= d->a_total, SY_EINVAL, "head_pred_backward: anchor range");
+  const int rows = sy_head_pred_bwd_rows(f.n, f.h, f.w);
+  SY_REQUIRE(d->n_partials >= rows, SY_EWORKSPACE, "head_pred_backward: %d partial rows, need %d", d->n_partials, rows);
+  HeadBwdArgs q{};
+  q.g = d->grad_raw;
+  q.cf = reinterpret_cast<const __nv_bfloat16*>(f.ptr); q.cfp = f.pitch;
+  q.rf = reinterpret_cast<const __nv_bfloat16*>(d->reg_feat.ptr); q.rfp = d->reg_feat.pitch;
+  q.w_reg = d->w_reg; q.w_obj = d->w_obj; q.w_cls = d->w_cls;
+  q.B = f.n; q.H = f.h; q.W = f.w; q.C = f.c; q.NO = 5 + d->num_classes; q.a_total = d->a_total; q.anchor_offset = d->anchor_offset;
+  q.dcf = reinterpret_cast<__nv_bfloat16*>(d->d_cls_feat.ptr); q.dcfp = d->d_cls_feat.pitch;
+  q.drf = reinterpret_cast<__nv_bfloat16*>(d->d_reg_feat.ptr); q.drfp = d->d_reg_feat.pitch;
+  q.partial = d->partials;
+  const long long total = (long long)f.n * f.h * f.w * (f.c / 8);
+  head_pred_bwd_data_kernel<<<grid_cap(total, 256), 256, 0, stream>>>(q);
+  head_pred_bwd_weight_kernel<<<rows, 256, sizeof(float) * kHeadBwdPix * q.NO, stream>>>(q);
+  const int n_out = q.NO * (f.c + 1);
+  head_pred_bwd_finalize_kernel<<<cdiv(n_out, 256), 256, 0, stream>>>(d->partials, rows, q.NO, f.c, d->dw_reg, d->dw_obj, d->dw_cls,
+                                                                     d->db_reg, d->db_obj, d->db_cls, d->accumulate);
+  return launch_status("head_pred_backward kernels");
+}

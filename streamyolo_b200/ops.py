@@ -76,6 +76,15 @@ class SyBnActBwdDesc(C.Structure):
                 ("n_partials", C.c_int32), ("coef", C.c_void_p)]
 
 
+class SyHeadPredBwdDesc(C.Structure):
+    _fields_ = [("grad_raw", C.c_void_p), ("cls_feat", SyTensor), ("reg_feat", SyTensor), ("d_cls_feat", SyTensor),
+                ("d_reg_feat", SyTensor), ("w_reg", C.c_void_p), ("w_obj", C.c_void_p), ("w_cls", C.c_void_p),
+                ("num_classes", C.c_int32), ("a_total", C.c_int32), ("anchor_offset", C.c_int32),
+                ("dw_reg", C.c_void_p), ("dw_obj", C.c_void_p), ("dw_cls", C.c_void_p), ("db_reg", C.c_void_p),
+                ("db_obj", C.c_void_p), ("db_cls", C.c_void_p), ("accumulate", C.c_int32), ("partials", C.c_void_p),
+                ("n_partials", C.c_int32)]
+
+
 class SyTalLossBwdDesc(C.Structure):
     _fields_ = [("outputs", C.c_void_p), ("origin", C.c_void_p), ("labels_fut", C.c_void_p),
                 ("b", C.c_int32), ("a_total", C.c_int32), ("max_labels", C.c_int32), ("num_classes", C.c_int32),
@@ -109,6 +118,10 @@ _SIG = {
     "sy_tal_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "sy_tal_loss": (C.c_int, [C.POINTER(SyTalLossDesc), C.c_void_p]),
     "sy_tal_loss_backward": (C.c_int, [C.POINTER(SyTalLossBwdDesc), C.c_void_p]),
+    "sy_dilate2": (C.c_int, [SyTensor, SyTensor, C.c_void_p]),
+    "sy_upsample_nearest_backward": (C.c_int, [SyTensor, SyTensor, C.c_void_p]),
+    "sy_head_pred_bwd_rows": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    "sy_head_pred_backward": (C.c_int, [C.POINTER(SyHeadPredBwdDesc), C.c_void_p]),
     "sy_bn_act_bwd_rows": (C.c_int, [C.c_int32, C.c_int32]),
     "sy_bn_act_backward": (C.c_int, [C.POINTER(SyBnActBwdDesc), C.c_void_p]),
     "sy_postprocess_nms_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
@@ -442,3 +455,35 @@ def bn_act_backward(raw: View, dy: View, draw: View, scale, shift, mean, invstd,
     d.dgamma, d.dbeta, d.accumulate = dgamma.data_ptr(), dbeta.data_ptr(), int(accumulate)
     d.partials, d.n_partials, d.coef = partials.data_ptr(), rows, coef.data_ptr()
     _check(lib().sy_bn_act_backward(C.byref(d), _stream()), kernels=3)
+
+
+def dilate2(g: View, D: View):
+    _check(lib().sy_dilate2(g.st(), D.st(), _stream()))
+
+
+def conv2d_dgrad_stride2(dy: View, w, dx: View, k=3):
+    """Data gradient of a stride-2 conv: zero-insert dy to dx's spatial size, then the stride-1 forward kernel on the
+    flipped, channel-transposed filter (``w`` = the forward OIHW weights)."""
+    D = View.empty(dx.n, dx.h, dx.w, dy.c, dy.buf.device)
+    dilate2(dy, D)
+    conv2d(D, pack_conv_weight_dgrad(w), dx, k, 1, SY_CONV_RAW)
+
+
+def upsample_nearest_backward(dy: View, dx: View):
+    _check(lib().sy_upsample_nearest_backward(dy.st(), dx.st(), _stream()))
+
+
+def head_pred_backward(grad_raw, cls_feat: View, reg_feat: View, d_cls_feat: View, d_reg_feat: View, w_reg, w_obj, w_cls,
+                       a_total, anchor_offset, dw_reg, dw_obj, dw_cls, db_reg, db_obj, db_cls, accumulate=False):
+    nc = w_cls.shape[0]
+    rows = load_library().sy_head_pred_bwd_rows(cls_feat.n, cls_feat.h, cls_feat.w)
+    partials = torch.empty((rows, (5 + nc) * (cls_feat.c + 1)), dtype=torch.float32, device=grad_raw.device)
+    d = SyHeadPredBwdDesc()
+    d.grad_raw = grad_raw.data_ptr()
+    d.cls_feat, d.reg_feat, d.d_cls_feat, d.d_reg_feat = cls_feat.st(), reg_feat.st(), d_cls_feat.st(), d_reg_feat.st()
+    d.w_reg, d.w_obj, d.w_cls = w_reg.data_ptr(), w_obj.data_ptr(), w_cls.data_ptr()
+    d.num_classes, d.a_total, d.anchor_offset = nc, a_total, anchor_offset
+    d.dw_reg, d.dw_obj, d.dw_cls = dw_reg.data_ptr(), dw_obj.data_ptr(), dw_cls.data_ptr()
+    d.db_reg, d.db_obj, d.db_cls = db_reg.data_ptr(), db_obj.data_ptr(), db_cls.data_ptr()
+    d.accumulate, d.partials, d.n_partials = int(accumulate), partials.data_ptr(), rows
+    _check(lib().sy_head_pred_backward(C.byref(d), _stream()), kernels=3)

@@ -414,3 +414,58 @@ def test_baseconv_backward_chain(case):
     assert rel(dgamma, gr.grad) < 5e-3 and rel(dbeta, br.grad) < 5e-3, (rel(dgamma, gr.grad), rel(dbeta, br.grad))
     assert rel(dx.nchw_float(), xr.grad) < 1e-2, rel(dx.nchw_float(), xr.grad)
     assert rel(dw, wr.grad) < 1e-2, rel(dw, wr.grad)
+
+
+@pytest.mark.parametrize("case", [(2, 64, 128, 40, 60), (2, 128, 256, 75, 120), (3, 16, 32, 15, 21)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv_dgrad_stride2(case):
+    """Data gradient of a stride-2 3x3 conv: zero insertion + the stride-1 forward kernel on the flipped filter."""
+    n, ci, co, h, w = case
+    x = rand_act(n, ci, h, w, 51).requires_grad_(True)
+    wt = rand_w(co, ci, 3, 52)
+    ho, wo = ops.conv_out_hw(h, w, 3, 2)
+    dy = rand_act(n, co, ho, wo, 53)
+    F.conv2d(x, wt, None, 2, 1).backward(dy)
+    dx = View.empty(n, h, w, ci, DEV)
+    ops.conv2d_dgrad_stride2(ops.from_nchw(dy), wt, dx)
+    torch.cuda.synchronize()
+    check_close(dx.nchw_float(), x.grad, f"dgrad_s2{case}")
+
+
+@pytest.mark.parametrize("hi,wi,ho,wo", [(19, 30, 38, 60), (38, 60, 75, 120), (4, 5, 8, 10), (8, 10, 15, 20)])
+def test_upsample_nearest_backward(hi, wi, ho, wo):
+    n, c = 2, 64
+    x = rand_act(n, c, hi, wi, 61).requires_grad_(True)
+    dy = rand_act(n, c, ho, wo, 62)
+    F.interpolate(x, size=(ho, wo), mode="nearest").backward(dy)
+    dx = View.empty(n, hi, wi, c, DEV)
+    ops.upsample_nearest_backward(ops.from_nchw(dy), dx)
+    torch.cuda.synchronize()
+    check_close(dx.nchw_float(), x.grad, "upsample backward", ulp=2.0 ** -8)
+
+
+def test_head_pred_backward():
+    b, c, h, w, nc = 2, 64, 19, 30, 8
+    a_total, off = h * w + 100, 60
+    cls_feat, reg_feat = rand_act(b, c, h, w, 71), rand_act(b, c, h, w, 72)
+    g = torch.Generator().manual_seed(73)
+    w_reg, w_obj, w_cls = [(torch.randn(o, c, generator=g) * 0.1).to(DEV).requires_grad_(True) for o in (4, 1, nc)]
+    b_reg, b_obj, b_cls = [torch.zeros(o, device=DEV, requires_grad=True) for o in (4, 1, nc)]
+    grad_raw = torch.zeros(b, a_total, 5 + nc, device=DEV)
+    gsub = (torch.randn(b, h * w, 5 + nc, generator=g) * 0.05).to(DEV)
+    grad_raw[:, off:off + h * w] = gsub
+    cf, rf = cls_feat.clone().requires_grad_(True), reg_feat.clone().requires_grad_(True)
+    out = torch.cat([F.conv2d(rf, w_reg[:, :, None, None], b_reg), F.conv2d(rf, w_obj[:, :, None, None], b_obj),
+                     F.conv2d(cf, w_cls[:, :, None, None], b_cls)], 1)
+    out.flatten(2).permute(0, 2, 1).backward(gsub)
+    dcf, drf = View.empty(b, h, w, c, DEV), View.empty(b, h, w, c, DEV)
+    dws = [torch.full_like(t, float("nan")).detach() for t in (w_reg, w_obj, w_cls)]
+    dbs = [torch.full_like(t, float("nan")).detach() for t in (b_reg, b_obj, b_cls)]
+    ops.head_pred_backward(grad_raw, ops.from_nchw(cls_feat), ops.from_nchw(reg_feat), dcf, drf, w_reg.detach(),
+                           w_obj.detach(), w_cls.detach(), a_total, off, dws[0], dws[1], dws[2], dbs[0], dbs[1], dbs[2])
+    torch.cuda.synchronize()
+    check_close(dcf.nchw_float(), cf.grad, "d cls_feat")
+    check_close(drf.nchw_float(), rf.grad, "d reg_feat")
+    for got, ref, name in zip(dws + dbs, [w_reg.grad, w_obj.grad, w_cls.grad, b_reg.grad, b_obj.grad, b_cls.grad],
+                              ["dw_reg", "dw_obj", "dw_cls", "db_reg", "db_obj", "db_cls"]):
+        assert (got - ref).abs().max().item() <= 2e-4 * ref.abs().max().item() + 1e-7, name
