@@ -86,6 +86,8 @@ typedef struct {
   SyBnSegment bn[2];     /* bn[0].gamma != NULL: finalize BatchNorm in the kernel tail (1-2 parameter segments) */
   float momentum, eps;
   float* scale_shift;    /* [2 (scale|shift)][2 groups][Cout]: y = x*scale + shift, ready when the kernel ends */
+  float* mean_invstd;    /* optional [2 (mean|invstd)][2 groups][Cout]: the batch statistics themselves, saved for
+                          * sy_bn_act_backward (NULL: not written) */
   uint32_t* sync;        /* four zero-initialised counters (grid barriers); the kernel leaves them at zero */
   /* With bn[]: optional normalise + act (+ residual) pass INSIDE the same launch (after a second grid barrier
    * every CTA re-reads the raw tiles it stored -- L2 resident -- and writes apply_y = act(y*scale+shift) (+ apply_res)).
@@ -240,6 +242,17 @@ int sy_dilate2(SyTensor g, SyTensor D, sy_stream_t stream);
 /* Backward of F.interpolate(mode="nearest") (exps/model/dfp_pafpn.py:126,131): dx[n, iy, ix] = sum of dy over the
  * destination pixels whose source index (the forward's fp32 expression) is (iy, ix). */
 int sy_upsample_nearest_backward(SyTensor dy, SyTensor dx, sy_stream_t stream);
+
+/* y += x (bf16): gradient accumulation where a tensor feeds several consumers (Bottleneck shortcuts,
+ * exps/model/dfp_pafpn.py:168-170 "+ cur", FPN features read by two branches). */
+int sy_add(SyTensor x, SyTensor y, sy_stream_t stream);
+
+/* Backward of the three SPP max pools ([yolox] SPPBottleneck, exps/model/darknet.py:156): dx = gradient reaching x
+ * through MaxPool2d(5), (9), (13) (stride 1, padding k/2), each window's gradient going to its first maximum in
+ * row-major order like PyTorch.  The identity branch of the concat is not included.  Deterministic (gather). */
+size_t sy_spp_maxpool_backward_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t c);
+int sy_spp_maxpool_backward(SyTensor x, SyTensor d5, SyTensor d9, SyTensor d13, SyTensor dx, void* workspace,
+                            size_t workspace_bytes, sy_stream_t stream);
 
 /* Backward of the three 1x1 prediction convs of one head level (exps/model/tal_head.py:101-131, 163-171):
  * grad_raw [b, a_total, 5 + nc] (d loss / d raw head outputs, sy_tal_loss_backward) -> gradients w.r.t. the cls / reg

@@ -148,6 +148,114 @@ __global__ void head_pred_bwd_finalize_kernel(const float* __restrict__ partial,
   *dst = accumulate ? *dst + s : s;
 }
 
+// y += x (bf16, fp32 add, one rounding): gradient accumulation where a tensor feeds several consumers (residual
+// shortcuts, FPN features read by two branches, the DFP fusion's "+ cur")
+__global__ void add_kernel(const __nv_bfloat16* x, long long xp, __nv_bfloat16* y, long long yp, long long npix, int C) {
+  const int G = C / 8;
+  const long long total = npix * G;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % G);
+    const long long pix = idx / G;
+    float a[8], b[8];
+    unpack8g(*reinterpret_cast<const uint4*>(x + pix * xp + cg * 8), a);
+    unpack8g(*reinterpret_cast<const uint4*>(y + pix * yp + cg * 8), b);
+    *reinterpret_cast<uint4*>(y + pix * yp + cg * 8) =
+        make_uint4(pack_bf16(a[0] + b[0], a[1] + b[1]), pack_bf16(a[2] + b[2], a[3] + b[3]), pack_bf16(a[4] + b[4], a[5] + b[5]),
+                   pack_bf16(a[6] + b[6], a[7] + b[7]));
+  }
+}
+
+// ---- SPP max pools backward ([yolox] SPPBottleneck: MaxPool2d(k, stride 1, padding k/2), k = 5, 9, 13, each applied to
+// the same x).  PyTorch routes a window's gradient to its FIRST maximum in row-major scan order (strict >): pass 1 records
+// that position per output element and pool, pass 2 lets every input element gather the outputs that point at it
+// (deterministic, no atomics).
+__device__ __forceinline__ void gt8(const uint4& v, const uint4& m, bool* g) {
+  float a[8], b[8];
+  unpack8g(v, a);
+  unpack8g(m, b);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) g[i] = a[i] > b[i];
+}
+
+// amax[k][n][y][x][c] = (window row * 16 + window col) of the first maximum, as uint8 (13 x 13 windows fit)
+__global__ void spp_argmax_kernel(const __nv_bfloat16* x, long long xp, int N, int H, int W, int C, uint8_t* amax) {
+  const int G = C / 8;
+  const long long total = (long long)N * H * W * G;
+  const int ks[3] = {5, 9, 13};
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % G);
+    const long long pix = idx / G;
+    const int px = (int)(pix % W), py = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    for (int kk = 0; kk < 3; ++kk) {
+      const int r = ks[kk] / 2;
+      float best[8];
+      uint8_t pos[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; pos[i] = 0; }
+      for (int dy = -r; dy <= r; ++dy) {
+        const int yy = py + dy;
+        if (yy < 0 || yy >= H) continue;
+        for (int dx = -r; dx <= r; ++dx) {
+          const int xx = px + dx;
+          if (xx < 0 || xx >= W) continue;
+          float v[8];
+          unpack8g(*reinterpret_cast<const uint4*>(x + (((long long)n * H + yy) * W + xx) * xp + cg * 8), v);
+          const uint8_t code = (uint8_t)((dy + r) * 16 + (dx + r));
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (v[i] > best[i]) { best[i] = v[i]; pos[i] = code; }
+        }
+      }
+      uint8_t* dst = amax + (((size_t)kk * N * H * W + pix) * C) + cg * 8;
+      *reinterpret_cast<uint2*>(dst) = make_uint2(pos[0] | (pos[1] << 8) | (pos[2] << 16) | ((uint32_t)pos[3] << 24),
+                                                  pos[4] | (pos[5] << 8) | (pos[6] << 16) | ((uint32_t)pos[7] << 24));
+    }
+  }
+}
+
+// dx[p] = sum over pools k and outputs o whose window contains p and whose recorded maximum is p of dy_k[o]
+__global__ void spp_bwd_gather_kernel(const uint8_t* amax, const __nv_bfloat16* d5, long long p5, const __nv_bfloat16* d9, long long p9,
+                                      const __nv_bfloat16* d13, long long p13, int N, int H, int W, int C, __nv_bfloat16* dx,
+                                      long long dxp) {
+  const int G = C / 8;
+  const long long total = (long long)N * H * W * G;
+  const int ks[3] = {5, 9, 13};
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % G);
+    const long long pix = idx / G;
+    const int px = (int)(pix % W), py = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int kk = 0; kk < 3; ++kk) {
+      const int r = ks[kk] / 2;
+      const __nv_bfloat16* dk = kk == 0 ? d5 : (kk == 1 ? d9 : d13);
+      const long long dp = kk == 0 ? p5 : (kk == 1 ? p9 : p13);
+      for (int oy = max(0, py - r); oy <= min(H - 1, py + r); ++oy) {
+        for (int ox = max(0, px - r); ox <= min(W - 1, px + r); ++ox) {
+          const long long opix = ((long long)n * H + oy) * W + ox;
+          const uint2 pk = *reinterpret_cast<const uint2*>(amax + (((size_t)kk * N * H * W + opix) * C) + cg * 8);
+          const uint8_t want = (uint8_t)((py - oy + r) * 16 + (px - ox + r));    // p's position inside o's window
+          uint32_t any = 0;
+          uint8_t code[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { code[i] = (pk.x >> (8 * i)) & 0xff; code[4 + i] = (pk.y >> (8 * i)) & 0xff; }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) any |= (code[i] == want);
+          if (!any) continue;
+          float g[8];
+          unpack8g(*reinterpret_cast<const uint4*>(dk + opix * dp + cg * 8), g);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (code[i] == want) acc[i] += g[i];
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + pix * dxp + cg * 8) =
+        make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+  }
+}
+
 static inline int grid_cap(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   return (int)(b < 1 ? 1 : (b < 148LL * 16 ? b : 148LL * 16));
@@ -212,4 +320,37 @@ extern "C" int sy_head_pred_backward(const SyHeadPredBwdDesc* d, sy_stream_t str
   head_pred_bwd_finalize_kernel<<<cdiv(n_out, 256), 256, 0, stream>>>(d->partials, rows, q.NO, f.c, d->dw_reg, d->dw_obj, d->dw_cls,
                                                                      d->db_reg, d->db_obj, d->db_cls, d->accumulate);
   return launch_status("head_pred_backward kernels");
+}
+
+extern "C" int sy_add(SyTensor x, SyTensor y, sy_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SY_REQUIRE(view_ok(x) && view_ok(y) && x.n == y.n && x.h == y.h && x.w == y.w && x.c == y.c, SY_EINVAL, "add: view mismatch");
+  const long long npix = (long long)x.n * x.h * x.w;
+  add_kernel<<<grid_cap(npix * (x.c / 8), 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x.ptr), x.pitch,
+                                                                 reinterpret_cast<__nv_bfloat16*>(y.ptr), y.pitch, npix, x.c);
+  return launch_status("add_kernel");
+}
+
+extern "C" size_t sy_spp_maxpool_backward_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t c) {
+  return (size_t)3 * n * h * w * c;
+}
+
+extern "C" int sy_spp_maxpool_backward(SyTensor x, SyTensor d5, SyTensor d9, SyTensor d13, SyTensor dx, void* workspace,
+                                       size_t workspace_bytes, sy_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SY_REQUIRE(view_ok(x) && view_ok(d5) && view_ok(d9) && view_ok(d13) && view_ok(dx), SY_EINVAL, "spp_backward: bad views");
+  SY_REQUIRE(d5.c == x.c && d9.c == x.c && d13.c == x.c && dx.c == x.c && d5.h == x.h && d5.w == x.w && d5.n == x.n &&
+                 dx.h == x.h && dx.w == x.w && dx.n == x.n,
+             SY_EINVAL, "spp_backward: shape mismatch");
+  SY_REQUIRE(workspace != nullptr && workspace_bytes >= sy_spp_maxpool_backward_workspace_bytes(x.n, x.h, x.w, x.c) &&
+                 ((uintptr_t)workspace % 16) == 0,
+             SY_EWORKSPACE, "spp_backward: workspace too small or misaligned");
+  const long long total = (long long)x.n * x.h * x.w * (x.c / 8);
+  spp_argmax_kernel<<<grid_cap(total, 128), 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x.ptr), x.pitch, x.n, x.h, x.w,
+                                                              x.c, reinterpret_cast<uint8_t*>(workspace));
+  spp_bwd_gather_kernel<<<grid_cap(total, 128), 128, 0, stream>>>(
+      reinterpret_cast<const uint8_t*>(workspace), reinterpret_cast<const __nv_bfloat16*>(d5.ptr), d5.pitch,
+      reinterpret_cast<const __nv_bfloat16*>(d9.ptr), d9.pitch, reinterpret_cast<const __nv_bfloat16*>(d13.ptr), d13.pitch, x.n, x.h,
+      x.w, x.c, reinterpret_cast<__nv_bfloat16*>(dx.ptr), dx.pitch);
+  return launch_status("spp backward kernels");
 }

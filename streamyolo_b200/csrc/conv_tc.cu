@@ -87,6 +87,7 @@ struct Params {
   BnSeg seg[2];
   float momentum, eps;
   float* ss;                // [2 (scale|shift)][2 groups][Cout]
+  float* mi;                // optional [2 (mean|invstd)][2 groups][Cout] for the backward pass
   unsigned int* sync;       // three counters (two grid barriers + exit ticket), zero between launches
   // normalise + act (+ residual) pass done by this kernel after the statistics are final (nullptr: separate launch)
   __nv_bfloat16* ap_y; long long ap_y_pitch;
@@ -728,6 +729,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float sc = sg.gamma[cs] * (float)(1.0 / sqrt(var + (double)p.eps));
               p.ss[(0 * 2 + g) * p.Cout + c] = sc;
               p.ss[(1 * 2 + g) * p.Cout + c] = sg.beta[cs] - (float)mean * sc;
+              if (p.mi != nullptr) {
+                p.mi[(0 * 2 + g) * p.Cout + c] = (float)mean;
+                p.mi[(1 * 2 + g) * p.Cout + c] = (float)(1.0 / sqrt(var + (double)p.eps));
+              }
               const double unbiased = cnt > 1.0 ? var * (cnt / (cnt - 1.0)) : var;
               rm = (1.f - p.momentum) * rm + p.momentum * (float)mean;
               rv = (1.f - p.momentum) * rv + p.momentum * (float)unbiased;
@@ -1051,6 +1056,7 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
     SY_REQUIRE(p.seg[0].c_begin == 0, SY_EINVAL, "conv2d_tc: first BN segment must start at channel 0");
     p.momentum = d->momentum; p.eps = d->eps;
     p.ss = d->scale_shift;
+    p.mi = d->mean_invstd;
     p.sync = d->sync;
     if (d->apply_y.ptr != nullptr) {
       const SyTensor& ay = d->apply_y;

@@ -29,7 +29,8 @@ class SyConvDesc(C.Structure):
                 ("stride", C.c_int32), ("mode", C.c_int32), ("act", C.c_int32), ("scale", C.c_void_p),
                 ("shift", C.c_void_p), ("res", SyTensor), ("split_n", C.c_int32), ("stat_partials", C.c_void_p),
                 ("n_partials", C.c_int32), ("rows_written", C.POINTER(C.c_int32)), ("bn", SyBnSegment * 2),
-                ("momentum", C.c_float), ("eps", C.c_float), ("scale_shift", C.c_void_p), ("sync", C.c_void_p),
+                ("momentum", C.c_float), ("eps", C.c_float), ("scale_shift", C.c_void_p), ("mean_invstd", C.c_void_p),
+                ("sync", C.c_void_p),
                 ("apply_y", SyTensor), ("apply_res", SyTensor), ("apply_y_group1_offset", C.c_int64),
                 ("apply_res_group1_offset", C.c_int64),
                 ("debug_timeline", C.c_void_p),
@@ -118,6 +119,10 @@ _SIG = {
     "sy_tal_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "sy_tal_loss": (C.c_int, [C.POINTER(SyTalLossDesc), C.c_void_p]),
     "sy_tal_loss_backward": (C.c_int, [C.POINTER(SyTalLossBwdDesc), C.c_void_p]),
+    "sy_add": (C.c_int, [SyTensor, SyTensor, C.c_void_p]),
+    "sy_spp_maxpool_backward_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "sy_spp_maxpool_backward": (C.c_int, [SyTensor, SyTensor, SyTensor, SyTensor, SyTensor, C.c_void_p, C.c_size_t,
+                                          C.c_void_p]),
     "sy_dilate2": (C.c_int, [SyTensor, SyTensor, C.c_void_p]),
     "sy_upsample_nearest_backward": (C.c_int, [SyTensor, SyTensor, C.c_void_p]),
     "sy_head_pred_bwd_rows": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
@@ -252,7 +257,7 @@ def conv_stat_rows():
 
 def conv2d(x: View, wpk, y: View, k, s, mode, impl="tc", scale=None, shift=None, act=1, res: View = None,
            partials=None, split_n=0, timeline=None, debug_flags=0, bn=None, momentum=0.03, eps=1e-3, scale_shift=None,
-           sync=None, apply_y: View = None, apply_res: View = None, y_goff1=0, res_goff1=0):
+           sync=None, apply_y: View = None, apply_res: View = None, y_goff1=0, res_goff1=0, mean_invstd=None):
     """``k`` is an int (square) or (kh, kw).  With ``partials`` (RAW mode, tensor-core path) returns the number
     of per-CTA statistic rows the launch writes."""
     d = SyConvDesc()
@@ -278,6 +283,7 @@ def conv2d(x: View, wpk, y: View, k, s, mode, impl="tc", scale=None, shift=None,
             seg.c_begin = c0
         d.momentum, d.eps = momentum, eps
         d.scale_shift, d.sync = scale_shift.data_ptr(), sync.data_ptr()
+        d.mean_invstd = mean_invstd.data_ptr() if mean_invstd is not None else None
         if apply_y is not None:
             d.apply_y = apply_y.st()
             d.apply_res = apply_res.st() if apply_res is not None else NULL_T
@@ -487,3 +493,15 @@ def head_pred_backward(grad_raw, cls_feat: View, reg_feat: View, d_cls_feat: Vie
     d.db_reg, d.db_obj, d.db_cls = db_reg.data_ptr(), db_obj.data_ptr(), db_cls.data_ptr()
     d.accumulate, d.partials, d.n_partials = int(accumulate), partials.data_ptr(), rows
     _check(lib().sy_head_pred_backward(C.byref(d), _stream()), kernels=3)
+
+
+def add_(x: View, y: View):
+    """y += x"""
+    _check(lib().sy_add(x.st(), y.st(), _stream()))
+
+
+def spp_maxpool_backward(x: View, d5: View, d9: View, d13: View, dx: View):
+    ws = torch.empty(load_library().sy_spp_maxpool_backward_workspace_bytes(x.n, x.h, x.w, x.c), dtype=torch.uint8,
+                     device=x.buf.device)
+    _check(lib().sy_spp_maxpool_backward(x.st(), d5.st(), d9.st(), d13.st(), dx.st(), ws.data_ptr(), ws.numel(), _stream()),
+           kernels=2)

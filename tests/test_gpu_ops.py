@@ -398,10 +398,21 @@ def test_baseconv_backward_chain(case):
     invstd = (var + eps).rsqrt()
     scale = (gamma[None] * invstd).contiguous()
     shift = (beta[None] - mean * scale).contiguous()
+    # the forward kernel's own statistics (BatchNorm finalize in the conv tail, saved for the backward pass)
+    ss, mi = torch.empty((2, 2, co), device=DEV), torch.full((2, 2, co), float("nan"), device=DEV)
+    rm, rv, nbt = torch.zeros(co, device=DEV), torch.ones(co, device=DEV), torch.zeros((), dtype=torch.long, device=DEV)
+    raw2 = View.empty(n, h, w, co, DEV)
+    ops.conv2d(xv, ops.pack_conv_weight(wt), raw2, k, 1, ops.SY_CONV_RAW, split_n=split,
+               partials=torch.empty((ops.conv_stat_rows(), 4 * co), device=DEV), bn=[(gamma, beta, rm, rv, nbt, 0)],
+               momentum=0.03, eps=eps, scale_shift=ss, sync=torch.zeros(4, dtype=torch.int32, device=DEV), mean_invstd=mi)
+    torch.cuda.synchronize()
+    ng = len(groups)
+    assert torch.equal(raw2.torch(), raw.torch())
+    assert torch.allclose(mi[0, :ng], mean[:ng], rtol=1e-4, atol=1e-5) and torch.allclose(mi[1, :ng], invstd[:ng], rtol=1e-4)
+    assert torch.allclose(ss[0, :ng], scale[:ng], rtol=1e-4) and torch.allclose(ss[1, :ng], shift[:ng], rtol=1e-4, atol=1e-5)
     draw = View.empty(n, h, w, co, DEV)
     dgamma, dbeta = torch.full((co,), float("nan"), device=DEV), torch.full((co,), float("nan"), device=DEV)
-    ops.bn_act_backward(raw, ops.from_nchw(dy), draw, scale, shift, mean.contiguous(), invstd.contiguous(), split, 1,
-                        dgamma, dbeta)
+    ops.bn_act_backward(raw, ops.from_nchw(dy), draw, ss[0], ss[1], mi[0], mi[1], split, 1, dgamma, dbeta)
     dx = View.empty(n, h, w, ci, DEV)
     ops.conv2d(draw, ops.pack_conv_weight_dgrad(wt), dx, k, 1, ops.SY_CONV_RAW)
     dw = torch.empty((co, ci, k, k), device=DEV)
@@ -469,3 +480,22 @@ def test_head_pred_backward():
     for got, ref, name in zip(dws + dbs, [w_reg.grad, w_obj.grad, w_cls.grad, b_reg.grad, b_obj.grad, b_cls.grad],
                               ["dw_reg", "dw_obj", "dw_cls", "db_reg", "db_obj", "db_cls"]):
         assert (got - ref).abs().max().item() <= 2e-4 * ref.abs().max().item() + 1e-7, name
+
+
+def test_add_and_spp_backward():
+    n, c, h, w = 2, 64, 19, 30
+    a, b_ = rand_act(n, c, h, w, 81), rand_act(n, c, h, w, 82)
+    av, bv = ops.from_nchw(a), ops.from_nchw(b_)
+    ops.add_(av, bv)
+    torch.cuda.synchronize()
+    assert torch.equal(bv.nchw_float(), bf(a + b_))
+    # SPP pools: quantised input so that ties are common (first maximum in row-major order must win, like PyTorch)
+    g = torch.Generator().manual_seed(83)
+    x = (torch.randint(-6, 7, (n, c, h, w), generator=g).float() * 0.25).to(DEV).requires_grad_(True)
+    dys = [rand_act(n, c, h, w, 84 + i) for i in range(3)]
+    for k, d in zip((5, 9, 13), dys):
+        F.max_pool2d(x, k, 1, k // 2).backward(d)
+    dx = View.empty(n, h, w, c, DEV)
+    ops.spp_maxpool_backward(ops.from_nchw(x.detach()), *[ops.from_nchw(d) for d in dys], dx)
+    torch.cuda.synchronize()
+    check_close(dx.nchw_float(), x.grad, "spp backward", ulp=2.0 ** -8)
