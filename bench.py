@@ -248,10 +248,30 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": round(v, 4), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": "%d pairs/step, oracle restatement of the reference PyTorch path (yolox not installable)" % pairs},
             "e2e": {"value": round(v, 4), "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(json.dumps(line))
+
+
+_JSON_OUT = None
+
+
+def guard_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on fd 1
+    whatever NCCL_DEBUG says), so keep a private copy of the real stdout for the JSON line and point fd 1 at stderr for
+    everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(text):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    print(text, file=out, flush=True)
 
 
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -430,7 +450,7 @@ def main():
                                     "kind": "port", "sample": "2 pairs/step x 2 steps, fp32 oracle of the reference path"}
         except Exception as ex:  # never lose the GPU numbers to a host-side problem
             line["cpu_baseline"] = {"value": None, "error": str(ex)[:200]}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 if __name__ == "__main__":

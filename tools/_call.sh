@@ -1,4 +1,4 @@
 cd /root/repo
 mkdir -p gpurun_out
-(timeout 300 python -m pytest tests/test_gpu_ops.py -q --maxfail=30 -p no:cacheprovider -k "backward_chain or add_and_spp or bn_finalize" 2>&1 | tail -40) > gpurun_out/t_bwd3.txt
-tail -30 gpurun_out/t_bwd3.txt | cut -c1-240
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_2gpu_r1f.json 2> gpurun_out/bench_2gpu_r1f.err
+echo "stdout lines: $(wc -l < gpurun_out/bench_2gpu_r1f.json)"; head -c 200 gpurun_out/bench_2gpu_r1f.json; echo; ls /tmp/sy_nccl* 2>/dev/null | head -3
