@@ -1,0 +1,306 @@
+"""Training step with gradients: a recording forward + the reverse walk over the recorded kernels.
+
+    losses = backward.forward_backward(model, x, (labels_future, labels_current))     # fills p.grad of every parameter
+
+What ``loss.backward()`` does for the reference (/root/reference/exps/train_utils/double_trainer.py:110-114) through
+exps/model/{yolox,dfp_pafpn,darknet,tal_head}.py, expressed over the kernels of libstreamyolo_sm100:
+
+  * the forward is the product's forward (same kernels, same batching of the two frames with grouped BatchNorm statistics)
+    with two differences that a backward pass needs: nothing is updated in place (every conv keeps its input, its raw
+    output and the batch statistics), and the DFP fusion runs its two jian convs as two launches;
+  * every recorded op then runs its backward in reverse order.  Gradients of activations live in bf16 buffers that mirror
+    the activation buffers (a channel / image slice of an activation is the same slice of its gradient buffer) and are
+    *accumulated*: a tensor read by several consumers (Bottleneck shortcuts, FPN features, the concat buffers) simply
+    receives several contributions -- the conv data gradient accumulates through the FUSED epilogue's residual input.
+  * parameter gradients are fp32 in PyTorch's layouts (conv OIHW, BN weight / bias, pred-conv weight / bias) and are added
+    to ``p.grad`` like autograd does.
+
+STATUS (round 1): every kernel used here is tested on the GPU against autograd, and this module's routing is tested on
+CPU with the kernels emulated in torch (tests/test_cpu_backward.py: all parameter gradients against autograd through the
+oracle).  The module as a whole has not yet run on a GPU; it is not used by bench.py or by YOLOX.forward."""
+import torch
+
+from . import engine
+from .. import ops
+from ..ops import View
+
+
+class Tape:
+    def __init__(self, device):
+        self.device = device
+        self.ops = []
+        self.gbuf = {}          # id(activation buffer) -> gradient buffer (bf16, zero-initialised)
+        self.keep = []          # keeps the activation buffers (and so their ids) alive
+
+    def g(self, v: View) -> View:
+        key = id(v.buf)
+        if key not in self.gbuf:
+            self.gbuf[key] = torch.zeros_like(v.buf)
+            self.keep.append(v.buf)
+        return View(self.gbuf[key], v.c0, v.c, v.n0, v.n)
+
+    def rec(self, **kw):
+        self.ops.append(kw)
+
+
+def _acc(p, g):
+    g = g.to(p.dtype).reshape(p.shape)
+    p.grad = g.clone() if p.grad is None else p.grad + g
+
+
+# ------------------------------------------------------------------------------------------------ recording forward
+def conv_rec(T: Tape, mods, x: View, wpk, k, s, y: View, split, res: View = None, act=1, kind="normal"):
+    """conv -> train-mode BatchNorm (statistics groups split at image ``split``; 0 = one group) -> act (+ res) into ``y``;
+    keeps what the backward needs.  ``mods``: one BaseConv, or the conv1 | conv2 pair of a CSPLayer (one GEMM)."""
+    kh, kw = (k, k) if isinstance(k, int) else k
+    ho = (x.h + 2 * ((kh - 1) // 2) - kh) // s + 1
+    wo = (x.w + 2 * ((kw - 1) // 2) - kw) // s + 1
+    cout = sum(m.conv.out_channels for m in mods)
+    dev = T.device
+    raw = View.empty(x.n, ho, wo, cout, dev)
+    bn0 = mods[0].bn
+    mom = float(0.1 if bn0.momentum is None else bn0.momentum)
+    for m in mods:
+        m._stats_epoch = getattr(m, "_stats_epoch", 0) + 1
+    partials = torch.empty((ops.conv_stat_rows(), 4 * cout), dtype=torch.float32, device=dev)
+    segs, c0 = [], 0
+    for m in mods:
+        segs.append(engine._bn_seg(m, c0))
+        c0 += m.conv.out_channels
+    ss = torch.empty((2, 2, cout), dtype=torch.float32, device=dev)
+    mi = torch.empty((2, 2, cout), dtype=torch.float32, device=dev)
+    ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="tc", partials=partials, split_n=split, bn=segs, momentum=mom,
+               eps=float(bn0.eps), scale_shift=ss, sync=engine._sync(mods[0], dev), mean_invstd=mi)
+    ops.bn_act_apply(raw, ss[0].data_ptr(), ss[1].data_ptr(), split if split else x.n, act, res, y)
+    T.rec(t="conv", mods=mods, x=x, k=(kh, kw), s=s, raw=raw, y=y, res=res, ss=ss, mi=mi, split=split, act=act, kind=kind)
+    return y
+
+
+def base_conv_rec(T, m, x, split, y=None, res=None):
+    k, s = m.ksize, m.stride
+    ho, wo = ops.conv_out_hw(x.h, x.w, k, s)
+    if y is None:
+        y = View.empty(x.n, ho, wo, m.conv.out_channels, T.device)
+    return conv_rec(T, (m,), x, engine._packed(m), k, s, y, split, res, 1 if m.act_name == "silu" else 0)
+
+
+def csp_rec(T, m, x, split, out=None):
+    """CSPLayer without in-place updates: conv1 | conv2 as one GEMM into ``u0``; the bottleneck chain in fresh buffers, its
+    last output straight into the concat buffer ``u``; conv2's half copied next to it; conv3."""
+    hid = m.conv1.conv.out_channels
+    dev = T.device
+    u0 = View.empty(x.n, x.h, x.w, 2 * hid, dev)
+    conv_rec(T, (m.conv1, m.conv2), x, engine._packed_pair(m.conv1, m.conv2), 1, 1, u0, split)
+    u = View.empty(x.n, x.h, x.w, 2 * hid, dev)
+    a = u0.ch(0, hid)
+    nblk = len(m.m)
+    for i, blk in enumerate(m.m):
+        t = base_conv_rec(T, blk.conv1, a, split)
+        dst = u.ch(0, hid) if i == nblk - 1 else View.empty(x.n, x.h, x.w, hid, dev)
+        base_conv_rec(T, blk.conv2, t, split, dst, res=a if blk.use_add else None)
+        a = dst
+    if nblk == 0:
+        ops.copy(a, u.ch(0, hid))
+        T.rec(t="copy", src=a, dst=u.ch(0, hid))
+    ops.copy(u0.ch(hid, hid), u.ch(hid, hid))
+    T.rec(t="copy", src=u0.ch(hid, hid), dst=u.ch(hid, hid))
+    return base_conv_rec(T, m.conv3, u, split, out)
+
+
+def pafpn_rec(T, net, x, frames, split):
+    """engine.pafpn_frames in recording mode (same buffers / concat slices, no in-place bottleneck chain)."""
+    bb = net.backbone
+    dev = T.device
+    c3 = net.C3_p3.conv3.conv.out_channels
+    c4 = net.C3_p4.conv3.conv.out_channels
+    b, ch, h, w = x.shape
+    n = frames * b
+    stem = bb.stem.conv
+    xin = View.empty(n, h // 2, w // 2, 64, dev)
+    ops.focus_pack(x, frames, xin)
+    t = View.empty(n, h // 2, w // 2, stem.conv.out_channels, dev)
+    conv_rec(T, (stem,), xin, engine._packed_stem(stem), ops.STEM_K, 1, t, split, kind="stem")
+    t = base_conv_rec(T, bb.dark2[0], t, split)
+    t = csp_rec(T, bb.dark2[1], t, split)
+    t = base_conv_rec(T, bb.dark3[0], t, split)
+    h8, w8 = t.h, t.w
+    f1 = View.empty(n, h8, w8, 2 * c3, dev)              # cat(up(fpn_out1), dark3)
+    x2 = csp_rec(T, bb.dark3[1], t, split, f1.ch(c3, c3))
+    t = base_conv_rec(T, bb.dark4[0], x2, split)
+    h16, w16 = t.h, t.w
+    f0 = View.empty(n, h16, w16, 2 * c4, dev)            # cat(up(fpn_out0), dark4)
+    x1 = csp_rec(T, bb.dark4[1], t, split, f0.ch(c4, c4))
+    t = base_conv_rec(T, bb.dark5[0], x1, split)
+    h32, w32 = t.h, t.w
+    spp = bb.dark5[1]
+    hid = spp.conv1.conv.out_channels
+    sbuf = View.empty(n, h32, w32, 4 * hid, dev)
+    base_conv_rec(T, spp.conv1, t, split, sbuf.ch(0, hid))
+    ops.spp_maxpool(sbuf.ch(0, hid), sbuf.ch(hid, hid), sbuf.ch(2 * hid, hid), sbuf.ch(3 * hid, hid))
+    T.rec(t="spp", x=sbuf.ch(0, hid), y5=sbuf.ch(hid, hid), y9=sbuf.ch(2 * hid, hid), y13=sbuf.ch(3 * hid, hid))
+    t = base_conv_rec(T, spp.conv2, sbuf, split)
+    x0 = csp_rec(T, bb.dark5[2], t, split)
+    z0 = View.empty(n, h32, w32, 2 * c4, dev)            # cat(bu_conv1, fpn_out0)
+    fpn0 = base_conv_rec(T, net.lateral_conv0, x0, split, z0.ch(c4, c4))
+    ops.upsample_nearest(fpn0, f0.ch(0, c4))
+    T.rec(t="upsample", x=fpn0, y=f0.ch(0, c4))
+    fo0 = csp_rec(T, net.C3_p4, f0, split)
+    z1 = View.empty(n, h16, w16, 2 * c3, dev)            # cat(bu_conv2, fpn_out1)
+    fpn1 = base_conv_rec(T, net.reduce_conv1, fo0, split, z1.ch(c3, c3))
+    ops.upsample_nearest(fpn1, f1.ch(0, c3))
+    T.rec(t="upsample", x=fpn1, y=f1.ch(0, c3))
+    pan2 = csp_rec(T, net.C3_p3, f1, split)
+    base_conv_rec(T, net.bu_conv2, pan2, split, z1.ch(0, c3))
+    pan1 = csp_rec(T, net.C3_n3, z1, split)
+    base_conv_rec(T, net.bu_conv1, pan1, split, z0.ch(0, c4))
+    pan0 = csp_rec(T, net.C3_n4, z0, split)
+    return pan2, pan1, pan0
+
+
+def dfp_rec(T, net, cur, sup):
+    """out = cat(jian(cur), jian(sup)) + cur (dfp_pafpn.py:168-170); two launches per level, one statistics group each,
+    like the reference's two jian calls."""
+    outs = []
+    for m, c, s in zip((net.jian2, net.jian1, net.jian0), cur, sup):
+        half = m.conv.out_channels
+        out = View.empty(c.n, c.h, c.w, 2 * half, T.device)
+        wpk = engine._packed(m)
+        conv_rec(T, (m,), c, wpk, 1, 1, out.ch(0, half), 0, res=c.ch(0, half))
+        conv_rec(T, (m,), s, wpk, 1, 1, out.ch(half, half), 0, res=c.ch(half, half))
+        outs.append(out)
+    return outs
+
+
+def _f32(p):
+    return p.detach().float().contiguous().view(p.shape[0], -1) if p.dim() > 1 else p.detach().float().contiguous()
+
+
+def head_rec(T, head, fused, labels):
+    dev = T.device
+    b = fused[0].n
+    hw = [(v.h, v.w) for v in fused]
+    head.hw = hw
+    a_total = sum(h * w for h, w in hw)
+    no = 5 + head.num_classes
+    out = torch.empty((b, a_total, no), dtype=torch.float32, device=dev)
+    origin = torch.empty((b, a_total, 4), dtype=torch.float32, device=dev)
+    off = 0
+    levels = []
+    for k, v in enumerate(fused):
+        x = base_conv_rec(T, head.stems[k], v, 0)
+        cf = base_conv_rec(T, head.cls_convs[k][1], base_conv_rec(T, head.cls_convs[k][0], x, 0), 0)
+        rf = base_conv_rec(T, head.reg_convs[k][1], base_conv_rec(T, head.reg_convs[k][0], x, 0), 0)
+        ops.head_pred_decode(cf, rf, _f32(head.reg_preds[k].weight), _f32(head.reg_preds[k].bias),
+                             _f32(head.obj_preds[k].weight), _f32(head.obj_preds[k].bias), _f32(head.cls_preds[k].weight),
+                             _f32(head.cls_preds[k].bias), head.strides[k], off, a_total, out, origin, sigmoid=False, decode=True)
+        levels.append((k, cf, rf, off))
+        off += v.h * v.w
+    fut = labels[0][..., :5].to(dev, torch.float32).contiguous()
+    cur = labels[1][..., :5].to(dev, torch.float32).contiguous()
+    wsb = ops.tal_loss_workspace_bytes(b, a_total, fut.shape[1], head.num_classes)
+    ws = torch.empty((wsb + 255) // 256 * 256, dtype=torch.uint8, device=dev)
+    loss = torch.empty(6, dtype=torch.float32, device=dev)
+    ops.tal_loss(out, origin, fut, cur, hw, head.strides, float(head.gamma), float(head.ignore_thr), float(head.ignore_value),
+                 True, ws, loss)
+    T.rec(t="head", levels=levels, out=out, origin=origin, fut=fut, ws=ws, hw=hw, a_total=a_total)
+    return loss
+
+
+# ------------------------------------------------------------------------------------------------ reverse walk
+def _conv_backward(T: Tape, r):
+    mods, x, raw, y, res = r["mods"], r["x"], r["raw"], r["y"], r["res"]
+    kh, kw = r["k"]
+    s = r["s"]
+    dev = T.device
+    cout, cin = raw.c, x.c
+    gy = T.g(y)
+    if res is not None:
+        ops.add_(gy, T.g(res))                                   # shortcut / "+ cur" branch
+    draw = View.empty(raw.n, raw.h, raw.w, cout, dev)
+    dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
+    ops.bn_act_backward(raw, gy, draw, r["ss"][0], r["ss"][1], r["mi"][0], r["mi"][1], r["split"], r["act"], dgamma, dbeta)
+    dw = torch.empty((cout, cin, kh, kw), dtype=torch.float32, device=dev)
+    ops.conv2d_wgrad(x, draw, (kh, kw), s, dw)
+    c0 = 0
+    for m in mods:
+        c = m.conv.out_channels
+        _acc(m.bn.weight, dgamma[c0:c0 + c])
+        _acc(m.bn.bias, dbeta[c0:c0 + c])
+        if r["kind"] == "stem":
+            # packed stem weights: wpk[o][row r][s * 16 + fc] = w[o][fc][r][s]  ->  dw[o][s * 16 + fc][r][0]
+            g = dw[c0:c0 + c, :48, :, 0].reshape(c, 3, 16, 3)[:, :, :12, :]      # [o, s, fc, r]
+            _acc(m.conv.weight, g.permute(0, 2, 3, 1))                          # [o, fc, r, s]
+        else:
+            _acc(m.conv.weight, dw[c0:c0 + c])
+        c0 += c
+    if r["kind"] == "stem":
+        return                                                    # the input frames need no gradient
+    gx = T.g(x)
+    w_cat = torch.cat([m.conv.weight.detach() for m in mods], 0) if len(mods) > 1 else mods[0].conv.weight.detach()
+    one = torch.ones(cin, dtype=torch.float32, device=dev)
+    zero = torch.zeros(cin, dtype=torch.float32, device=dev)
+    src = draw
+    if s == 2:
+        src = View.empty(x.n, x.h, x.w, cout, dev)
+        ops.dilate2(draw, src)
+    # data gradient, accumulated in place: gx = conv(src, flipped / transposed filter) * 1 + 0 + gx
+    ops.conv2d(src, ops.pack_conv_weight_dgrad(w_cat), gx, (kh, kw), 1, ops.SY_CONV_FUSED, scale=one, shift=zero, act=0, res=gx)
+
+
+def _head_backward(T: Tape, head, r, grad_scale):
+    dev = T.device
+    out, origin = r["out"], r["origin"]
+    g_raw = torch.empty_like(out)
+    ops.tal_loss_backward(out, origin, r["fut"], r["hw"], head.strides, float(head.gamma), True, r["ws"], grad_scale,
+                          grad_raw=g_raw)
+    for k, cf, rf, off in r["levels"]:
+        regp, objp, clsp = head.reg_preds[k], head.obj_preds[k], head.cls_preds[k]
+        c = cf.c
+        dws = [torch.empty((o, c), dtype=torch.float32, device=dev) for o in (4, 1, head.num_classes)]
+        dbs = [torch.empty((o,), dtype=torch.float32, device=dev) for o in (4, 1, head.num_classes)]
+        ops.head_pred_backward(g_raw, cf, rf, T.g(cf), T.g(rf), _f32(regp.weight), _f32(objp.weight), _f32(clsp.weight),
+                               r["a_total"], off, dws[0], dws[1], dws[2], dbs[0], dbs[1], dbs[2])
+        for p, g in zip((regp.weight, objp.weight, clsp.weight, regp.bias, objp.bias, clsp.bias), dws + dbs):
+            _acc(p, g)
+
+
+def _walk(T: Tape, head, grad_scale):
+    for r in reversed(T.ops):
+        t = r["t"]
+        if t == "conv":
+            _conv_backward(T, r)
+        elif t == "head":
+            _head_backward(T, head, r, grad_scale)
+        elif t == "copy":
+            ops.add_(T.g(r["dst"]), T.g(r["src"]))
+        elif t == "upsample":
+            tmp = View.empty(r["x"].n, r["x"].h, r["x"].w, r["x"].c, T.device)
+            ops.upsample_nearest_backward(T.g(r["y"]), tmp)
+            ops.add_(tmp, T.g(r["x"]))
+        elif t == "spp":
+            x = r["x"]
+            tmp = View.empty(x.n, x.h, x.w, x.c, T.device)
+            ops.spp_maxpool_backward(x, T.g(r["y5"]), T.g(r["y9"]), T.g(r["y13"]), tmp)
+            ops.add_(tmp, T.g(x))
+        else:
+            raise RuntimeError(t)
+
+
+def forward_backward(model, x, targets, grad_scale=1.0):
+    """One training forward + backward of YOLOX(DFPPAFPN, TALHead) in train mode on a frame-pair batch ``x`` [B, 6, H, W].
+    Returns the loss dict of YOLOX.forward (0-dim tensors) and accumulates into ``p.grad`` of every parameter."""
+    assert model.training and model.head.use_l1
+    net, head = model.backbone, model.head
+    xin = x.float().contiguous()
+    b = xin.shape[0]
+    T = Tape(xin.device)
+    with torch.no_grad():
+        pans = pafpn_rec(T, net, xin, 2, b)
+        cur = tuple(p.imgs(0, b) for p in pans)
+        sup = tuple(p.imgs(b, b) for p in pans)
+        fused = dfp_rec(T, net, cur, sup)
+        loss = head_rec(T, head, fused, targets)
+        _walk(T, head, grad_scale)
+    return {"total_loss": loss[0], "iou_loss": loss[1], "l1_loss": loss[4], "conf_loss": loss[2], "cls_loss": loss[3],
+            "num_fg": loss[5]}

@@ -1,0 +1,299 @@
+"""CPU emulation of the ``streamyolo_b200.ops`` entry points in plain PyTorch -- TEST INFRASTRUCTURE ONLY.
+
+The product has no CPU path (``ops.lib()`` raises without the CUDA library and an sm_100 device).  The host-side logic above
+the C ABI -- which buffers feed which kernel, in-place concat slices, gradient routing of the backward walk -- is plain
+Python, though, and can be checked without a GPU if every kernel call is replaced by a few lines of torch with the same
+contract (same arguments, same bf16 rounding points).  ``install(monkeypatch)`` swaps the functions of ``ops`` for these;
+tests/test_cpu_backward.py then runs the whole recording forward + backward walk on CPU tensors and compares every
+parameter gradient with autograd through the oracle.  Each kernel itself is tested on the GPU against autograd /
+the oracle in tests/test_gpu_ops.py and tests/test_gpu_model.py."""
+import torch
+import torch.nn.functional as F
+
+from oracle.streamyolo_oracle import OracleCfg, StreamYoloOracle
+from streamyolo_b200 import ops
+from streamyolo_b200.ops import View
+
+PTRS = {}        # data_ptr -> tensor, for the entry points that take raw device pointers (bn_act_apply)
+LOSS_STATE = {}  # workspace data_ptr -> what tal_loss leaves for tal_loss_backward
+
+
+EXACT = False    # True: fp32 "storage" everywhere (no bf16 rounding), so that the emulated product equals the fp32 oracle up to
+                 # float roundoff -- a random-init train-mode BatchNorm net amplifies bf16 rounding noise to tens of percent
+                 # in the gradients, which would hide routing mistakes
+
+
+def _bf(t):
+    return t.float() if EXACT else t.to(torch.bfloat16)
+
+
+def _nchw(v: View):
+    return v.torch().permute(0, 3, 1, 2).float()
+
+
+def _store(v: View, t_nchw):
+    v.torch().copy_(_bf(t_nchw.permute(0, 2, 3, 1)))
+
+
+def _unpack(wpk, kh, kw):
+    """bf16 [O][kh*kw][I] -> float OIHW"""
+    o, taps, i = wpk.shape
+    return wpk.float().reshape(o, kh, kw, i).permute(0, 3, 1, 2).contiguous()
+
+
+def conv_stat_rows():
+    return 148
+
+
+def conv2d(x, wpk, y, k, s, mode, impl="tc", scale=None, shift=None, act=1, res=None, partials=None, split_n=0,
+           timeline=None, debug_flags=0, bn=None, momentum=0.03, eps=1e-3, scale_shift=None, sync=None, apply_y=None,
+           apply_res=None, y_goff1=0, res_goff1=0, mean_invstd=None):
+    kh, kw = (k, k) if isinstance(k, int) else k
+    w = _unpack(wpk, kh, kw)
+    out = F.conv2d(_nchw(x), w, None, s, ((kh - 1) // 2, (kw - 1) // 2))
+    if mode == ops.SY_CONV_FUSED:
+        if scale is not None:
+            out = out * scale.float()[None, :, None, None] + shift.float()[None, :, None, None]
+        if act:
+            out = F.silu(out)
+        if res is not None:
+            out = out + _nchw(res)
+        _store(y, out)
+        return 0
+    _store(y, out)
+    if bn:
+        stored = _nchw(y)
+        n = stored.shape[0]
+        sp = split_n if 0 < split_n < n else n
+        groups = [(0, sp), (sp, n)] if sp < n else [(0, n)]
+        c0s = [seg[5] for seg in bn] + [stored.shape[1]]
+        for gi, (a, b) in enumerate(groups):
+            part = stored[a:b]
+            mean = part.mean((0, 2, 3))
+            var = part.var((0, 2, 3), unbiased=False)
+            cnt = part.numel() / part.shape[1]
+            invstd = (var + eps).rsqrt()
+            for si, (gamma, beta, rm, rv, nbt, c0) in enumerate(bn):
+                sl = slice(c0, c0s[si + 1])
+                sc = gamma.detach().float() * invstd[sl]
+                scale_shift[0, gi, sl] = sc
+                scale_shift[1, gi, sl] = beta.detach().float() - mean[sl] * sc
+                if mean_invstd is not None:
+                    mean_invstd[0, gi, sl] = mean[sl]
+                    mean_invstd[1, gi, sl] = invstd[sl]
+                if rm is not None:
+                    rm.mul_(1 - momentum).add_(momentum * mean[sl])
+                    rv.mul_(1 - momentum).add_(momentum * var[sl] * (cnt / max(cnt - 1, 1)))
+                if nbt is not None:
+                    nbt.add_(1)
+        PTRS[scale_shift[0].data_ptr()] = scale_shift[0]
+        PTRS[scale_shift[1].data_ptr()] = scale_shift[1]
+    return 148
+
+
+def bn_act_apply(x, scale_ptr, shift_ptr, split_n, act, res, y, y_goff1=0, res_goff1=0):
+    assert y_goff1 == 0 and res_goff1 == 0, "group-offset destinations are not emulated (the recording forward avoids them)"
+    scale, shift = PTRS[scale_ptr], PTRS[shift_ptr]          # [2 groups][C]
+    t = _nchw(x)
+    n = t.shape[0]
+    sp = split_n if 0 < split_n < n else n
+    out = torch.empty_like(t)
+    out[:sp] = t[:sp] * scale[0][None, :, None, None] + shift[0][None, :, None, None]
+    if sp < n:
+        out[sp:] = t[sp:] * scale[1][None, :, None, None] + shift[1][None, :, None, None]
+    if act:
+        out = F.silu(out)
+    if res is not None:
+        out = out + _nchw(res)
+    _store(y, out)
+
+
+def focus_pack(x, frames, y):
+    b = x.shape[0]
+    xs = torch.cat([x[:, 3 * f:3 * f + 3] for f in range(frames)], 0)
+    xs = xs.float() if EXACT else xs.to(torch.bfloat16).float()
+    foc = torch.cat([xs[..., ::2, ::2], xs[..., 1::2, ::2], xs[..., ::2, 1::2], xs[..., 1::2, 1::2]], 1)   # [n,12,h,w]
+    n, _, h, w = foc.shape
+    out = torch.zeros(n, 64, h, w)
+    out[:, 16:28] = foc
+    out[:, 0:12, :, 1:] = foc[..., :-1]
+    out[:, 32:44, :, :-1] = foc[..., 1:]
+    _store(y, out)
+    assert n == frames * b
+
+
+def upsample_nearest(x, y):
+    _store(y, F.interpolate(_nchw(x), size=(y.h, y.w), mode="nearest"))
+
+
+def spp_maxpool(x, y5, y9, y13):
+    t = _nchw(x)
+    for k, v in ((5, y5), (9, y9), (13, y13)):
+        _store(v, F.max_pool2d(t, k, 1, k // 2))
+
+
+def copy(x, y):
+    y.torch().copy_(x.torch())
+
+
+def head_pred_decode(cls_feat, reg_feat, w_reg, b_reg, w_obj, b_obj, w_cls, b_cls, stride, anchor_offset, a_total, out,
+                     origin, sigmoid, decode):
+    cf, rf = _nchw(cls_feat), _nchw(reg_feat)
+    o = torch.cat([F.conv2d(rf, w_reg[:, :, None, None], b_reg), F.conv2d(rf, w_obj[:, :, None, None], b_obj),
+                   F.conv2d(cf, w_cls[:, :, None, None], b_cls)], 1)
+    b, no, h, w = o.shape
+    flat = o.flatten(2).permute(0, 2, 1).clone()
+    sl = slice(anchor_offset, anchor_offset + h * w)
+    if origin is not None:
+        origin[:, sl] = flat[..., :4]
+    if decode:
+        yv, xv = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+        flat[..., 0] = (flat[..., 0] + xv.reshape(-1)) * stride
+        flat[..., 1] = (flat[..., 1] + yv.reshape(-1)) * stride
+        flat[..., 2:4] = torch.exp(flat[..., 2:4]) * stride
+    if sigmoid:
+        flat[..., 4:] = torch.sigmoid(flat[..., 4:])
+    out[:, sl] = flat
+
+
+def tal_loss_workspace_bytes(b, a_total, max_labels, num_classes):
+    return 256
+
+
+def _loss_oracle(hw, strides, gamma, thr, val, nc):
+    o = StreamYoloOracle(OracleCfg(gamma=gamma, ignore_thr=thr, ignore_value=val, num_classes=nc, strides=tuple(strides)), {})
+    grid = o.grids(list(hw), o.cfg.strides)
+    return o, tuple(g.float() for g in grid)
+
+
+def tal_loss(outputs, origin, labels_fut, labels_cur, hw, strides, gamma, ignore_thr, ignore_value, use_l1, workspace,
+             loss_out, fg_out=None, matched_out=None, pred_iou_out=None):
+    o, grid = _loss_oracle(hw, strides, gamma, ignore_thr, ignore_value, outputs.shape[2] - 5)
+    with torch.enable_grad():
+        out_l, org_l = outputs.clone().requires_grad_(True), origin.clone().requires_grad_(True)
+        r = o.losses(out_l, org_l, grid, (labels_fut, labels_cur))
+        r["total_loss"].backward()
+    LOSS_STATE[workspace.data_ptr()] = (out_l.grad, org_l.grad, grid)
+    vals = [r["total_loss"], r["iou_loss"], r["conf_loss"], r["cls_loss"], r["l1_loss"], r["num_fg"]]
+    loss_out.copy_(torch.tensor([float(v) for v in vals]))
+
+
+def tal_loss_backward(outputs, origin, labels_fut, hw, strides, gamma, use_l1, workspace, grad_scale=1.0, grad_outputs=None,
+                      grad_origin=None, grad_raw=None):
+    g_out, g_org, grid = LOSS_STATE[workspace.data_ptr()]
+    gs = grid[2]
+    if grad_outputs is not None:
+        grad_outputs.copy_(g_out * grad_scale)
+    if grad_origin is not None:
+        grad_origin.copy_(g_org * grad_scale)
+    if grad_raw is not None:
+        raw = g_out.clone()
+        raw[..., 0:2] = g_out[..., 0:2] * gs[None, :, None] + g_org[..., 0:2]
+        raw[..., 2:4] = g_out[..., 2:4] * outputs[..., 2:4] + g_org[..., 2:4]
+        grad_raw.copy_(raw * grad_scale)
+
+
+def head_pred_backward(grad_raw, cls_feat, reg_feat, d_cls_feat, d_reg_feat, w_reg, w_obj, w_cls, a_total, anchor_offset,
+                       dw_reg, dw_obj, dw_cls, db_reg, db_obj, db_cls, accumulate=False):
+    h, w = cls_feat.h, cls_feat.w
+    g = grad_raw[:, anchor_offset:anchor_offset + h * w]                    # [b, hw, no]
+    cf, rf = cls_feat.torch().float().flatten(1, 2), reg_feat.torch().float().flatten(1, 2)   # [b, hw, c]
+    d_rf = g[..., 0:4] @ w_reg + g[..., 4:5] @ w_obj
+    d_cf = g[..., 5:] @ w_cls
+    d_reg_feat.torch().copy_(_bf(d_rf.reshape(d_reg_feat.torch().shape)))
+    d_cls_feat.torch().copy_(_bf(d_cf.reshape(d_cls_feat.torch().shape)))
+    res = [torch.einsum("bpo,bpc->oc", g[..., 0:4], rf), torch.einsum("bpo,bpc->oc", g[..., 4:5], rf),
+           torch.einsum("bpo,bpc->oc", g[..., 5:], cf), g[..., 0:4].sum((0, 1)), g[..., 4:5].sum((0, 1)), g[..., 5:].sum((0, 1))]
+    for dst, val in zip((dw_reg, dw_obj, dw_cls, db_reg, db_obj, db_cls), res):
+        dst.copy_(dst + val.reshape(dst.shape) if accumulate else val.reshape(dst.shape))
+
+
+def bn_act_backward(raw, dy, draw, scale, shift, mean, invstd, split_n, act, dgamma, dbeta, accumulate=False):
+    r, d = _nchw(raw), _nchw(dy)
+    n = r.shape[0]
+    sp = split_n if 0 < split_n < n else n
+    out = torch.empty_like(r)
+    dg, db = torch.zeros_like(dgamma), torch.zeros_like(dbeta)
+    for gi, (a, b) in enumerate([(0, sp), (sp, n)] if sp < n else [(0, n)]):
+        sc, sh, mu, iv = (t[gi][None, :, None, None] for t in (scale, shift, mean, invstd))
+        z = r[a:b] * sc + sh
+        s = torch.sigmoid(z)
+        dz = d[a:b] * (s * (1 + z * (1 - s))) if act else d[a:b]
+        xh = (r[a:b] - mu) * iv
+        m1, m2 = dz.mean((0, 2, 3), keepdim=True), (dz * xh).mean((0, 2, 3), keepdim=True)
+        out[a:b] = sc * (dz - m1 - xh * m2)
+        db += dz.sum((0, 2, 3))
+        dg += (dz * xh).sum((0, 2, 3))
+    _store(draw, out)
+    dgamma.copy_(dgamma + dg if accumulate else dg)
+    dbeta.copy_(dbeta + db if accumulate else db)
+
+
+def conv2d_wgrad(x, dy, k, s, dw, accumulate=False, workspace=None):
+    kh, kw = (k, k) if isinstance(k, int) else k
+    g = torch.nn.grad.conv2d_weight(_nchw(x), dw.shape, _nchw(dy), stride=s, padding=((kh - 1) // 2, (kw - 1) // 2))
+    dw.copy_(dw + g if accumulate else g)
+    return workspace
+
+
+def dilate2(g, D):
+    D.torch().zero_()
+    D.torch()[:, ::2, ::2, :][:, :g.h, :g.w] = g.torch()
+
+
+def upsample_nearest_backward(dy, dx):
+    with torch.enable_grad():
+        x = torch.zeros(dx.n, dx.c, dx.h, dx.w, requires_grad=True)
+        F.interpolate(x, size=(dy.h, dy.w), mode="nearest").backward(_nchw(dy))
+    _store(dx, x.grad)
+
+
+def spp_maxpool_backward(x, d5, d9, d13, dx):
+    with torch.enable_grad():
+        t = _nchw(x).requires_grad_(True)
+        for k, d in ((5, d5), (9, d9), (13, d13)):
+            F.max_pool2d(t, k, 1, k // 2).backward(_nchw(d))
+    _store(dx, t.grad)
+
+
+def add_(x, y):
+    _store(y, _nchw(x) + _nchw(y))
+
+
+NAMES = ["conv_stat_rows", "conv2d", "bn_act_apply", "focus_pack", "upsample_nearest", "spp_maxpool", "copy",
+         "head_pred_decode", "tal_loss_workspace_bytes", "tal_loss", "tal_loss_backward", "head_pred_backward",
+         "bn_act_backward", "conv2d_wgrad", "dilate2", "upsample_nearest_backward", "spp_maxpool_backward", "add_"]
+
+
+def _view_init(self, buf, c0=0, c=None, n0=0, n=None):
+    assert buf.dim() == 4 and buf.is_contiguous()
+    self.buf, self.c0, self.n0, self.off = buf, c0, n0, 0
+    self.c = buf.shape[3] - c0 if c is None else c
+    self.n = buf.shape[0] - n0 if n is None else n
+
+
+def _pack_conv_weight_f32(w):
+    o, i, kh, kw = w.shape
+    return w.detach().permute(0, 2, 3, 1).reshape(o, kh * kw, i).float().contiguous()
+
+
+def _pack_stem_weight_f32(w):
+    o = w.shape[0]
+    p = torch.zeros((o, 3, 4, 16), dtype=torch.float32)
+    p[:, :, :3, :12] = w.detach().permute(0, 2, 3, 1).float()
+    return p.reshape(o, 3, 64).contiguous()
+
+
+def install(monkeypatch, exact=False):
+    g = globals()
+    for n in NAMES:
+        monkeypatch.setattr(ops, n, g[n])
+    monkeypatch.setitem(g, "EXACT", exact)
+    if exact:
+        monkeypatch.setattr(View, "__init__", _view_init)
+        monkeypatch.setattr(View, "empty", staticmethod(lambda n, h, w, c, device: View(torch.empty((n, h, w, c), dtype=torch.float32,
+                                                                                               device=device))))
+        monkeypatch.setattr(ops, "pack_conv_weight", _pack_conv_weight_f32)
+        monkeypatch.setattr(ops, "pack_stem_weight", _pack_stem_weight_f32)
+    PTRS.clear()
+    LOSS_STATE.clear()
