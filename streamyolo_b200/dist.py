@@ -61,3 +61,32 @@ def sum_over_ranks(value: float, device="cpu") -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def allreduce_grads(params, bucket_bytes: int = 25 << 20):
+    """What DistributedDataParallel adds around the model (/root/reference/exps/train_utils/double_trainer.py:171): the MEAN
+    of every parameter gradient over the ranks.  Gradients are packed into flat fp32 buckets of ~``bucket_bytes`` in reverse
+    parameter order (the order in which the backward walk finishes them), one all-reduce per bucket (NCCL over
+    NVLink / NVSwitch on GPUs, gloo in the CPU tests), then unpacked in place.  BatchNorm buffers are not exchanged
+    (``broadcast_buffers=False``).  No-op in a single process."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return 0
+    world = dist.get_world_size()
+    todo = [p for p in reversed(list(params)) if p.grad is not None]
+    n_buckets, i = 0, 0
+    while i < len(todo):
+        bucket, size = [], 0
+        while i < len(todo) and (not bucket or size + todo[i].grad.numel() * 4 <= bucket_bytes):
+            bucket.append(todo[i])
+            size += todo[i].grad.numel() * 4
+            i += 1
+        flat = torch.cat([p.grad.detach().float().reshape(-1) for p in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(world)
+        off = 0
+        for p in bucket:
+            n = p.grad.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            off += n
+        n_buckets += 1
+    return n_buckets

@@ -79,3 +79,81 @@ def test_backward_routing_bf16_storage(monkeypatch):
     assert abs(got - want) < 2e-2 * abs(want)
     cos = sorted(c_ for _, c_, _ in report)
     assert cos[len(cos) // 2] > 0.8, f"median cosine {cos[len(cos) // 2]:.3f}"
+
+
+def test_train_steps_reduce_the_loss(monkeypatch):
+    """The reference's optimiser setup (SGD nesterov, three parameter groups) on top of the backward walk: the parameter
+    groups cover every parameter exactly once, and a few steps on a fixed batch bring the loss down."""
+    from streamyolo_b200 import train
+    c = CASES["tiny_120x160"]
+    emul_ops.install(monkeypatch, exact=True)
+    model = build_product(c)
+    opt = train.build_optimizer(model, lr=2e-4)
+    ids = [id(p) for g in opt.param_groups for p in g["params"]]
+    assert sorted(ids) == sorted(id(p) for p in model.parameters()) and len(set(ids)) == len(ids)
+    assert opt.param_groups[0].get("weight_decay", 0) == 0 and opt.param_groups[1]["weight_decay"] == 5e-4
+    ema = train.ModelEMA(model)
+    x = synth.synth_frames(c["B"], c["H"], c["W"])
+    tg = synth.synth_labels(c["B"], c["H"], c["W"])
+    losses = [float(train.train_step(model, opt, x, tg, ema)["total_loss"]) for _ in range(4)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    assert ema.updates == 4
+
+
+DDP_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import torch
+import emul_ops, test_cpu_backward as T
+from oracle.make_golden import CASES
+from streamyolo_b200 import dist as d, synth
+from streamyolo_b200.model import backward
+
+
+class MP:
+    def setattr(self, o, n, v): setattr(o, n, v)
+    def setitem(self, dct, k, v): dct[k] = v
+
+
+rank, local, world = d.init("gloo")
+emul_ops.install(MP(), exact=True)
+c = CASES["tiny_120x160"]
+x = synth.synth_frames(4, c["H"], c["W"])
+fut, cur = synth.synth_labels(4, c["H"], c["W"])
+
+
+def grads(lo, hi):
+    m = T.build_product(c)
+    backward.forward_backward(m, x[lo:hi], (fut[lo:hi], cur[lo:hi]))
+    return m
+
+
+lo, hi = d.shard_pairs(4, world, rank)
+mine = grads(lo, hi)                                    # this rank's shard
+nb = d.allreduce_grads(mine.parameters(), bucket_bytes=64 << 10)
+assert nb > 1, nb
+a, b = grads(0, 2), grads(2, 4)                         # both shards in one process: the expected mean
+for (k, p), pa, pb in zip(mine.named_parameters(), a.parameters(), b.parameters()):
+    want = 0.5 * (pa.grad + pb.grad)
+    assert torch.allclose(p.grad, want, rtol=1e-5, atol=1e-7 * float(want.abs().max()) + 1e-12), k
+print("ok", rank)
+"""
+
+
+def test_ddp_gradient_allreduce_gloo_world2(tmp_path):
+    """Row a19, host side: two processes (gloo), each runs the training backward on its shard of the global batch, then
+    the bucketed all-reduce; every parameter gradient must equal the mean of the two shards' gradients (DDP semantics:
+    BatchNorm statistics and the loss normaliser stay per rank)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "ddp_w.py"
+    script.write_text(DDP_WORKER)
+    port = 29900 + os.getpid() % 90
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   OMP_NUM_THREADS="4")
+        procs.append(subprocess.Popen([sys.executable, str(script), root], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[-2000:] for o in outs)
