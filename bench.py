@@ -243,8 +243,11 @@ def run_reference(args, rank):
             "value": round(v, 4), "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "StreamYOLO-%s 600x960 frame pairs, forward+loss (train-mode BN), CPU" % args.model,
-                       "pairs_per_step": pairs},
+            # the same workload as the GPU arm (its `config.workload` string), timed on a bounded sample of it
+            "config": {"workload": "StreamYOLO-%s (random init) 600x960 frame pairs, forward+loss, train-mode BN, "
+                                   "%d pairs/GPU" % (args.model, args.batch),
+                       "pairs_per_gpu": args.batch, "sample_pairs_per_step": pairs,
+                       "device": "host CPU cores (the reference's own CPU path: fp32 PyTorch)"},
             "cpu_baseline": {"value": round(v, 4), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": "%d pairs/step, oracle restatement of the reference PyTorch path (yolox not installable)" % pairs},
             "e2e": {"value": round(v, 4), "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
