@@ -91,21 +91,29 @@ def conv2d(x, wpk, y, k, s, mode, impl="tc", scale=None, shift=None, act=1, res=
     return 148
 
 
+def _strided(v: View, img0, nimg, goff):
+    """NHWC torch view of images [img0, img0 + nimg) of ``v`` with the base address moved by ``goff`` elements (the
+    group-offset destinations of the batched DFP fusion address image n - B, channels [half, 2 half) that way)."""
+    b = v.buf
+    H, W, Ct = b.shape[1], b.shape[2], b.shape[3]
+    return torch.as_strided(b.view(-1), (nimg, H, W, v.c), (H * W * Ct, W * Ct, Ct, 1),
+                            (v.n0 + img0) * H * W * Ct + v.c0 + v.off + goff)
+
+
 def bn_act_apply(x, scale_ptr, shift_ptr, split_n, act, res, y, y_goff1=0, res_goff1=0):
-    assert y_goff1 == 0 and res_goff1 == 0, "group-offset destinations are not emulated (the recording forward avoids them)"
     scale, shift = PTRS[scale_ptr], PTRS[shift_ptr]          # [2 groups][C]
     t = _nchw(x)
     n = t.shape[0]
     sp = split_n if 0 < split_n < n else n
-    out = torch.empty_like(t)
-    out[:sp] = t[:sp] * scale[0][None, :, None, None] + shift[0][None, :, None, None]
-    if sp < n:
-        out[sp:] = t[sp:] * scale[1][None, :, None, None] + shift[1][None, :, None, None]
-    if act:
-        out = F.silu(out)
-    if res is not None:
-        out = out + _nchw(res)
-    _store(y, out)
+    for gi, (a, b, yo, ro) in enumerate([(0, sp, 0, 0), (sp, n, y_goff1, res_goff1)]):
+        if a >= b:
+            continue
+        out = t[a:b] * scale[gi][None, :, None, None] + shift[gi][None, :, None, None]
+        if act:
+            out = F.silu(out)
+        if res is not None:
+            out = out + _strided(res, a, b - a, ro).permute(0, 3, 1, 2).float()
+        _strided(y, a, b - a, yo).copy_(_bf(out.permute(0, 2, 3, 1)))
 
 
 def focus_pack(x, frames, y):
@@ -293,6 +301,15 @@ def install(monkeypatch, exact=False):
         monkeypatch.setattr(View, "__init__", _view_init)
         monkeypatch.setattr(View, "empty", staticmethod(lambda n, h, w, c, device: View(torch.empty((n, h, w, c), dtype=torch.float32,
                                                                                                device=device))))
+        from streamyolo_b200.model import engine
+
+        def as_view_f32(t):
+            if isinstance(t, View):
+                return t
+            p = t.permute(0, 2, 3, 1)
+            return View(p if p.is_contiguous() else p.contiguous())
+
+        monkeypatch.setattr(engine, "as_view", as_view_f32)
         monkeypatch.setattr(ops, "pack_conv_weight", _pack_conv_weight_f32)
         monkeypatch.setattr(ops, "pack_stem_weight", _pack_stem_weight_f32)
     PTRS.clear()

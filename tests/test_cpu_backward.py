@@ -157,3 +157,34 @@ def test_ddp_gradient_allreduce_gloo_world2(tmp_path):
                                       stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(o[-2000:] for o in outs)
+
+
+@pytest.mark.parametrize("name", ["tiny_120x160", "tiny_empty_96x160"])
+def test_forward_engine_routing_exact(name, monkeypatch):
+    """The product's ordinary forward (engine.py: in-place concat slices, the two frames batched with grouped statistics,
+    the DFP fusion with group-offset destinations, eval with folded BN, on_pipe with a buffer) with emulated kernels and
+    fp32 storage, against the fp32 oracle: losses, eval outputs and streaming outputs to float roundoff."""
+    c = CASES[name]
+    emul_ops.install(monkeypatch, exact=True)
+    x = synth.synth_frames(c["B"], c["H"], c["W"])
+    tg = synth.synth_labels(c["B"], c["H"], c["W"], empty_image=c["empty"])
+    cfg = OracleCfg(depth=c["depth"], width=c["width"], gamma=c["gamma"], ignore_thr=c["thr"], ignore_value=c["val"])
+    o = StreamYoloOracle(cfg, synth.synth_state_dict(model_shapes(c["depth"], c["width"])), q=None)
+    model = build_product(c)
+    loss = model(x, tg)
+    ref = o.forward(x, tg)
+    for k in ("total_loss", "iou_loss", "l1_loss", "conf_loss", "cls_loss", "num_fg"):
+        assert abs(float(loss[k]) - float(ref[k])) <= 2e-5 * abs(float(ref[k])) + 1e-6, k
+    sd = model.state_dict()
+    for k in ("backbone.backbone.stem.conv.bn.running_var", "backbone.jian2.bn.running_mean", "head.stems.0.bn.running_var"):
+        assert torch.allclose(sd[k], o.P[k], rtol=1e-4, atol=1e-6), k
+    model.eval()
+    o.training = False
+    with torch.no_grad():
+        ev, ev_ref = model(x), o.forward(x, mode="off_pipe")
+        assert torch.allclose(ev, ev_ref, rtol=2e-4, atol=2e-4), float((ev - ev_ref).abs().max())
+        o1, buf = model(x[:1, 0:3], mode="on_pipe")
+        o2, _ = model(x[1:2, 0:3], buffer=buf, mode="on_pipe")
+        r1, rbuf = o.forward(x[:1, 0:3], mode="on_pipe")
+        r2, _ = o.forward(x[1:2, 0:3], buffer=rbuf, mode="on_pipe")
+        assert torch.allclose(o1, r1, rtol=2e-4, atol=2e-4) and torch.allclose(o2, r2, rtol=2e-4, atol=2e-4)
