@@ -55,6 +55,22 @@ def _run(c, monkeypatch, exact):
     return float(loss["total_loss"]), float(ref["total_loss"].detach()), report, model, o
 
 
+# deeper variants of the same graph (2 and 3 bottlenecks per CSP stage, 6 and 9 in dark3/dark4: StreamYOLO-m / -l depth)
+DEPTH_CASES = {
+    "m_depth_96x128": dict(depth=0.67, width=0.125, H=96, W=128, B=2, gamma=1.0, thr=0.5, val=1.5, empty=-1),
+    "l_depth_64x96": dict(depth=1.0, width=0.125, H=64, W=96, B=2, gamma=1.5, thr=0.4, val=1.7, empty=-1),
+}
+
+
+@pytest.mark.parametrize("name", list(DEPTH_CASES))
+def test_backward_routing_exact_deeper_models(name, monkeypatch):
+    got, want, report, _, _ = _run(DEPTH_CASES[name], monkeypatch, exact=True)
+    assert abs(got - want) < 1e-5 * abs(want)
+    msg = "\n".join(f"{rel:8.3e} cos {cos:.5f} {k}" for rel, cos, k in report[:10])
+    # deeper tiny nets amplify float roundoff a little more (a routing mistake would be O(1), with cosine far from 1)
+    assert report[0][0] < 1e-2 and min(c_ for _, c_, _ in report) > 0.9999, "largest deviations:\n" + msg
+
+
 @pytest.mark.parametrize("name", ["tiny_120x160", "tiny_empty_96x160"])
 def test_backward_routing_exact(name, monkeypatch):
     """fp32 storage everywhere (no bf16 rounding): the routing of the backward walk must reproduce autograd through the
