@@ -17,7 +17,8 @@ exps/model/{yolox,dfp_pafpn,darknet,tal_head}.py, expressed over the kernels of 
 
 STATUS (round 1): every kernel used here is tested on the GPU against autograd, and this module's routing is tested on
 CPU with the kernels emulated in torch (tests/test_cpu_backward.py: all parameter gradients against autograd through the
-oracle).  The module as a whole has not yet run on a GPU; it is not used by bench.py or by YOLOX.forward."""
+oracle).  The module as a whole has not yet run on a GPU; bench.py does not use it and YOLOX.forward only with
+``model.train_with_autograd = True`` (``loss_with_autograd``: the step as one autograd node)."""
 import torch
 
 from . import engine
@@ -31,6 +32,7 @@ class Tape:
         self.ops = []
         self.gbuf = {}          # id(activation buffer) -> gradient buffer (bf16, zero-initialised)
         self.keep = []          # keeps the activation buffers (and so their ids) alive
+        self.pgrad = {}         # id(parameter) -> accumulated fp32 gradient
 
     def g(self, v: View) -> View:
         key = id(v.buf)
@@ -43,9 +45,10 @@ class Tape:
         self.ops.append(kw)
 
 
-def _acc(p, g):
+def _acc(T, p, g):
     g = g.to(p.dtype).reshape(p.shape)
-    p.grad = g.clone() if p.grad is None else p.grad + g
+    k = id(p)
+    T.pgrad[k] = g.clone() if k not in T.pgrad else T.pgrad[k] + g
 
 
 # ------------------------------------------------------------------------------------------------ recording forward
@@ -225,14 +228,14 @@ def _conv_backward(T: Tape, r):
     c0 = 0
     for m in mods:
         c = m.conv.out_channels
-        _acc(m.bn.weight, dgamma[c0:c0 + c])
-        _acc(m.bn.bias, dbeta[c0:c0 + c])
+        _acc(T, m.bn.weight, dgamma[c0:c0 + c])
+        _acc(T, m.bn.bias, dbeta[c0:c0 + c])
         if r["kind"] == "stem":
             # packed stem weights: wpk[o][row r][s * 16 + fc] = w[o][fc][r][s]  ->  dw[o][s * 16 + fc][r][0]
             g = dw[c0:c0 + c, :48, :, 0].reshape(c, 3, 16, 3)[:, :, :12, :]      # [o, s, fc, r]
-            _acc(m.conv.weight, g.permute(0, 2, 3, 1))                          # [o, fc, r, s]
+            _acc(T, m.conv.weight, g.permute(0, 2, 3, 1))                       # [o, fc, r, s]
         else:
-            _acc(m.conv.weight, dw[c0:c0 + c])
+            _acc(T, m.conv.weight, dw[c0:c0 + c])
         c0 += c
     if r["kind"] == "stem":
         return                                                    # the input frames need no gradient
@@ -262,7 +265,7 @@ def _head_backward(T: Tape, head, r, grad_scale):
         ops.head_pred_backward(g_raw, cf, rf, T.g(cf), T.g(rf), _f32(regp.weight), _f32(objp.weight), _f32(clsp.weight),
                                r["a_total"], off, dws[0], dws[1], dws[2], dbs[0], dbs[1], dbs[2])
         for p, g in zip((regp.weight, objp.weight, clsp.weight, regp.bias, objp.bias, clsp.bias), dws + dbs):
-            _acc(p, g)
+            _acc(T, p, g)
 
 
 def _walk(T: Tape, head, grad_scale):
@@ -287,9 +290,8 @@ def _walk(T: Tape, head, grad_scale):
             raise RuntimeError(t)
 
 
-def forward_backward(model, x, targets, grad_scale=1.0):
-    """One training forward + backward of YOLOX(DFPPAFPN, TALHead) in train mode on a frame-pair batch ``x`` [B, 6, H, W].
-    Returns the loss dict of YOLOX.forward (0-dim tensors) and accumulates into ``p.grad`` of every parameter."""
+def _record(model, x, targets):
+    """Recording forward of YOLOX(DFPPAFPN, TALHead) in train mode; returns (tape, loss vector [total, iou, conf, cls, l1, num_fg])."""
     assert model.training and model.head.use_l1
     net, head = model.backbone, model.head
     xin = x.float().contiguous()
@@ -301,6 +303,54 @@ def forward_backward(model, x, targets, grad_scale=1.0):
         sup = tuple(p.imgs(b, b) for p in pans)
         fused = dfp_rec(T, net, cur, sup)
         loss = head_rec(T, head, fused, targets)
-        _walk(T, head, grad_scale)
+    return T, loss
+
+
+def _loss_dict(loss):
     return {"total_loss": loss[0], "iou_loss": loss[1], "l1_loss": loss[4], "conf_loss": loss[2], "cls_loss": loss[3],
             "num_fg": loss[5]}
+
+
+def forward_backward(model, x, targets, grad_scale=1.0):
+    """One training forward + backward of YOLOX(DFPPAFPN, TALHead) in train mode on a frame-pair batch ``x`` [B, 6, H, W].
+    Returns the loss dict of YOLOX.forward (0-dim tensors) and accumulates into ``p.grad`` of every parameter."""
+    T, loss = _record(model, x, targets)
+    with torch.no_grad():
+        _walk(T, model.head, grad_scale)
+    for p in model.parameters():
+        g = T.pgrad.get(id(p))
+        if g is not None:
+            p.grad = g if p.grad is None else p.grad + g
+    return _loss_dict(loss)
+
+
+class _TrainLoss(torch.autograd.Function):
+    """The whole training forward as ONE autograd node: forward = recording forward, backward = the reverse walk.  The
+    parameters are inputs of the node, so ``loss.backward()`` hands their gradients to autograd like any other op --
+    optimizers, ``GradScaler`` (the incoming gradient is the loss scale) and ``DistributedDataParallel``'s reducer hooks see
+    nothing unusual (/root/reference/exps/train_utils/double_trainer.py:105-123, 171)."""
+
+    @staticmethod
+    def forward(ctx, model, x, fut, cur, *params):
+        T, loss = _record(model, x, (fut, cur))
+        ctx.tape, ctx.model, ctx.params = T, model, params
+        ctx.mark_non_differentiable(loss)
+        return loss[0].clone(), loss
+
+    @staticmethod
+    def backward(ctx, g_total, _g_all):
+        T, model = ctx.tape, ctx.model
+        with torch.no_grad():
+            _walk(T, model.head, float(g_total))          # one host sync per step: the loss scale as a kernel argument
+        grads = tuple(T.pgrad.get(id(p)) for p in ctx.params)
+        ctx.tape = None
+        return (None, None, None, None) + grads
+
+
+def loss_with_autograd(model, x, targets):
+    """Loss dict whose ``total_loss`` carries a grad_fn (see _TrainLoss); the other entries are detached values."""
+    params = tuple(p for p in model.parameters() if p.requires_grad)
+    total, loss = _TrainLoss.apply(model, x, targets[0], targets[1], *params)
+    d = _loss_dict(loss)
+    d["total_loss"] = total
+    return d

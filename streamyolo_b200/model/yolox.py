@@ -1,4 +1,5 @@
 """YOLOX wrapper (mirror of /root/reference/exps/model/yolox.py:11-55)."""
+import torch
 import torch.nn as nn
 
 from .dfp_pafpn import DFPPAFPN
@@ -10,10 +11,17 @@ class YOLOX(nn.Module):
         super().__init__()
         self.backbone = DFPPAFPN() if backbone is None else backbone
         self.head = TALHead(20) if head is None else head
+        self.train_with_autograd = False     # True: training forward returns a differentiable loss (model/backward.py)
 
     def forward(self, x, targets=None, buffer=None, mode="off_pipe"):
         assert mode in ["off_pipe", "on_pipe"]
         if mode == "off_pipe":
+            if self.training and self.train_with_autograd and torch.is_grad_enabled():
+                # opt-in (round 1: verified on CPU with emulated kernels, not yet on a GPU): the loss carries a grad_fn, so
+                # the reference trainer's scaler.scale(loss).backward() / optimizer.step() work unchanged
+                from . import backward
+                assert targets is not None
+                return backward.loss_with_autograd(self, x, targets)
             fpn_outs = self.backbone(x, buffer=buffer, mode="off_pipe")
             if self.training:
                 assert targets is not None

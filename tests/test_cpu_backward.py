@@ -116,6 +116,30 @@ def test_train_steps_reduce_the_loss(monkeypatch):
     assert ema.updates == 4
 
 
+def test_loss_backward_through_autograd(monkeypatch):
+    """Opt-in drop-in for the reference trainer (double_trainer.py:105-123): with ``model.train_with_autograd`` the training
+    forward returns a loss with a grad_fn; ``(scale * loss).backward()`` must hand autograd exactly the gradients of the
+    explicit walk, times the scale (GradScaler semantics), and accumulate over two calls like autograd does."""
+    c = CASES["tiny_120x160"]
+    emul_ops.install(monkeypatch, exact=True)
+    x = synth.synth_frames(c["B"], c["H"], c["W"])
+    tg = synth.synth_labels(c["B"], c["H"], c["W"])
+    ref_model = build_product(c)
+    want_loss = backward.forward_backward(ref_model, x, tg)
+    model = build_product(c)
+    model.train_with_autograd = True
+    out = model(x, tg)
+    assert out["total_loss"].requires_grad and not out["iou_loss"].requires_grad
+    assert float(out["total_loss"]) == float(want_loss["total_loss"])
+    (out["total_loss"] * 64.0).backward()
+    for (k, p), q in zip(model.named_parameters(), ref_model.parameters()):
+        assert p.grad is not None, k
+        assert torch.allclose(p.grad, 64.0 * q.grad, rtol=1e-5, atol=1e-6 * float(q.grad.abs().max()) + 1e-12), k
+    with torch.no_grad():                                    # evaluation-style call inside training mode: the plain forward
+        plain = model(x, tg)
+    assert not plain["total_loss"].requires_grad
+
+
 DDP_WORKER = r"""
 import os, sys
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
