@@ -110,3 +110,35 @@ def test_dropin_aliases():
             "import streamyolo_b200.model as m; assert YOLOX is m.YOLOX and TALHead is m.TALHead; print('ok')")
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """Every descriptor struct of include/streamyolo_sm100.h, compiled by gcc, has the size and the field offsets of its
+    ctypes twin in streamyolo_b200/ops.py (a silent mismatch would corrupt kernel arguments)."""
+    import ctypes
+    import re
+    import shutil
+    from streamyolo_b200 import ops
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    names = [n for n in dir(ops) if n.startswith("Sy") and isinstance(getattr(ops, n), type)
+             and issubclass(getattr(ops, n), ctypes.Structure)]
+    header = open(os.path.join(ROOT, "include", "streamyolo_sm100.h")).read()
+    assert set(names) == set(re.findall(r"\}\s*(Sy\w+)\s*;", header)), "ctypes stubs and header structs differ"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "streamyolo_sm100.h"', "int main(void) {"]
+    for n in names:
+        lines.append(f'  printf("{n} size %zu\\n", sizeof({n}));')
+        for f, _ in getattr(ops, n)._fields_:
+            lines.append(f'  printf("{n} {f} %zu\\n", offsetof({n}, {f}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    r = subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout.split("\n")
+    for line in filter(None, out):
+        n, f, v = line.split()
+        cls = getattr(ops, n)
+        want = ctypes.sizeof(cls) if f == "size" else getattr(cls, f).offset
+        assert int(v) == want, f"{n}.{f}: header {v}, ctypes {want}"
