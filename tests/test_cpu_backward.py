@@ -228,3 +228,18 @@ def test_forward_engine_routing_exact(name, monkeypatch):
         r1, rbuf = o.forward(x[:1, 0:3], mode="on_pipe")
         r2, _ = o.forward(x[1:2, 0:3], buffer=rbuf, mode="on_pipe")
         assert torch.allclose(o1, r1, rtol=2e-4, atol=2e-4) and torch.allclose(o2, r2, rtol=2e-4, atol=2e-4)
+
+
+def test_half_model_eval_forward(monkeypatch):
+    """tools/eval.py --fp16 path: ``model.half()`` and half inputs go through the same kernels (parameters are repacked
+    from whatever dtype they have); outputs stay close to the fp32-parameter model (fp16 parameter rounding only)."""
+    c = CASES["tiny_120x160"]
+    emul_ops.install(monkeypatch, exact=False)
+    x = synth.synth_frames(c["B"], c["H"], c["W"])
+    m32 = build_product(c).eval()
+    m16 = build_product(c).eval().half()
+    with torch.no_grad():
+        a, b = m32(x), m16(x.half())
+    assert b.dtype == torch.float32 and torch.isfinite(b).all()
+    rel = float((a - b).norm() / a.norm())
+    assert rel < 5e-2, rel
