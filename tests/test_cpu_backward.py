@@ -243,3 +243,19 @@ def test_half_model_eval_forward(monkeypatch):
     assert b.dtype == torch.float32 and torch.isfinite(b).all()
     rel = float((a - b).norm() / a.norm())
     assert rel < 5e-2, rel
+
+
+def test_decode_outputs_path(monkeypatch):
+    """tools/eval.py:187-188: ``head.decode_in_inference = False`` + ``head.decode_outputs(outputs, dtype)`` must give what the
+    in-kernel decode gives."""
+    c = CASES["tiny_120x160"]
+    emul_ops.install(monkeypatch, exact=True)
+    x = synth.synth_frames(c["B"], c["H"], c["W"])
+    m = build_product(c).eval()
+    with torch.no_grad():
+        want = m(x)
+        m.head.decode_in_inference = False
+        raw = m(x)
+        got = m.head.decode_outputs(raw.clone(), dtype=raw.type())
+    assert not torch.allclose(raw[..., :4], want[..., :4])
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
