@@ -1153,3 +1153,30 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
   if (lin) return tc::launch_bn<1>(bn, ta, tb, ty, p, stream);
   return tc::launch_bn<0>(bn, ta, tb, ty, p, stream);
 }
+
+// Host-only query (no launch, works without a GPU): the tiling decisions sy_conv2d_tc takes for a layer shape.
+extern "C" int sy_conv2d_plan(int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t kh, int32_t kw, int32_t stride,
+                              SyConvPlan* out) {
+  SY_REQUIRE(out != nullptr && n > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, SY_EINVAL, "conv2d_plan: bad arguments");
+  SY_REQUIRE((kh == 1 || kh == 3) && (kw == 1 || kw == 3) && (stride == 1 || stride == 2), SY_EINVAL,
+             "conv2d_plan: kernel %dx%d stride %d unsupported", kh, kw, stride);
+  const int ph = (kh - 1) / 2, pw = (kw - 1) / 2;
+  const int ho = (h + 2 * ph - kh) / stride + 1, wo = (w + 2 * pw - kw) / stride + 1;
+  const int cblocks = cdiv(cin, tc::kBlockK), kblocks = kh * kw * cblocks;
+  const bool halo = kh == 3 && kw == 3 && stride == 1 && tc::linear_tiles() && tc::use_halo(n, ho, wo, cout, kblocks);
+  const bool lin = !halo && tc::linear_tiles();
+  int th = 16, tw = 8;
+  if (!halo) tc::pick_patch(ho, wo, &th, &tw);
+  const int lin_tiles = cdiv(n * ho * wo, tc::kBlockM);
+  const int m_tiles = lin ? lin_tiles : n * cdiv(ho, th) * cdiv(wo, tw);
+  const int bn = tc::pick_bn(cout, halo ? lin_tiles : m_tiles, kblocks);
+  out->mode = halo ? 2 : (lin ? 1 : 0);
+  out->bn = bn;
+  out->m_tiles = m_tiles;
+  out->n_tiles = cdiv(cout, bn);
+  out->rounds = cdiv(m_tiles * out->n_tiles, tc::num_sms());
+  out->kblocks = kblocks;
+  out->patch_h = lin ? 0 : th;
+  out->patch_w = lin ? 0 : tw;
+  return SY_OK;
+}

@@ -86,6 +86,10 @@ class SyHeadPredBwdDesc(C.Structure):
                 ("n_partials", C.c_int32)]
 
 
+class SyConvPlan(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("mode", "bn", "m_tiles", "n_tiles", "rounds", "kblocks", "patch_h", "patch_w")]
+
+
 class SyTalLossBwdDesc(C.Structure):
     _fields_ = [("outputs", C.c_void_p), ("origin", C.c_void_p), ("labels_fut", C.c_void_p),
                 ("b", C.c_int32), ("a_total", C.c_int32), ("max_labels", C.c_int32), ("num_classes", C.c_int32),
@@ -102,6 +106,7 @@ _SIG = {
     "sy_check_device": (C.c_int, []),
     "sy_conv_stat_rows": (C.c_int, []),
     "sy_conv2d_tc": (C.c_int, [C.POINTER(SyConvDesc), C.c_void_p]),
+    "sy_conv2d_plan": (C.c_int, [C.c_int32] * 8 + [C.POINTER(SyConvPlan)]),
     "sy_conv2d_simt": (C.c_int, [C.POINTER(SyConvDesc), C.c_void_p]),
     "sy_focus_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, SyTensor,
                                 C.c_void_p]),
@@ -505,3 +510,13 @@ def spp_maxpool_backward(x: View, d5: View, d9: View, d13: View, dx: View):
                      device=x.buf.device)
     _check(lib().sy_spp_maxpool_backward(x.st(), d5.st(), d9.st(), d13.st(), dx.st(), ws.data_ptr(), ws.numel(), _stream()),
            kernels=2)
+
+
+def conv2d_plan(n, h, w, cin, cout, k, s):
+    """Tiling decisions of the tensor-core conv for a layer shape (host-only: works without a GPU)."""
+    kh, kw = (k, k) if isinstance(k, int) else k
+    p = SyConvPlan()
+    rc = load_library().sy_conv2d_plan(n, h, w, cin, cout, kh, kw, s, C.byref(p))
+    if rc != 0:
+        raise RuntimeError("conv2d_plan: " + (load_library().sy_last_error_string() or b"").decode())
+    return {f: getattr(p, f) for f, _ in SyConvPlan._fields_}

@@ -142,3 +142,23 @@ def test_struct_layouts_match_header(tmp_path):
         cls = getattr(ops, n)
         want = ctypes.sizeof(cls) if f == "size" else getattr(cls, f).offset
         assert int(v) == want, f"{n}.{f}: header {v}, ctypes {want}"
+
+
+def test_conv_plan_query_without_gpu(monkeypatch):
+    """sy_conv2d_plan is host-only: the tiling decisions of the tensor-core conv can be inspected (and are pinned here for the
+    layers that motivated them) without a device.  148 SMs are assumed when no GPU is present."""
+    monkeypatch.delenv("SY_CONV_TILES", raising=False)
+    monkeypatch.delenv("SY_CONV_A", raising=False)
+    p = ops.conv2d_plan(16, 38, 60, 256, 256, 3, 1)          # linear tiles: 285 tiles = 2 rounds (patch tiles would need 3)
+    assert (p["mode"], p["bn"], p["m_tiles"], p["rounds"]) == (1, 256, 285, 2)
+    p = ops.conv2d_plan(16, 19, 30, 512, 512, 3, 1)          # 72 x 2 tiles: one round
+    assert (p["mode"], p["bn"], p["rounds"]) == (1, 256, 1)
+    p = ops.conv2d_plan(16, 75, 120, 128, 128, 3, 1)         # BN = 128 on a large map: halo mode, 16 x 8 patches
+    assert (p["mode"], p["bn"], p["patch_h"], p["patch_w"], p["kblocks"]) == (2, 128, 16, 8, 18)
+    p = ops.conv2d_plan(16, 75, 120, 128, 128, 1, 1)         # 1x1: never halo
+    assert p["mode"] == 1 and p["kblocks"] == 2
+    monkeypatch.setenv("SY_CONV_TILES", "patch")
+    p = ops.conv2d_plan(16, 38, 60, 256, 256, 3, 1)
+    assert p["mode"] == 0 and p["rounds"] == 3
+    with pytest.raises(RuntimeError):
+        ops.conv2d_plan(1, 8, 8, 8, 8, 5, 1)
