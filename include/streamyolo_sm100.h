@@ -321,6 +321,44 @@ typedef struct SyNmsDesc {
 size_t sy_postprocess_nms_workspace_bytes(int32_t b, int32_t a_total);
 int sy_postprocess_nms(const SyNmsDesc* d, sy_stream_t stream);
 
+/* -------- training step glue (streamyolo_b200/csrc/train_glue.cu) ---------------------------------------------- */
+/* fp32 OIHW conv parameter -> bf16 GEMM operand, on the device (one launch per parameter per optimiser step):
+ *   mode 0  out[o][r*kw+s][i] = w[o][i][r][s]                          forward B operand of sy_conv2d_tc
+ *   mode 1  out[i][taps-1-(r*kw+s)][co_offset + o] = w[o][i][r][s]     data-gradient operand (flipped taps, transposed
+ *           channels; rows of out_pitch elements so that the conv1 | conv2 pair of a CSPLayer packs into one operand)
+ *   mode 2  out[o][r][s*16 + i] = w[o][i][r][s], 64 columns per (o, r) Focus stem (see sy_focus_pack)
+ * Replaces the weight.to(bf16).permute chain a PyTorch host would run after every optimizer.step()
+ * (exps/train_utils/double_trainer.py:119-121). */
+int sy_pack_conv_weight(const float* w, int32_t cout, int32_t cin, int32_t kh, int32_t kw, int32_t mode, void* out,
+                        int64_t out_pitch, int32_t co_offset, sy_stream_t stream);
+
+/* The optimiser step of the reference trainer as one launch over flat fp32 state:
+ * GradScaler.unscale_ + [yolox] Exp.get_optimizer's SGD(momentum, nesterov) with weight decay on the conv / linear weights
+ * only + [yolox] ModelEMA.update (exps/train_utils/double_trainer.py:113-123, 173-175).  Elements [0, n_param) are
+ * parameters in the order (BatchNorm weights, biases | decayed weights from decay_begin); [n_param, n_total) are the
+ * floating-point buffers (BatchNorm running statistics) that only the EMA follows.  Step-by-step the same roundings as
+ * torch.optim.SGD / ModelEMA in fp32.  found_inf (device float, may be NULL): non-zero skips the whole update. */
+typedef struct SySgdEmaDesc {
+  float* param;              /* [n_total] model state (parameters then float buffers) */
+  const float* grad;         /* [n_param] (the all-reduced flat gradient buffer) */
+  float* momentum_buf;       /* [n_param] */
+  float* ema;                /* [n_total] or NULL (no EMA) */
+  int64_t n_param, n_total, decay_begin;
+  float lr, momentum, weight_decay, inv_scale;
+  int32_t nesterov;
+  float ema_decay, ema_one_minus_decay;
+  const float* found_inf;
+} SySgdEmaDesc;
+int sy_sgd_nesterov_ema_step(const SySgdEmaDesc* d, sy_stream_t stream);
+
+/* Input pipeline on the device: Exp.preprocess (cfgs/s_s50_onex_dfp_tal_flip.py:160-171) =
+ * F.interpolate(inputs, size=tsize, mode="bilinear", align_corners=False) on the NCHW fp32 frame-pair batch
+ * (x: [nc = B*6][hi][wi] -> y: [nc][ho][wo]) and the label rescale targets[..., 1::2] *= sx, [..., 2::2] *= sy
+ * (labels: rows x cols floats, column 0 = class, in place). */
+int sy_resize_bilinear(const float* x, int32_t nc, int32_t hi, int32_t wi, float* y, int32_t ho, int32_t wo,
+                       sy_stream_t stream);
+int sy_scale_labels(float* labels, int64_t rows, int32_t cols, float sx, float sy, sy_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,7 @@ SOURCES = {
     "bn_glue.cu": [],
     "bn_bwd.cu": [],
     "bwd_glue.cu": [],
+    "train_glue.cu": [],
     "head_loss.cu": ["-fmad=false"],
     "postprocess.cu": ["-fmad=false"],
 }

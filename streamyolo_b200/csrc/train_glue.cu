@@ -1,0 +1,160 @@
+// Kernels around the training step that are neither convolutions nor BatchNorm:
+//   * sy_pack_conv_weight      fp32 OIHW parameter -> bf16 GEMM operand of the tensor-core kernels (forward layout
+//                              [Cout][taps][Cin], data-gradient layout = flipped taps + transposed channels, Focus-stem layout):
+//                              one launch per parameter per optimiser step instead of an ATen permute + cast chain
+//   * sy_sgd_nesterov_ema_step the optimiser step of the reference trainer as ONE launch over flat fp32 buffers:
+//                              GradScaler unscale + weight decay + SGD momentum (nesterov) + ModelEMA
+//                              (/root/reference/exps/train_utils/double_trainer.py:113-123, 173-175; [yolox 0.3.0]
+//                              Exp.get_optimizer, ModelEMA)
+//   * sy_resize_bilinear       the multi-scale resize of Exp.preprocess (/root/reference/cfgs/s_s50_onex_dfp_tal_flip.py:160-171:
+//                              F.interpolate(mode="bilinear", align_corners=False)) + sy_scale_labels for the box rescale
+#include <math.h>
+
+#include "common.cuh"
+
+namespace sy {
+
+// mode 0: out[o][t][i]                      = w[o][i][r][s],               t = r * kw + s                (forward B operand)
+// mode 1: out[i][(kh-1-r)*kw + (kw-1-s)][o] = w[o][i][r][s]   (row pitch out_pitch, column offset co_off: data gradient)
+// mode 2: out[o][r][s * 16 + i]             = w[o][i][r][s], i < 12, 64 columns per (o, r), rest zero     (Focus stem)
+__global__ void pack_weight_kernel(const float* __restrict__ w, int O, int I, int kh, int kw, int mode, __nv_bfloat16* out,
+                                   long long out_pitch, int co_off) {
+  const int taps = kh * kw;
+  if (mode == 2) {
+    const long long total = (long long)O * kh * 64;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+      const int col = (int)(idx % 64);
+      const int r = (int)((idx / 64) % kh);
+      const int o = (int)(idx / (64 * kh));
+      const int s = col >> 4, i = col & 15;
+      float v = 0.f;
+      if (s < kw && i < I) v = w[(((long long)o * I + i) * kh + r) * kw + s];
+      out[idx] = __float2bfloat16_rn(v);
+    }
+    return;
+  }
+  const long long total = (long long)O * I * taps;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    if (mode == 0) {                       // idx walks the OUTPUT: (o, t, i), i fastest (coalesced bf16 stores)
+      const int i = (int)(idx % I);
+      const int t = (int)((idx / I) % taps);
+      const int o = (int)(idx / ((long long)I * taps));
+      out[idx] = __float2bfloat16_rn(w[((long long)o * I + i) * taps + t]);
+    } else {                               // idx walks (i, t', o), o fastest
+      const int o = (int)(idx % O);
+      const int t2 = (int)((idx / O) % taps);
+      const int i = (int)(idx / ((long long)O * taps));
+      const int t = taps - 1 - t2;         // (kh-1-r)*kw + (kw-1-s) = taps - 1 - (r*kw + s)
+      out[((long long)i * taps + t2) * out_pitch + co_off + o] = __float2bfloat16_rn(w[((long long)o * I + i) * taps + t]);
+    }
+  }
+}
+
+// One thread per element of the flat state.  Elements [0, n_param) are parameters (gradient, momentum), of which
+// [decay_begin, n_param) get weight decay; elements [n_param, n_total) are floating-point buffers (BatchNorm running
+// statistics) that only the EMA tracks.  Arithmetic mirrors torch.optim.SGD (foreach) and yolox ModelEMA step by step,
+// including which operations are fused multiply-adds there (a.add(b, alpha) -> fma) and which are two roundings.
+__global__ void sgd_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mbuf,
+                               float* __restrict__ ema, long long n_param, long long n_total, long long decay_begin, float lr,
+                               float momentum, float wd, float inv_scale, int nesterov, float ema_d, float ema_1md,
+                               const float* __restrict__ found_inf) {
+  if (found_inf != nullptr && *found_inf != 0.f) return;          // GradScaler.step skips the update on inf / nan
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_total; i += (long long)gridDim.x * blockDim.x) {
+    float v = p[i];
+    if (i < n_param) {
+      float d = g[i];
+      if (inv_scale != 1.0f) d = __fmul_rn(d, inv_scale);         // GradScaler.unscale_: grad.mul_(inv_scale)
+      if (i >= decay_begin && wd != 0.f) d = fmaf(wd, v, d);      // grad.add(param, alpha=wd)
+      float b = __fadd_rn(__fmul_rn(mbuf[i], momentum), d);       // buf.mul_(momentum).add_(grad)
+      mbuf[i] = b;
+      d = nesterov ? fmaf(momentum, b, d) : b;                    // grad.add(buf, alpha=momentum)
+      v = fmaf(-lr, d, v);                                        // param.add_(grad, alpha=-lr)
+      p[i] = v;
+    }
+    if (ema != nullptr) ema[i] = __fadd_rn(__fmul_rn(ema[i], ema_d), __fmul_rn(ema_1md, v));   // v *= d; v += (1 - d) * model
+  }
+}
+
+// F.interpolate(x, size=(Ho, Wo), mode="bilinear", align_corners=False) on NCHW fp32 (ATen upsample_bilinear2d:
+// src = max(0, scale * (dst + 0.5) - 0.5), scale = in / out, lambda from the fractional part, index clamped at the border)
+__global__ void resize_bilinear_kernel(const float* __restrict__ x, int NC, int Hi, int Wi, float* __restrict__ y, int Ho, int Wo) {
+  const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+  const long long total = (long long)NC * Ho * Wo;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % Wo), oy = (int)((idx / Wo) % Ho);
+    const long long nc = idx / ((long long)Wo * Ho);
+    const float fy = fmaxf(sh * ((float)oy + 0.5f) - 0.5f, 0.f);     // contracted like ATen's own kernel
+    const float fx = fmaxf(sw * ((float)ox + 0.5f) - 0.5f, 0.f);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float* s = x + nc * (long long)Hi * Wi;
+    const float a = s[(long long)y0 * Wi + x0], b = s[(long long)y0 * Wi + x1];
+    const float c = s[(long long)y1 * Wi + x0], d = s[(long long)y1 * Wi + x1];
+    y[idx] = hy * (hx * a + lx * b) + ly * (hx * c + lx * d);
+  }
+}
+
+// labels [rows][5] (cls, cx, cy, w, h): x-like columns (1, 3) *= sx, y-like columns (2, 4) *= sy
+// (targets[..., 1::2] *= scale_x; targets[..., 2::2] *= scale_y)
+__global__ void scale_labels_kernel(float* lab, long long rows, int cols, float sx, float sy) {
+  const long long total = rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cols);
+    if (c == 0) continue;
+    lab[idx] = lab[idx] * ((c & 1) ? sx : sy);
+  }
+}
+
+static int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  if (g > 148ll * 16) g = 148ll * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace sy
+
+using namespace sy;
+
+extern "C" int sy_pack_conv_weight(const float* w, int32_t cout, int32_t cin, int32_t kh, int32_t kw, int32_t mode, void* out,
+                                   int64_t out_pitch, int32_t co_offset, sy_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SY_REQUIRE(w != nullptr && out != nullptr && cout > 0 && cin > 0 && kh > 0 && kw > 0, SY_EINVAL, "pack_conv_weight: bad arguments");
+  SY_REQUIRE(mode >= 0 && mode <= 2, SY_EINVAL, "pack_conv_weight: mode %d", mode);
+  if (mode == 1) SY_REQUIRE(out_pitch >= co_offset + cout, SY_EINVAL, "pack_conv_weight: pitch %lld < %d + %d", (long long)out_pitch, co_offset, cout);
+  if (mode == 2) SY_REQUIRE(cin <= 16 && kw <= 4, SY_EINVAL, "pack_conv_weight(stem): cin %d kw %d", cin, kw);
+  const long long total = mode == 2 ? (long long)cout * kh * 64 : (long long)cout * cin * kh * kw;
+  pack_weight_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, cout, cin, kh, kw, mode, reinterpret_cast<__nv_bfloat16*>(out),
+                                                              out_pitch, co_offset);
+  return launch_status("pack_weight_kernel");
+}
+
+extern "C" int sy_sgd_nesterov_ema_step(const SySgdEmaDesc* d, sy_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SY_REQUIRE(d != nullptr && d->param != nullptr && d->n_total > 0, SY_EINVAL, "sgd_ema_step: null state");
+  SY_REQUIRE(d->n_param >= 0 && d->n_param <= d->n_total && d->decay_begin >= 0 && d->decay_begin <= d->n_param, SY_EINVAL,
+             "sgd_ema_step: bad segment bounds");
+  SY_REQUIRE(d->n_param == 0 || (d->grad != nullptr && d->momentum_buf != nullptr), SY_EINVAL, "sgd_ema_step: null grad / momentum");
+  sgd_ema_kernel<<<grid_for(d->n_total, 256), 256, 0, stream>>>(d->param, d->grad, d->momentum_buf, d->ema, d->n_param, d->n_total,
+                                                               d->decay_begin, d->lr, d->momentum, d->weight_decay,
+                                                               d->inv_scale, d->nesterov, d->ema_decay, d->ema_one_minus_decay,
+                                                               d->found_inf);
+  return launch_status("sgd_ema_kernel");
+}
+
+extern "C" int sy_resize_bilinear(const float* x, int32_t nc, int32_t hi, int32_t wi, float* y, int32_t ho, int32_t wo,
+                                  sy_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SY_REQUIRE(x != nullptr && y != nullptr && nc > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0, SY_EINVAL, "resize_bilinear: bad arguments");
+  resize_bilinear_kernel<<<grid_for((long long)nc * ho * wo, 256), 256, 0, stream>>>(x, nc, hi, wi, y, ho, wo);
+  return launch_status("resize_bilinear_kernel");
+}
+
+extern "C" int sy_scale_labels(float* labels, int64_t rows, int32_t cols, float sx, float sy_, sy_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SY_REQUIRE(labels != nullptr && rows > 0 && cols > 0, SY_EINVAL, "scale_labels: bad arguments");
+  scale_labels_kernel<<<grid_for(rows * cols, 256), 256, 0, stream>>>(labels, rows, cols, sx, sy_);
+  return launch_status("scale_labels_kernel");
+}

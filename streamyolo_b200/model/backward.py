@@ -240,7 +240,6 @@ def _conv_backward(T: Tape, r):
     if r["kind"] == "stem":
         return                                                    # the input frames need no gradient
     gx = T.g(x)
-    w_cat = torch.cat([m.conv.weight.detach() for m in mods], 0) if len(mods) > 1 else mods[0].conv.weight.detach()
     one = torch.ones(cin, dtype=torch.float32, device=dev)
     zero = torch.zeros(cin, dtype=torch.float32, device=dev)
     src = draw
@@ -248,7 +247,7 @@ def _conv_backward(T: Tape, r):
         src = View.empty(x.n, x.h, x.w, cout, dev)
         ops.dilate2(draw, src)
     # data gradient, accumulated in place: gx = conv(src, flipped / transposed filter) * 1 + 0 + gx
-    ops.conv2d(src, ops.pack_conv_weight_dgrad(w_cat), gx, (kh, kw), 1, ops.SY_CONV_FUSED, scale=one, shift=zero, act=0, res=gx)
+    ops.conv2d(src, engine._packed_dgrad(mods), gx, (kh, kw), 1, ops.SY_CONV_FUSED, scale=one, shift=zero, act=0, res=gx)
 
 
 def _head_backward(T: Tape, head, r, grad_scale):

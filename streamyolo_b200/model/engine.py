@@ -58,6 +58,17 @@ def _packed(m):
     return m._pk
 
 
+def _packed_dgrad(mods):
+    """Data-gradient operand (flipped taps, transposed channels) of one BaseConv or of a conv1 | conv2 pair."""
+    ws = [m.conv.weight for m in mods]
+    key = tuple((w._version, w.data_ptr()) for w in ws)
+    m0 = mods[0]
+    if getattr(m0, "_pkd_key", None) != key:
+        m0._pkd = ops.pack_conv_weight_dgrad(*ws)
+        m0._pkd_key = key
+    return m0._pkd
+
+
 def _folded(m):
     """Eval: scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale (fp32)."""
     bn = m.bn
@@ -170,7 +181,7 @@ def _packed_pair(m1, m2):
     w1, w2 = m1.conv.weight, m2.conv.weight
     key = (w1._version, w2._version, w1.data_ptr(), w2.data_ptr(), w1.device)
     if getattr(m1, "_pk2_key", None) != key:
-        m1._pk2 = torch.cat([ops.pack_conv_weight(w1), ops.pack_conv_weight(w2)], 0).contiguous()
+        m1._pk2 = ops.pack_conv_weight(w1, w2)
         m1._pk2_key = key
     return m1._pk2
 

@@ -86,6 +86,14 @@ class SyHeadPredBwdDesc(C.Structure):
                 ("n_partials", C.c_int32)]
 
 
+class SySgdEmaDesc(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("momentum_buf", C.c_void_p), ("ema", C.c_void_p),
+                ("n_param", C.c_int64), ("n_total", C.c_int64), ("decay_begin", C.c_int64),
+                ("lr", C.c_float), ("momentum", C.c_float), ("weight_decay", C.c_float), ("inv_scale", C.c_float),
+                ("nesterov", C.c_int32), ("ema_decay", C.c_float), ("ema_one_minus_decay", C.c_float),
+                ("found_inf", C.c_void_p)]
+
+
 class SyConvPlan(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("mode", "bn", "m_tiles", "n_tiles", "rounds", "kblocks", "patch_h", "patch_w")]
 
@@ -138,6 +146,12 @@ _SIG = {
     "sy_postprocess_nms": (C.c_int, [C.POINTER(SyNmsDesc), C.c_void_p]),
     "sy_conv2d_wgrad_workspace_bytes": (C.c_size_t, [C.POINTER(SyConvWgradDesc)]),
     "sy_conv2d_wgrad_tc": (C.c_int, [C.POINTER(SyConvWgradDesc), C.c_void_p]),
+    "sy_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                      C.c_int64, C.c_int32, C.c_void_p]),
+    "sy_sgd_nesterov_ema_step": (C.c_int, [C.POINTER(SySgdEmaDesc), C.c_void_p]),
+    "sy_resize_bilinear": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_void_p]),
+    "sy_scale_labels": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIG)
 
@@ -245,10 +259,26 @@ def from_nchw(x):
     return View(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
 
 
-def pack_conv_weight(w):
-    """OIHW float -> bf16 [O][kh*kw][I] contiguous (GEMM B operand, K-major)."""
-    o, i, kh, kw = w.shape
-    return w.detach().permute(0, 2, 3, 1).reshape(o, kh * kw, i).to(torch.bfloat16).contiguous()
+def _w32(w):
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    return w
+
+
+def pack_conv_weight(*ws):
+    """OIHW fp32 parameter(s) -> bf16 [sum O][kh*kw][I] contiguous (GEMM B operand, K-major), packed on the device
+    (sy_pack_conv_weight).  Several weights with the same [I, kh, kw] (CSPLayer conv1 | conv2) land in one operand."""
+    _, i, kh, kw = ws[0].shape
+    out = torch.empty((sum(w.shape[0] for w in ws), kh * kw, i), dtype=torch.bfloat16, device=ws[0].device)
+    o0 = 0
+    for w in ws:
+        w = _w32(w)
+        assert tuple(w.shape[1:]) == (i, kh, kw)
+        _check(lib().sy_pack_conv_weight(w.data_ptr(), w.shape[0], i, kh, kw, 0, out.data_ptr() + 2 * o0 * kh * kw * i, 0, 0,
+                                         _stream()))
+        o0 += w.shape[0]
+    return out
 
 
 def conv_out_hw(h, w, k, s):
@@ -311,11 +341,12 @@ STEM_K = (3, 1)      # the stem runs as a 3x1 conv over the W-gathered 64-channe
 
 
 def pack_stem_weight(w):
-    """[O,12,3,3] float -> bf16 [O][3 (row)][64 = 3 taps x (12 focus + 4 zero) + 16 zero]."""
-    o = w.shape[0]
-    p = torch.zeros((o, 3, 4, 16), dtype=torch.bfloat16, device=w.device)
-    p[:, :, :3, :12] = w.detach().permute(0, 2, 3, 1).to(torch.bfloat16)  # [O, r, s, fc]
-    return p.reshape(o, 3, 64).contiguous()
+    """[O,12,3,3] float -> bf16 [O][3 (row)][64 = 3 taps x (12 focus + 4 zero) + 16 zero] (sy_pack_conv_weight, mode 2)."""
+    w = _w32(w)
+    o, i, kh, kw = w.shape
+    out = torch.empty((o, kh, 64), dtype=torch.bfloat16, device=w.device)
+    _check(lib().sy_pack_conv_weight(w.data_ptr(), o, i, kh, kw, 2, out.data_ptr(), 0, 0, _stream()))
+    return out
 
 
 def stats_num_partials(n, hw):
@@ -412,10 +443,19 @@ def tal_loss_backward(outputs, origin, labels_fut, hw, strides, gamma, use_l1, w
     _check(lib().sy_tal_loss_backward(C.byref(d), _stream()), kernels=1)
 
 
-def pack_conv_weight_dgrad(w):
+def pack_conv_weight_dgrad(*ws):
     """Weights for the data gradient of a stride-1 conv: dx = conv(dy, w') with w'[ci][kh-1-r][kw-1-s][co] = w[co][ci][r][s]
-    (same padding), i.e. the forward tensor-core kernel on the flipped, channel-transposed filter."""
-    return pack_conv_weight(w.detach().flip(2, 3).transpose(0, 1).contiguous())
+    (same padding), i.e. the forward tensor-core kernel on the flipped, channel-transposed filter; packed on the device
+    (sy_pack_conv_weight, mode 1).  Several weights (CSPLayer conv1 | conv2) are concatenated along co."""
+    _, i, kh, kw = ws[0].shape
+    ot = sum(w.shape[0] for w in ws)
+    out = torch.empty((i, kh * kw, ot), dtype=torch.bfloat16, device=ws[0].device)
+    o0 = 0
+    for w in ws:
+        w = _w32(w)
+        _check(lib().sy_pack_conv_weight(w.data_ptr(), w.shape[0], i, kh, kw, 1, out.data_ptr(), ot, o0, _stream()))
+        o0 += w.shape[0]
+    return out
 
 
 def conv2d_wgrad(x: View, dy: View, k, s, dw, accumulate=False, workspace=None):
@@ -520,3 +560,33 @@ def conv2d_plan(n, h, w, cin, cout, k, s):
     if rc != 0:
         raise RuntimeError("conv2d_plan: " + (load_library().sy_last_error_string() or b"").decode())
     return {f: getattr(p, f) for f, _ in SyConvPlan._fields_}
+
+
+def sgd_nesterov_ema_step(param, grad, momentum_buf, ema, n_param, decay_begin, lr, momentum=0.9, weight_decay=5e-4,
+                          inv_scale=1.0, nesterov=True, ema_decay=0.0, found_inf=None):
+    """One fused optimiser step over flat fp32 state (sy_sgd_nesterov_ema_step); ``ema`` may be None."""
+    d = SySgdEmaDesc()
+    d.param, d.grad, d.momentum_buf = param.data_ptr(), grad.data_ptr(), momentum_buf.data_ptr()
+    d.ema = ema.data_ptr() if ema is not None else None
+    d.n_param, d.n_total, d.decay_begin = n_param, param.numel(), decay_begin
+    d.lr, d.momentum, d.weight_decay, d.inv_scale, d.nesterov = lr, momentum, weight_decay, inv_scale, int(nesterov)
+    d.ema_decay, d.ema_one_minus_decay = ema_decay, 1.0 - ema_decay
+    d.found_inf = found_inf.data_ptr() if found_inf is not None else None
+    _check(lib().sy_sgd_nesterov_ema_step(C.byref(d), _stream()))
+
+
+def resize_bilinear(x, size):
+    """F.interpolate(x, size=size, mode="bilinear", align_corners=False) of an NCHW fp32 batch on the device."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    b, c, hi, wi = x.shape
+    y = torch.empty((b, c, size[0], size[1]), dtype=torch.float32, device=x.device)
+    _check(lib().sy_resize_bilinear(x.data_ptr(), b * c, hi, wi, y.data_ptr(), size[0], size[1], _stream()))
+    return y
+
+
+def scale_labels_(labels, sx, sy):
+    """labels[..., 1::2] *= sx; labels[..., 2::2] *= sy (in place; [.., cols] fp32 contiguous)."""
+    assert labels.dtype == torch.float32 and labels.is_contiguous()
+    cols = labels.shape[-1]
+    _check(lib().sy_scale_labels(labels.data_ptr(), labels.numel() // cols, cols, sx, sy, _stream()))
+    return labels

@@ -270,7 +270,8 @@ def add_(x, y):
 
 NAMES = ["conv_stat_rows", "conv2d", "bn_act_apply", "focus_pack", "upsample_nearest", "spp_maxpool", "copy",
          "head_pred_decode", "tal_loss_workspace_bytes", "tal_loss", "tal_loss_backward", "head_pred_backward",
-         "bn_act_backward", "conv2d_wgrad", "dilate2", "upsample_nearest_backward", "spp_maxpool_backward", "add_"]
+         "bn_act_backward", "conv2d_wgrad", "dilate2", "upsample_nearest_backward", "spp_maxpool_backward", "add_",
+         "pack_conv_weight", "pack_conv_weight_dgrad", "pack_stem_weight"]
 
 
 def _view_init(self, buf, c0=0, c=None, n0=0, n=None):
@@ -280,16 +281,24 @@ def _view_init(self, buf, c0=0, c=None, n0=0, n=None):
     self.n = buf.shape[0] - n0 if n is None else n
 
 
-def _pack_conv_weight_f32(w):
-    o, i, kh, kw = w.shape
-    return w.detach().permute(0, 2, 3, 1).reshape(o, kh * kw, i).float().contiguous()
+def pack_conv_weight(*ws):
+    """what sy_pack_conv_weight (mode 0) writes: [sum O][kh*kw][I] in the emulated storage type"""
+    return torch.cat([_bf(w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], w.shape[2] * w.shape[3], w.shape[1]))
+                      for w in ws], 0).contiguous()
 
 
-def _pack_stem_weight_f32(w):
+def pack_conv_weight_dgrad(*ws):
+    """mode 1: the forward layout of the flipped, channel-transposed filter, pairs concatenated along co"""
+    w = torch.cat([x.detach() for x in ws], 0)
+    return pack_conv_weight(w.flip(2, 3).transpose(0, 1).contiguous())
+
+
+def pack_stem_weight(w):
+    """mode 2"""
     o = w.shape[0]
     p = torch.zeros((o, 3, 4, 16), dtype=torch.float32)
     p[:, :, :3, :12] = w.detach().permute(0, 2, 3, 1).float()
-    return p.reshape(o, 3, 64).contiguous()
+    return _bf(p.reshape(o, 3, 64)).contiguous()
 
 
 def install(monkeypatch, exact=False):
@@ -310,7 +319,5 @@ def install(monkeypatch, exact=False):
             return View(p if p.is_contiguous() else p.contiguous())
 
         monkeypatch.setattr(engine, "as_view", as_view_f32)
-        monkeypatch.setattr(ops, "pack_conv_weight", _pack_conv_weight_f32)
-        monkeypatch.setattr(ops, "pack_stem_weight", _pack_stem_weight_f32)
     PTRS.clear()
     LOSS_STATE.clear()
