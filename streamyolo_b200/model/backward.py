@@ -15,10 +15,15 @@ exps/model/{yolox,dfp_pafpn,darknet,tal_head}.py, expressed over the kernels of 
   * parameter gradients are fp32 in PyTorch's layouts (conv OIHW, BN weight / bias, pred-conv weight / bias) and are added
     to ``p.grad`` like autograd does.
 
-STATUS (round 1): every kernel used here is tested on the GPU against autograd, and this module's routing is tested on
-CPU with the kernels emulated in torch (tests/test_cpu_backward.py: all parameter gradients against autograd through the
-oracle).  The module as a whole has not yet run on a GPU; bench.py does not use it and YOLOX.forward only with
-``model.train_with_autograd = True`` (``loss_with_autograd``: the step as one autograd node)."""
+Where the parameter gradients go is decided by a *gradient sink*: ``TensorSink`` (fresh fp32 tensors, what autograd /
+``forward_backward`` hand out) or ``train.FlatSink`` (slices of the trainer's flat gradient buffer in walk order, whose
+buckets are all-reduced over NCCL as soon as their last gradient has been enqueued -- the overlap DistributedDataParallel
+gives the reference, /root/reference/exps/train_utils/double_trainer.py:171).
+
+Every kernel used here is tested on the GPU against autograd, the routing on CPU with the kernels emulated in torch
+(tests/test_cpu_backward.py), the assembled walk on the GPU against autograd through the oracle
+(tests/test_gpu_model.py::test_forward_backward_vs_oracle_autograd, tests/test_gpu_train.py).  ``YOLOX.forward`` in training
+mode with gradients enabled returns ``loss_with_autograd`` (the step as one autograd node)."""
 import torch
 
 from . import engine
@@ -32,7 +37,7 @@ class Tape:
         self.ops = []
         self.gbuf = {}          # id(activation buffer) -> gradient buffer (bf16, zero-initialised)
         self.keep = []          # keeps the activation buffers (and so their ids) alive
-        self.pgrad = {}         # id(parameter) -> accumulated fp32 gradient
+        self.uses = {}          # id(BaseConv) -> number of recorded launches (a module used twice accumulates: DFP jian)
 
     def g(self, v: View) -> View:
         key = id(v.buf)
@@ -45,10 +50,58 @@ class Tape:
         self.ops.append(kw)
 
 
-def _acc(T, p, g):
-    g = g.to(p.dtype).reshape(p.shape)
-    k = id(p)
-    T.pgrad[k] = g.clone() if k not in T.pgrad else T.pgrad[k] + g
+class TensorSink:
+    """Gradient sink that hands out fresh fp32 tensors (one per launch group, the members' gradients are views of it)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.store = {}         # key -> tensor
+        self.seen = set()
+        self.views = {}         # id(parameter) -> gradient view
+
+    def _get(self, key, shape, params, splits):
+        """tensor for ``key`` (+ whether it already holds a contribution); ``params`` / ``splits``: the parameters it covers
+        along dim 0"""
+        if key in self.store:
+            return self.store[key], True
+        t = torch.empty(shape, dtype=torch.float32, device=self.device)
+        self.store[key] = t
+        o = 0
+        for p, n in zip(params, splits):
+            self.views[id(p)] = t[o:o + n].view(p.shape) if tuple(t[o:o + n].shape) != tuple(p.shape) else t[o:o + n]
+            o += n
+        return t, False
+
+    def conv_weight(self, mods, cin, kh, kw, stem=False):
+        couts = [m.conv.out_channels for m in mods]
+        if stem:                # the stem's gradient arrives in the packed layout and is unpacked by the caller
+            return self._get(("ws", id(mods[0])), tuple(mods[0].conv.weight.shape), [mods[0].conv.weight], [couts[0]])
+        return self._get(("w", id(mods[0])), (sum(couts), cin, kh, kw), [m.conv.weight for m in mods], couts)
+
+    def bn(self, mods):
+        couts = [m.conv.out_channels for m in mods]
+        g, acc = self._get(("g", id(mods[0])), (sum(couts),), [m.bn.weight for m in mods], couts)
+        b, _ = self._get(("b", id(mods[0])), (sum(couts),), [m.bn.bias for m in mods], couts)
+        return g, b, acc
+
+    def head(self, head, k):
+        ps = (head.reg_preds[k].weight, head.obj_preds[k].weight, head.cls_preds[k].weight,
+              head.reg_preds[k].bias, head.obj_preds[k].bias, head.cls_preds[k].bias)
+        out = []
+        for p in ps:
+            shape = (p.shape[0], p.shape[1]) if p.dim() == 4 else tuple(p.shape)
+            t, _ = self._get(("h", id(p)), shape, [p], [p.shape[0]])
+            out.append(t)
+        return out[:3], out[3:], False
+
+    def done(self, params):
+        pass
+
+    def finish(self):
+        pass
+
+    def grad_of(self, p):
+        return self.views.get(id(p))
 
 
 # ------------------------------------------------------------------------------------------------ recording forward
@@ -76,6 +129,7 @@ def conv_rec(T: Tape, mods, x: View, wpk, k, s, y: View, split, res: View = None
                eps=float(bn0.eps), scale_shift=ss, sync=engine._sync(mods[0], dev), mean_invstd=mi)
     ops.bn_act_apply(raw, ss[0].data_ptr(), ss[1].data_ptr(), split if split else x.n, act, res, y)
     T.rec(t="conv", mods=mods, x=x, k=(kh, kw), s=s, raw=raw, y=y, res=res, ss=ss, mi=mi, split=split, act=act, kind=kind)
+    T.uses[id(mods[0])] = T.uses.get(id(mods[0]), 0) + 1
     return y
 
 
@@ -210,38 +264,37 @@ def head_rec(T, head, fused, labels):
 
 
 # ------------------------------------------------------------------------------------------------ reverse walk
-def _conv_backward(T: Tape, r):
+def _conv_backward(T: Tape, r, sink):
     mods, x, raw, y, res = r["mods"], r["x"], r["raw"], r["y"], r["res"]
     kh, kw = r["k"]
     s = r["s"]
     dev = T.device
     cout, cin = raw.c, x.c
+    stem = r["kind"] == "stem"
     gy = T.g(y)
     if res is not None:
         ops.add_(gy, T.g(res))                                   # shortcut / "+ cur" branch
     draw = View.empty(raw.n, raw.h, raw.w, cout, dev)
-    dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
-    dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
-    ops.bn_act_backward(raw, gy, draw, r["ss"][0], r["ss"][1], r["mi"][0], r["mi"][1], r["split"], r["act"], dgamma, dbeta)
-    dw = torch.empty((cout, cin, kh, kw), dtype=torch.float32, device=dev)
-    ops.conv2d_wgrad(x, draw, (kh, kw), s, dw)
-    c0 = 0
-    for m in mods:
-        c = m.conv.out_channels
-        _acc(T, m.bn.weight, dgamma[c0:c0 + c])
-        _acc(T, m.bn.bias, dbeta[c0:c0 + c])
-        if r["kind"] == "stem":
-            # packed stem weights: wpk[o][row r][s * 16 + fc] = w[o][fc][r][s]  ->  dw[o][s * 16 + fc][r][0]
-            g = dw[c0:c0 + c, :48, :, 0].reshape(c, 3, 16, 3)[:, :, :12, :]      # [o, s, fc, r]
-            _acc(T, m.conv.weight, g.permute(0, 2, 3, 1))                       # [o, fc, r, s]
+    dgamma, dbeta, acc_bn = sink.bn(mods)
+    ops.bn_act_backward(raw, gy, draw, r["ss"][0], r["ss"][1], r["mi"][0], r["mi"][1], r["split"], r["act"], dgamma, dbeta,
+                        accumulate=acc_bn)
+    if stem:
+        # packed stem weights: wpk[o][row r][s * 16 + fc] = w[o][fc][r][s]  ->  dw[o][s * 16 + fc][r][0]
+        dw = torch.empty((cout, cin, kh, kw), dtype=torch.float32, device=dev)
+        ops.conv2d_wgrad(x, draw, (kh, kw), s, dw)
+        gw, acc_w = sink.conv_weight(mods, cin, kh, kw, stem=True)
+        g = dw[:, :48, :, 0].reshape(cout, 3, 16, 3)[:, :, :12, :].permute(0, 2, 3, 1)     # [o, s, fc, r] -> [o, fc, r, s]
+        if acc_w:
+            gw.add_(g)
         else:
-            _acc(T, m.conv.weight, dw[c0:c0 + c])
-        c0 += c
-    if r["kind"] == "stem":
+            gw.copy_(g)
+        sink.done([mods[0].conv.weight, mods[0].bn.weight, mods[0].bn.bias])
         return                                                    # the input frames need no gradient
+    dw, acc_w = sink.conv_weight(mods, cin, kh, kw)
+    ops.conv2d_wgrad(x, draw, (kh, kw), s, dw, accumulate=acc_w)
+    sink.done([p for m in mods for p in (m.conv.weight, m.bn.weight, m.bn.bias)])
     gx = T.g(x)
-    one = torch.ones(cin, dtype=torch.float32, device=dev)
-    zero = torch.zeros(cin, dtype=torch.float32, device=dev)
+    one, zero = _one_zero(T, cin)
     src = draw
     if s == 2:
         src = View.empty(x.n, x.h, x.w, cout, dev)
@@ -250,30 +303,34 @@ def _conv_backward(T: Tape, r):
     ops.conv2d(src, engine._packed_dgrad(mods), gx, (kh, kw), 1, ops.SY_CONV_FUSED, scale=one, shift=zero, act=0, res=gx)
 
 
-def _head_backward(T: Tape, head, r, grad_scale):
-    dev = T.device
+def _one_zero(T, c):
+    """per-channel scale 1 / shift 0 of the data-gradient launches (one pair of constants per width and tape)"""
+    cache = T.__dict__.setdefault("_oz", {})
+    if c not in cache:
+        cache[c] = (torch.ones(c, dtype=torch.float32, device=T.device), torch.zeros(c, dtype=torch.float32, device=T.device))
+    return cache[c]
+
+
+def _head_backward(T: Tape, head, r, grad_scale, sink):
     out, origin = r["out"], r["origin"]
     g_raw = torch.empty_like(out)
     ops.tal_loss_backward(out, origin, r["fut"], r["hw"], head.strides, float(head.gamma), True, r["ws"], grad_scale,
                           grad_raw=g_raw)
     for k, cf, rf, off in r["levels"]:
         regp, objp, clsp = head.reg_preds[k], head.obj_preds[k], head.cls_preds[k]
-        c = cf.c
-        dws = [torch.empty((o, c), dtype=torch.float32, device=dev) for o in (4, 1, head.num_classes)]
-        dbs = [torch.empty((o,), dtype=torch.float32, device=dev) for o in (4, 1, head.num_classes)]
+        dws, dbs, acc = sink.head(head, k)
         ops.head_pred_backward(g_raw, cf, rf, T.g(cf), T.g(rf), _f32(regp.weight), _f32(objp.weight), _f32(clsp.weight),
-                               r["a_total"], off, dws[0], dws[1], dws[2], dbs[0], dbs[1], dbs[2])
-        for p, g in zip((regp.weight, objp.weight, clsp.weight, regp.bias, objp.bias, clsp.bias), dws + dbs):
-            _acc(T, p, g)
+                               r["a_total"], off, dws[0], dws[1], dws[2], dbs[0], dbs[1], dbs[2], accumulate=acc)
+        sink.done([regp.weight, objp.weight, clsp.weight, regp.bias, objp.bias, clsp.bias])
 
 
-def _walk(T: Tape, head, grad_scale):
+def _walk(T: Tape, head, grad_scale, sink):
     for r in reversed(T.ops):
         t = r["t"]
         if t == "conv":
-            _conv_backward(T, r)
+            _conv_backward(T, r, sink)
         elif t == "head":
-            _head_backward(T, head, r, grad_scale)
+            _head_backward(T, head, r, grad_scale, sink)
         elif t == "copy":
             ops.add_(T.g(r["dst"]), T.g(r["src"]))
         elif t == "upsample":
@@ -287,6 +344,7 @@ def _walk(T: Tape, head, grad_scale):
             ops.add_(tmp, T.g(x))
         else:
             raise RuntimeError(t)
+    sink.finish()
 
 
 def _record(model, x, targets):
@@ -310,16 +368,22 @@ def _loss_dict(loss):
             "num_fg": loss[5]}
 
 
-def forward_backward(model, x, targets, grad_scale=1.0):
+def forward_backward(model, x, targets, grad_scale=1.0, sink=None):
     """One training forward + backward of YOLOX(DFPPAFPN, TALHead) in train mode on a frame-pair batch ``x`` [B, 6, H, W].
-    Returns the loss dict of YOLOX.forward (0-dim tensors) and accumulates into ``p.grad`` of every parameter."""
+    Returns the loss dict of YOLOX.forward (0-dim tensors).  Without ``sink`` the gradients are accumulated into ``p.grad``
+    of every parameter (like autograd); with a sink (train.FlatSink) they are written where the sink says."""
     T, loss = _record(model, x, targets)
+    own = sink is None
+    if own:
+        sink = TensorSink(T.device)
     with torch.no_grad():
-        _walk(T, model.head, grad_scale)
-    for p in model.parameters():
-        g = T.pgrad.get(id(p))
-        if g is not None:
-            p.grad = g if p.grad is None else p.grad + g
+        _walk(T, model.head, grad_scale, sink)
+    if own:
+        for p in model.parameters():
+            g = sink.grad_of(p)
+            if g is not None:
+                g = g.to(p.dtype)
+                p.grad = g if p.grad is None else p.grad + g
     return _loss_dict(loss)
 
 
@@ -339,9 +403,10 @@ class _TrainLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_total, _g_all):
         T, model = ctx.tape, ctx.model
+        sink = TensorSink(T.device)
         with torch.no_grad():
-            _walk(T, model.head, float(g_total))          # one host sync per step: the loss scale as a kernel argument
-        grads = tuple(T.pgrad.get(id(p)) for p in ctx.params)
+            _walk(T, model.head, float(g_total), sink)    # one host sync per step: the loss scale as a kernel argument
+        grads = tuple(None if sink.grad_of(p) is None else sink.grad_of(p).to(p.dtype) for p in ctx.params)
         ctx.tape = None
         return (None, None, None, None) + grads
 

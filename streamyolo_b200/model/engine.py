@@ -24,6 +24,8 @@ from ..ops import View
 # switch; SY_FUSE_APPLY_MAX_MB fuses only the layers whose raw output is at most that many MB (L2 resident, launch-bound)
 FUSE_APPLY = os.environ.get("SY_FUSE_APPLY", "0") != "0"
 FUSE_APPLY_MAX_BYTES = float(os.environ.get("SY_FUSE_APPLY_MAX_MB", "0")) * 1e6
+WEIGHT_EPOCH = 0  # bumped by whoever updates parameters through raw pointers (train.Trainer's fused optimiser kernel does
+                  # not touch torch's version counters): part of every packed-operand cache key
 TRACE = None      # debugging: set to a dict to capture every BaseConv's stored output by module name
 
 
@@ -51,7 +53,7 @@ class Ctx:
 
 def _packed(m):
     w = m.conv.weight
-    key = (w._version, w.data_ptr(), w.device)
+    key = (w._version, w.data_ptr(), w.device, WEIGHT_EPOCH)
     if getattr(m, "_pk_key", None) != key:
         m._pk = ops.pack_conv_weight(w)
         m._pk_key = key
@@ -61,7 +63,7 @@ def _packed(m):
 def _packed_dgrad(mods):
     """Data-gradient operand (flipped taps, transposed channels) of one BaseConv or of a conv1 | conv2 pair."""
     ws = [m.conv.weight for m in mods]
-    key = tuple((w._version, w.data_ptr()) for w in ws)
+    key = tuple((w._version, w.data_ptr()) for w in ws) + (WEIGHT_EPOCH,)
     m0 = mods[0]
     if getattr(m0, "_pkd_key", None) != key:
         m0._pkd = ops.pack_conv_weight_dgrad(*ws)
@@ -73,7 +75,7 @@ def _folded(m):
     """Eval: scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale (fp32)."""
     bn = m.bn
     key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
-           getattr(m, "_stats_epoch", 0), bn.weight.data_ptr(), bn.eps)
+           getattr(m, "_stats_epoch", 0), bn.weight.data_ptr(), bn.eps, WEIGHT_EPOCH)
     if getattr(m, "_fold_key", None) != key:
         with torch.no_grad():
             scale = bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps)
@@ -95,6 +97,16 @@ def _sync(m, device):
 def _bn_seg(m, c_begin=0):
     bn = m.bn
     return (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, c_begin)
+
+
+def _dbg_skip_apply(nbytes):
+    """timing experiments only (tools/ab_step.py): SY_DBG_SKIP_APPLY="lo:hi" (MB) drops the normalise pass of the layers whose
+    raw output size lies in [lo, hi) -- the results are garbage, the step time shows what those launches really cost"""
+    e = os.environ.get("SY_DBG_SKIP_APPLY")
+    if not e:
+        return False
+    lo, hi = (float(v) for v in e.split(":"))
+    return lo * 1e6 <= nbytes < hi * 1e6
 
 
 def conv_bn_act(ctx: Ctx, mods, x: View, wpk, k, s, y: View, res: View = None, act=1, y_goff1=0, res_goff1=0):
@@ -127,8 +139,9 @@ def conv_bn_act(ctx: Ctx, mods, x: View, wpk, k, s, y: View, res: View = None, a
         else:
             ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="tc", partials=partials, split_n=split, bn=segs,
                        momentum=mom, eps=float(bn0.eps), scale_shift=ss, sync=_sync(mods[0], ctx.device))
-            ops.bn_act_apply(raw, ss[0].data_ptr(), ss[1].data_ptr(), split if split else n, act, res, y, y_goff1,
-                             res_goff1)
+            if not _dbg_skip_apply(n * ho * wo * cout * 2):
+                ops.bn_act_apply(raw, ss[0].data_ptr(), ss[1].data_ptr(), split if split else n, act, res, y, y_goff1,
+                                 res_goff1)
         return
     # CUDA-core cross-check path: conv, separate statistics pass, separate finalize per module, apply
     ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="simt")
@@ -179,7 +192,7 @@ def base_conv(ctx: Ctx, m, x: View, y: View = None, res: View = None) -> View:
 def _packed_pair(m1, m2):
     """conv1 | conv2 of a CSPLayer as one [2*hidden][1][Cin] GEMM operand."""
     w1, w2 = m1.conv.weight, m2.conv.weight
-    key = (w1._version, w2._version, w1.data_ptr(), w2.data_ptr(), w1.device)
+    key = (w1._version, w2._version, w1.data_ptr(), w2.data_ptr(), w1.device, WEIGHT_EPOCH)
     if getattr(m1, "_pk2_key", None) != key:
         m1._pk2 = ops.pack_conv_weight(w1, w2)
         m1._pk2_key = key
@@ -218,7 +231,7 @@ def csp_layer(ctx: Ctx, m, x: View, out: View = None) -> View:
 
 def _packed_stem(bc):
     w = bc.conv.weight
-    key = (w._version, w.data_ptr(), w.device)
+    key = (w._version, w.data_ptr(), w.device, WEIGHT_EPOCH)
     if getattr(bc, "_pk_key", None) != key:
         bc._pk = ops.pack_stem_weight(w)
         bc._pk_key = key

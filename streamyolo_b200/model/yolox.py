@@ -11,14 +11,15 @@ class YOLOX(nn.Module):
         super().__init__()
         self.backbone = DFPPAFPN() if backbone is None else backbone
         self.head = TALHead(20) if head is None else head
-        self.train_with_autograd = False     # True: training forward returns a differentiable loss (model/backward.py)
+        # training forward with gradients enabled returns a loss that carries a grad_fn (model/backward.py), so the reference
+        # trainer's scaler.scale(loss).backward() works unchanged; False = always the plain (no-gradient) forward
+        self.train_with_autograd = True
 
     def forward(self, x, targets=None, buffer=None, mode="off_pipe"):
         assert mode in ["off_pipe", "on_pipe"]
         if mode == "off_pipe":
             if self.training and self.train_with_autograd and torch.is_grad_enabled():
-                # opt-in (round 1: verified on CPU with emulated kernels, not yet on a GPU): the loss carries a grad_fn, so
-                # the reference trainer's scaler.scale(loss).backward() / optimizer.step() work unchanged
+                # /root/reference/exps/train_utils/double_trainer.py:108-116: outputs = model(inps, targets); loss.backward()
                 from . import backward
                 assert targets is not None
                 return backward.loss_with_autograd(self, x, targets)

@@ -268,10 +268,36 @@ def add_(x, y):
     _store(y, _nchw(x) + _nchw(y))
 
 
+def sgd_nesterov_ema_step(param, grad, momentum_buf, ema, n_param, decay_begin, lr, momentum=0.9, weight_decay=5e-4,
+                          inv_scale=1.0, nesterov=True, ema_decay=0.0, found_inf=None):
+    """what sy_sgd_nesterov_ema_step does, in torch (same order of operations as torch.optim.SGD / yolox ModelEMA)"""
+    if found_inf is not None and float(found_inf) != 0.0:
+        return
+    p = param[:n_param]
+    g = grad[:n_param] * inv_scale if inv_scale != 1.0 else grad[:n_param].clone()
+    g[decay_begin:] = g[decay_begin:].add(p[decay_begin:], alpha=weight_decay)
+    momentum_buf.mul_(momentum).add_(g)
+    g = g.add(momentum_buf, alpha=momentum) if nesterov else momentum_buf
+    p.add_(g, alpha=-lr)
+    if ema is not None:
+        ema.mul_(ema_decay).add_((1.0 - ema_decay) * param)
+
+
+def resize_bilinear(x, size):
+    return F.interpolate(x, size=size, mode="bilinear", align_corners=False)
+
+
+def scale_labels_(labels, sx, sy):
+    labels[..., 1::2] = labels[..., 1::2] * sx
+    labels[..., 2::2] = labels[..., 2::2] * sy
+    return labels
+
+
 NAMES = ["conv_stat_rows", "conv2d", "bn_act_apply", "focus_pack", "upsample_nearest", "spp_maxpool", "copy",
          "head_pred_decode", "tal_loss_workspace_bytes", "tal_loss", "tal_loss_backward", "head_pred_backward",
          "bn_act_backward", "conv2d_wgrad", "dilate2", "upsample_nearest_backward", "spp_maxpool_backward", "add_",
-         "pack_conv_weight", "pack_conv_weight_dgrad", "pack_stem_weight"]
+         "pack_conv_weight", "pack_conv_weight_dgrad", "pack_stem_weight", "sgd_nesterov_ema_step", "resize_bilinear",
+         "scale_labels_"]
 
 
 def _view_init(self, buf, c0=0, c=None, n0=0, n=None):

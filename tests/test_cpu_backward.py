@@ -211,7 +211,8 @@ def test_forward_engine_routing_exact(name, monkeypatch):
     cfg = OracleCfg(depth=c["depth"], width=c["width"], gamma=c["gamma"], ignore_thr=c["thr"], ignore_value=c["val"])
     o = StreamYoloOracle(cfg, synth.synth_state_dict(model_shapes(c["depth"], c["width"])), q=None)
     model = build_product(c)
-    loss = model(x, tg)
+    with torch.no_grad():                                    # the plain forward (engine.py), not the recording one
+        loss = model(x, tg)
     ref = o.forward(x, tg)
     for k in ("total_loss", "iou_loss", "l1_loss", "conf_loss", "cls_loss", "num_fg"):
         assert abs(float(loss[k]) - float(ref[k])) <= 2e-5 * abs(float(ref[k])) + 1e-6, k

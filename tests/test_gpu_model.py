@@ -88,7 +88,8 @@ def test_train_forward_vs_oracle(case, impl):
     # full forward + loss
     m2 = build_product(c["depth"], c["width"], c["gamma"], c["thr"], c["val"])
     m2.train()
-    loss = m2(x.cuda(), (tg[0].cuda(), tg[1].cuda()))
+    with torch.no_grad():                                    # the plain forward (engine.py); the recording forward has its own tests
+        loss = m2(x.cuda(), (tg[0].cuda(), tg[1].cuda()))
     torch.cuda.synchronize()
     assert int(m2.state_dict()["head.stems.0.bn.num_batches_tracked"]) == 1
     o2 = build_oracle(c["depth"], c["width"], c["gamma"], c["thr"], c["val"])
@@ -242,7 +243,8 @@ def test_s_model_full_resolution_golden():
     m = build_product(c["depth"], c["width"])
     m.train()
     m.head.keep_assignment = True
-    loss = m(x.cuda(), (tg[0].cuda(), tg[1].cuda()))
+    with torch.no_grad():
+        loss = m(x.cuda(), (tg[0].cuda(), tg[1].cuda()))
     torch.cuda.synchronize()
     got = np.array([float(loss[k]) for k in ORDER])
     gold = np.load(os.path.join(GOLD, "s_600x960.npz"))

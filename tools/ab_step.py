@@ -37,10 +37,19 @@ SETTINGS = [
     ("apply cap 3/SM", {"SY_APPLY_CAP": "3"}, 0),
     ("patch tiles", {"SY_CONV_TILES": "patch"}, 0),
     ("no pdl", {"SY_PDL": "0"}, 0),
+    # marginal cost of whole kernel classes inside the graph (results are garbage, only the time counts)
+    ("skip every normalise pass", {"SY_DBG_SKIP_APPLY": "0:1000000"}, 0),
+    ("skip normalise <= 8 MB", {"SY_DBG_SKIP_APPLY": "0:8"}, 0),
+    ("skip normalise 8-40 MB", {"SY_DBG_SKIP_APPLY": "8:40"}, 0),
+    ("skip normalise > 40 MB", {"SY_DBG_SKIP_APPLY": "40:1000000"}, 0),
+    ("conv without MMAs", {"SY_CONV_DEBUG": "1"}, 0),
+    ("conv without TMA loads", {"SY_CONV_DEBUG": "2"}, 0),
+    ("conv without MMAs and loads", {"SY_CONV_DEBUG": "3"}, 0),
+    ("no applies, conv w/o MMAs+loads", {"SY_CONV_DEBUG": "3", "SY_DBG_SKIP_APPLY": "0:1000000"}, 0),
 ]
 if len(sys.argv) > 3:
     SETTINGS = [s for s in SETTINGS if any(k in s[0] for k in sys.argv[3].split(","))]
-SWITCHES = ("SY_CONV_TILES", "SY_PDL", "SY_APPLY", "SY_APPLY_CAP", "SY_STAGE_TILES", "SY_APPLY_CARVEOUT", "SY_CONV_DEBUG", "SY_CONV_A")
+SWITCHES = ("SY_DBG_SKIP_APPLY", "SY_CONV_TILES", "SY_PDL", "SY_APPLY", "SY_APPLY_CAP", "SY_STAGE_TILES", "SY_APPLY_CARVEOUT", "SY_CONV_DEBUG", "SY_CONV_A")
 
 
 def measure(label, env, fuse_mb, steps=20, warmup=4):
