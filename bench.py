@@ -235,12 +235,18 @@ def cpu_oracle_run(tag, pairs, steps, warmup, height=600, width_px=960):
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's own CPU path for this workload, timed on the host cores with EXACTLY the --steps /
+    --warmup it prints.  It is the fp32 oracle (kind "port"): the reference's modules need the un-vendored yolox==0.3.0
+    package and /root/reference does not exist on the GPU box; the oracle is pinned to outputs of the
+    unmodified reference files (oracle/make_golden.py).  Each step = one forward+loss over a bounded sample of the per-GPU
+    batch (2 frame pairs of the same 600x960 workload), so that the run stays within a few minutes."""
     if rank != 0:
         return
     pairs = 2
-    v, sec = cpu_oracle_run(args.model, pairs, max(1, min(args.steps, 3)), min(args.warmup, 1))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    v, sec = cpu_oracle_run(args.model, pairs, steps, warmup)
     line = {"impl": "reference", "metric": "frame-pairs/sec StreamYOLO-%s 600x960 fwd+loss" % args.model,
-            "value": round(v, 4), "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "value": round(v, 4), "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             # the same workload as the GPU arm (its `config.workload` string), timed on a bounded sample of it
@@ -249,7 +255,8 @@ def run_reference(args, rank):
                        "pairs_per_gpu": args.batch, "sample_pairs_per_step": pairs,
                        "device": "host CPU cores (the reference's own CPU path: fp32 PyTorch)"},
             "cpu_baseline": {"value": round(v, 4), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "%d pairs/step, oracle restatement of the reference PyTorch path (yolox not installable)" % pairs},
+                             "sample": "%d pairs/step x %d steps (+%d warm-up), fp32 oracle restatement of the reference PyTorch "
+                                       "path (yolox not installable, /root/reference absent on the GPU box)" % (pairs, steps, warmup)},
             "e2e": {"value": round(v, 4), "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(json.dumps(line))
 

@@ -99,6 +99,10 @@ typedef struct {
   void* debug_timeline;  /* device buffer of 2*debug_timeline_events int64, or NULL */
   int32_t debug_timeline_events;
   int32_t debug_flags;   /* 0 in production; 1 = skip MMAs, 2 = skip TMA loads (pipeline dissection, results invalid) */
+  /* ---- validation only: the fp32 accumulators themselves, before the bf16 rounding of the stored result:
+   * debug_f32[pixel][Cout] (pixel = flattened (n, oh, ow)), written next to the normal output.  This is where
+   * north_star's "within 1e-3 of the reference" is literal (tests/test_gpu_ops.py::test_conv_fp32_accumulators). ---- */
+  float* debug_f32;
 } SyConvDesc;
 
 /* Rows of the statistics workspace (= SM count: one row per persistent CTA). */
@@ -348,6 +352,10 @@ typedef struct SySgdEmaDesc {
   int32_t nesterov;
   float ema_decay, ema_one_minus_decay;
   const float* found_inf;
+  /* optional device array [lr, momentum, weight_decay, inv_scale, ema_decay, 1 - ema_decay]: when non-NULL it REPLACES the
+   * six scalars above, so that a step captured in a CUDA graph follows the LR schedule / EMA ramp / loss scale of the
+   * iteration it is replayed in (the host rewrites the 24 bytes before each replay). */
+  const float* hyper;
 } SySgdEmaDesc;
 int sy_sgd_nesterov_ema_step(const SySgdEmaDesc* d, sy_stream_t stream);
 

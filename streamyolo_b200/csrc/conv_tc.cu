@@ -97,6 +97,7 @@ struct Params {
   long long* timeline;      // debug: CTA 0 records (event id, clock) pairs; nullptr in production
   int timeline_cap;
   int debug_flags;          // debug: 1 = skip the MMAs, 2 = skip the TMA loads (barriers still cycle), 4 = skip epilogue work
+  float* dbg_f32;           // validation: fp32 accumulators [pixel][Cout] written next to the stored result (nullptr in production)
 };
 
 // debug timeline: event = role<<28 | phase<<24 | tile<<8 | kb ; written by CTA 0 only
@@ -631,6 +632,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tcgen05_fence_before();
           mbar_arrive(tempty_bar(acc));
         }
+        if (p.dbg_f32 != nullptr && valid) {       // validation only: the accumulators before any rounding
+          float* o = p.dbg_f32 + pix * p.Cout + n0 + cl;
+#pragma unroll                                   // (static indices: v[] must stay in registers)
+          for (int i = 0; i < 32; ++i)
+            if (n0 + cl + i < p.Cout) o[i] = __uint_as_float(v[i]);
+        }
         uint32_t packed[16];
         if (p.mode == SY_CONV_RAW) {
 #pragma unroll
@@ -1038,6 +1045,7 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
     SY_REQUIRE(d->n_partials >= tc::num_sms(), SY_EWORKSPACE, "conv2d_tc: %d statistic rows, need %d (sy_conv_stat_rows)",
                d->n_partials, tc::num_sms());
   }
+  p.dbg_f32 = d->debug_f32;
   p.timeline = reinterpret_cast<long long*>(d->debug_timeline);
   p.timeline_cap = d->debug_timeline ? d->debug_timeline_events : 0;
   p.n_seg = 0;

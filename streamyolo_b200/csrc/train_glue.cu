@@ -57,8 +57,11 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int O, int I, in
 __global__ void sgd_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mbuf,
                                float* __restrict__ ema, long long n_param, long long n_total, long long decay_begin, float lr,
                                float momentum, float wd, float inv_scale, int nesterov, float ema_d, float ema_1md,
-                               const float* __restrict__ found_inf) {
+                               const float* __restrict__ found_inf, const float* __restrict__ hyper) {
   if (found_inf != nullptr && *found_inf != 0.f) return;          // GradScaler.step skips the update on inf / nan
+  if (hyper != nullptr) {                                          // graph-replay safe hyper-parameters
+    lr = hyper[0]; momentum = hyper[1]; wd = hyper[2]; inv_scale = hyper[3]; ema_d = hyper[4]; ema_1md = hyper[5];
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_total; i += (long long)gridDim.x * blockDim.x) {
     float v = p[i];
     if (i < n_param) {
@@ -140,7 +143,7 @@ extern "C" int sy_sgd_nesterov_ema_step(const SySgdEmaDesc* d, sy_stream_t strea
   sgd_ema_kernel<<<grid_for(d->n_total, 256), 256, 0, stream>>>(d->param, d->grad, d->momentum_buf, d->ema, d->n_param, d->n_total,
                                                                d->decay_begin, d->lr, d->momentum, d->weight_decay,
                                                                d->inv_scale, d->nesterov, d->ema_decay, d->ema_one_minus_decay,
-                                                               d->found_inf);
+                                                               d->found_inf, d->hyper);
   return launch_status("sgd_ema_kernel");
 }
 

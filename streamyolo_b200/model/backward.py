@@ -31,6 +31,10 @@ from .. import ops
 from ..ops import View
 
 
+DEBUG_HOOK = None     # tests: callable(stage, record, **tensors) invoked inside the walk (tests/test_gpu_train.py checks every
+                      # recorded conv's backward in situ against torch on the very tensors the kernels saw)
+
+
 class Tape:
     def __init__(self, device):
         self.device = device
@@ -276,6 +280,8 @@ def _conv_backward(T: Tape, r, sink):
         ops.add_(gy, T.g(res))                                   # shortcut / "+ cur" branch
     draw = View.empty(raw.n, raw.h, raw.w, cout, dev)
     dgamma, dbeta, acc_bn = sink.bn(mods)
+    if DEBUG_HOOK is not None:
+        DEBUG_HOOK("pre", r, gy=gy, dgamma=dgamma, dbeta=dbeta, acc_bn=acc_bn)
     ops.bn_act_backward(raw, gy, draw, r["ss"][0], r["ss"][1], r["mi"][0], r["mi"][1], r["split"], r["act"], dgamma, dbeta,
                         accumulate=acc_bn)
     if stem:
@@ -291,6 +297,8 @@ def _conv_backward(T: Tape, r, sink):
         sink.done([mods[0].conv.weight, mods[0].bn.weight, mods[0].bn.bias])
         return                                                    # the input frames need no gradient
     dw, acc_w = sink.conv_weight(mods, cin, kh, kw)
+    if DEBUG_HOOK is not None:
+        DEBUG_HOOK("pre_w", r, dw=dw, acc_w=acc_w, gx=T.g(x))
     ops.conv2d_wgrad(x, draw, (kh, kw), s, dw, accumulate=acc_w)
     sink.done([p for m in mods for p in (m.conv.weight, m.bn.weight, m.bn.bias)])
     gx = T.g(x)
@@ -301,6 +309,8 @@ def _conv_backward(T: Tape, r, sink):
         ops.dilate2(draw, src)
     # data gradient, accumulated in place: gx = conv(src, flipped / transposed filter) * 1 + 0 + gx
     ops.conv2d(src, engine._packed_dgrad(mods), gx, (kh, kw), 1, ops.SY_CONV_FUSED, scale=one, shift=zero, act=0, res=gx)
+    if DEBUG_HOOK is not None:
+        DEBUG_HOOK("post", r, draw=draw, dgamma=dgamma, dbeta=dbeta, dw=dw, gx=gx)
 
 
 def _one_zero(T, c):

@@ -34,7 +34,7 @@ class SyConvDesc(C.Structure):
                 ("apply_y", SyTensor), ("apply_res", SyTensor), ("apply_y_group1_offset", C.c_int64),
                 ("apply_res_group1_offset", C.c_int64),
                 ("debug_timeline", C.c_void_p),
-                ("debug_timeline_events", C.c_int32), ("debug_flags", C.c_int32)]
+                ("debug_timeline_events", C.c_int32), ("debug_flags", C.c_int32), ("debug_f32", C.c_void_p)]
 
 
 class SyHeadPredDesc(C.Structure):
@@ -91,7 +91,7 @@ class SySgdEmaDesc(C.Structure):
                 ("n_param", C.c_int64), ("n_total", C.c_int64), ("decay_begin", C.c_int64),
                 ("lr", C.c_float), ("momentum", C.c_float), ("weight_decay", C.c_float), ("inv_scale", C.c_float),
                 ("nesterov", C.c_int32), ("ema_decay", C.c_float), ("ema_one_minus_decay", C.c_float),
-                ("found_inf", C.c_void_p)]
+                ("found_inf", C.c_void_p), ("hyper", C.c_void_p)]
 
 
 class SyConvPlan(C.Structure):
@@ -292,7 +292,7 @@ def conv_stat_rows():
 
 def conv2d(x: View, wpk, y: View, k, s, mode, impl="tc", scale=None, shift=None, act=1, res: View = None,
            partials=None, split_n=0, timeline=None, debug_flags=0, bn=None, momentum=0.03, eps=1e-3, scale_shift=None,
-           sync=None, apply_y: View = None, apply_res: View = None, y_goff1=0, res_goff1=0, mean_invstd=None):
+           sync=None, apply_y: View = None, apply_res: View = None, y_goff1=0, res_goff1=0, mean_invstd=None, debug_f32=None):
     """``k`` is an int (square) or (kh, kw).  With ``partials`` (RAW mode, tensor-core path) returns the number
     of per-CTA statistic rows the launch writes."""
     d = SyConvDesc()
@@ -324,6 +324,7 @@ def conv2d(x: View, wpk, y: View, k, s, mode, impl="tc", scale=None, shift=None,
             d.apply_res = apply_res.st() if apply_res is not None else NULL_T
             d.apply_y_group1_offset, d.apply_res_group1_offset = y_goff1, res_goff1
     d.debug_flags = debug_flags
+    d.debug_f32 = debug_f32.data_ptr() if debug_f32 is not None else None
     if timeline is not None:
         d.debug_timeline, d.debug_timeline_events = timeline.data_ptr(), timeline.numel() // 2
     fn = lib().sy_conv2d_tc if impl == "tc" else lib().sy_conv2d_simt
@@ -563,8 +564,9 @@ def conv2d_plan(n, h, w, cin, cout, k, s):
 
 
 def sgd_nesterov_ema_step(param, grad, momentum_buf, ema, n_param, decay_begin, lr, momentum=0.9, weight_decay=5e-4,
-                          inv_scale=1.0, nesterov=True, ema_decay=0.0, found_inf=None):
-    """One fused optimiser step over flat fp32 state (sy_sgd_nesterov_ema_step); ``ema`` may be None."""
+                          inv_scale=1.0, nesterov=True, ema_decay=0.0, found_inf=None, hyper=None):
+    """One fused optimiser step over flat fp32 state (sy_sgd_nesterov_ema_step); ``ema`` may be None.  ``hyper``: device
+    fp32 [lr, momentum, weight_decay, inv_scale, ema_decay, 1 - ema_decay] replacing the scalars (CUDA-graph replays)."""
     d = SySgdEmaDesc()
     d.param, d.grad, d.momentum_buf = param.data_ptr(), grad.data_ptr(), momentum_buf.data_ptr()
     d.ema = ema.data_ptr() if ema is not None else None
@@ -572,6 +574,7 @@ def sgd_nesterov_ema_step(param, grad, momentum_buf, ema, n_param, decay_begin, 
     d.lr, d.momentum, d.weight_decay, d.inv_scale, d.nesterov = lr, momentum, weight_decay, inv_scale, int(nesterov)
     d.ema_decay, d.ema_one_minus_decay = ema_decay, 1.0 - ema_decay
     d.found_inf = found_inf.data_ptr() if found_inf is not None else None
+    d.hyper = hyper.data_ptr() if hyper is not None else None
     _check(lib().sy_sgd_nesterov_ema_step(C.byref(d), _stream()))
 
 

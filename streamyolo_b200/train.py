@@ -219,6 +219,7 @@ class FlatSink:
         self._close(0, fs.decay_begin, small)
         self.work = []
         self.launched = []
+        self.on_bucket = None
 
     def _close(self, a, b, members):
         if not members:
@@ -290,7 +291,10 @@ class FlatSink:
     def _launch(self, b):
         self.launched.append((b[0], b[1]))
         if self.world > 1:
-            self.work.append(dist.all_reduce(self.fs.grad[b[0]:b[1]], op=dist.ReduceOp.SUM, async_op=True))
+            if self.on_bucket is not None:
+                self.on_bucket(b[0], b[1])          # graph capture: the trainer cuts the graph here and owns the collective
+            else:
+                self.work.append(dist.all_reduce(self.fs.grad[b[0]:b[1]], op=dist.ReduceOp.SUM, async_op=True))
 
     def finish(self):
         for b in self.buckets:
@@ -325,18 +329,90 @@ class Trainer:
             backward._walk(T, self.model.head, loss_scale, self.sink)
         return loss
 
-    def optimizer_step(self, lr=None, loss_scale=1.0, found_inf=None):
-        self.updates += 1
+    def _hyper_values(self, lr, loss_scale):
         d = self.ema_decay * (1 - math.exp(-self.updates / 2000)) if self.fs.ema is not None else 0.0
+        return [self.lr if lr is None else lr, self.momentum, self.weight_decay, 1.0 / (self.world * loss_scale), d, 1.0 - d]
+
+    def optimizer_step(self, lr=None, loss_scale=1.0, found_inf=None, hyper=None):
+        if hyper is None:
+            self.updates += 1
+        h = self._hyper_values(lr, loss_scale)
         ops.sgd_nesterov_ema_step(self.fs.state, self.fs.grad, self.fs.mom, self.fs.ema, self.fs.n_param, self.fs.decay_begin,
-                                  self.lr if lr is None else lr, self.momentum, self.weight_decay,
-                                  inv_scale=1.0 / (self.world * loss_scale), nesterov=True, ema_decay=d, found_inf=found_inf)
+                                  h[0], h[1], h[2], inv_scale=h[3], nesterov=True, ema_decay=h[4], found_inf=found_inf,
+                                  hyper=hyper)
         engine.WEIGHT_EPOCH += 1            # the conv operands are re-packed from the new masters on their next use
 
     def step(self, x, targets, lr=None, loss_scale=1.0):
         loss = self.forward_backward(x, targets, loss_scale)
         self.optimizer_step(lr, loss_scale)
         return backward._loss_dict(loss)
+
+    # ---- the whole step as CUDA graph(s) (the eager step is bound by the host's launch rate: ~800-1300 launches)
+    def capture(self, x, targets, loss_scale=1.0):
+        """Capture forward + backward + weight re-pack + optimiser step on static input buffers (``x`` / ``targets`` become the
+        graph's inputs: copy new data into them, then ``replay(lr)``).  One process: ONE graph.  Several ranks: the walk is cut
+        into one graph segment per gradient bucket; between two segments the host enqueues that bucket's NCCL all-reduce on the
+        communication stream, where it overlaps the following segments (the collectives themselves stay outside the
+        captured graphs); a last segment holds the optimiser step."""
+        dev = self.fs.state.device
+        self._hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        self._hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self._loss_scale = loss_scale
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up on a side stream (allocator, lazy module attributes)
+            self._set_hyper(None)
+            self.forward_backward(x, targets, loss_scale)
+            self.optimizer_step(hyper=self._hyper)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        pool = torch.cuda.graph_pool_handle()
+        self._plan = []                                    # [(graph, bucket range or None)]
+        cur = [None]
+
+        def begin():
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin(pool=pool)
+            cur[0] = g
+
+        def cut(a, b):
+            cur[0].capture_end()
+            self._plan.append((cur[0], (a, b)))
+            begin()
+
+        self.sink.on_bucket = cut if self.world > 1 else None
+        with torch.cuda.stream(side):
+            begin()
+            loss = self.forward_backward(x, targets, loss_scale)
+            if self.world > 1:                             # the optimiser step waits for the collectives: its own segment
+                cur[0].capture_end()
+                self._plan.append((cur[0], None))
+                begin()
+            self.optimizer_step(hyper=self._hyper)
+            cur[0].capture_end()
+            self._plan.append((cur[0], None))
+        self.sink.on_bucket = None
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph_loss = loss
+        return len(self._plan)
+
+    def _set_hyper(self, lr):
+        self.updates += 1
+        self._hyper_host[:6] = torch.tensor(self._hyper_values(lr, self._loss_scale))
+        self._hyper.copy_(self._hyper_host, non_blocking=True)
+
+    def replay(self, lr=None):
+        self._set_hyper(lr)
+        works = []
+        for i, (g, bucket) in enumerate(self._plan):
+            if i == len(self._plan) - 1:
+                for w in works:
+                    w.wait()
+            g.replay()
+            if bucket is not None:
+                works.append(dist.all_reduce(self.fs.grad[bucket[0]:bucket[1]], op=dist.ReduceOp.SUM, async_op=True))
+        return backward._loss_dict(self._graph_loss)
 
     def ema_state_dict(self):
         return self.fs.ema_state_dict(self.model)

@@ -47,7 +47,7 @@ def conv_stat_rows():
 
 def conv2d(x, wpk, y, k, s, mode, impl="tc", scale=None, shift=None, act=1, res=None, partials=None, split_n=0,
            timeline=None, debug_flags=0, bn=None, momentum=0.03, eps=1e-3, scale_shift=None, sync=None, apply_y=None,
-           apply_res=None, y_goff1=0, res_goff1=0, mean_invstd=None):
+           apply_res=None, y_goff1=0, res_goff1=0, mean_invstd=None, debug_f32=None):
     kh, kw = (k, k) if isinstance(k, int) else k
     w = _unpack(wpk, kh, kw)
     out = F.conv2d(_nchw(x), w, None, s, ((kh - 1) // 2, (kw - 1) // 2))
@@ -269,10 +269,12 @@ def add_(x, y):
 
 
 def sgd_nesterov_ema_step(param, grad, momentum_buf, ema, n_param, decay_begin, lr, momentum=0.9, weight_decay=5e-4,
-                          inv_scale=1.0, nesterov=True, ema_decay=0.0, found_inf=None):
+                          inv_scale=1.0, nesterov=True, ema_decay=0.0, found_inf=None, hyper=None):
     """what sy_sgd_nesterov_ema_step does, in torch (same order of operations as torch.optim.SGD / yolox ModelEMA)"""
     if found_inf is not None and float(found_inf) != 0.0:
         return
+    if hyper is not None:
+        lr, momentum, weight_decay, inv_scale, ema_decay = (float(v) for v in hyper[:5])
     p = param[:n_param]
     g = grad[:n_param] * inv_scale if inv_scale != 1.0 else grad[:n_param].clone()
     g[decay_begin:] = g[decay_begin:].add(p[decay_begin:], alpha=weight_decay)

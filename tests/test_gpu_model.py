@@ -313,15 +313,17 @@ def test_loss_backward_vs_oracle_autograd():
                 f"head.{name}_preds.{k}.bias: {sums[sl].tolist()} vs {want.tolist()}"
 
 
-@pytest.mark.skipif(os.environ.get("SY_E2E_BACKWARD") != "1",
-                    reason="whole-model backward: kernels are GPU-tested one by one and the routing is CPU-tested "
-                           "(tests/test_cpu_backward.py); the assembled walk has not run on a GPU yet -- set SY_E2E_BACKWARD=1")
 def test_forward_backward_vs_oracle_autograd():
-    """streamyolo_b200.model.backward.forward_backward on the GPU against autograd through the oracle with bf16 storage.
-    A random-init train-mode BatchNorm net amplifies rounding noise, so gradients are judged like the forward features:
-    against the deviation the oracle itself shows when its inputs are nudged by 1e-6."""
+    """streamyolo_b200.model.backward.forward_backward on the GPU against autograd through the oracle with bf16 storage
+    (which tests/test_oracle_golden.py pins to the reference's loss.backward()).  A random-init train-mode BatchNorm net is
+    chaotic under bf16 storage (tools/diag_bwd.py, profiles/r02_backward_noise_floor.txt: nudging the inputs by half a bf16
+    ulp decorrelates the stride-32 gradients of the ORACLE ITSELF at 120x160, rel ~1.0), so the element-wise bar lives in
+    tests/test_gpu_train.py::test_walk_in_situ_every_conv_backward (identical inputs per op); here, on a larger map where
+    the noise is moderate, every parameter gradient must be finite, point the right way and have the right size:
+    per-parameter deviation within 2 x the oracle's own rounding-noise floor + 0.25, median cosine >= 0.85, 10th
+    percentile >= 0.6."""
     from streamyolo_b200.model import backward
-    c = CASES["tiny_120x160"]
+    c = dict(CASES["tiny_120x160"], H=256, W=320)
     x = synth.synth_frames(c["B"], c["H"], c["W"])
     tg = synth.synth_labels(c["B"], c["H"], c["W"], empty_image=c["empty"])
     m = build_product(c["depth"], c["width"], c["gamma"], c["thr"], c["val"])
@@ -339,12 +341,16 @@ def test_forward_backward_vs_oracle_autograd():
         return float(r["total_loss"].detach()), {k: t.grad for k, t in o.P.items() if t.grad is not None}
 
     want_loss, want = oracle_grads(x)
-    _, pert = oracle_grads(x * (1 + 1e-6))
+    _, pert = oracle_grads(x * (1 + 2.0 ** -9))            # half a bf16 ulp on every input
     assert abs(float(loss["total_loss"]) - want_loss) < 5e-2 * abs(want_loss)
-    bad = []
+    bad, cos = [], []
     for k, p in m.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        g, w = p.grad.float().cpu().flatten(), want[k].float().flatten()
+        cos.append(float(torch.dot(g, w) / (g.norm() * w.norm() + 1e-20)))
         r, floor = rel(p.grad, want[k]), rel(pert[k], want[k])
-        if r > 2.0 * floor + 5e-2:
+        if r > 2.0 * floor + 0.25:
             bad.append(f"{k}: rel {r:.3f} vs rounding-noise floor {floor:.3f}")
+    cos.sort()
     assert not bad, "\n".join(bad[:20])
+    assert cos[len(cos) // 2] >= 0.85 and cos[len(cos) // 10] >= 0.6, (cos[len(cos) // 2], cos[len(cos) // 10], cos[0])
