@@ -249,8 +249,12 @@ def head_rec(T, head, fused, labels):
     levels = []
     for k, v in enumerate(fused):
         x = base_conv_rec(T, head.stems[k], v, 0)
-        cf = base_conv_rec(T, head.cls_convs[k][1], base_conv_rec(T, head.cls_convs[k][0], x, 0), 0)
-        rf = base_conv_rec(T, head.reg_convs[k][1], base_conv_rec(T, head.reg_convs[k][0], x, 0), 0)
+        c0, r0 = head.cls_convs[k][0], head.reg_convs[k][0]          # same input: one launch (engine.conv_pair)
+        hw_c = c0.conv.out_channels
+        u = View.empty(x.n, x.h, x.w, 2 * hw_c, dev)
+        conv_rec(T, (c0, r0), x, engine._packed_pair(c0, r0), c0.ksize, c0.stride, u, 0)
+        cf = base_conv_rec(T, head.cls_convs[k][1], u.ch(0, hw_c), 0)
+        rf = base_conv_rec(T, head.reg_convs[k][1], u.ch(hw_c, hw_c), 0)
         ops.head_pred_decode(cf, rf, _f32(head.reg_preds[k].weight), _f32(head.reg_preds[k].bias),
                              _f32(head.obj_preds[k].weight), _f32(head.obj_preds[k].bias), _f32(head.cls_preds[k].weight),
                              _f32(head.cls_preds[k].bias), head.strides[k], off, a_total, out, origin, sigmoid=False, decode=True)

@@ -208,6 +208,25 @@ def _folded_pair(m1, m2):
     return m1._fold2
 
 
+def conv_pair(ctx: Ctx, m1, m2, x: View) -> View:
+    """Two BaseConvs with the same geometry reading the same input as ONE launch: [.., c1 + c2] output, one BatchNorm
+    parameter segment per module (CSPLayer conv1 | conv2; the first cls / reg tower convs of a head level)."""
+    c1, c2 = m1.conv.out_channels, m2.conv.out_channels
+    k, s = m1.ksize, m1.stride
+    assert (m2.ksize, m2.stride, m2.conv.in_channels) == (k, s, m1.conv.in_channels)
+    ho, wo = ops.conv_out_hw(x.h, x.w, k, s)
+    u = View.empty(x.n, ho, wo, c1 + c2, ctx.device)
+    wpk = _packed_pair(m1, m2)
+    if not ctx.train:
+        scale, shift = _folded_pair(m1, m2)
+        ops.conv2d(x, wpk, u, k, s, ops.SY_CONV_FUSED, impl=ctx.impl, scale=scale, shift=shift, act=1)
+    else:
+        conv_bn_act(ctx, (m1, m2), x, wpk, k, s, u)
+    _trace(m1, u.ch(0, c1))
+    _trace(m2, u.ch(c1, c2))
+    return u
+
+
 def csp_layer(ctx: Ctx, m, x: View, out: View = None) -> View:
     """[yolox] CSPLayer: conv3(cat(m(conv1 x), conv2 x)).  conv1 and conv2 read the same input, so they
     run as ONE GEMM with 2*hidden output channels written straight into the concat buffer; the

@@ -65,8 +65,12 @@ class TALHead(nn.Module):
             off = 0
             for k, v in enumerate(views):
                 x = engine.base_conv(ctx, self.stems[k], v)
-                cf = engine.base_conv(ctx, self.cls_convs[k][1], engine.base_conv(ctx, self.cls_convs[k][0], x))
-                rf = engine.base_conv(ctx, self.reg_convs[k][1], engine.base_conv(ctx, self.reg_convs[k][0], x))
+                # cls_convs[k][0] and reg_convs[k][0] read the same stem output (tal_head.py:159-171): ONE conv launch with
+                # 2 x hw output channels and two BatchNorm segments, like the conv1 | conv2 pair of a CSPLayer
+                u = engine.conv_pair(ctx, self.cls_convs[k][0], self.reg_convs[k][0], x)
+                hw_c = self.cls_convs[k][0].conv.out_channels
+                cf = engine.base_conv(ctx, self.cls_convs[k][1], u.ch(0, hw_c))
+                rf = engine.base_conv(ctx, self.reg_convs[k][1], u.ch(hw_c, hw_c))
                 ops.head_pred_decode(cf, rf, self._f32(self.reg_preds[k].weight), self._f32(self.reg_preds[k].bias),
                                      self._f32(self.obj_preds[k].weight), self._f32(self.obj_preds[k].bias),
                                      self._f32(self.cls_preds[k].weight), self._f32(self.cls_preds[k].bias),

@@ -108,8 +108,8 @@ def conv_groups_forward_order(model):
     bc(net.jian2); bc(net.jian1); bc(net.jian0)
     for k in range(len(head.stems)):
         bc(head.stems[k])
-        bc(head.cls_convs[k][0]); bc(head.cls_convs[k][1])
-        bc(head.reg_convs[k][0]); bc(head.reg_convs[k][1])
+        out.append((head.cls_convs[k][0], head.reg_convs[k][0]))
+        bc(head.cls_convs[k][1]); bc(head.reg_convs[k][1])
     return out
 
 

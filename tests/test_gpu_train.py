@@ -216,7 +216,8 @@ def test_walk_in_situ_every_conv_backward():
         torch.cuda.synchronize()
     finally:
         backward.DEBUG_HOOK = None
-    assert len(seen) == 77 - 8 + 3 - 1, len(seen)      # 77 BaseConvs: 8 CSP conv2 ride with their conv1, jian x2, the stem has no dx
+    # 77 BaseConvs: 8 CSP conv2 ride with their conv1, 3 head reg towers with their cls twin, jian x2, the stem has no dx
+    assert len(seen) == 77 - 8 - 3 + 3 - 1, len(seen)
 
 
 def test_trainer_graph_replay_equals_eager_steps():

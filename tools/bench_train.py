@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--no-ema", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--split", action="store_true", help="also time forward+backward and the optimiser step separately")
+    ap.add_argument("--eager", action="store_true", help="no CUDA graph: every kernel launched from Python each step")
     args = ap.parse_args()
     bench.guard_stdout()
     rank, local_rank, world = sydist.env_world()
@@ -44,9 +45,12 @@ def main():
     tg = (fut.to(dev), cur.to(dev))
     if args.impl == "trainer":
         tr = train.Trainer(model, lr=lr, use_ema=not args.no_ema, overlap=not args.no_overlap)
+        segments = 0
+        if not args.eager:
+            segments = tr.capture(x, tg)
 
         def step():
-            return tr.step(x, tg)
+            return tr.step(x, tg) if args.eager else tr.replay()
     else:
         opt = train.build_optimizer(model, lr=lr)
         ema = None if args.no_ema else train.ModelEMA(model)
@@ -70,7 +74,7 @@ def main():
     sydist.barrier()
     ms = sydist.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
     extra = {}
-    if args.split and args.impl == "trainer":
+    if args.split and args.impl == "trainer" and args.eager:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         ev[0].record()
         for _ in range(args.steps):
@@ -96,6 +100,7 @@ def main():
             "host_enqueue_ms_per_step": round(host_ms, 3), "launches_per_step": launches // max(1, args.steps)}
         if args.impl == "trainer":
             line["allreduce"] = {"buckets": len(tr.sink.launched), "bytes": 4 * tr.fs.n_param, "world": world}
+            line["config"]["cuda_graph_segments"] = segments
         line.update(extra)
         bench.emit(json.dumps(line))
     sydist.shutdown()
