@@ -224,14 +224,152 @@ def cpu_oracle_run(tag, pairs, steps, warmup, height=600, width_px=960):
     x = synth.synth_frames(pairs, height, width_px)
     tg = synth.synth_labels(pairs, height, width_px)
     ts = []
+    global LAST_ORACLE_LOSS
     with torch.no_grad():
         for i in range(warmup + steps):
+            if i > 0:                                   # every run on fresh running statistics: same result each time
+                o = StreamYoloOracle(o.cfg, synth.synth_state_dict(model_shapes(depth, width)))
             t0 = time.perf_counter()
-            o.forward(x, tg)
+            r = o.forward(x, tg)
             if i >= warmup:
                 ts.append(time.perf_counter() - t0)
+    LAST_ORACLE_LOSS = {k: float(v) for k, v in r.items()}
     sec = sum(ts) / len(ts)
     return pairs / sec, sec
+
+
+LAST_ORACLE_LOSS = None
+LOSS_KEYS = ("total_loss", "iou_loss", "l1_loss", "conf_loss", "cls_loss", "num_fg")
+
+
+def capture(fn):
+    """fn() captured as a CUDA graph after one warm-up call on a side stream; returns (graph, fn's result)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = fn()
+    return g, out
+
+
+def time_replays(g, steps, warmup=3):
+    for _ in range(warmup):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def conv_family_time(model, x_dev, tg_dev):
+    """The dominant kernel family -- every conv_tc_kernel launch of one step -- timed live: one eager step with a CUDA event
+    pair around each launch on the launching stream (warm caches; no overlap with the neighbouring kernels, so this is an
+    upper bound of what the family costs inside the graph).  Returns (sum of durations in ms, launches)."""
+    from streamyolo_b200 import ops
+    evs = []
+    orig = ops.conv2d
+
+    def timed(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig(*a, **k)
+        e1.record()
+        evs.append((e0, e1))
+        return r
+
+    ops.conv2d = timed
+    try:
+        with torch.no_grad():
+            model(x_dev, tg_dev)
+        torch.cuda.synchronize()
+    finally:
+        ops.conv2d = orig
+    return sum(a.elapsed_time(b) for a, b in evs), len(evs)
+
+
+def measure_train(tag, batch, dev, rank, world, steps, warmup, peaks):
+    """BASELINE.json configs 2-4: one optimisation step = recording forward + backward walk + (N > 1: bucketed NCCL gradient
+    all-reduce launched from the walk) + fused SGD-nesterov/EMA kernel, streamyolo_b200.train.Trainer, replayed as CUDA
+    graph(s).  Same barrier / CUDA-event / max-over-ranks protocol as the headline."""
+    from streamyolo_b200 import dist as sydist, ops, synth, train
+    model = build_model(tag, dev)
+    tr = train.Trainer(model, lr=0.01 / 64 * batch * world)
+    x = synth.synth_frames(batch, 600, 960, seed=4321 + rank).to(dev)
+    fut, cur = synth.synth_labels(batch, 600, 960, seed=11 + rank)
+    tg = (fut.to(dev), cur.to(dev))
+    ops.LAUNCHES = 0
+    segments = tr.capture(x, tg)
+    launches = ops.LAUNCHES // 2                        # capture() runs the step twice (warm-up + capture)
+    for _ in range(warmup):
+        loss = tr.replay()
+    torch.cuda.synchronize()
+    sydist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = tr.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    sydist.barrier()
+    ms = sydist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+    pairs = world * batch / (ms * 1e-3)
+    gf = GFLOP_PER_PAIR[tag] * 3.0
+    tf = pairs / world * gf / 1e3
+    out = {"metric": "frame-pairs/sec StreamYOLO-%s 600x960 fwd+bwd+optimizer step" % tag, "value": round(pairs, 2),
+           "unit": "pairs/s", "ms_per_step": round(ms, 3), "pairs_per_gpu": batch, "steps": steps, "warmup": warmup,
+           "tflops_per_gpu": round(tf, 1), "frac_of_sustained_peak": round(tf / peaks["sustained"], 4), "gflop_per_pair": gf,
+           "loss": float(loss["total_loss"]), "launches_per_step": launches, "cuda_graph_segments": segments,
+           "allreduce": {"world": world, "bytes_per_step": 4 * tr.fs.n_param if world > 1 else 0,
+                         "buckets": len(tr.sink.launched), "in_timed_region": world > 1,
+                         "how": "one NCCL all-reduce per ~25 MB bucket of the flat gradient buffer, enqueued when the walk "
+                                "finishes the bucket (between two graph segments), overlapping the rest of the walk"}}
+    del tr, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_eval_modes(model, dev, batch, steps):
+    """BASELINE.json config 5 (eval forward, decoded [B, 11850, 13], NMS excluded) and SURVEY 8f-1 (on_pipe streaming, one
+    frame per call with the buffered previous-frame features, CUDA-graphed)."""
+    from streamyolo_b200 import synth
+    out = {}
+    model.eval()
+    try:
+        with torch.no_grad():
+            x = synth.synth_frames(batch, 600, 960, seed=99).to(dev)
+            for _ in range(2):
+                model(x)
+            g, y = capture(lambda: model(x))
+            ms = time_replays(g, steps)
+            out["eval"] = {"metric": "frame-pairs/sec eval forward (model.eval()(imgs) -> [B, 11850, 13], NMS excluded)",
+                           "value": round(batch / ms * 1e3, 1), "unit": "pairs/s", "ms_per_step": round(ms, 4),
+                           "pairs_per_gpu": batch, "out_shape": list(y.shape)}
+            f0 = synth.synth_frames(1, 600, 960, seed=98)[:, :3].contiguous().to(dev)
+            _, buf = model(f0, mode="on_pipe")
+            buf_static = tuple(b.clone() for b in buf)
+
+            def frame():
+                o2, nb = model(f0, buffer=buf_static, mode="on_pipe")
+                for d_, s_ in zip(buf_static, nb):
+                    d_.copy_(s_)                          # carry the feature buffer to the next frame
+                return o2
+            frame()
+            g2, _ = capture(frame)
+            ms2 = time_replays(g2, max(steps, 20))
+            out["on_pipe"] = {"metric": "ms per 600x960 frame, on_pipe streaming (batch 1, buffered features, CUDA graph)",
+                              "value": round(ms2, 4), "unit": "ms/frame", "higher_is_better": False, "fps": round(1e3 / ms2, 1),
+                              "budget_ms": 33.3}
+    finally:
+        model.train()
+    return out
 
 
 def run_reference(args, rank):
@@ -291,6 +429,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="frame pairs per GPU")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurements (configs 2-4)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sustained run, eval / on_pipe modes and the conv-family timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -423,6 +563,44 @@ def main():
         h2d = x_host.numel() * 4 + fut_host.numel() * 4 + cur_host.numel() * 4
         loss_e2e = float(res_host[0])
 
+        # ---------------- sustained: the same graph replayed for >= 3 s (clocks settle under the power cap), own clock record
+        extras = {}
+        if graph is not None and not args.no_extras:
+            n_sus = max(args.steps, int(3200.0 / ms_step) + 1)
+            sampler2 = ClockSampler(local_rank)
+            sampler2.start()
+            sydist.barrier()
+            e0.record()
+            for _ in range(n_sus):
+                graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            sus_ms = sydist.max_over_ranks(e0.elapsed_time(e1), dev) / n_sus
+            extras["sustained"] = {"value": round(world * B / (sus_ms * 1e-3), 2), "unit": "pairs/s", "ms_per_step": round(sus_ms, 4),
+                                   "steps": n_sus, "seconds": round(sus_ms * n_sus * 1e-3, 2), "clocks": sampler2.stop()}
+        if rank == 0 and not args.no_extras and args.model in GFLOP_PER_PAIR:
+            fam_ms, fam_n = conv_family_time(model, x_dev, (fut_dev, cur_dev))
+            extras["conv_family"] = (fam_ms, fam_n)
+            extras.update(measure_eval_modes(model, dev, B, args.steps))
+            # parity of the timed model: its loss on the oracle's own sample (2 pairs, default seeds) -- compared below
+            x2 = synth.synth_frames(2, H, W).to(dev)
+            t2 = synth.synth_labels(2, H, W)
+            o2 = model(x2, (t2[0].to(dev), t2[1].to(dev)))
+            extras["product_loss_2pairs"] = {k: float(o2[k]) for k in LOSS_KEYS}
+        del graph
+        torch.cuda.empty_cache()
+
+    # ---------------- training step (BASELINE.json configs 2-4), all ranks: N > 1 puts the NCCL gradient all-reduce in the timed region
+    train_out = {}
+    if not args.no_train and args.model in GFLOP_PER_PAIR:
+        tsteps = max(5, min(args.steps, 20))
+        try:
+            train_out["l_b4_ddp"] = measure_train("l", 4, dev, rank, world, tsteps, 3, peaks)        # config 4: 32 pairs / 8 GPUs
+            if world == 1:
+                train_out["s_b8"] = measure_train("s", 8, dev, rank, world, tsteps, 3, peaks)       # config 2
+                train_out["m_b8"] = measure_train("m", 8, dev, rank, world, tsteps, 3, peaks)       # config 3
+        except Exception as ex:  # never lose the headline to the secondary measurement
+            train_out["error"] = "%s: %s" % (type(ex).__name__, str(ex)[:300])
     sydist.shutdown()
     if rank != 0:
         return
@@ -436,7 +614,7 @@ def main():
         "config": {"workload": "StreamYOLO-%s (random init) 600x960 frame pairs, forward+loss, train-mode BN, "
                                "%d pairs/GPU" % (args.model, B),
                    "pairs_per_gpu": B, "global_pairs": world * B, "parallelism": "dp%d (no data-path collective)" % world,
-                   "cuda_graph": graph is not None,
+                   "cuda_graph": not args.no_graph,
                    "l2": "per-step inputs (%.0f MB) + activations (>1 GB) exceed the 126 MB L2" % (h2d / 1e6)},
         "e2e": {"value": round(e2e_value, 2), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 24,
                 "ms_per_step": round(e2e_ms, 4), "note": "pinned fp32 frames+labels copied every step on a copy stream "
@@ -446,18 +624,42 @@ def main():
         "clocks": clocks,
         "loss_check": {"eager": loss_ref, "timed": float(loss_vec[0]), "e2e": loss_e2e},
     }
+    if train_out:
+        line["train"] = train_out
+    for k in ("sustained", "eval", "on_pipe"):
+        if k in extras:
+            line[k] = extras[k]
     if gf:
         tf = value / world * gf / 1e3
         line["roofline_step"] = {"bound": "tensor", "achieved": round(tf, 1), "peak": peaks["sustained"], "unit": "TFLOP/s",
                                  "frac": round(tf / peaks["sustained"], 4), "gflop_per_pair": gf,
                                  "peak_source": peaks["source"] + " cuBLAS bf16 sustained"}
     if roof:
+        line["roofline_best_shape"] = roof
         line["roofline"] = roof
+    if gf and "conv_family" in extras:
+        # the dominant kernel FAMILY over the step: every conv_tc_kernel launch, FLOP-weighted (the whole conv work of the
+        # step / the sum of their live event-timed durations); the best single shape stays in roofline_best_shape
+        fam_ms, fam_n = extras["conv_family"]
+        ach = B * gf / fam_ms                      # GFLOP / ms = TFLOP/s
+        line["roofline"] = {"bound": "tensor", "kernel": "conv_tc_kernel<*>: all %d conv launches of one step" % fam_n,
+                            "achieved": round(ach, 1), "peak": peaks["burst"], "unit": "TFLOP/s", "frac": round(ach / peaks["burst"], 4),
+                            "peak_source": peaks["source"] + " cuBLAS bf16 burst", "launches": fam_n,
+                            "avg_launch_ms": round(fam_ms / fam_n, 5), "sum_launch_ms": round(fam_ms, 4),
+                            "algorithmic_flop_per_step": B * gf * 1e9, "traffic": None,
+                            "how": "one eager step, CUDA events around every conv launch on the launching stream (warm, no overlap "
+                                   "with neighbours: upper bound of the in-graph cost); ncu launch list: profiles/"}
     if not args.no_cpu_baseline:
         try:
             v, sec = cpu_oracle_run(args.model, 2, 2, 1)
             line["cpu_baseline"] = {"value": round(v, 4), "unit": "pairs/s", "cores": torch.get_num_threads(),
                                     "kind": "port", "sample": "2 pairs/step x 2 steps, fp32 oracle of the reference path"}
+            if LAST_ORACLE_LOSS and "product_loss_2pairs" in extras:
+                got, want = extras["product_loss_2pairs"], LAST_ORACLE_LOSS
+                dev_rel = {k: round(abs(got[k] - want[k]) / (abs(want[k]) + 1e-12), 5) for k in LOSS_KEYS}
+                line["parity_check"] = {"what": "losses of the timed model (bf16 storage) vs the fp32 oracle on the same 2 frame pairs",
+                                        "product": got, "oracle": want, "rel_dev": dev_rel,
+                                        "ok": bool(max(dev_rel[k] for k in LOSS_KEYS[:5]) < 0.08)}
         except Exception as ex:  # never lose the GPU numbers to a host-side problem
             line["cpu_baseline"] = {"value": None, "error": str(ex)[:200]}
     emit(json.dumps(line))

@@ -231,7 +231,7 @@ int sy_conv2d_wgrad_tc(const SyConvWgradDesc* d, sy_stream_t stream);
  * the BaseConv output; scale / shift / mean / invstd = [2 groups][c] as published by the forward (scale = gamma * invstd,
  * shift = beta - mean * scale; images >= split_n form statistics group 1).  Writes draw (bf16, gradient w.r.t. the conv
  * output, input of the conv data / weight gradient kernels), dgamma / dbeta (fp32, (+)=).  partials: sy_bn_act_bwd_rows(n,
- * h*w) rows of 2*c floats; coef: 4*c floats of scratch. */
+ * h*w) rows of 2*c floats; coef: 8*c floats of scratch. */
 typedef struct SyBnActBwdDesc {
   SyTensor raw, dy, draw;
   const float* scale; const float* shift; const float* mean; const float* invstd;

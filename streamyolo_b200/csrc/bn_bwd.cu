@@ -7,23 +7,29 @@
 //   dbeta   = sum dz             dgamma = sum dz * xhat               (over both groups)
 //   draw    = gamma * invstd_g * (dz - mean_g(dz) - xhat * mean_g(dz * xhat))
 //
-// Three launches: per-(image, pixel chunk) partial sums (deterministic, fixed order), a finalize that produces dgamma,
-// dbeta and the two per-group coefficients, and the element-wise pass that writes draw in bf16 for the conv's data /
-// weight gradient kernels.  HBM-bound 16-byte accesses over NHWC bf16 views.
+// Three launches: partial sums (up to 296 rows per statistics group so that the pass fills the GPU whatever the map size;
+// deterministic, fixed order), a finalize (one warp per channel) that produces dgamma, dbeta and the per-(group, channel)
+// coefficients, and the element-wise pass that writes draw in bf16 for the conv's data / weight gradient kernels.
+// HBM-bound 16-byte accesses over NHWC bf16 views.
 #include <math.h>
 
 #include "common.cuh"
 
 namespace sy {
 
-constexpr int kBwdChunk = 512;     // pixels per partial row
+constexpr int kBwdRowsPerGroup = 296;   // partial rows per statistics group (2 per SM): fills the GPU whatever the map size
+constexpr int kBwdThreads = 256;
+constexpr int kBwdUnroll = 4;
 
 __device__ __forceinline__ void unpack8b(const uint4& v, float* f) {
   f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
   f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
 }
+// silu'(z) = s (1 + z (1 - s)), s = sigmoid(z) on the approximate SFU ops (ex2 / rcp, ~2 ulp fp32; the result is stored as bf16)
 __device__ __forceinline__ float dsilu(float z) {
-  const float s = 1.0f / (1.0f + __expf(-z));
+  float e, s;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.0f + e));
   return s * (1.0f + z * (1.0f - s));
 }
 
@@ -31,104 +37,178 @@ struct BwdArgs {
   const __nv_bfloat16* raw; long long raw_pitch;
   const __nv_bfloat16* dy; long long dy_pitch;
   const float* scale; const float* shift; const float* mean; const float* invstd;   // [2 groups][C]
-  int HW, C, split_n, act;
+  long long npix, split_pix;       // pixels [0, split_pix) = statistics group 0, the rest group 1
+  int C, act;
+  int rows0, rows1;                // partial rows of group 0 / group 1
 };
 
-// partial rows [n * chunks][2 (sum dz | sum dz*xhat)][C]
-__global__ void bn_act_bwd_reduce_kernel(const BwdArgs q, float* partials) {
-  __shared__ float red[256][17];
-  const int chunks = cdiv(q.HW, kBwdChunk);
-  const int n = blockIdx.x / chunks, ch = blockIdx.x % chunks;
-  const int p0 = ch * kBwdChunk, p1 = min(q.HW, p0 + kBwdChunk);
-  const int grp = n >= q.split_n ? 1 : 0;
-  const int C = q.C, G = C / 8;
-  const int lanes = G < 256 ? G : 256, PL = 256 / lanes;
-  const int gl = threadIdx.x % lanes, pl = threadIdx.x / lanes;
+// Partial rows [rows0 + rows1][2 (sum dz | sum dz * xhat)][C].  Row r of a group covers an equal share of the group's
+// pixels; inside the block a thread owns one 8-channel chunk and every (256 / G)-th pixel (kBwdUnroll 16-byte load pairs in
+// flight), then the pixel lanes are combined through shared memory in a fixed order (deterministic).
+__global__ void __launch_bounds__(kBwdThreads) bn_act_bwd_reduce_kernel(const BwdArgs q, float* partials) {
+  __shared__ float red[kBwdThreads][17];
+  const int grp = (int)blockIdx.x >= q.rows0 ? 1 : 0;
+  const int row = grp ? (int)blockIdx.x - q.rows0 : (int)blockIdx.x, nrows = grp ? q.rows1 : q.rows0;
+  const long long gbeg = grp ? q.split_pix : 0, gend = grp ? q.npix : q.split_pix;
+  const long long share = (gend - gbeg + nrows - 1) / nrows;
+  const long long p0 = gbeg + (long long)row * share, p1 = min(gend, p0 + share);
+  const int C = q.C, G = C >> 3;
   float* out = partials + (size_t)blockIdx.x * 2 * C;
+  const int lanes = G < kBwdThreads ? G : kBwdThreads, PL = kBwdThreads / lanes;
+  const int gl = (int)threadIdx.x % lanes, pl = (int)threadIdx.x / lanes;
   for (int g0 = 0; g0 < G; g0 += lanes) {
     const int g = g0 + gl;
     float s[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) s[i] = 0.f;
     if (g < G && pl < PL) {
-      float sc[8], sh[8], mu[8], is[8];
+      float sc[8], sh[8], k1[8], k0[8];          // z = r * sc + sh,  xhat = r * k1 + k0
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int c = grp * C + g * 8 + i;
-        sc[i] = q.scale[c]; sh[i] = q.shift[c]; mu[i] = q.mean[c]; is[i] = q.invstd[c];
+        sc[i] = q.scale[c]; sh[i] = q.shift[c];
+        k1[i] = q.invstd[c]; k0[i] = -q.mean[c] * q.invstd[c];
       }
-      for (int pp = p0 + pl; pp < p1; pp += PL) {
-        const long long pix = (long long)n * q.HW + pp;
-        float r[8], d[8];
-        unpack8b(*reinterpret_cast<const uint4*>(q.raw + pix * q.raw_pitch + g * 8), r);
-        unpack8b(*reinterpret_cast<const uint4*>(q.dy + pix * q.dy_pitch + g * 8), d);
+      const __nv_bfloat16* rp = q.raw + g * 8;
+      const __nv_bfloat16* dp = q.dy + g * 8;
+      for (long long pp = p0 + pl; pp < p1; pp += (long long)PL * kBwdUnroll) {
+        uint4 rv[kBwdUnroll], dv[kBwdUnroll];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float z = r[i] * sc[i] + sh[i];
-          const float dz = q.act ? d[i] * dsilu(z) : d[i];
-          s[i] += dz;
-          s[8 + i] += dz * ((r[i] - mu[i]) * is[i]);
+        for (int j = 0; j < kBwdUnroll; ++j) {
+          const long long pix = pp + (long long)j * PL;
+          if (pix < p1) {
+            rv[j] = *reinterpret_cast<const uint4*>(rp + pix * q.raw_pitch);
+            dv[j] = *reinterpret_cast<const uint4*>(dp + pix * q.dy_pitch);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kBwdUnroll; ++j) {
+          if (pp + (long long)j * PL >= p1) continue;
+          float r[8], d[8];
+          unpack8b(rv[j], r);
+          unpack8b(dv[j], d);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float dz = q.act ? d[i] * dsilu(r[i] * sc[i] + sh[i]) : d[i];
+            s[i] += dz;
+            s[8 + i] += dz * (r[i] * k1[i] + k0[i]);
+          }
         }
       }
     }
+    if (PL > 1) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) red[threadIdx.x][i] = s[i];
-    __syncthreads();
-    if (pl == 0 && g < G) {
-      for (int i = 0; i < 16; ++i) {
-        float a = 0.f;
-        for (int k = 0; k < PL; ++k) a += red[k * lanes + gl][i];
-        out[(i >> 3) * C + g * 8 + (i & 7)] = a;
+      for (int i = 0; i < 16; ++i) red[threadIdx.x][i] = s[i];
+      __syncthreads();
+      // 16 values x `lanes` chunks, each summed over the PL pixel lanes in order: spread over all threads
+      for (int o = (int)threadIdx.x; o < lanes * 16; o += kBwdThreads) {
+        const int l = o >> 4, i = o & 15;
+        if (g0 + l < G) {
+          float a = 0.f;
+          for (int k = 0; k < PL; ++k) a += red[k * lanes + l][i];
+          out[(i >> 3) * C + (g0 + l) * 8 + (i & 7)] = a;
+        }
       }
+      __syncthreads();
+    } else if (g < G) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) out[(i >> 3) * C + g * 8 + (i & 7)] = s[i];
     }
-    __syncthreads();
   }
 }
 
-// rows [0, rows0) belong to group 0, [rows0, rows) to group 1.  coef [2 groups][2 (mean dz | mean dz*xhat)][C];
-// dgamma / dbeta (+)= sums over both groups.  One thread per channel, fixed order, fp64.
-__global__ void bn_act_bwd_finalize_kernel(const float* __restrict__ partials, int rows0, int rows, double cnt0, double cnt1, int C,
-                                           float* dgamma, float* dbeta, int accumulate, float* coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per channel: lane l sums the partial rows l, l + 32, ... of each group in order (fp64), a fixed shuffle tree
+// combines the lanes (deterministic).  Writes dgamma / dbeta ((+)= sums over both groups) and, per (group, channel), the
+// four coefficients of the element-wise pass:  z = r * A + B,  draw = A * dz + C1 * r + C0
+//   with A = scale, B = shift, C1 = -scale * mb * invstd, C0 = -scale * (ma - mb * mean * invstd),
+//   ma = mean_g(dz), mb = mean_g(dz * xhat)     (draw = scale * (dz - ma - xhat * mb), xhat = (r - mean) * invstd)
+// coef layout [2 groups][4 (A | B | C1 | C0)][C].
+__global__ void __launch_bounds__(256) bn_act_bwd_finalize_kernel(const float* __restrict__ partials, int rows0, int rows1, double cnt0,
+                                                                  double cnt1, int C, const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift, const float* __restrict__ mean,
+                                                                  const float* __restrict__ invstd, float* dgamma, float* dbeta,
+                                                                  int accumulate, float* coef) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   double s[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-  for (int r = 0; r < rows; ++r) {
-    const int g = r >= rows0 ? 1 : 0;
-    s[g][0] += (double)partials[(size_t)r * 2 * C + c];
-    s[g][1] += (double)partials[(size_t)r * 2 * C + C + c];
+  for (int g = 0; g < 2; ++g) {
+    const int rb = g ? rows0 : 0, re = g ? rows0 + rows1 : rows0;
+    for (int r = rb + lane; r < re; r += 32) {
+      s[g][0] += (double)__ldg(partials + (size_t)r * 2 * C + c);
+      s[g][1] += (double)__ldg(partials + (size_t)r * 2 * C + C + c);
+    }
   }
-  coef[(0 * 2 + 0) * C + c] = (float)(s[0][0] / cnt0);
-  coef[(0 * 2 + 1) * C + c] = (float)(s[0][1] / cnt0);
-  coef[(1 * 2 + 0) * C + c] = cnt1 > 0.0 ? (float)(s[1][0] / cnt1) : 0.f;
-  coef[(1 * 2 + 1) * C + c] = cnt1 > 0.0 ? (float)(s[1][1] / cnt1) : 0.f;
+#pragma unroll
+  for (int g = 0; g < 2; ++g)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) s[g][i] += __shfl_xor_sync(0xffffffffu, s[g][i], m);
+  if (lane != 0) return;
+  for (int g = 0; g < 2; ++g) {
+    const double cnt = g ? cnt1 : cnt0;
+    const float ma = cnt > 0.0 ? (float)(s[g][0] / cnt) : 0.f, mb = cnt > 0.0 ? (float)(s[g][1] / cnt) : 0.f;
+    const float A = scale[g * C + c], B = shift[g * C + c], mu = mean[g * C + c], is = invstd[g * C + c];
+    coef[(g * 4 + 0) * C + c] = A;
+    coef[(g * 4 + 1) * C + c] = B;
+    coef[(g * 4 + 2) * C + c] = -A * mb * is;
+    coef[(g * 4 + 3) * C + c] = -A * (ma - mb * mu * is);
+  }
   const float db = (float)(s[0][0] + s[1][0]), dg = (float)(s[0][1] + s[1][1]);
   dbeta[c] = accumulate ? dbeta[c] + db : db;
   dgamma[c] = accumulate ? dgamma[c] + dg : dg;
 }
 
-__global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const BwdArgs q, const float* __restrict__ coef, long long npix,
-                                                               __nv_bfloat16* draw, long long draw_pitch) {
-  const int C = q.C, G = C / 8;
-  const long long total = npix * G;
-  const long long split_pix = (long long)q.split_n * q.HW;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % G);
-    const long long pix = idx / G;
-    const int grp = pix >= split_pix ? 1 : 0;
-    float r[8], d[8], o[8];
-    unpack8b(*reinterpret_cast<const uint4*>(q.raw + pix * q.raw_pitch + g * 8), r);
-    unpack8b(*reinterpret_cast<const uint4*>(q.dy + pix * q.dy_pitch + g * 8), d);
+// draw = A * dz + C1 * r + C0 (bf16), dz = dy * silu'(r * A + B).  Same thread mapping as the forward normalise pass: a
+// thread owns one 8-channel chunk for its whole life (coefficients in registers), kBwdUnroll load pairs in flight.
+__global__ void __launch_bounds__(kBwdThreads, 2) bn_act_bwd_apply_kernel(const BwdArgs q, const float* __restrict__ coef,
+                                                                          __nv_bfloat16* draw, long long draw_pitch) {
+  const int C = q.C, G = C >> 3;
+  const int ppb = kBwdThreads / G;
+  const int prow = (int)threadIdx.x / G, g = (int)threadIdx.x - prow * G;
+  if (prow >= ppb) return;
+  float A[8], B[8], C1[8], C0[8];
+  int cur = -1;
+  auto load_group = [&](int grp) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int c = grp * C + g * 8 + i;
-      const float z = r[i] * q.scale[c] + q.shift[c];
-      const float dz = q.act ? d[i] * dsilu(z) : d[i];
-      const float xh = (r[i] - q.mean[c]) * q.invstd[c];
-      const float a = coef[(grp * 2 + 0) * C + g * 8 + i], b = coef[(grp * 2 + 1) * C + g * 8 + i];
-      o[i] = q.scale[c] * (dz - a - xh * b);
+      A[i] = coef[(grp * 4 + 0) * C + g * 8 + i]; B[i] = coef[(grp * 4 + 1) * C + g * 8 + i];
+      C1[i] = coef[(grp * 4 + 2) * C + g * 8 + i]; C0[i] = coef[(grp * 4 + 3) * C + g * 8 + i];
     }
-    *reinterpret_cast<uint4*>(draw + pix * draw_pitch + g * 8) =
-        make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    cur = grp;
+  };
+  const long long step = (long long)gridDim.x * ppb;
+  const __nv_bfloat16* rp = q.raw + g * 8;
+  const __nv_bfloat16* dp = q.dy + g * 8;
+  __nv_bfloat16* op = draw + g * 8;
+  for (long long pix0 = (long long)blockIdx.x * ppb + prow; pix0 < q.npix; pix0 += step * kBwdUnroll) {
+    uint4 rv[kBwdUnroll], dv[kBwdUnroll];
+#pragma unroll
+    for (int j = 0; j < kBwdUnroll; ++j) {
+      const long long pix = pix0 + j * step;
+      if (pix < q.npix) {
+        rv[j] = *reinterpret_cast<const uint4*>(rp + pix * q.raw_pitch);
+        dv[j] = *reinterpret_cast<const uint4*>(dp + pix * q.dy_pitch);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kBwdUnroll; ++j) {
+      const long long pix = pix0 + j * step;
+      if (pix >= q.npix) continue;
+      const int grp = pix >= q.split_pix ? 1 : 0;
+      if (grp != cur) load_group(grp);
+      float r[8], d[8], o[8];
+      unpack8b(rv[j], r);
+      unpack8b(dv[j], d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float dz = q.act ? d[i] * dsilu(r[i] * A[i] + B[i]) : d[i];
+        o[i] = A[i] * dz + (C1[i] * r[i] + C0[i]);
+      }
+      *reinterpret_cast<uint4*>(op + pix * draw_pitch) =
+          make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    }
   }
 }
 
@@ -136,7 +216,17 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const BwdArgs q, 
 
 using namespace sy;
 
-extern "C" int sy_bn_act_bwd_rows(int32_t n, int32_t hw) { return n * cdiv(hw, kBwdChunk); }
+static int bwd_rows_for(long long npix_group) {
+  if (npix_group <= 0) return 0;
+  long long r = (npix_group + 255) / 256;            // at least ~256 pixels per row
+  if (r > kBwdRowsPerGroup) r = kBwdRowsPerGroup;
+  return (int)r;
+}
+
+extern "C" int sy_bn_act_bwd_rows(int32_t n, int32_t hw) {
+  (void)n; (void)hw;
+  return 2 * kBwdRowsPerGroup;                       // upper bound for any split
+}
 
 extern "C" int sy_bn_act_backward(const SyBnActBwdDesc* d, sy_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -150,23 +240,25 @@ extern "C" int sy_bn_act_backward(const SyBnActBwdDesc* d, sy_stream_t stream_) 
              SY_EINVAL, "bn_act_backward: shape mismatch");
   SY_REQUIRE(d->scale && d->shift && d->mean && d->invstd && d->dgamma && d->dbeta && d->partials && d->coef, SY_EINVAL,
              "bn_act_backward: null pointer");
+  SY_REQUIRE(raw.c <= 8 * kBwdThreads, SY_EINVAL, "bn_act_backward: C=%d > %d", raw.c, 8 * kBwdThreads);
   const int hw = raw.h * raw.w;
-  const int rows = sy_bn_act_bwd_rows(raw.n, hw);
-  SY_REQUIRE(d->n_partials >= rows, SY_EWORKSPACE, "bn_act_backward: %d partial rows, need %d", d->n_partials, rows);
   const int split = (d->split_n > 0 && d->split_n < raw.n) ? d->split_n : raw.n;
   BwdArgs q{};
   q.raw = reinterpret_cast<const __nv_bfloat16*>(raw.ptr); q.raw_pitch = raw.pitch;
   q.dy = reinterpret_cast<const __nv_bfloat16*>(dy.ptr); q.dy_pitch = dy.pitch;
   q.scale = d->scale; q.shift = d->shift; q.mean = d->mean; q.invstd = d->invstd;
-  q.HW = hw; q.C = raw.c; q.split_n = split; q.act = d->act;
-  bn_act_bwd_reduce_kernel<<<rows, 256, 0, stream>>>(q, d->partials);
-  const int chunks = cdiv(hw, kBwdChunk);
-  bn_act_bwd_finalize_kernel<<<cdiv(raw.c, 128), 128, 0, stream>>>(d->partials, split * chunks, rows, (double)split * hw,
-                                                                   (double)(raw.n - split) * hw, raw.c, d->dgamma, d->dbeta,
-                                                                   d->accumulate, d->coef);
-  const long long npix = (long long)raw.n * hw;
-  const long long total = npix * (raw.c / 8);
-  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  bn_act_bwd_apply_kernel<<<blocks, 256, 0, stream>>>(q, d->coef, npix, reinterpret_cast<__nv_bfloat16*>(dr.ptr), dr.pitch);
+  q.npix = (long long)raw.n * hw; q.split_pix = (long long)split * hw;
+  q.C = raw.c; q.act = d->act;
+  q.rows0 = bwd_rows_for(q.split_pix); q.rows1 = bwd_rows_for(q.npix - q.split_pix);
+  const int rows = q.rows0 + q.rows1;
+  SY_REQUIRE(d->n_partials >= rows, SY_EWORKSPACE, "bn_act_backward: %d partial rows, need %d", d->n_partials, rows);
+  bn_act_bwd_reduce_kernel<<<rows, kBwdThreads, 0, stream>>>(q, d->partials);
+  bn_act_bwd_finalize_kernel<<<cdiv(raw.c, 8), 256, 0, stream>>>(d->partials, q.rows0, q.rows1, (double)q.split_pix,
+                                                                 (double)(q.npix - q.split_pix), raw.c, d->scale, d->shift, d->mean,
+                                                                 d->invstd, d->dgamma, d->dbeta, d->accumulate, d->coef);
+  const int G = raw.c / 8, ppb = kBwdThreads / G;
+  long long blocks = (q.npix + (long long)ppb * kBwdUnroll - 1) / ((long long)ppb * kBwdUnroll);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  bn_act_bwd_apply_kernel<<<(int)blocks, kBwdThreads, 0, stream>>>(q, d->coef, reinterpret_cast<__nv_bfloat16*>(dr.ptr), dr.pitch);
   return launch_status("bn_act_backward kernels");
 }

@@ -429,6 +429,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // channel slice.  Issuing it here keeps its issue + drain latency off the epilogue warps' path.
     const uint32_t stage_base = smem_u32(sStage);
     int sbuf = 0, prev = -1;
+    int tl_s = 7 * (p.timeline_cap / 8);
     bar_free_arrive(0);                          // both tiles start out free
     if (sflip) bar_free_arrive(1);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -443,6 +444,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       for (int slab = 0; slab < BN / kSlabCols; ++slab, sbuf ^= sflip) {
         bar_staged_wait(sbuf);
+        if (lane == 0) tl_rec<TL>(p, tl_s, 6, 0, tile, slab);
         if (elect_one()) {
           tma_store_4d(&tmY, stage_base + (uint32_t)(sbuf * kSlabBytes), n_tile * BN + slab * kSlabCols, c1, c2, c3);
           bulk_commit();
@@ -453,6 +455,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         __syncwarp();
+        if (lane == 0) tl_rec<TL>(p, tl_s, 6, 1, tile, slab);
         if (sflip) {
           if (prev >= 0) bar_free_arrive(prev);
           prev = sbuf;
@@ -488,6 +491,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int i = st; i < 4 * p.Cout; i += 256) sAcc[i] = 0.f;
     }
     int sbuf = 0;
+    int tl_t = (st == 0) ? 5 * (p.timeline_cap / 8) : p.timeline_cap;
     bar_free_arrive(0);                          // both tiles start out free
     if (sflip) bar_free_arrive(1);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -503,6 +507,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       for (int slab = 0; slab < BN / kSlabCols; ++slab, sbuf ^= sflip) {
         bar_staged_wait(sbuf);
+        tl_rec<TL>(p, tl_t, 5, 0, tile, slab);
         const uint32_t tile_base = stage_base + (uint32_t)(sbuf * kSlabBytes);
         // warp ew reduces columns [8*ew, 8*ew+8) of the slab: lane l reads rows l, l+32, l+64, l+96
         float x[4][8];
@@ -516,6 +521,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         bar_free_arrive(sbuf);                   // the values are in registers: the tile may be overwritten
+        tl_rec<TL>(p, tl_t, 5, 1, tile, slab);
         if (do_stats) {
 #pragma unroll 1
           for (int grp = 0; grp < 2; ++grp) {
@@ -570,6 +576,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        tl_rec<TL>(p, tl_t, 5, 2, tile, slab);
       }
     }
   } else if (warp < 8) {
@@ -938,6 +945,23 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     smem = fixed_bytes + acc_bytes + stages * stage_bytes;
   }
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  if (p.n_seg > 0) {
+    // The BatchNorm tail ends in a grid-wide barrier: every CTA of this launch must be resident at once.  The launch is
+    // not a cooperative launch (it carries the programmatic-dependent-launch attribute instead), so check what a
+    // cooperative launch would check -- per (instantiation, shared-memory size), once.
+    static int ok_smem[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool seen = false;
+    for (int i = 0; i < 8; ++i) seen = seen || ok_smem[i] == smem;
+    if (!seen) {
+      int per_sm = 0;
+      SY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_tc_kernel<BN, false, AM>, kThreads, (size_t)smem));
+      SY_REQUIRE(per_sm >= 1 && per_sm * num_sms() >= grid, SY_ELAUNCH,
+                 "conv2d_tc: %d CTAs cannot be co-resident (%d per SM x %d SMs): the BatchNorm grid barrier would hang", grid,
+                 per_sm, num_sms());
+      for (int i = 0; i < 8; ++i)
+        if (ok_smem[i] == 0) { ok_smem[i] = smem; break; }
+    }
+  }
   if (p.timeline != nullptr)
     SY_CUDA(launch_pdl(conv_tc_kernel<BN, true, AM>, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
   else

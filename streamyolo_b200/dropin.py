@@ -3,13 +3,13 @@
 
     import streamyolo_b200.dropin; streamyolo_b200.dropin.install()     # before get_exp(...)
 
-Registers ``exps``, ``exps.model`` and the four model modules in ``sys.modules`` (existing ``exps`` packages are
+Registers ``exps``, ``exps.model`` and the five model modules (yolox, dfp_pafpn, darknet, tal_head, pipe_head) in ``sys.modules`` (existing ``exps`` packages are
 kept: only the ``exps.model.*`` names are redirected)."""
 import importlib
 import sys
 import types
 
-_NAMES = ("yolox", "dfp_pafpn", "darknet", "tal_head")
+_NAMES = ("yolox", "dfp_pafpn", "darknet", "tal_head", "pipe_head")      # every module of the reference's exps/model/
 
 
 def install(postprocess: bool = True) -> None:

@@ -5,4 +5,5 @@ from .network_blocks import BaseConv, Bottleneck, CSPLayer, DWConv, Focus, SPPBo
 from .darknet import CSPDarknet  # noqa: F401
 from .dfp_pafpn import DFPPAFPN  # noqa: F401
 from .tal_head import TALHead  # noqa: F401
+from .pipe_head import PIPEHead  # noqa: F401
 from .yolox import YOLOX  # noqa: F401

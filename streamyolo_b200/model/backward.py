@@ -368,7 +368,7 @@ def _record(model, x, targets):
     xin = x.float().contiguous()
     b = xin.shape[0]
     T = Tape(xin.device)
-    with torch.no_grad():
+    with torch.no_grad(), engine.forward_scope(xin.device):
         pans = pafpn_rec(T, net, xin, 2, b)
         cur = tuple(p.imgs(0, b) for p in pans)
         sup = tuple(p.imgs(b, b) for p in pans)

@@ -41,7 +41,7 @@ class DFPPAFPN(nn.Module):
         x = input.float().contiguous()
         b = x.shape[0]
         ctx = engine.Ctx(self.training, 2 * b, b, x.device)
-        with torch.no_grad():
+        with torch.no_grad(), engine.forward_scope(x.device):
             pans = engine.pafpn_frames(ctx, self, x, 2)
             cur = tuple(p.imgs(0, b) for p in pans)
             sup = tuple(p.imgs(b, b) for p in pans)
@@ -53,7 +53,7 @@ class DFPPAFPN(nn.Module):
         x = input.float().contiguous()
         b = x.shape[0]
         ctx = engine.Ctx(self.training, b, b, x.device)
-        with torch.no_grad():
+        with torch.no_grad(), engine.forward_scope(x.device):
             cur = engine.pafpn_frames(ctx, self, x, 1)
             sup = cur if node == "star" else tuple(engine.as_view(t) for t in buffer)
             fused = engine.dfp_fuse(ctx, self, cur, sup)

@@ -85,13 +85,49 @@ def _folded(m):
     return m._fold
 
 
+SYNC_SLOTS = 1024
+_SYNC_POOLS = {}      # (device, stream) -> [int32 tensor of 4 * SYNC_SLOTS counters, next slot, scope depth]
+
+
+def _sync_pool(device):
+    key = (str(device), torch.cuda.current_stream().cuda_stream if torch.device(device).type == "cuda" else 0)
+    st = _SYNC_POOLS.get(key)
+    if st is None:
+        st = [torch.zeros(4 * SYNC_SLOTS, dtype=torch.int32, device=device), 0, 0]
+        _SYNC_POOLS[key] = st
+    return st
+
+
+class forward_scope:
+    """Outermost scope of one forward (YOLOX / DFPPAFPN / TALHead / a stand-alone block / the recording forward): rewinds the
+    grid-barrier counter pool of the current stream, so that the first train-mode conv of the forward zeroes it (ONE memset
+    per forward, captured into the CUDA graph with it).  Every launch then takes its own counter slot: a launch that was
+    aborted, or a module used by two forwards, can no longer leave a stale count for the next launch (the kernels also
+    leave their slot at zero when they complete).  Launches on ONE stream only: two concurrent train-mode convs would each
+    need every SM for their grid barrier (include/streamyolo_sm100.h)."""
+
+    def __init__(self, device):
+        self.st = _sync_pool(device)
+
+    def __enter__(self):
+        if self.st[2] == 0:
+            self.st[1] = 0
+        self.st[2] += 1
+        return self
+
+    def __exit__(self, *a):
+        self.st[2] -= 1
+        return False
+
+
 def _sync(m, device):
-    """Two persistent zero-initialised counters per module (bn_train_apply leaves them at zero)."""
-    t = getattr(m, "_sy_sync", None)
-    if t is None or t.device != device:
-        t = torch.zeros(4, dtype=torch.int32, device=device)
-        m._sy_sync = t
-    return t
+    """Four zeroed counters for one train-mode conv launch (two grid barriers + exit ticket), from the stream's pool."""
+    st = _sync_pool(device)
+    if st[1] == 0:
+        st[0].zero_()
+    i = st[1]
+    st[1] = (i + 1) % SYNC_SLOTS
+    return st[0][4 * i:4 * i + 4]
 
 
 def _bn_seg(m, c_begin=0):

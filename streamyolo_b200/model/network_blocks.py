@@ -15,7 +15,7 @@ from ..ops import View
 def _run_standalone(module, fn, x):
     v = engine.as_view(x)
     ctx = engine.Ctx(module.training, v.n, v.n, x.device)
-    with torch.no_grad():
+    with torch.no_grad(), engine.forward_scope(x.device):
         return engine.as_nchw(fn(ctx, v))
 
 
@@ -87,7 +87,7 @@ class Focus(nn.Module):
     def forward(self, x):
         x = x.float().contiguous()
         ctx = engine.Ctx(self.training, x.shape[0], x.shape[0], x.device)
-        with torch.no_grad():
+        with torch.no_grad(), engine.forward_scope(x.device):
             return engine.as_nchw(engine.focus_stem(ctx, self, x, 1))
 
 

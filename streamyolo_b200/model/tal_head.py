@@ -12,12 +12,20 @@ from .. import ops
 from .network_blocks import BaseConv
 
 
+SUPPORTED_NUM_CLASSES = (8, 1, 20)     # head_pred_kernel<5 + nc> instantiations
+
+
 class TALHead(nn.Module):
     def __init__(self, num_classes, width=1.0, strides=[8, 16, 32], in_channels=[256, 512, 1024], act="silu",
                  depthwise=False, gamma=1.5, ignore_thr=0.2, ignore_value=0.2):
         super().__init__()
         if depthwise:
             raise NotImplementedError("depthwise=True is never used by the reference cfgs")
+        if num_classes not in SUPPORTED_NUM_CLASSES:
+            # the prediction-conv + decode kernel is instantiated per class count (csrc/head_loss.cu): fail at construction,
+            # not at the first forward
+            raise NotImplementedError(f"num_classes={num_classes}: libstreamyolo_sm100 builds the head kernels for "
+                                      f"{SUPPORTED_NUM_CLASSES} (Argoverse-HD: 8)")
         self.gamma, self.ignore_thr, self.ignore_value = gamma, ignore_thr, ignore_value
         self.n_anchors = 1
         self.num_classes = num_classes
@@ -59,7 +67,7 @@ class TALHead(nn.Module):
         a_total = sum(h * w for h, w in self.hw)
         no = 5 + self.num_classes
         train = self.training
-        with torch.no_grad():
+        with torch.no_grad(), engine.forward_scope(dev):
             out = torch.empty((b, a_total, no), dtype=torch.float32, device=dev)
             origin = torch.empty((b, a_total, 4), dtype=torch.float32, device=dev) if (train and self.use_l1) else None
             off = 0

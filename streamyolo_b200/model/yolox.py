@@ -16,6 +16,11 @@ class YOLOX(nn.Module):
         self.train_with_autograd = True
 
     def forward(self, x, targets=None, buffer=None, mode="off_pipe"):
+        from . import engine
+        with engine.forward_scope(x.device):       # one grid-barrier counter pool rewind for backbone + head
+            return self._forward(x, targets, buffer, mode)
+
+    def _forward(self, x, targets=None, buffer=None, mode="off_pipe"):
         assert mode in ["off_pipe", "on_pipe"]
         if mode == "off_pipe":
             if self.training and self.train_with_autograd and torch.is_grad_enabled():

@@ -499,7 +499,7 @@ def bn_act_backward(raw: View, dy: View, draw: View, scale, shift, mean, invstd,
     """BatchNorm(train) + SiLU backward of one BaseConv; scale/shift/mean/invstd: fp32 [2, C] (group-major)."""
     rows = load_library().sy_bn_act_bwd_rows(raw.n, raw.h * raw.w)
     partials = torch.empty((rows, 2 * raw.c), dtype=torch.float32, device=dgamma.device)
-    coef = torch.empty((4 * raw.c,), dtype=torch.float32, device=dgamma.device)
+    coef = torch.empty((8 * raw.c,), dtype=torch.float32, device=dgamma.device)
     d = SyBnActBwdDesc()
     d.raw, d.dy, d.draw = raw.st(), dy.st(), draw.st()
     d.scale, d.shift, d.mean, d.invstd = scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr()

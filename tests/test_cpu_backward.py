@@ -260,3 +260,30 @@ def test_decode_outputs_path(monkeypatch):
         got = m.head.decode_outputs(raw.clone(), dtype=raw.type())
     assert not torch.allclose(raw[..., :4], want[..., :4])
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
+
+
+def test_pipe_head_is_tal_head_without_trend_weights(monkeypatch):
+    """exps/model/pipe_head.py (cfgs/l_s50_still_dfp_flip.py): one label tensor, no TAL weighting -- the oracle with
+    gamma = 0 (constant weight, normalised to 1) on (labels, labels) is the reference's PIPEHead loss."""
+    from streamyolo_b200.model import PIPEHead
+    c = CASES["tiny_120x160"]
+    emul_ops.install(monkeypatch, exact=True)
+    x = synth.synth_frames(c["B"], c["H"], c["W"])
+    fut, _ = synth.synth_labels(c["B"], c["H"], c["W"])
+    ch = [256, 512, 1024]
+    m = YOLOX(DFPPAFPN(c["depth"], c["width"], in_channels=ch), PIPEHead(8, c["width"], in_channels=ch))
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.eps, mod.momentum = 1e-3, 0.03
+    m.load_state_dict(synth.synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}), strict=True)
+    m.head.use_l1 = True
+    m.train()
+    with torch.no_grad():
+        loss = m(x, fut)
+    cfg = OracleCfg(depth=c["depth"], width=c["width"], gamma=0.0, ignore_thr=0.0, ignore_value=1.0)
+    o = StreamYoloOracle(cfg, synth.synth_state_dict(model_shapes(c["depth"], c["width"])), q=None)
+    ref = o.forward(x, (fut, fut))
+    for k in ("total_loss", "iou_loss", "l1_loss", "conf_loss", "cls_loss", "num_fg"):
+        assert abs(float(loss[k]) - float(ref[k])) <= 2e-5 * abs(float(ref[k])) + 1e-6, k
+    with pytest.raises(NotImplementedError):
+        TALHead(80)

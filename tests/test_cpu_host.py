@@ -107,6 +107,7 @@ def test_dropin_aliases():
     code = ("import streamyolo_b200.dropin as d; d.install();"
             "from exps.model.yolox import YOLOX; from exps.model.dfp_pafpn import DFPPAFPN;"
             "from exps.model.tal_head import TALHead; from exps.model.darknet import CSPDarknet;"
+            "from exps.model.pipe_head import PIPEHead; assert issubclass(PIPEHead, TALHead);"
             "import streamyolo_b200.model as m; assert YOLOX is m.YOLOX and TALHead is m.TALHead; print('ok')")
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr

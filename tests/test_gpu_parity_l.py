@@ -206,7 +206,8 @@ def test_simota_bit_exact_full_anchor_count(n_gt, ties):
 @pytest.mark.parametrize("tag,depth,width,tal", [("l", 1.0, 1.0, (1.0, 0.5, 1.6)), ("m", 0.67, 0.75, (1.0, 0.4, 1.7))])
 def test_benchmarked_model_train_forward_vs_oracle(tag, depth, width, tal):
     """StreamYOLO-l / -m, 600x960, B = 2, train mode: fused FPN features against the bf16-storage oracle with the
-    rounding-noise-floor criterion (the same oracle code on inputs nudged by 1e-6), the six losses, the running statistics
+    rounding-noise-floor criterion (the same oracle code on inputs nudged by 1e-6), the six losses (within 5 % + twice the
+    oracle's own deviation under that nudge), the running statistics
     of the first and the deepest BatchNorm."""
     B, H, W = 2, 600, 960
     x = synth.synth_frames(B, H, W)
@@ -230,8 +231,11 @@ def test_benchmarked_model_train_forward_vs_oracle(tag, depth, width, tal):
         loss = m2(x.cuda(), (tg[0].cuda(), tg[1].cuda()))
         torch.cuda.synchronize()
     ref = build_oracle(depth, width, *tal).forward(x, tg)
+    pert = build_oracle(depth, width, *tal).forward(x * (1 + 1e-6), tg)      # the oracle's own rounding-noise floor on the losses
     got = np.array([float(loss[k]) for k in ORDER])
     want = np.array([float(ref[k]) for k in ORDER])
-    np.testing.assert_allclose(got[:5], want[:5], rtol=5e-2, atol=5e-3)
-    assert abs(got[5] - want[5]) <= 0.15
+    floor = np.abs(np.array([float(pert[k]) for k in ORDER]) - want)
+    tol = 2.0 * floor + 5e-2 * np.abs(want) + 5e-3
+    assert (np.abs(got - want)[:5] <= tol[:5]).all(), f"{tag} losses {got} vs oracle {want} (noise floor {floor})"
+    assert abs(got[5] - want[5]) <= 0.15 + 2.0 * floor[5]
     assert m2.head.hw == [(75, 120), (38, 60), (19, 30)]

@@ -41,7 +41,8 @@ ev = [(int(c), int(e) >> 28, (int(e) >> 24) & 15, (int(e) >> 8) & 0xffff, int(e)
 ev.sort()
 t0 = ev[0][0]
 names = {(0, 0): "PA slot-free", (3, 0): "PB slot-free", (1, 0): "M acc-free", (1, 1): "M data-landed", (1, 2): "M issued", (1, 3): "M committed", (4, 0): "K entry", (4, 1): "K setup-done", (4, 2): "K tiles-done", (4, 3): "K all-synced", (4, 4): "K tmem-freed", (2, 0): "E tile-start", (2, 1): "E acc-ready",
-         (2, 2): "E converted", (2, 3): "E staged", (2, 4): "E slab-done"}
+         (2, 2): "E converted", (2, 3): "E staged", (2, 4): "E slab-done", (5, 0): "S staged-seen", (5, 1): "S rows-loaded",
+         (5, 2): "S reduced", (6, 0): "T staged-seen", (6, 1): "T store-read-done"}
 tiles = sorted({e[3] for e in ev})
 print("events", len(ev), "tiles of CTA0", len(tiles), "span cycles", ev[-1][0] - t0)
 import time
@@ -57,5 +58,5 @@ with torch.cuda.stream(st):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
     print("graph of 20 back-to-back launches: us per launch", e0.elapsed_time(e1) * 1e3 / 20)
-for c, role, ph, tile, kb in ev[:400]:
+for c, role, ph, tile, kb in ev[:int(os.environ.get('SY_TL_EVENTS', 260))]:
     print(f"{c - t0:9d}  tile {tile:5d} kb {kb:3d}  {names.get((role, ph), (role, ph))}")
