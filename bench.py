@@ -238,6 +238,19 @@ def cpu_oracle_run(tag, pairs, steps, warmup, height=600, width_px=960):
     return pairs / sec, sec
 
 
+def oracle_losses(tag, pairs, bf16_storage, height=600, width_px=960):
+    from oracle.streamyolo_oracle import OracleCfg, StreamYoloOracle, bf16_round, model_shapes
+    from streamyolo_b200 import synth
+    depth, width = MODELS[tag]
+    gamma, thr, val = TAL[tag]
+    torch.set_num_threads(host_threads())
+    o = StreamYoloOracle(OracleCfg(depth=depth, width=width, gamma=gamma, ignore_thr=thr, ignore_value=val),
+                         synth.synth_state_dict(model_shapes(depth, width)), q=bf16_round if bf16_storage else None)
+    with torch.no_grad():
+        r = o.forward(synth.synth_frames(pairs, height, width_px), synth.synth_labels(pairs, height, width_px))
+    return {k: float(v) for k, v in r.items()}
+
+
 LAST_ORACLE_LOSS = None
 LOSS_KEYS = ("total_loss", "iou_loss", "l1_loss", "conf_loss", "cls_loss", "num_fg")
 
@@ -269,30 +282,32 @@ def time_replays(g, steps, warmup=3):
     return e0.elapsed_time(e1) / steps
 
 
-def conv_family_time(model, x_dev, tg_dev):
-    """The dominant kernel family -- every conv_tc_kernel launch of one step -- timed live: one eager step with a CUDA event
-    pair around each launch on the launching stream (warm caches; no overlap with the neighbouring kernels, so this is an
-    upper bound of what the family costs inside the graph).  Returns (sum of durations in ms, launches)."""
+def conv_family_time(model, x_dev, tg_dev, reps=5):
+    """The dominant kernel family -- every conv_tc_kernel launch of one step -- timed live: the conv launches of one step are
+    recorded (same descriptors, same buffers) and re-issued alone, in order, as one CUDA graph (programmatic edges like the
+    real step); CUDA events around the replay on the launching stream.  Returns (ms per pass over all launches, launches)."""
     from streamyolo_b200 import ops
-    evs = []
+    calls = []
     orig = ops.conv2d
 
-    def timed(*a, **k):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r = orig(*a, **k)
-        e1.record()
-        evs.append((e0, e1))
-        return r
+    def spy(*a, **k):
+        calls.append((a, k))
+        return orig(*a, **k)
 
-    ops.conv2d = timed
+    ops.conv2d = spy
     try:
         with torch.no_grad():
             model(x_dev, tg_dev)
         torch.cuda.synchronize()
     finally:
         ops.conv2d = orig
-    return sum(a.elapsed_time(b) for a, b in evs), len(evs)
+
+    def all_convs():
+        for a, k in calls:
+            orig(*a, **k)
+    g, _ = capture(all_convs)
+    best = min(time_replays(g, 5, warmup=2) for _ in range(reps))
+    return best, len(calls)
 
 
 def measure_train(tag, batch, dev, rank, world, steps, warmup, peaks):
@@ -647,18 +662,21 @@ def main():
                             "peak_source": peaks["source"] + " cuBLAS bf16 burst", "launches": fam_n,
                             "avg_launch_ms": round(fam_ms / fam_n, 5), "sum_launch_ms": round(fam_ms, 4),
                             "algorithmic_flop_per_step": B * gf * 1e9, "traffic": None,
-                            "how": "one eager step, CUDA events around every conv launch on the launching stream (warm, no overlap "
-                                   "with neighbours: upper bound of the in-graph cost); ncu launch list: profiles/"}
+                            "how": "the step's conv launches re-issued alone, in order, as one CUDA graph on the step's own buffers; "
+                                   "CUDA events around the replay, best of 5; ncu launch list of the step: profiles/"}
     if not args.no_cpu_baseline:
         try:
             v, sec = cpu_oracle_run(args.model, 2, 2, 1)
             line["cpu_baseline"] = {"value": round(v, 4), "unit": "pairs/s", "cores": torch.get_num_threads(),
                                     "kind": "port", "sample": "2 pairs/step x 2 steps, fp32 oracle of the reference path"}
-            if LAST_ORACLE_LOSS and "product_loss_2pairs" in extras:
-                got, want = extras["product_loss_2pairs"], LAST_ORACLE_LOSS
+            if "product_loss_2pairs" in extras:
+                got = extras["product_loss_2pairs"]
+                want = oracle_losses(args.model, 2, bf16_storage=True)
                 dev_rel = {k: round(abs(got[k] - want[k]) / (abs(want[k]) + 1e-12), 5) for k in LOSS_KEYS}
-                line["parity_check"] = {"what": "losses of the timed model (bf16 storage) vs the fp32 oracle on the same 2 frame pairs",
-                                        "product": got, "oracle": want, "rel_dev": dev_rel,
+                line["parity_check"] = {"what": "losses of the timed model vs the oracle with the same bf16 storage points, same 2 frame pairs "
+                                                "(a random-init train-mode BN net is chaotic under bf16 storage: the fp32 oracle's "
+                                                "own losses are listed for scale)",
+                                        "product": got, "oracle_bf16_storage": want, "oracle_fp32": LAST_ORACLE_LOSS, "rel_dev": dev_rel,
                                         "ok": bool(max(dev_rel[k] for k in LOSS_KEYS[:5]) < 0.08)}
         except Exception as ex:  # never lose the GPU numbers to a host-side problem
             line["cpu_baseline"] = {"value": None, "error": str(ex)[:200]}

@@ -192,19 +192,23 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   }
 }
 
-// dw[co][ci][r][s] (+)= sum over the K splits, fixed order
+// dw[co][ci][r][s] (+)= sum over the K splits, fixed order.  Threads walk (co, tap, ci) with ci fastest: the partial reads
+// (the bulk: ksplit per output) are coalesced along the N = input-channel dimension; only the single store per output is
+// strided (by the tap count) in the optimizer's OIHW layout.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int BN, int m_tiles, int n_tiles, int taps, int ksplit,
                                     int Cout, int Cin, float* dw, int accumulate) {
   const long long total = (long long)Cout * Cin * taps;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int tap = (int)(idx % taps);
-    const int ci = (int)((idx / taps) % Cin);
+    const int ci = (int)(idx % Cin);
+    const int tap = (int)((idx / Cin) % taps);
     const int co = (int)(idx / ((long long)taps * Cin));
     const int m_tile = co / 128, row = co % 128, n_tile = ci / BN, col = ci % BN;
     const size_t item0 = ((size_t)(m_tile * n_tiles + n_tile) * taps + tap) * ksplit;
+    const float* src = partial + (item0 * 128 + row) * BN + col;
     float acc = 0.f;
-    for (int ks = 0; ks < ksplit; ++ks) acc += partial[((item0 + ks) * 128 + row) * BN + col];
-    dw[idx] = accumulate ? dw[idx] + acc : acc;
+    for (int ks = 0; ks < ksplit; ++ks) acc += __ldg(src + (size_t)ks * 128 * BN);
+    const long long o = ((long long)co * Cin + ci) * taps + tap;
+    dw[o] = accumulate ? dw[o] + acc : acc;
   }
 }
 
