@@ -125,6 +125,12 @@ int sy_conv2d_plan(int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout, i
  * device-side cross-check of the tensor-core kernel. */
 int sy_conv2d_simt(const SyConvDesc* d, sy_stream_t stream);
 
+/* Depthwise k x k convolution (groups = channels, k in {1, 3, 5}, stride 1 / 2): the first half of [yolox] DWConv, selected
+ * by depthwise=True at exps/model/darknet.py:109, dfp_pafpn.py:31, tal_head.py:53.  Same descriptor and RAW / FUSED contract
+ * as sy_conv2d_tc with x.c == y.c and w = bf16 [kh*kw][C]; the statistics fields are ignored (train-mode BatchNorm runs
+ * through sy_channel_stats / sy_bn_finalize / sy_bn_act_apply).  Coalesced, vectorised CUDA-core kernel (HBM-bound). */
+int sy_dwconv2d(const SyConvDesc* d, sy_stream_t stream);
+
 /* Focus stem, part 1: [yolox] Focus space-to-depth (TL/BL/TR/BR channel order), used at
  * exps/model/darknet.py:115.  x is the NCHW float32 frame-pair batch [b, in_ch, h, w]
  * (exps/model/dfp_pafpn.py:120,145 split it); image n of y takes frame n / b (0 = current,

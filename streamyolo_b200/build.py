@@ -22,6 +22,7 @@ SOURCES = {
     "conv_tc.cu": [],
     "conv_wgrad.cu": [],
     "conv_simt.cu": [],
+    "dwconv.cu": [],
     "bn_glue.cu": [],
     "bn_bwd.cu": [],
     "bwd_glue.cu": [],

@@ -364,6 +364,8 @@ def _walk(T: Tape, head, grad_scale, sink):
 def _record(model, x, targets):
     """Recording forward of YOLOX(DFPPAFPN, TALHead) in train mode; returns (tape, loss vector [total, iou, conf, cls, l1, num_fg])."""
     assert model.training and model.head.use_l1
+    if any(getattr(m, "groups", 1) > 1 for m in model.modules() if isinstance(m, torch.nn.Conv2d)):
+        raise NotImplementedError("the training backward does not cover depthwise convolutions (depthwise=True): forward only")
     net, head = model.backbone, model.head
     xin = x.float().contiguous()
     b = xin.shape[0]

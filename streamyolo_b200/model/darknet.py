@@ -4,28 +4,27 @@ import torch
 from torch import nn
 
 from . import engine
-from .network_blocks import BaseConv, CSPLayer, Focus, SPPBottleneck
+from .network_blocks import BaseConv, CSPLayer, DWConv, Focus, SPPBottleneck
 
 
 class CSPDarknet(nn.Module):
     def __init__(self, dep_mul, wid_mul, out_features=("dark3", "dark4", "dark5"), depthwise=False, act="silu"):
         super().__init__()
         assert out_features, "please provide output features of Darknet"
-        if depthwise:
-            raise NotImplementedError("depthwise=True is never used by the reference cfgs")
         self.out_features = out_features
         base = int(wid_mul * 64)
         depth = max(round(dep_mul * 3), 1)
+        Conv = DWConv if depthwise else BaseConv
         self.stem = Focus(3, base, ksize=3, act=act)
-        self.dark2 = nn.Sequential(BaseConv(base, base * 2, 3, 2, act=act),
-                                   CSPLayer(base * 2, base * 2, n=depth, act=act))
-        self.dark3 = nn.Sequential(BaseConv(base * 2, base * 4, 3, 2, act=act),
-                                   CSPLayer(base * 4, base * 4, n=depth * 3, act=act))
-        self.dark4 = nn.Sequential(BaseConv(base * 4, base * 8, 3, 2, act=act),
-                                   CSPLayer(base * 8, base * 8, n=depth * 3, act=act))
-        self.dark5 = nn.Sequential(BaseConv(base * 8, base * 16, 3, 2, act=act),
+        self.dark2 = nn.Sequential(Conv(base, base * 2, 3, 2, act=act),
+                                   CSPLayer(base * 2, base * 2, n=depth, depthwise=depthwise, act=act))
+        self.dark3 = nn.Sequential(Conv(base * 2, base * 4, 3, 2, act=act),
+                                   CSPLayer(base * 4, base * 4, n=depth * 3, depthwise=depthwise, act=act))
+        self.dark4 = nn.Sequential(Conv(base * 4, base * 8, 3, 2, act=act),
+                                   CSPLayer(base * 8, base * 8, n=depth * 3, depthwise=depthwise, act=act))
+        self.dark5 = nn.Sequential(Conv(base * 8, base * 16, 3, 2, act=act),
                                    SPPBottleneck(base * 16, base * 16, activation=act),
-                                   CSPLayer(base * 16, base * 16, n=depth, shortcut=False, act=act))
+                                   CSPLayer(base * 16, base * 16, n=depth, shortcut=False, depthwise=depthwise, act=act))
 
     def forward(self, x):
         """Standalone use: NCHW 3-channel float input -> {name: NCHW tensor}."""

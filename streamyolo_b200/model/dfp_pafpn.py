@@ -8,33 +8,32 @@ from torch import nn
 
 from . import engine
 from .darknet import CSPDarknet
-from .network_blocks import BaseConv, CSPLayer
+from .network_blocks import BaseConv, CSPLayer, DWConv
 
 
 class DFPPAFPN(nn.Module):
     def __init__(self, depth=1.0, width=1.0, in_features=("dark3", "dark4", "dark5"),
                  in_channels=[256, 512, 1024], depthwise=False, act="silu"):
         super().__init__()
-        if depthwise:
-            raise NotImplementedError("depthwise=True is never used by the reference cfgs")
         if tuple(in_features) != ("dark3", "dark4", "dark5"):
             raise NotImplementedError("in_features other than (dark3, dark4, dark5)")
         self.backbone = CSPDarknet(depth, width, depthwise=depthwise, act=act)
         self.in_features = in_features
         self.in_channels = in_channels
         c3, c4, c5 = (int(c * width) for c in in_channels)
+        Conv = DWConv if depthwise else BaseConv            # dfp_pafpn.py:31
         n = round(3 * depth)
         self.lateral_conv0 = BaseConv(c5, c4, 1, 1, act=act)
-        self.C3_p4 = CSPLayer(2 * c4, c4, n, False, act=act)
+        self.C3_p4 = CSPLayer(2 * c4, c4, n, False, depthwise=depthwise, act=act)
         self.reduce_conv1 = BaseConv(c4, c3, 1, 1, act=act)
-        self.C3_p3 = CSPLayer(2 * c3, c3, n, False, act=act)
-        self.bu_conv2 = BaseConv(c3, c3, 3, 2, act=act)
-        self.C3_n3 = CSPLayer(2 * c3, c4, n, False, act=act)
-        self.bu_conv1 = BaseConv(c4, c4, 3, 2, act=act)
-        self.C3_n4 = CSPLayer(2 * c4, c5, n, False, act=act)
-        self.jian2 = BaseConv(c3, c3 // 2, 1, 1, act=act)
-        self.jian1 = BaseConv(c4, c4 // 2, 1, 1, act=act)
-        self.jian0 = BaseConv(c5, c5 // 2, 1, 1, act=act)
+        self.C3_p3 = CSPLayer(2 * c3, c3, n, False, depthwise=depthwise, act=act)
+        self.bu_conv2 = Conv(c3, c3, 3, 2, act=act)
+        self.C3_n3 = CSPLayer(2 * c3, c4, n, False, depthwise=depthwise, act=act)
+        self.bu_conv1 = Conv(c4, c4, 3, 2, act=act)
+        self.C3_n4 = CSPLayer(2 * c4, c5, n, False, depthwise=depthwise, act=act)
+        self.jian2 = Conv(c3, c3 // 2, 1, 1, act=act)
+        self.jian1 = Conv(c4, c4 // 2, 1, 1, act=act)
+        self.jian0 = Conv(c5, c5 // 2, 1, 1, act=act)
 
     # ---- reference: off_forward (:109-175)
     def off_forward(self, input):

@@ -60,6 +60,16 @@ def _packed(m):
     return m._pk
 
 
+def _packed_dw(m):
+    """depthwise BaseConv: bf16 [k*k][C]"""
+    w = m.conv.weight
+    key = (w._version, w.data_ptr(), w.device, WEIGHT_EPOCH)
+    if getattr(m, "_pk_key", None) != key:
+        m._pk = ops.pack_dw_weight(w)
+        m._pk_key = key
+    return m._pk
+
+
 def _packed_dgrad(mods):
     """Data-gradient operand (flipped taps, transposed channels) of one BaseConv or of a conv1 | conv2 pair."""
     ws = [m.conv.weight for m in mods]
@@ -145,7 +155,7 @@ def _dbg_skip_apply(nbytes):
     return lo * 1e6 <= nbytes < hi * 1e6
 
 
-def conv_bn_act(ctx: Ctx, mods, x: View, wpk, k, s, y: View, res: View = None, act=1, y_goff1=0, res_goff1=0):
+def conv_bn_act(ctx: Ctx, mods, x: View, wpk, k, s, y: View, res: View = None, act=1, y_goff1=0, res_goff1=0, impl=None):
     """Train mode: conv -> batch statistics -> BatchNorm (running-stat update) -> act (+res) into ``y``.
     Tensor-core path = 2 launches: the conv writes the raw bf16 result, accumulates the statistics and
     (grid barrier + parallel reduce in its tail) publishes scale/shift; then the normalise pass.  ``mods``: one BaseConv, or two whose
@@ -161,7 +171,8 @@ def conv_bn_act(ctx: Ctx, mods, x: View, wpk, k, s, y: View, res: View = None, a
     split = ctx.split if ctx.groups == 2 else 0
     for m in mods:
         m._stats_epoch = getattr(m, "_stats_epoch", 0) + 1
-    if ctx.impl == "tc":
+    impl = impl or ctx.impl
+    if impl == "tc":
         partials = torch.empty((ops.conv_stat_rows(), 4 * cout), dtype=torch.float32, device=ctx.device)
         segs, c0 = [], 0
         for m in mods:
@@ -179,8 +190,9 @@ def conv_bn_act(ctx: Ctx, mods, x: View, wpk, k, s, y: View, res: View = None, a
                 ops.bn_act_apply(raw, ss[0].data_ptr(), ss[1].data_ptr(), split if split else n, act, res, y, y_goff1,
                                  res_goff1)
         return
-    # CUDA-core cross-check path: conv, separate statistics pass, separate finalize per module, apply
-    ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl="simt")
+    # CUDA-core path (cross-check of the tensor-core kernel; depthwise convs): conv, separate statistics pass, separate
+    # finalize per module, apply
+    ops.conv2d(x, wpk, raw, k, s, ops.SY_CONV_RAW, impl=impl)
     sc = torch.empty((2, 2, cout), dtype=torch.float32, device=ctx.device)
     sp = split if split else n
     c0 = 0
@@ -197,30 +209,35 @@ def conv_bn_act(ctx: Ctx, mods, x: View, wpk, k, s, y: View, res: View = None, a
         sc[:, :, c0:c0 + c] = tmp
         c0 += c
     if y_goff1 == 0 and res_goff1 == 0:
-        ops.bn_act_apply(raw, sc[0].data_ptr(), sc[1].data_ptr(), sp, act, res, y)
+        ops.bn_act_apply(raw, sc[0], sc[1], sp, act, res, y)
     else:   # group-1 images go to a shifted destination (DFP fusion): one call per group
         nb = sp
-        ops.bn_act_apply(raw.imgs(0, nb), sc[0, 0].data_ptr(), sc[1, 0].data_ptr(), nb, act,
+        ops.bn_act_apply(raw.imgs(0, nb), sc[0, 0], sc[1, 0], nb, act,
                          res.imgs(0, nb) if res is not None else None, y.imgs(0, nb))
         y1 = View(y.buf, y.c0, y.c, y.n0, nb).shifted(y_goff1 + nb * y.img_elems())
         r1 = View(res.buf, res.c0, res.c, res.n0, nb).shifted(res_goff1 + nb * res.img_elems()) if res is not None else None
-        ops.bn_act_apply(raw.imgs(nb, nb), sc[0, 1].data_ptr(), sc[1, 1].data_ptr(), nb, act, r1, y1)
+        ops.bn_act_apply(raw.imgs(nb, nb), sc[0, 1], sc[1, 1], nb, act, r1, y1)
 
 
 def base_conv(ctx: Ctx, m, x: View, y: View = None, res: View = None) -> View:
-    """[yolox] BaseConv: act(bn(conv(x))) (+ res).  ``y`` may be a slice of a concat buffer."""
+    """[yolox] BaseConv: act(bn(conv(x))) (+ res).  ``y`` may be a slice of a concat buffer.  Also takes a [yolox] DWConv
+    (depthwise BaseConv then pointwise BaseConv) wherever the reference's ``Conv = DWConv if depthwise else BaseConv`` puts one."""
+    if hasattr(m, "dconv"):
+        return base_conv(ctx, m.pconv, base_conv(ctx, m.dconv, x), y, res)
     k, s = m.ksize, m.stride
     ho, wo = ops.conv_out_hw(x.h, x.w, k, s)
     cout = m.conv.out_channels
     if y is None:
         y = View.empty(x.n, ho, wo, cout, ctx.device)
-    wpk = _packed(m)
+    dw = m.conv.groups > 1
+    wpk = _packed_dw(m) if dw else _packed(m)
+    impl = "dw" if dw else ctx.impl
     act = 1 if m.act_name == "silu" else 0
     if not ctx.train:
         scale, shift = _folded(m)
-        ops.conv2d(x, wpk, y, k, s, ops.SY_CONV_FUSED, impl=ctx.impl, scale=scale, shift=shift, act=act, res=res)
+        ops.conv2d(x, wpk, y, k, s, ops.SY_CONV_FUSED, impl=impl, scale=scale, shift=shift, act=act, res=res)
     else:
-        conv_bn_act(ctx, (m,), x, wpk, k, s, y, res, act)
+        conv_bn_act(ctx, (m,), x, wpk, k, s, y, res, act, impl=impl)
     _trace(m, y)
     return y
 
@@ -247,6 +264,12 @@ def _folded_pair(m1, m2):
 def conv_pair(ctx: Ctx, m1, m2, x: View) -> View:
     """Two BaseConvs with the same geometry reading the same input as ONE launch: [.., c1 + c2] output, one BatchNorm
     parameter segment per module (CSPLayer conv1 | conv2; the first cls / reg tower convs of a head level)."""
+    if hasattr(m1, "dconv") or hasattr(m2, "dconv"):          # depthwise variants: two ordinary launches into one buffer
+        c1, c2 = m1.pconv.conv.out_channels, m2.pconv.conv.out_channels
+        u = View.empty(x.n, x.h, x.w, c1 + c2, ctx.device)
+        base_conv(ctx, m1, x, u.ch(0, c1))
+        base_conv(ctx, m2, x, u.ch(c1, c2))
+        return u
     c1, c2 = m1.conv.out_channels, m2.conv.out_channels
     k, s = m1.ksize, m1.stride
     assert (m2.ksize, m2.stride, m2.conv.in_channels) == (k, s, m1.conv.in_channels)
@@ -364,8 +387,16 @@ def dfp_fuse(ctx: Ctx, net, cur, sup):
     ``cur`` / ``sup`` are per-level views with the same image count."""
     outs = []
     for m, c, s in zip((net.jian2, net.jian1, net.jian0), cur, sup):
-        half = m.conv.out_channels
         nb = c.n
+        if hasattr(m, "dconv"):                               # depthwise=True: jian is a DWConv (dfp_pafpn.py:83-105)
+            half = m.pconv.conv.out_channels
+            out = View.empty(nb, c.h, c.w, 2 * half, ctx.device)
+            sub = Ctx(ctx.train, nb, nb, ctx.device)          # two calls = two BatchNorm batches, like the reference
+            base_conv(sub, m, c, out.ch(0, half), res=c.ch(0, half))
+            base_conv(sub, m, s, out.ch(half, half), res=c.ch(half, half))
+            outs.append(out)
+            continue
+        half = m.conv.out_channels
         out = View.empty(nb, c.h, c.w, 2 * half, ctx.device)
         wpk = _packed(m)
         if not ctx.train:

@@ -24,12 +24,11 @@ class BaseConv(nn.Module):
 
     def __init__(self, in_channels, out_channels, ksize, stride, groups=1, bias=False, act="silu"):
         super().__init__()
-        if groups != 1 or bias:
-            raise NotImplementedError("streamyolo_b200: grouped / biased BaseConv is not on the hot path "
-                                      "(no shipped cfg uses depthwise=True)")
+        if bias or groups not in (1, in_channels) or (groups > 1 and in_channels != out_channels):
+            raise NotImplementedError("streamyolo_b200: BaseConv is dense (groups=1) or depthwise (groups=in=out), without bias")
         if act not in ("silu",):
             raise NotImplementedError(f"activation {act!r}: only 'silu' is used by the StreamYOLO cfgs")
-        self.conv = nn.Conv2d(in_channels, out_channels, ksize, stride, (ksize - 1) // 2, bias=False)
+        self.conv = nn.Conv2d(in_channels, out_channels, ksize, stride, (ksize - 1) // 2, groups=groups, bias=False)
         self.bn = nn.BatchNorm2d(out_channels)
         self.act = nn.SiLU(inplace=True)
         self.ksize, self.stride, self.act_name = ksize, stride, act
@@ -42,19 +41,27 @@ class BaseConv(nn.Module):
 
 
 class DWConv(nn.Module):
-    def __init__(self, *a, **k):
+    """[yolox] DWConv: depthwise k x k BaseConv (groups = in_channels) then 1x1 pointwise BaseConv.  Forward only (train-mode
+    BatchNorm and eval): the depthwise half runs on sy_dwconv2d (coalesced CUDA-core kernel, HBM-bound), the pointwise half
+    on the tensor-core kernel.  The training backward (model/backward.py) does not cover depthwise layers -- no shipped cfg
+    sets depthwise=True."""
+
+    def __init__(self, in_channels, out_channels, ksize, stride=1, act="silu"):
         super().__init__()
-        raise NotImplementedError("depthwise=True is never used by the reference cfgs; not built")
+        self.dconv = BaseConv(in_channels, in_channels, ksize, stride, groups=in_channels, act=act)
+        self.pconv = BaseConv(in_channels, out_channels, 1, 1, groups=1, act=act)
+
+    def forward(self, x):
+        return _run_standalone(self, lambda c, v: engine.base_conv(c, self, v), x)
 
 
 class Bottleneck(nn.Module):
     def __init__(self, in_channels, out_channels, shortcut=True, expansion=0.5, depthwise=False, act="silu"):
         super().__init__()
-        if depthwise:
-            raise NotImplementedError("depthwise=True is never used by the reference cfgs")
         hidden = int(out_channels * expansion)
+        Conv = DWConv if depthwise else BaseConv
         self.conv1 = BaseConv(in_channels, hidden, 1, 1, act=act)
-        self.conv2 = BaseConv(hidden, out_channels, 3, 1, act=act)
+        self.conv2 = Conv(hidden, out_channels, 3, 1, act=act)
         self.use_add = shortcut and in_channels == out_channels
 
     def forward(self, x):

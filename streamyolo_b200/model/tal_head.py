@@ -9,7 +9,7 @@ from torch import nn
 
 from . import engine
 from .. import ops
-from .network_blocks import BaseConv
+from .network_blocks import BaseConv, DWConv
 
 
 SUPPORTED_NUM_CLASSES = (8, 1, 20)     # head_pred_kernel<5 + nc> instantiations
@@ -19,8 +19,6 @@ class TALHead(nn.Module):
     def __init__(self, num_classes, width=1.0, strides=[8, 16, 32], in_channels=[256, 512, 1024], act="silu",
                  depthwise=False, gamma=1.5, ignore_thr=0.2, ignore_value=0.2):
         super().__init__()
-        if depthwise:
-            raise NotImplementedError("depthwise=True is never used by the reference cfgs")
         if num_classes not in SUPPORTED_NUM_CLASSES:
             # the prediction-conv + decode kernel is instantiated per class count (csrc/head_loss.cu): fail at construction,
             # not at the first forward
@@ -34,10 +32,11 @@ class TALHead(nn.Module):
         self.cls_preds, self.reg_preds, self.obj_preds = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
         self.stems = nn.ModuleList()
         hw = int(256 * width)
+        Conv = DWConv if depthwise else BaseConv            # tal_head.py:53
         for cin in in_channels:
             self.stems.append(BaseConv(int(cin * width), hw, 1, 1, act=act))
-            self.cls_convs.append(nn.Sequential(BaseConv(hw, hw, 3, 1, act=act), BaseConv(hw, hw, 3, 1, act=act)))
-            self.reg_convs.append(nn.Sequential(BaseConv(hw, hw, 3, 1, act=act), BaseConv(hw, hw, 3, 1, act=act)))
+            self.cls_convs.append(nn.Sequential(Conv(hw, hw, 3, 1, act=act), Conv(hw, hw, 3, 1, act=act)))
+            self.reg_convs.append(nn.Sequential(Conv(hw, hw, 3, 1, act=act), Conv(hw, hw, 3, 1, act=act)))
             self.cls_preds.append(nn.Conv2d(hw, self.n_anchors * num_classes, 1, 1, 0))
             self.reg_preds.append(nn.Conv2d(hw, 4, 1, 1, 0))
             self.obj_preds.append(nn.Conv2d(hw, self.n_anchors * 1, 1, 1, 0))
@@ -76,7 +75,7 @@ class TALHead(nn.Module):
                 # cls_convs[k][0] and reg_convs[k][0] read the same stem output (tal_head.py:159-171): ONE conv launch with
                 # 2 x hw output channels and two BatchNorm segments, like the conv1 | conv2 pair of a CSPLayer
                 u = engine.conv_pair(ctx, self.cls_convs[k][0], self.reg_convs[k][0], x)
-                hw_c = self.cls_convs[k][0].conv.out_channels
+                hw_c = u.c // 2
                 cf = engine.base_conv(ctx, self.cls_convs[k][1], u.ch(0, hw_c))
                 rf = engine.base_conv(ctx, self.reg_convs[k][1], u.ch(hw_c, hw_c))
                 ops.head_pred_decode(cf, rf, self._f32(self.reg_preds[k].weight), self._f32(self.reg_preds[k].bias),

@@ -116,6 +116,7 @@ _SIG = {
     "sy_conv2d_tc": (C.c_int, [C.POINTER(SyConvDesc), C.c_void_p]),
     "sy_conv2d_plan": (C.c_int, [C.c_int32] * 8 + [C.POINTER(SyConvPlan)]),
     "sy_conv2d_simt": (C.c_int, [C.POINTER(SyConvDesc), C.c_void_p]),
+    "sy_dwconv2d": (C.c_int, [C.POINTER(SyConvDesc), C.c_void_p]),
     "sy_focus_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, SyTensor,
                                 C.c_void_p]),
     "sy_stats_num_partials": (C.c_int, [C.c_int32, C.c_int32]),
@@ -327,7 +328,7 @@ def conv2d(x: View, wpk, y: View, k, s, mode, impl="tc", scale=None, shift=None,
     d.debug_f32 = debug_f32.data_ptr() if debug_f32 is not None else None
     if timeline is not None:
         d.debug_timeline, d.debug_timeline_events = timeline.data_ptr(), timeline.numel() // 2
-    fn = lib().sy_conv2d_tc if impl == "tc" else lib().sy_conv2d_simt
+    fn = {"tc": lib().sy_conv2d_tc, "simt": lib().sy_conv2d_simt, "dw": lib().sy_dwconv2d}[impl]
     _check(fn(C.byref(d), _stream()))
     return rows.value
 
@@ -339,6 +340,13 @@ def focus_pack(x, frames, y: View):
 
 
 STEM_K = (3, 1)      # the stem runs as a 3x1 conv over the W-gathered 64-channel focus tensor
+
+
+def pack_dw_weight(w):
+    """depthwise [C, 1, k, k] fp32 parameter -> bf16 [k*k][C] (sy_pack_conv_weight mode 0 on the [1, C, k, k] view)."""
+    c, one, kh, kw = w.shape
+    assert one == 1
+    return pack_conv_weight(_w32(w).view(1, c, kh, kw)).view(kh * kw, c)
 
 
 def pack_stem_weight(w):
@@ -369,6 +377,9 @@ def bn_finalize(partials, p_split, groups, count, gamma, beta, rmean, rvar, nbt,
 
 
 def bn_act_apply(x: View, scale_ptr, shift_ptr, split_n, act, res, y: View, y_goff1=0, res_goff1=0):
+    """``scale_ptr`` / ``shift_ptr``: fp32 [groups][C] tensors (or their raw device addresses)"""
+    if torch.is_tensor(scale_ptr):
+        scale_ptr, shift_ptr = scale_ptr.data_ptr(), shift_ptr.data_ptr()
     _check(lib().sy_bn_act_apply(x.st(), scale_ptr, shift_ptr, split_n, act,
                                  res.st() if res is not None else NULL_T, y.st(), y_goff1, res_goff1, _stream()))
 

@@ -49,8 +49,11 @@ def conv2d(x, wpk, y, k, s, mode, impl="tc", scale=None, shift=None, act=1, res=
            timeline=None, debug_flags=0, bn=None, momentum=0.03, eps=1e-3, scale_shift=None, sync=None, apply_y=None,
            apply_res=None, y_goff1=0, res_goff1=0, mean_invstd=None, debug_f32=None):
     kh, kw = (k, k) if isinstance(k, int) else k
-    w = _unpack(wpk, kh, kw)
-    out = F.conv2d(_nchw(x), w, None, s, ((kh - 1) // 2, (kw - 1) // 2))
+    if impl == "dw":                                # depthwise: wpk [kh*kw][C]
+        c = wpk.shape[1]
+        out = F.conv2d(_nchw(x), wpk.float().t().reshape(c, 1, kh, kw), None, s, ((kh - 1) // 2, (kw - 1) // 2), groups=c)
+    else:
+        out = F.conv2d(_nchw(x), _unpack(wpk, kh, kw), None, s, ((kh - 1) // 2, (kw - 1) // 2))
     if mode == ops.SY_CONV_FUSED:
         if scale is not None:
             out = out * scale.float()[None, :, None, None] + shift.float()[None, :, None, None]
@@ -101,7 +104,7 @@ def _strided(v: View, img0, nimg, goff):
 
 
 def bn_act_apply(x, scale_ptr, shift_ptr, split_n, act, res, y, y_goff1=0, res_goff1=0):
-    scale, shift = PTRS[scale_ptr], PTRS[shift_ptr]          # [2 groups][C]
+    scale, shift = (scale_ptr, shift_ptr) if torch.is_tensor(scale_ptr) else (PTRS[scale_ptr], PTRS[shift_ptr])   # [2 groups][C]
     t = _nchw(x)
     n = t.shape[0]
     sp = split_n if 0 < split_n < n else n
@@ -299,7 +302,7 @@ NAMES = ["conv_stat_rows", "conv2d", "bn_act_apply", "focus_pack", "upsample_nea
          "head_pred_decode", "tal_loss_workspace_bytes", "tal_loss", "tal_loss_backward", "head_pred_backward",
          "bn_act_backward", "conv2d_wgrad", "dilate2", "upsample_nearest_backward", "spp_maxpool_backward", "add_",
          "pack_conv_weight", "pack_conv_weight_dgrad", "pack_stem_weight", "sgd_nesterov_ema_step", "resize_bilinear",
-         "scale_labels_"]
+         "scale_labels_", "pack_dw_weight", "stats_num_partials", "channel_stats", "bn_finalize"]
 
 
 def _view_init(self, buf, c0=0, c=None, n0=0, n=None):
@@ -319,6 +322,40 @@ def pack_conv_weight_dgrad(*ws):
     """mode 1: the forward layout of the flipped, channel-transposed filter, pairs concatenated along co"""
     w = torch.cat([x.detach() for x in ws], 0)
     return pack_conv_weight(w.flip(2, 3).transpose(0, 1).contiguous())
+
+
+def pack_dw_weight(w):
+    c, _, kh, kw = w.shape
+    return _bf(w.detach().reshape(c, kh * kw).t()).contiguous()
+
+
+def stats_num_partials(n, hw):
+    return n
+
+
+def channel_stats(x, partials):
+    t = _nchw(x)
+    partials[:, 0] = t.sum((2, 3))
+    partials[:, 1] = t.pow(2).sum((2, 3))
+
+
+def bn_finalize(partials, p_split, groups, count, gamma, beta, rmean, rvar, nbt, momentum, eps, scale, shift):
+    for gi in range(groups):
+        rows = partials[:p_split] if (gi == 0 and groups == 2) else (partials[p_split:] if groups == 2 else partials)
+        s1, s2 = rows[:, 0].sum(0), rows[:, 1].sum(0)
+        cnt = count if gi == 0 else count * (partials.shape[0] - p_split) / max(p_split, 1)
+        mean = s1 / cnt
+        var = (s2 / cnt - mean * mean).clamp_min(0)
+        sc = gamma.detach().float() * (var + eps).rsqrt()
+        scale[gi] = sc
+        shift[gi] = beta.detach().float() - mean * sc
+        if rmean is not None:
+            rmean.mul_(1 - momentum).add_(momentum * mean)
+            rvar.mul_(1 - momentum).add_(momentum * var * (cnt / max(cnt - 1, 1)))
+        if nbt is not None:
+            nbt.add_(1)
+    PTRS[scale.data_ptr()] = scale
+    PTRS[shift.data_ptr()] = shift
 
 
 def pack_stem_weight(w):
