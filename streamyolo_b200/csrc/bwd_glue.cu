@@ -104,8 +104,12 @@ __global__ void head_pred_bwd_data_kernel(const HeadBwdArgs q) {
 
 constexpr int kHeadBwdPix = 256;      // pixels per partial row
 // block = one chunk of pixels; thread t owns channels t, t + 256, ...; partial[blk][o][c] = sum_p g[p][o] * feat_o[p][c]
+// NO (5 + classes) is a template parameter so that the accumulators stay in registers (a runtime bound put them in local
+// memory: 227 us per launch at 8 x 75 x 120 anchors); 0 = generic runtime bound for unusual class counts.
+template <int TNO>
 __global__ void __launch_bounds__(256) head_pred_bwd_weight_kernel(const HeadBwdArgs q) {
   extern __shared__ float gsm[];       // [kHeadBwdPix][NO]
+  const int NO = TNO > 0 ? TNO : q.NO;
   const long long npix = (long long)q.B * q.H * q.W;
   const long long p0 = (long long)blockIdx.x * kHeadBwdPix;
   const int np = (int)min((long long)kHeadBwdPix, npix - p0);
@@ -116,20 +120,26 @@ __global__ void __launch_bounds__(256) head_pred_bwd_weight_kernel(const HeadBwd
     gsm[i] = q.g[a * q.NO + i % q.NO];
   }
   __syncthreads();
-  float* out = q.partial + (size_t)blockIdx.x * q.NO * (q.C + 1);
+  float* out = q.partial + (size_t)blockIdx.x * NO * (q.C + 1);
   for (int c = threadIdx.x; c < q.C; c += blockDim.x) {
-    float acc[32];
-    for (int o = 0; o < q.NO; ++o) acc[o] = 0.f;
+    constexpr int kA = TNO > 0 ? TNO : 32;
+    float acc[kA];
+#pragma unroll
+    for (int o = 0; o < kA; ++o) acc[o] = 0.f;
     for (int pp = 0; pp < np; ++pp) {
       const float r = __bfloat162float(q.rf[(p0 + pp) * q.rfp + c]), cv = __bfloat162float(q.cf[(p0 + pp) * q.cfp + c]);
-      const float* g = gsm + pp * q.NO;
-      for (int o = 0; o < q.NO; ++o) acc[o] += g[o] * (o < 5 ? r : cv);
+      const float* g = gsm + pp * NO;
+#pragma unroll
+      for (int o = 0; o < kA; ++o)
+        if (TNO > 0 || o < NO) acc[o] += g[o] * (o < 5 ? r : cv);
     }
-    for (int o = 0; o < q.NO; ++o) out[(size_t)o * (q.C + 1) + c] = acc[o];
+#pragma unroll
+    for (int o = 0; o < kA; ++o)
+      if (TNO > 0 || o < NO) out[(size_t)o * (q.C + 1) + c] = acc[o];
   }
-  if (threadIdx.x < q.NO) {              // bias gradient of this chunk
+  if (threadIdx.x < NO) {              // bias gradient of this chunk
     float s = 0.f;
-    for (int pp = 0; pp < np; ++pp) s += gsm[pp * q.NO + threadIdx.x];
+    for (int pp = 0; pp < np; ++pp) s += gsm[pp * NO + threadIdx.x];
     out[(size_t)threadIdx.x * (q.C + 1) + q.C] = s;
   }
 }
@@ -315,7 +325,13 @@ extern "C" int sy_head_pred_backward(const SyHeadPredBwdDesc* d, sy_stream_t str
   q.partial = d->partials;
   const long long total = (long long)f.n * f.h * f.w * (f.c / 8);
   head_pred_bwd_data_kernel<<<grid_cap(total, 256), 256, 0, stream>>>(q);
-  head_pred_bwd_weight_kernel<<<rows, 256, sizeof(float) * kHeadBwdPix * q.NO, stream>>>(q);
+  const size_t wsm = sizeof(float) * kHeadBwdPix * q.NO;
+  switch (q.NO) {
+    case 13: head_pred_bwd_weight_kernel<13><<<rows, 256, wsm, stream>>>(q); break;
+    case 6: head_pred_bwd_weight_kernel<6><<<rows, 256, wsm, stream>>>(q); break;
+    case 25: head_pred_bwd_weight_kernel<25><<<rows, 256, wsm, stream>>>(q); break;
+    default: head_pred_bwd_weight_kernel<0><<<rows, 256, wsm, stream>>>(q); break;
+  }
   const int n_out = q.NO * (f.c + 1);
   head_pred_bwd_finalize_kernel<<<cdiv(n_out, 256), 256, 0, stream>>>(d->partials, rows, q.NO, f.c, d->dw_reg, d->dw_obj, d->dw_cls,
                                                                      d->db_reg, d->db_obj, d->db_cls, d->accumulate);

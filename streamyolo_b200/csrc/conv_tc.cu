@@ -68,6 +68,7 @@ struct Params {
   FastDiv fd_hw, fd_wo;
   int cblocks, kblocks, stages;
   int stage_tiles;          // 1 or 2 epilogue staging tiles
+  int team;                 // 1: the two convert warpgroups work on alternate slabs (needs stage_tiles == 2, RAW mode)
   // halo mode (AM == 2)
   int stagesA;              // halo ring depth
   int halo_pitch;           // pixels per halo row in shared memory (16, or 10 with debug flag 128)
@@ -121,10 +122,14 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: 
 //               tile b are done; the convert warps WAIT on it before overwriting the tile
 //   staged(b) : convert warps arrive after writing tile b (+ proxy fence); store and statistics warps WAIT on it
 // so the convert warps never wait for the statistics arithmetic or the store issue, only for the tile to be read.
-__device__ __forceinline__ void bar_free_wait(int b) { asm volatile("bar.sync %0, 544;" ::"r"(2 + 4 * b) : "memory"); }
-__device__ __forceinline__ void bar_free_arrive(int b) { asm volatile("bar.arrive %0, 544;" ::"r"(2 + 4 * b) : "memory"); }
-__device__ __forceinline__ void bar_staged_wait(int b) { asm volatile("bar.sync %0, 544;" ::"r"(3 + 4 * b) : "memory"); }
-__device__ __forceinline__ void bar_staged_arrive(int b) { asm volatile("bar.arrive %0, 544;" ::"r"(3 + 4 * b) : "memory"); }
+// Team mode (Params::team, epilogue-bound RAW layers with two staging tiles): the two convert warpgroups stop sharing a slab;
+// warpgroup t converts every slab of parity t on its own, into staging tile t -- two slabs in flight, the latency chain
+// TMEM load -> pack -> wait free -> store -> fence -> arrive of one overlaps the other's.  The barriers of tile t then
+// count 128 + 256 + 32 = 416 threads.
+__device__ __forceinline__ void bar_free_wait(int b, int n = 544) { asm volatile("bar.sync %0, %1;" ::"r"(2 + 4 * b), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_free_arrive(int b, int n = 544) { asm volatile("bar.arrive %0, %1;" ::"r"(2 + 4 * b), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_staged_wait(int b, int n = 544) { asm volatile("bar.sync %0, %1;" ::"r"(3 + 4 * b), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_staged_arrive(int b, int n = 544) { asm volatile("bar.arrive %0, %1;" ::"r"(3 + 4 * b), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_stats_done() { asm volatile("bar.sync 5, 512;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
@@ -225,7 +230,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiThreads);
+      // arrivals per accumulator hand-back: both convert warpgroups, except in team mode at BN = 64 (one slab per tile:
+      // only the warpgroup that owns the tile's slab ever reads the accumulator)
+      mbar_init(tempty_bar(a), (p.team && BN == kSlabCols) ? kEpiThreads / 2 : kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -430,8 +437,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t stage_base = smem_u32(sStage);
     int sbuf = 0, prev = -1;
     int tl_s = 7 * (p.timeline_cap / 8);
-    bar_free_arrive(0);                          // both tiles start out free
-    if (sflip) bar_free_arrive(1);
+    const int nbar = p.team ? 416 : 544;
+    bar_free_arrive(0, nbar);                    // both tiles start out free
+    if (sflip) bar_free_arrive(1, nbar);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
       int c1, c2, c3;                            // store coordinates below the channel: (x, y, image) | (pixel, 0, 0)
@@ -443,7 +451,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         c1 = px * p.tw; c2 = py * p.th; c3 = img;
       }
       for (int slab = 0; slab < BN / kSlabCols; ++slab, sbuf ^= sflip) {
-        bar_staged_wait(sbuf);
+        bar_staged_wait(sbuf, nbar);
         if (lane == 0) tl_rec<TL>(p, tl_s, 6, 0, tile, slab);
         if (elect_one()) {
           tma_store_4d(&tmY, stage_base + (uint32_t)(sbuf * kSlabBytes), n_tile * BN + slab * kSlabCols, c1, c2, c3);
@@ -457,17 +465,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) tl_rec<TL>(p, tl_s, 6, 1, tile, slab);
         if (sflip) {
-          if (prev >= 0) bar_free_arrive(prev);
+          if (prev >= 0) bar_free_arrive(prev, nbar);
           prev = sbuf;
         } else {
-          bar_free_arrive(0);
+          bar_free_arrive(0, nbar);
         }
       }
     }
     if (sflip && prev >= 0) {
       if (elect_one()) bulk_wait_read();
       __syncwarp();
-      bar_free_arrive(prev);
+      bar_free_arrive(prev, nbar);
     }
     if (lane == 0) {
       if (p.ap_y != nullptr) {
@@ -492,8 +500,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     int sbuf = 0;
     int tl_t = (st == 0) ? 5 * (p.timeline_cap / 8) : p.timeline_cap;
-    bar_free_arrive(0);                          // both tiles start out free
-    if (sflip) bar_free_arrive(1);
+    const int nbar = p.team ? 416 : 544;
+    bar_free_arrive(0, nbar);                    // both tiles start out free
+    if (sflip) bar_free_arrive(1, nbar);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
       const int n0 = n_tile * BN;
@@ -506,7 +515,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         cut = fdiv(m_tile, p.fd_per_img) >= p.split_n ? 0 : kBlockM;
       }
       for (int slab = 0; slab < BN / kSlabCols; ++slab, sbuf ^= sflip) {
-        bar_staged_wait(sbuf);
+        bar_staged_wait(sbuf, nbar);
         tl_rec<TL>(p, tl_t, 5, 0, tile, slab);
         const uint32_t tile_base = stage_base + (uint32_t)(sbuf * kSlabBytes);
         // Warp ew owns columns [8*ew, 8*ew+8) of the slab (one 16-byte chunk per 128-byte row).  The column sums run on the
@@ -523,7 +532,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ldmatrix_x2_trans(mx[ks][0], mx[ks][1], tile_base + r * 128u + ((((uint32_t)ew) ^ (r & 7u)) << 4));
           }
         }
-        bar_free_arrive(sbuf);                   // the values are in registers: the tile may be overwritten
+        bar_free_arrive(sbuf, nbar);             // the values are in registers: the tile may be overwritten
         tl_rec<TL>(p, tl_t, 5, 1, tile, slab);
         if (do_stats) {
           const bool pure = (cut <= 0) || (cut >= kBlockM);
@@ -576,6 +585,86 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int it = 0;
     int sbuf = 0;
     int tl_n = (et == 0) ? p.timeline_cap / 2 : p.timeline_cap;
+    if (p.team) {
+      // ------------------------------------------------------------ team mode (RAW only): warpgroup `half` owns the slabs
+      // of parity `half` (global slab counter of this CTA) and staging tile `half`, 64 columns = two TMEM loads per slab
+      const int team = half;
+      constexpr int kSlabs = BN / kSlabCols;
+      const uint32_t my_tile_row = my_row + (uint32_t)(team * kSlabBytes);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int gs0 = it * kSlabs;                                   // global index of this tile's first slab
+        int first = ((gs0 & 1) == team) ? 0 : 1;                       // first slab of the tile this warpgroup owns
+        if (first >= kSlabs) continue;
+        int last = first;
+        while (last + 2 < kSlabs) last += 2;
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
+        bool valid;
+        long long pix;
+        if constexpr (LIN) {
+          pix = (long long)m_tile * kBlockM + row;
+          valid = pix < p.P_total;
+        } else {
+          const int img = fdiv(m_tile, p.fd_per_img), rem = m_tile - img * per_img;
+          const int py = fdiv(rem, p.fd_tiles_x), px = rem - py * p.tiles_x;
+          const int oy = py * p.th + ty, ox = px * p.tw + tx;
+          valid = in_patch && (oy < p.Ho) && (ox < p.Wo);
+          pix = ((long long)img * p.Ho + oy) * p.Wo + ox;
+        }
+        const int n0 = n_tile * BN;
+        tl_rec<TL>(p, tl_n, 2, 0, tile, 0);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tl_rec<TL>(p, tl_n, 2, 1, tile, 0);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int slab = first; slab < kSlabs; slab += 2) {
+          const int cl = slab * kSlabCols;
+          uint32_t v[32], packed[16];
+          tmem_ld32(taddr + (uint32_t)cl, v);
+          tmem_ld_wait();
+          if (p.dbg_f32 != nullptr && valid) {
+            float* o = p.dbg_f32 + pix * p.Cout + n0 + cl;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0 + cl + i < p.Cout) o[i] = __uint_as_float(v[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            packed[i] = valid ? pack_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) : 0u;
+          tmem_ld32(taddr + (uint32_t)(cl + 32), v);                  // second half of the slab: in flight during the stores
+          tl_rec<TL>(p, tl_n, 2, 2, tile, slab);
+          bar_free_wait(team, 416);                                    // staging tile free: its store has read it, statistics loaded
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            sts128(my_tile_row + ((((uint32_t)g) ^ rsw) << 4), packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+          tmem_ld_wait();
+          if (slab == last) {                                          // every TMEM read of this accumulator by this warpgroup is done
+            tcgen05_fence_before();
+            mbar_arrive(tempty_bar(acc));
+          }
+          if (p.dbg_f32 != nullptr && valid) {
+            float* o = p.dbg_f32 + pix * p.Cout + n0 + cl + 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0 + cl + 32 + i < p.Cout) o[i] = __uint_as_float(v[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            packed[i] = valid ? pack_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) : 0u;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            sts128(my_tile_row + ((((uint32_t)(4 + g)) ^ rsw) << 4), packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+          fence_proxy_async();
+          bar_staged_arrive(team, 416);
+          tl_rec<TL>(p, tl_n, 2, 3, tile, slab);
+        }
+      }
+      tl_epi = tl_n;
+      bar_free_wait(team, 416);                                        // drain the last arrivals of this warpgroup's tile
+      asm volatile("bar.sync 4, 288;" ::: "memory");
+    } else {
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
@@ -674,6 +763,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     bar_free_wait(0);                                // drain the last arrivals (balanced barriers at exit)
     if (sflip) bar_free_wait(1);
     asm volatile("bar.sync 4, 288;" ::: "memory");   // store warp: all TMA stores of this CTA are complete
+    }
   }
   if (warp < 16) {
     // ---------------------------------------------- per-CTA partial row, grid barrier, BatchNorm finalize, apply
@@ -905,6 +995,9 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     const double kbc = BN == 256 ? 665.0 : (BN == 128 ? 515.0 : 560.0);
     p.stage_tiles = (p.kblocks * kbc < 1900.0 * (BN / 64)) ? 2 : 1;
     if (const char* e = getenv("SY_STAGE_TILES")) p.stage_tiles = (e[0] == '2') ? 2 : 1;   // tuning aid
+    // epilogue-bound layers in RAW mode: the two convert warpgroups take alternate slabs (SY_CONV_TEAM=0 turns it off)
+    p.team = (p.stage_tiles == 2 && p.mode == SY_CONV_RAW) ? 1 : 0;
+    if (const char* e = getenv("SY_CONV_TEAM")) p.team = (e[0] != '0' && p.stage_tiles == 2 && p.mode == SY_CONV_RAW) ? 1 : 0;
   }
   const int fixed_bytes = Cfg<BN>::kFixedBytes + (p.stage_tiles - 1) * kSlabBytes;
   int smem;

@@ -50,6 +50,42 @@ class Tape:
             self.keep.append(v.buf)
         return View(self.gbuf[key], v.c0, v.c, v.n0, v.n)
 
+    def prepare_grads(self):
+        """One zero-filled arena (ONE memset) holding the gradient buffer of every activation buffer the walk will touch,
+        instead of one allocation + fill per buffer."""
+        bufs, seen = [], set()
+
+        def add(v):
+            if v is not None and id(v.buf) not in seen and id(v.buf) not in self.gbuf:
+                seen.add(id(v.buf))
+                bufs.append(v.buf)
+
+        for r in self.ops:
+            t = r["t"]
+            if t == "conv":
+                add(r["y"]); add(r["res"])
+                if r["kind"] != "stem":
+                    add(r["x"])
+            elif t == "copy":
+                add(r["dst"]); add(r["src"])
+            elif t == "upsample":
+                add(r["y"]); add(r["x"])
+            elif t == "spp":
+                for k in ("x", "y5", "y9", "y13"):
+                    add(r[k])
+            elif t == "head":
+                for _, cf, rf, _ in r["levels"]:
+                    add(cf); add(rf)
+        if not bufs:
+            return
+        sizes = [(b.numel() + 127) // 128 * 128 for b in bufs]            # 256-byte aligned slots
+        arena = torch.zeros(sum(sizes), dtype=bufs[0].dtype, device=self.device)
+        off = 0
+        for b, n in zip(bufs, sizes):
+            self.gbuf[id(b)] = arena[off:off + b.numel()].view(b.shape)
+            self.keep.append(b)
+            off += n
+
     def rec(self, **kw):
         self.ops.append(kw)
 
@@ -339,6 +375,7 @@ def _head_backward(T: Tape, head, r, grad_scale, sink):
 
 
 def _walk(T: Tape, head, grad_scale, sink):
+    T.prepare_grads()
     for r in reversed(T.ops):
         t = r["t"]
         if t == "conv":
