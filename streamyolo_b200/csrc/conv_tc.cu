@@ -540,7 +540,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int col0 = n0 + slab * kSlabCols + ew * 8;
 #pragma unroll 1
           for (int grp = (cut <= 0 ? 1 : 0); grp <= (cut >= kBlockM ? 0 : 1); ++grp) {
-            float sx[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+            // four independent accumulator sets per quantity (k steps ks, ks + 4 share one): a dependent chain of eight
+            // mma.sync per quantity was latency-bound (~1200 cycles per slab, measured); chains of two are not
+            float sx[4][4], sq[4][4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { sx[c][i] = 0.f; sq[c][i] = 0.f; }
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
               uint32_t a0 = mx[ks][0], a2 = mx[ks][1], o0 = 0x3F803F80u, o2 = 0x3F803F80u;     // bf16 (1.0, 1.0)
@@ -551,19 +557,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t k2 = (in_grp(r0 + 8) ? 0x0000FFFFu : 0u) | (in_grp(r0 + 9) ? 0xFFFF0000u : 0u);
                 a0 &= k0; o0 &= k0; a2 &= k2; o2 &= k2;
               }
-              mma_bf16_16816(sx, o0, 0u, o2, 0u, mx[ks][0], mx[ks][1]);
-              mma_bf16_16816(sq, a0, 0u, a2, 0u, mx[ks][0], mx[ks][1]);
+              mma_bf16_16816(sx[ks & 3], o0, 0u, o2, 0u, mx[ks][0], mx[ks][1]);
+              mma_bf16_16816(sq[ks & 3], a0, 0u, a2, 0u, mx[ks][0], mx[ks][1]);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {      // only [0], [1] (rows 0-7 of the D fragment) are used below; fixed order
+              sx[0][i] = (sx[0][i] + sx[1][i]) + (sx[2][i] + sx[3][i]);
+              sq[0][i] = (sq[0][i] + sq[1][i]) + (sq[2][i] + sq[3][i]);
             }
             // D fragment: (row g8, cols 2*t4, 2*t4+1) in [0], [1].  Column sums: any row (take row 0: lanes 0-3); the
             // diagonal of X^T X: row g8 == column 2*t4 + j.  One owner lane per (column, sum | sumsq): fixed order.
             if (g8 == 0) {
               const int c = col0 + 2 * t4;
-              if (c < p.Cout) sAcc[(grp * 2 + 0) * p.Cout + c] += sx[0];
-              if (c + 1 < p.Cout) sAcc[(grp * 2 + 0) * p.Cout + c + 1] += sx[1];
+              if (c < p.Cout) sAcc[(grp * 2 + 0) * p.Cout + c] += sx[0][0];
+              if (c + 1 < p.Cout) sAcc[(grp * 2 + 0) * p.Cout + c + 1] += sx[0][1];
             }
             if (t4 == (g8 >> 1)) {
               const int c = col0 + g8;
-              if (c < p.Cout) sAcc[(grp * 2 + 1) * p.Cout + c] += (g8 & 1) ? sq[1] : sq[0];
+              if (c < p.Cout) sAcc[(grp * 2 + 1) * p.Cout + c] += (g8 & 1) ? sq[0][1] : sq[0][0];
             }
           }
         }

