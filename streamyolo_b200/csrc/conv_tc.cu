@@ -503,6 +503,66 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nbar = p.team ? 416 : 544;
     bar_free_arrive(0, nbar);                    // both tiles start out free
     if (sflip) bar_free_arrive(1, nbar);
+    // Warp ew owns columns [8*ew, 8*ew+8) of every 64-column slab; lane l reads rows l, l+32, l+64, l+96 (one 16-byte
+    // chunk each).  The per-lane partial sums (8 columns x {sum, sum of squares}) stay in REGISTERS across slabs and tiles
+    // -- one set per slab index of the tile -- and are only combined across the 32 lanes (recursive-halving shuffles) and
+    // added to the CTA's shared-memory totals on a FLUSH: when the CTA moves to another n tile or statistics group, on a
+    // tile that straddles the group boundary, and at the end.  (Per-slab shuffle reductions made the statistics warps the
+    // bottleneck of every epilogue-bound layer: ~1400 cycles per slab, profiles/r02_timeline_*.)
+    constexpr int kSlabs = BN / kSlabCols;
+    constexpr int kAccSlabs = (BN <= 128) ? kSlabs : 1;      // BN = 256: registers do not allow four sets; flush every slab
+    float acc[kAccSlabs][16];
+#pragma unroll
+    for (int j = 0; j < kAccSlabs; ++j)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[j][i] = 0.f;
+    int pend_grp = -1, pend_n0 = 0;                          // what the register sums belong to (-1: nothing pending)
+    // lanes combine a[16] (fixed shuffle tree: deterministic) and the 16 owner lanes add into the shared totals
+    auto reduce_store = [&](float (&a)[16], int grp, int col_base) {
+      float b8[8], c4[4], d2[2], e1;
+      {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float send = up ? a[i] : a[8 + i], keep = up ? a[8 + i] : a[i];
+          b8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+      }
+      {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float send = up ? b8[i] : b8[4 + i], keep = up ? b8[4 + i] : b8[i];
+          c4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+      }
+      {
+        const bool up = (lane & 4) != 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float send = up ? c4[i] : c4[2 + i], keep = up ? c4[2 + i] : c4[i];
+          d2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+      }
+      {
+        const bool up = (lane & 2) != 0;
+        const float send = up ? d2[0] : d2[1], keep = up ? d2[1] : d2[0];
+        e1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      e1 += __shfl_xor_sync(0xffffffffu, e1, 1);
+      if ((lane & 1) == 0) {               // 16 owner lanes: bit4 = sum | sumsq, bits 3..1 = column in the group
+        const int col = col_base + ew * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        if (col < p.Cout) sAcc[(grp * 2 + (lane >> 4)) * p.Cout + col] += e1;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = 0.f;
+    };
+    auto flush = [&]() {
+      if (pend_grp < 0) return;
+#pragma unroll
+      for (int j = 0; j < kAccSlabs; ++j) reduce_store(acc[j], pend_grp, pend_n0 + j * kSlabCols);
+      pend_grp = -1;
+    };
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
       const int n0 = n_tile * BN;
@@ -514,73 +574,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else {
         cut = fdiv(m_tile, p.fd_per_img) >= p.split_n ? 0 : kBlockM;
       }
-      for (int slab = 0; slab < BN / kSlabCols; ++slab, sbuf ^= sflip) {
+      const bool pure = (cut <= 0) || (cut >= kBlockM);
+      const int tgrp = cut <= 0 ? 1 : 0;
+      if (do_stats && kAccSlabs == kSlabs && (!pure || pend_grp != tgrp || pend_n0 != n0)) flush();     // warp-uniform
+      for (int slab = 0; slab < kSlabs; ++slab, sbuf ^= sflip) {
         bar_staged_wait(sbuf, nbar);
         tl_rec<TL>(p, tl_t, 5, 0, tile, slab);
         const uint32_t tile_base = stage_base + (uint32_t)(sbuf * kSlabBytes);
-        // Warp ew owns columns [8*ew, 8*ew+8) of the slab (one 16-byte chunk per 128-byte row).  The column sums run on the
-        // legacy tensor path (mma.sync m16n8k16, bf16 in / fp32 accumulate) instead of ~350 CUDA-core instructions per warp
-        // and slab:  sum x   = ones[16 x 16 rows] * X[16 rows x 8 cols]          (every output row = the column sums)
-        //            sum x^2 = diag( X^T[8 cols x 16 rows] * X[16 rows x 8 cols] )
-        // One transposed ldmatrix.x2 of 16 rows yields BOTH fragments: thread t receives X[2(t%4)..+1][t/4] of rows 0-7
-        // (m0) and rows 8-15 (m1) -- the A fragment (m = column, k = row) of X^T and the B fragment (k = row, n = column).
-        uint32_t mx[8][2];
+        float x[4][8];
         if (do_stats) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t r = (uint32_t)(ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7));
-            ldmatrix_x2_trans(mx[ks][0], mx[ks][1], tile_base + r * 128u + ((((uint32_t)ew) ^ (r & 7u)) << 4));
+          for (int rr = 0; rr < 4; ++rr) {
+            const uint32_t r = (uint32_t)(lane + 32 * rr);
+            const uint4 u = lds128(tile_base + r * 128u + ((((uint32_t)ew) ^ (r & 7u)) << 4));
+            x[rr][0] = bf16_lo(u.x); x[rr][1] = bf16_hi(u.x); x[rr][2] = bf16_lo(u.y); x[rr][3] = bf16_hi(u.y);
+            x[rr][4] = bf16_lo(u.z); x[rr][5] = bf16_hi(u.z); x[rr][6] = bf16_lo(u.w); x[rr][7] = bf16_hi(u.w);
           }
         }
         bar_free_arrive(sbuf, nbar);             // the values are in registers: the tile may be overwritten
         tl_rec<TL>(p, tl_t, 5, 1, tile, slab);
         if (do_stats) {
-          const bool pure = (cut <= 0) || (cut >= kBlockM);
-          const int g8 = lane >> 2, t4 = lane & 3;
-          const int col0 = n0 + slab * kSlabCols + ew * 8;
+          if (pure) {
+            float (&a)[16] = acc[kAccSlabs == kSlabs ? slab : 0];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { a[i] += x[rr][i]; a[8 + i] += x[rr][i] * x[rr][i]; }
+            }
+            if (kAccSlabs == kSlabs) {
+              pend_grp = tgrp; pend_n0 = n0;
+            } else {
+              reduce_store(a, tgrp, n0 + slab * kSlabCols);
+            }
+          } else {
+            // the tile straddles the group boundary (at most one M tile per layer and N tile): masked, reduced at once
 #pragma unroll 1
-          for (int grp = (cut <= 0 ? 1 : 0); grp <= (cut >= kBlockM ? 0 : 1); ++grp) {
-            // four independent accumulator sets per quantity (k steps ks, ks + 4 share one): a dependent chain of eight
-            // mma.sync per quantity was latency-bound (~1200 cycles per slab, measured); chains of two are not
-            float sx[4][4], sq[4][4];
+            for (int grp = 0; grp < 2; ++grp) {
+              const int lo = grp ? cut : 0, hi = grp ? kBlockM : cut;
+              float a[16];
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+              for (int i = 0; i < 16; ++i) a[i] = 0.f;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) { sx[c][i] = 0.f; sq[c][i] = 0.f; }
+              for (int rr = 0; rr < 4; ++rr) {
+                const int r = lane + 32 * rr;
+                if (r >= lo && r < hi) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              uint32_t a0 = mx[ks][0], a2 = mx[ks][1], o0 = 0x3F803F80u, o2 = 0x3F803F80u;     // bf16 (1.0, 1.0)
-              if (!pure) {                     // the tile straddles the group boundary: keep the rows of this group only
-                const int r0 = ks * 16 + 2 * t4;                  // this thread's k rows: r0, r0 + 1 (a0) and r0 + 8, r0 + 9 (a2)
-                auto in_grp = [&](int r) { return (r < cut) == (grp == 0); };
-                const uint32_t k0 = (in_grp(r0) ? 0x0000FFFFu : 0u) | (in_grp(r0 + 1) ? 0xFFFF0000u : 0u);
-                const uint32_t k2 = (in_grp(r0 + 8) ? 0x0000FFFFu : 0u) | (in_grp(r0 + 9) ? 0xFFFF0000u : 0u);
-                a0 &= k0; o0 &= k0; a2 &= k2; o2 &= k2;
+                  for (int i = 0; i < 8; ++i) { a[i] += x[rr][i]; a[8 + i] += x[rr][i] * x[rr][i]; }
+                }
               }
-              mma_bf16_16816(sx[ks & 3], o0, 0u, o2, 0u, mx[ks][0], mx[ks][1]);
-              mma_bf16_16816(sq[ks & 3], a0, 0u, a2, 0u, mx[ks][0], mx[ks][1]);
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {      // only [0], [1] (rows 0-7 of the D fragment) are used below; fixed order
-              sx[0][i] = (sx[0][i] + sx[1][i]) + (sx[2][i] + sx[3][i]);
-              sq[0][i] = (sq[0][i] + sq[1][i]) + (sq[2][i] + sq[3][i]);
-            }
-            // D fragment: (row g8, cols 2*t4, 2*t4+1) in [0], [1].  Column sums: any row (take row 0: lanes 0-3); the
-            // diagonal of X^T X: row g8 == column 2*t4 + j.  One owner lane per (column, sum | sumsq): fixed order.
-            if (g8 == 0) {
-              const int c = col0 + 2 * t4;
-              if (c < p.Cout) sAcc[(grp * 2 + 0) * p.Cout + c] += sx[0][0];
-              if (c + 1 < p.Cout) sAcc[(grp * 2 + 0) * p.Cout + c + 1] += sx[0][1];
-            }
-            if (t4 == (g8 >> 1)) {
-              const int c = col0 + g8;
-              if (c < p.Cout) sAcc[(grp * 2 + 1) * p.Cout + c] += (g8 & 1) ? sq[0][1] : sq[0][0];
+              reduce_store(a, grp, n0 + slab * kSlabCols);
             }
           }
         }
         tl_rec<TL>(p, tl_t, 5, 2, tile, slab);
       }
     }
+    if (do_stats) flush();
   } else if (warp < 8) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;                    // TMEM lane quarter this warp may read

@@ -5,11 +5,11 @@ For every parameter, in walk order: rel(product, oracle) next to three noise flo
   rounds differently somewhere), product(x * (1 + 2^-9)) vs product(x) (the product against itself).
 A routing bug shows as product-vs-oracle far above product-vs-product; chaos shows all of them large together.
 
-    python tools/diag_bwd.py [case] [H W]"""
+    python tests/tools/diag_bwd.py [case] [H W]"""
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 
 from oracle.make_golden import CASES
