@@ -53,6 +53,12 @@ int sy_version(void);
 /* 0 when the current device is sm_100 and the driver exposes cuTensorMapEncodeTiled. */
 int sy_check_device(void);
 
+/* Mark [ptr, ptr + bytes) as a persisting-L2 access window for the kernels subsequently launched on `stream` (inherited by
+ * the kernel nodes of a stream capture); bytes = 0 clears it.  *granted = the window the device allows (0: none).  The host
+ * side (engine.py) draws the raw conv outputs of all train-mode BaseConvs that fit from one arena inside this window: the
+ * normalise pass then reads them from L2 and the next layer overwrites them before they reach HBM. */
+int sy_l2_persist_window(void* ptr, size_t bytes, float hit_ratio, size_t* granted, sy_stream_t stream);
+
 /* -------- convolution (replaces [yolox] BaseConv.conv / nn.Conv2d, e.g.
  * exps/model/darknet.py:115-165, exps/model/dfp_pafpn.py:33-105,
  * exps/model/tal_head.py:55-104) ------------------------------------------------- */

@@ -117,11 +117,13 @@ class forward_scope:
     need every SM for their grid barrier (include/streamyolo_sm100.h)."""
 
     def __init__(self, device):
+        self.device = device
         self.st = _sync_pool(device)
 
     def __enter__(self):
         if self.st[2] == 0:
             self.st[1] = 0
+            _arm_raw_window(self.device)
         self.st[2] += 1
         return self
 
@@ -145,6 +147,33 @@ def _bn_seg(m, c_begin=0):
     return (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, c_begin)
 
 
+# raw conv outputs of the plain (non-recording) train-mode forward: one arena per (device, stream), marked persisting in L2
+RAW_ARENA_MB = float(os.environ.get("SY_RAW_ARENA_MB", "40"))
+_RAW_ARENAS = {}
+
+
+def _raw_view(ctx, n, h, w, c):
+    """The raw bf16 conv output of a train-mode BaseConv: dead as soon as its normalise pass has run, so every layer whose
+    tensor fits aliases ONE arena that the launching stream treats as a persisting-L2 window (sy_l2_persist_window)."""
+    nbytes = n * h * w * c * 2
+    if RAW_ARENA_MB <= 0 or torch.device(ctx.device).type != "cuda" or nbytes > RAW_ARENA_MB * 1e6:
+        return View.empty(n, h, w, c, ctx.device)
+    key = str(ctx.device)
+    st = _RAW_ARENAS.get(key)
+    if st is None:
+        arena = torch.empty(int(RAW_ARENA_MB * 1e6) // 256 * 256, dtype=torch.uint8, device=ctx.device)
+        st = _RAW_ARENAS[key] = [arena, ops.l2_persist_window(arena)]
+    return View(st[0][:nbytes].view(torch.bfloat16).view(n, h, w, c))
+
+
+def _arm_raw_window(device):
+    """(re)apply the persisting window on the CURRENT stream: a forward may run on another stream than the one the arena
+    was created on (CUDA-graph capture streams); kernel nodes captured from a stream inherit its window"""
+    st = _RAW_ARENAS.get(str(device))
+    if st is not None and st[1] > 0:
+        ops.l2_persist_window(st[0])
+
+
 def _dbg_skip_apply(nbytes):
     """timing experiments only (tools/ab_step.py): SY_DBG_SKIP_APPLY="lo:hi" (MB) drops the normalise pass of the layers whose
     raw output size lies in [lo, hi) -- the results are garbage, the step time shows what those launches really cost"""
@@ -164,7 +193,7 @@ def conv_bn_act(ctx: Ctx, mods, x: View, wpk, k, s, y: View, res: View = None, a
     ho = (x.h + 2 * ((kh - 1) // 2) - kh) // s + 1
     wo = (x.w + 2 * ((kw - 1) // 2) - kw) // s + 1
     cout = sum(m.conv.out_channels for m in mods)
-    raw = View.empty(x.n, ho, wo, cout, ctx.device)
+    raw = _raw_view(ctx, x.n, ho, wo, cout)
     bn0 = mods[0].bn
     mom = float(0.1 if bn0.momentum is None else bn0.momentum)
     n = x.n

@@ -113,6 +113,7 @@ _SIG = {
     "sy_version": (C.c_int, []),
     "sy_check_device": (C.c_int, []),
     "sy_conv_stat_rows": (C.c_int, []),
+    "sy_l2_persist_window": (C.c_int, [C.c_void_p, C.c_size_t, C.c_float, C.POINTER(C.c_size_t), C.c_void_p]),
     "sy_conv2d_tc": (C.c_int, [C.POINTER(SyConvDesc), C.c_void_p]),
     "sy_conv2d_plan": (C.c_int, [C.c_int32] * 8 + [C.POINTER(SyConvPlan)]),
     "sy_conv2d_simt": (C.c_int, [C.POINTER(SyConvDesc), C.c_void_p]),
@@ -604,3 +605,14 @@ def scale_labels_(labels, sx, sy):
     cols = labels.shape[-1]
     _check(lib().sy_scale_labels(labels.data_ptr(), labels.numel() // cols, cols, sx, sy, _stream()))
     return labels
+
+
+def l2_persist_window(t, hit_ratio=1.0):
+    """Persisting-L2 window over tensor ``t`` (None: clear) for the kernels launched on the current stream; returns the
+    number of bytes the device granted."""
+    got = C.c_size_t(0)
+    if t is None:
+        _check(lib().sy_l2_persist_window(None, 0, 0.0, C.byref(got), _stream()), kernels=0)
+        return 0
+    _check(lib().sy_l2_persist_window(t.data_ptr(), t.numel() * t.element_size(), hit_ratio, C.byref(got), _stream()), kernels=0)
+    return got.value

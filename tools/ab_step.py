@@ -26,6 +26,7 @@ SETTINGS = [
     # (label, environment switches, fuse-apply threshold MB)
     ("base", {}, 0),
     ("team epilogue off", {"SY_CONV_TEAM": "0"}, 0),
+    ("raw arena off (no L2 window)", {"SY_RAW_ARENA_MB": "0"}, 0),
     ("halo off", {"SY_CONV_A": "off"}, 0),
     ("halo forced", {"SY_CONV_A": "halo"}, 0),
     ("apply carveout default", {"SY_APPLY_CARVEOUT": "-1"}, 0),
@@ -50,7 +51,7 @@ SETTINGS = [
 ]
 if len(sys.argv) > 3:
     SETTINGS = [s for s in SETTINGS if any(k in s[0] for k in sys.argv[3].split(","))]
-SWITCHES = ("SY_CONV_TEAM", "SY_DBG_SKIP_APPLY", "SY_CONV_TILES", "SY_PDL", "SY_APPLY", "SY_APPLY_CAP", "SY_STAGE_TILES", "SY_APPLY_CARVEOUT", "SY_CONV_DEBUG", "SY_CONV_A")
+SWITCHES = ("SY_RAW_ARENA_MB", "SY_CONV_TEAM", "SY_DBG_SKIP_APPLY", "SY_CONV_TILES", "SY_PDL", "SY_APPLY", "SY_APPLY_CAP", "SY_STAGE_TILES", "SY_APPLY_CARVEOUT", "SY_CONV_DEBUG", "SY_CONV_A")
 
 
 def measure(label, env, fuse_mb, steps=20, warmup=4):
@@ -58,6 +59,7 @@ def measure(label, env, fuse_mb, steps=20, warmup=4):
         os.environ.pop(k, None)
     os.environ.update(env)
     engine.FUSE_APPLY_MAX_BYTES = fuse_mb * 1e6
+    engine.RAW_ARENA_MB = float(os.environ.get("SY_RAW_ARENA_MB", "40"))
     with torch.no_grad():
         ops.LAUNCHES = 0
         out = model(x, (fut, cur))
