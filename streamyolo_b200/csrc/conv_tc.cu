@@ -1018,8 +1018,12 @@ static void pick_patch(int ho, int wo, int* th, int* tw) {
 
 // Tile width heuristic from measured costs (B200, 1.965 GHz): one 64-deep K block of a 128-row tile costs about
 // 665 / 515 / 560 cycles at BN = 256 / 128 / 64 (MMA issue + barrier hand-shake + operand supply; the MMA itself
-// would need 512 / 256 / 128), the epilogue about 1900 cycles per 64-column slab and overlaps the next tile's main
+// would need 512 / 256 / 128), the epilogue about 1000-1400 cycles per 64-column slab and overlaps the next tile's main
 // loop, and the persistent grid runs ceil(tiles / SMs) rounds -- so wide tiles win unless they add a round.
+// measured epilogue cost per 64-column slab (profiles/r02_timeline_*): BN <= 128 keeps the statistics in registers across
+// slabs and runs two slabs in flight (team mode): ~1000 cycles; BN = 256 reduces the statistics per slab: ~1400 cycles
+static double epi_cycles_per_slab(int bn) { return bn == 256 ? 1400.0 : 1000.0; }
+
 static int pick_bn(int cout, int m_tiles, int kblocks) {
   const int cands[3] = {256, 128, 64};
   const double kbc[3] = {665.0, 515.0, 560.0};
@@ -1031,7 +1035,7 @@ static int pick_bn(int cout, int m_tiles, int kblocks) {
     const int tiles = m_tiles * cdiv(cout, bn);
     const int rounds = cdiv(tiles, num_sms());
     const double main_c = kblocks * kbc[i];
-    const double epi = 1900.0 * (bn / 64);
+    const double epi = epi_cycles_per_slab(bn) * (bn / 64);
     const double t = rounds * ((main_c > epi ? main_c : epi) + 400.0) + (main_c < epi ? main_c : epi);
     if (t < best) { best = t; best_bn = bn; }
   }
@@ -1053,7 +1057,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   // stem) get a second staging tile: the store + statistics of a slab then overlap the conversion of the next
   {
     const double kbc = BN == 256 ? 665.0 : (BN == 128 ? 515.0 : 560.0);
-    p.stage_tiles = (p.kblocks * kbc < 1900.0 * (BN / 64)) ? 2 : 1;
+    p.stage_tiles = (p.kblocks * kbc < epi_cycles_per_slab(BN) * (BN / 64)) ? 2 : 1;
     if (const char* e = getenv("SY_STAGE_TILES")) p.stage_tiles = (e[0] == '2') ? 2 : 1;   // tuning aid
     // epilogue-bound layers in RAW mode: the two convert warpgroups take alternate slabs (SY_CONV_TEAM=0 turns it off)
     p.team = (p.stage_tiles == 2 && p.mode == SY_CONV_RAW) ? 1 : 0;
