@@ -263,8 +263,9 @@ def capture(fn):
         fn()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    from streamyolo_b200.model import engine
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
+    with torch.cuda.graph(g, stream=engine.graph_capture_stream(torch.cuda.current_device())):
         out = fn()
     return g, out
 
@@ -494,8 +495,9 @@ def main():
             with torch.cuda.stream(side):
                 model(x_dev, (fut_dev, cur_dev))
             torch.cuda.current_stream().wait_stream(side)
+            from streamyolo_b200.model import engine
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=engine.graph_capture_stream(dev)):
                 g_out = model(x_dev, (fut_dev, cur_dev))
                 g_loss = torch.stack([g_out[k] for k in ("total_loss", "iou_loss", "l1_loss", "conf_loss", "cls_loss", "num_fg")])
 

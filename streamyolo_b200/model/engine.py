@@ -161,17 +161,34 @@ def _raw_view(ctx, n, h, w, c):
     key = str(ctx.device)
     st = _RAW_ARENAS.get(key)
     if st is None:
+        if torch.cuda.is_current_stream_capturing():       # the device limit / stream attribute cannot be set during capture
+            return View.empty(n, h, w, c, ctx.device)
         arena = torch.empty(int(RAW_ARENA_MB * 1e6) // 256 * 256, dtype=torch.uint8, device=ctx.device)
         st = _RAW_ARENAS[key] = [arena, ops.l2_persist_window(arena)]
     return View(st[0][:nbytes].view(torch.bfloat16).view(n, h, w, c))
 
 
 def _arm_raw_window(device):
-    """(re)apply the persisting window on the CURRENT stream: a forward may run on another stream than the one the arena
-    was created on (CUDA-graph capture streams); kernel nodes captured from a stream inherit its window"""
+    """(re)apply the persisting window on the CURRENT stream (a forward may run on another stream than the one the arena was
+    created on).  Not during stream capture: capture on ``graph_capture_stream()``, which carries the window already."""
     st = _RAW_ARENAS.get(str(device))
-    if st is not None and st[1] > 0:
+    if st is not None and st[1] > 0 and not torch.cuda.is_current_stream_capturing():
         ops.l2_persist_window(st[0])
+
+
+_CAPTURE_STREAMS = {}
+
+
+def graph_capture_stream(device):
+    """A side stream to capture CUDA graphs of the forward on (``torch.cuda.graph(g, stream=...)``): the persisting-L2 window of
+    the raw arena is set on it BEFORE the capture starts, so the captured kernel nodes inherit it."""
+    key = str(device)
+    if key not in _CAPTURE_STREAMS:
+        _CAPTURE_STREAMS[key] = torch.cuda.Stream(device=device)
+    st = _CAPTURE_STREAMS[key]
+    with torch.cuda.stream(st):
+        _arm_raw_window(device)
+    return st
 
 
 def _dbg_skip_apply(nbytes):

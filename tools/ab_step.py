@@ -71,7 +71,7 @@ def measure(label, env, fuse_mb, steps=20, warmup=4):
             model(x, (fut, cur))
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=engine.graph_capture_stream(dev)):
             o = model(x, (fut, cur))
             loss = o["total_loss"]
         for _ in range(warmup):
