@@ -348,6 +348,19 @@ int sy_postprocess_nms(const SyNmsDesc* d, sy_stream_t stream);
 int sy_pack_conv_weight(const float* w, int32_t cout, int32_t cin, int32_t kh, int32_t kw, int32_t mode, void* out,
                         int64_t out_pitch, int32_t co_offset, sy_stream_t stream);
 
+/* The same for MANY parameters in one launch: items (a DEVICE array) lists (parameter, layout) pairs with the arguments of
+ * sy_pack_conv_weight; `begin` = index of the item's first element in the launch (prefix sum of the element counts:
+ * cout*cin*kh*kw for modes 0 / 1, cout*kh*64 for mode 2), `total` = their sum.  The trainer re-packs every conv operand of the
+ * model (forward and data-gradient layouts) with it after each optimiser step. */
+typedef struct SyPackItem {
+  const float* w;
+  void* out;
+  int32_t cout, cin, kh, taps, mode, co_offset;
+  int64_t out_pitch;
+  int64_t begin;
+} SyPackItem;
+int sy_pack_conv_weights_batch(const SyPackItem* items_dev, int32_t n_items, int64_t total, sy_stream_t stream);
+
 /* The optimiser step of the reference trainer as one launch over flat fp32 state:
  * GradScaler.unscale_ + [yolox] Exp.get_optimizer's SGD(momentum, nesterov) with weight decay on the conv / linear weights
  * only + [yolox] ModelEMA.update (exps/train_utils/double_trainer.py:113-123, 173-175).  Elements [0, n_param) are

@@ -50,6 +50,37 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int O, int I, in
   }
 }
 
+// All conv operands of a model in ONE launch: items[k] describes one (parameter, layout) pair like the arguments of
+// pack_weight_kernel; element idx of the launch belongs to the item with begin <= idx < next begin (binary search).
+__global__ void pack_weights_batch_kernel(const SyPackItem* __restrict__ items, int n_items, long long total) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n_items - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (items[mid].begin <= idx) lo = mid; else hi = mid - 1;
+    }
+    const SyPackItem it = items[lo];
+    const long long l = idx - it.begin;
+    const int taps = it.taps, O = it.cout, I = it.cin;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(it.out);
+    if (it.mode == 2) {
+      const int kh = it.kh;
+      const int col = (int)(l % 64), r = (int)((l / 64) % kh), o = (int)(l / (64 * kh));
+      const int s = col >> 4, i = col & 15, kw = taps / kh;
+      float v = 0.f;
+      if (s < kw && i < I) v = it.w[(((long long)o * I + i) * kh + r) * kw + s];
+      out[l] = __float2bfloat16_rn(v);
+    } else if (it.mode == 0) {
+      const int i = (int)(l % I), t = (int)((l / I) % taps), o = (int)(l / ((long long)I * taps));
+      out[l] = __float2bfloat16_rn(it.w[((long long)o * I + i) * taps + t]);
+    } else {
+      const int o = (int)(l % O), t2 = (int)((l / O) % taps), i = (int)(l / ((long long)O * taps));
+      out[((long long)i * taps + t2) * it.out_pitch + it.co_offset + o] =
+          __float2bfloat16_rn(it.w[((long long)o * I + i) * taps + (taps - 1 - t2)]);
+    }
+  }
+}
+
 // One thread per element of the flat state.  Elements [0, n_param) are parameters (gradient, momentum), of which
 // [decay_begin, n_param) get weight decay; elements [n_param, n_total) are floating-point buffers (BatchNorm running
 // statistics) that only the EMA tracks.  Arithmetic mirrors torch.optim.SGD (foreach) and yolox ModelEMA step by step,
@@ -132,6 +163,13 @@ extern "C" int sy_pack_conv_weight(const float* w, int32_t cout, int32_t cin, in
   pack_weight_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, cout, cin, kh, kw, mode, reinterpret_cast<__nv_bfloat16*>(out),
                                                               out_pitch, co_offset);
   return launch_status("pack_weight_kernel");
+}
+
+extern "C" int sy_pack_conv_weights_batch(const SyPackItem* items_dev, int32_t n_items, int64_t total, sy_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SY_REQUIRE(items_dev != nullptr && n_items > 0 && total > 0, SY_EINVAL, "pack_conv_weights_batch: bad arguments");
+  pack_weights_batch_kernel<<<grid_for(total, 256), 256, 0, stream>>>(items_dev, n_items, total);
+  return launch_status("pack_weights_batch_kernel");
 }
 
 extern "C" int sy_sgd_nesterov_ema_step(const SySgdEmaDesc* d, sy_stream_t stream_) {

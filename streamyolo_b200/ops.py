@@ -94,6 +94,12 @@ class SySgdEmaDesc(C.Structure):
                 ("found_inf", C.c_void_p), ("hyper", C.c_void_p)]
 
 
+class SyPackItem(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("out", C.c_void_p), ("cout", C.c_int32), ("cin", C.c_int32), ("kh", C.c_int32),
+                ("taps", C.c_int32), ("mode", C.c_int32), ("co_offset", C.c_int32), ("out_pitch", C.c_int64),
+                ("begin", C.c_int64)]
+
+
 class SyConvPlan(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("mode", "bn", "m_tiles", "n_tiles", "rounds", "kblocks", "patch_h", "patch_w")]
 
@@ -150,6 +156,7 @@ _SIG = {
     "sy_conv2d_wgrad_tc": (C.c_int, [C.POINTER(SyConvWgradDesc), C.c_void_p]),
     "sy_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_int64, C.c_int32, C.c_void_p]),
+    "sy_pack_conv_weights_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "sy_sgd_nesterov_ema_step": (C.c_int, [C.POINTER(SySgdEmaDesc), C.c_void_p]),
     "sy_resize_bilinear": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_void_p]),
@@ -616,3 +623,24 @@ def l2_persist_window(t, hit_ratio=1.0):
         return 0
     _check(lib().sy_l2_persist_window(t.data_ptr(), t.numel() * t.element_size(), hit_ratio, C.byref(got), _stream()), kernels=0)
     return got.value
+
+
+class PackBatch:
+    """Every conv operand of a model re-packed in ONE launch (sy_pack_conv_weights_batch).  ``add`` the (fp32 parameter,
+    bf16 destination, layout) pairs once -- the tensors must keep their addresses -- then ``run()`` after every update."""
+
+    def __init__(self, device):
+        self.device, self.items, self.total, self.table = device, [], 0, None
+
+    def add(self, w, out, mode, out_pitch=0, co_offset=0):
+        assert w.dtype == torch.float32 and w.is_contiguous() and out.dtype == torch.bfloat16
+        o, i, kh, kw = w.shape
+        it = SyPackItem(w.data_ptr(), out.data_ptr(), o, i, kh, kh * kw, mode, co_offset, out_pitch, self.total)
+        self.items.append(it)
+        self.total += o * kh * 64 if mode == 2 else o * i * kh * kw
+
+    def run(self):
+        if self.table is None:
+            arr = (SyPackItem * len(self.items))(*self.items)
+            self.table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+        _check(lib().sy_pack_conv_weights_batch(self.table.data_ptr(), len(self.items), self.total, _stream()))

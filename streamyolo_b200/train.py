@@ -318,6 +318,49 @@ class Trainer:
         self.sink = None
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         engine.WEIGHT_EPOCH += 1
+        self._build_repack()
+        self._repack()
+
+    # ---- conv operands: every (parameter, layout) pair of the model re-packed by ONE launch after each update
+    def _build_repack(self):
+        dev = self.fs.state.device
+        self.pack = ops.PackBatch(dev)
+        self._packed_groups = []
+        stem = self.model.backbone.backbone.stem.conv
+        dt = ops.pack_conv_weight(stem.conv.weight[:1]).dtype     # bf16 (fp32 only under the CPU emulation with fp32 "storage")
+        for g in conv_groups_forward_order(self.model):
+            ws = [m.conv.weight for m in g]
+            _, cin, kh, kw = ws[0].shape
+            ot = sum(w.shape[0] for w in ws)
+            if g[0] is stem:
+                out = torch.empty((ot, kh, 64), dtype=dt, device=dev)
+                self.pack.add(ws[0], out, 2)
+                self._packed_groups.append((g, out, None))
+                continue
+            fwd = torch.empty((ot, kh * kw, cin), dtype=dt, device=dev)
+            dg = torch.empty((cin, kh * kw, ot), dtype=dt, device=dev)
+            o0 = 0
+            for w in ws:
+                self.pack.add(w, fwd[o0:o0 + w.shape[0]], 0)
+                self.pack.add(w, dg, 1, out_pitch=ot, co_offset=o0)
+                o0 += w.shape[0]
+            self._packed_groups.append((g, fwd, dg))
+
+    def _repack(self):
+        """run the batched pack and hand the buffers to the engine's operand caches (keys of the current WEIGHT_EPOCH)"""
+        self.pack.run()
+        ep = engine.WEIGHT_EPOCH
+        for g, fwd, dg in self._packed_groups:
+            ws = [m.conv.weight for m in g]
+            if dg is None:                                  # stem
+                g[0]._pk, g[0]._pk_key = fwd, (ws[0]._version, ws[0].data_ptr(), ws[0].device, ep)
+                continue
+            if len(g) == 1:
+                g[0]._pk, g[0]._pk_key = fwd, (ws[0]._version, ws[0].data_ptr(), ws[0].device, ep)
+            else:
+                g[0]._pk2 = fwd
+                g[0]._pk2_key = (ws[0]._version, ws[1]._version, ws[0].data_ptr(), ws[1].data_ptr(), ws[0].device, ep)
+            g[0]._pkd, g[0]._pkd_key = dg, tuple((w._version, w.data_ptr()) for w in ws) + (ep,)
 
     def forward_backward(self, x, targets, loss_scale=1.0):
         T, loss = backward._record(self.model, x, targets)
@@ -340,7 +383,8 @@ class Trainer:
         ops.sgd_nesterov_ema_step(self.fs.state, self.fs.grad, self.fs.mom, self.fs.ema, self.fs.n_param, self.fs.decay_begin,
                                   h[0], h[1], h[2], inv_scale=h[3], nesterov=True, ema_decay=h[4], found_inf=found_inf,
                                   hyper=hyper)
-        engine.WEIGHT_EPOCH += 1            # the conv operands are re-packed from the new masters on their next use
+        engine.WEIGHT_EPOCH += 1            # the conv operands follow the new masters: one batched re-pack launch
+        self._repack()
 
     def step(self, x, targets, lr=None, loss_scale=1.0):
         loss = self.forward_backward(x, targets, loss_scale)

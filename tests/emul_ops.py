@@ -298,11 +298,30 @@ def scale_labels_(labels, sx, sy):
     return labels
 
 
+class PackBatch:
+    """what ops.PackBatch does, with the torch pack emulations (destinations are filled in place)"""
+
+    def __init__(self, device):
+        self.items = []
+
+    def add(self, w, out, mode, out_pitch=0, co_offset=0):
+        self.items.append((w, out, mode, out_pitch, co_offset))
+
+    def run(self):
+        for w, out, mode, pitch, co in self.items:
+            if mode == 2:
+                out.copy_(pack_stem_weight(w))
+            elif mode == 0:
+                out.copy_(pack_conv_weight(w))
+            else:
+                out[:, :, co:co + w.shape[0]].copy_(pack_conv_weight_dgrad(w))
+
+
 NAMES = ["conv_stat_rows", "conv2d", "bn_act_apply", "focus_pack", "upsample_nearest", "spp_maxpool", "copy",
          "head_pred_decode", "tal_loss_workspace_bytes", "tal_loss", "tal_loss_backward", "head_pred_backward",
          "bn_act_backward", "conv2d_wgrad", "dilate2", "upsample_nearest_backward", "spp_maxpool_backward", "add_",
          "pack_conv_weight", "pack_conv_weight_dgrad", "pack_stem_weight", "sgd_nesterov_ema_step", "resize_bilinear",
-         "scale_labels_", "pack_dw_weight", "stats_num_partials", "channel_stats", "bn_finalize"]
+         "scale_labels_", "pack_dw_weight", "stats_num_partials", "channel_stats", "bn_finalize", "PackBatch"]
 
 
 def _view_init(self, buf, c0=0, c=None, n0=0, n=None):

@@ -61,9 +61,12 @@ def test_trainer_step_matches_stock_pytorch_step(monkeypatch):
     model = T.build_product(c)
     tr = train.Trainer(model, lr=2e-4)
     assert len(tr.fs.params) == len(list(ref.parameters()))
+    wants = [train.train_step(ref, opt, x, tg, ema) for _ in range(3)]     # (not interleaved: the operand caches share one epoch)
     for i in range(3):
-        want = train.train_step(ref, opt, x, tg, ema)
+        want = wants[i]
         got = tr.step(x, tg)
+        d3 = model.backbone.backbone.dark3[0]
+        assert any(g[0] is d3 and d3._pk is fwd for g, fwd, _ in tr._packed_groups)      # the batched re-pack feeds the forward
         assert abs(float(got["total_loss"]) - float(want["total_loss"])) <= 1e-5 * abs(float(want["total_loss"])), i
     assert tr.sink.launched and sum(b - a for a, b in tr.sink.launched) == tr.fs.n_param      # every gradient in one bucket
     for (k, p), q in zip(model.named_parameters(), ref.parameters()):

@@ -239,3 +239,30 @@ def test_trainer_graph_replay_equals_eager_steps():
     torch.cuda.synchronize()
     assert got == want[1:], (got, want)
     assert torch.equal(ta.fs.state, tb.fs.state) and torch.equal(ta.fs.ema, tb.fs.ema) and torch.equal(ta.fs.mom, tb.fs.mom)
+
+
+def test_pack_batch_equals_single_packs():
+    """sy_pack_conv_weights_batch (every operand of a model in ONE launch) against the per-parameter launches, bit for bit:
+    forward layout, pair concatenation, data-gradient layout with pitch / column offset, the Focus-stem layout."""
+    g = torch.Generator().manual_seed(5)
+    ws = [torch.randn(s, generator=g).cuda() for s in ((64, 32, 3, 3), (24, 64, 1, 1), (40, 64, 1, 1), (16, 12, 3, 3), (128, 128, 3, 3))]
+    pb = ops.PackBatch(torch.device("cuda"))
+    f0 = torch.empty((64, 9, 32), dtype=torch.bfloat16, device="cuda")
+    d0 = torch.empty((32, 9, 64), dtype=torch.bfloat16, device="cuda")
+    pair_f = torch.empty((64, 1, 64), dtype=torch.bfloat16, device="cuda")
+    pair_d = torch.empty((64, 1, 64), dtype=torch.bfloat16, device="cuda")
+    stem = torch.empty((16, 3, 64), dtype=torch.bfloat16, device="cuda")
+    f4 = torch.empty((128, 9, 128), dtype=torch.bfloat16, device="cuda")
+    pb.add(ws[0], f0, 0)
+    pb.add(ws[0], d0, 1, out_pitch=64, co_offset=0)
+    pb.add(ws[1], pair_f[0:24], 0)
+    pb.add(ws[2], pair_f[24:64], 0)
+    pb.add(ws[1], pair_d, 1, out_pitch=64, co_offset=0)
+    pb.add(ws[2], pair_d, 1, out_pitch=64, co_offset=24)
+    pb.add(ws[3], stem, 2)
+    pb.add(ws[4], f4, 0)
+    pb.run()
+    torch.cuda.synchronize()
+    assert torch.equal(f0, ops.pack_conv_weight(ws[0])) and torch.equal(d0, ops.pack_conv_weight_dgrad(ws[0]))
+    assert torch.equal(pair_f, ops.pack_conv_weight(ws[1], ws[2])) and torch.equal(pair_d, ops.pack_conv_weight_dgrad(ws[1], ws[2]))
+    assert torch.equal(stem, ops.pack_stem_weight(ws[3])) and torch.equal(f4, ops.pack_conv_weight(ws[4]))
