@@ -663,7 +663,10 @@ def main():
                             "achieved": round(ach, 1), "peak": peaks["burst"], "unit": "TFLOP/s", "frac": round(ach / peaks["burst"], 4),
                             "peak_source": peaks["source"] + " cuBLAS bf16 burst", "launches": fam_n,
                             "avg_launch_ms": round(fam_ms / fam_n, 5), "sum_launch_ms": round(fam_ms, 4),
-                            "algorithmic_flop_per_step": B * gf * 1e9, "traffic": None,
+                            "algorithmic_flop_per_step": B * gf * 1e9,
+                            # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the family's 114 launches of
+                            # one step (ncu launch list of this command, profiles/r02_launch_summary.txt; StreamYOLO-l, 8 pairs only)
+                            "traffic": (50.4e6 if (args.model, B) == ("l", 8) else None), "traffic_unit": "bytes/launch (ncu, r02, family average)",
                             "how": "the step's conv launches re-issued alone, in order, as one CUDA graph on the step's own buffers; "
                                    "CUDA events around the replay, best of 5; ncu launch list of the step: profiles/"}
     if not args.no_cpu_baseline:

@@ -88,9 +88,12 @@ def measure(label, env, fuse_mb, steps=20, warmup=4):
     del g
 
 
+print("raw arena MB", engine.RAW_ARENA_MB, flush=True)
 for s in SETTINGS:
     try:
         measure(*s)
     except Exception as e:  # keep going: a failing switch must not hide the others
         print(f"{s[0]:30s} FAILED: {type(e).__name__}: {str(e)[:300]}", flush=True)
         torch.cuda.synchronize()
+
+print("persisting-L2 window granted (bytes):", {k: v[1] for k, v in engine._RAW_ARENAS.items()})
