@@ -6,7 +6,7 @@ LIB=${1:-streamyolo_b200/lib/libstreamyolo_sm100.so}
 cuobjdump -sass "$LIB" 2>/dev/null | awk '
 /Function :/ { fn=$3; next }
 /\/\*[0-9a-f]+\*\// {
-  for (i = 1; i <= NF; ++i) if ($i ~ /^(@!?U?P[0-9T]+)$/) continue; else if ($i ~ /^[A-Z][A-Z0-9_.]+;?$/) { op=$i; break }
+  for (i = 1; i <= NF; ++i) if ($i ~ /^(@!?U?P[0-9T]+)$/) continue; else if ($i ~ /^[A-Z][A-Za-z0-9_.]+;?$/) { op=$i; break }
   gsub(/;/, "", op);
   if (op ~ /^(UTC|UTMA|LDTM|STTM|HMMA|LDSM|UBLKCP|SYNCS|ELECT|UTCBAR)/) c[fn "\t" op]++
 }
