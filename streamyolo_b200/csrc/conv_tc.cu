@@ -62,6 +62,10 @@ struct Params {
   int th, tw, tiles_x, tiles_y;
   int m_tiles, n_tiles, total_tiles;
   FastDiv fd_m_tiles, fd_per_img, fd_tiles_x, fd_tw;
+  // pair mode (cta_group::2): the tile loop walks PAIR tiles = 256 consecutive output pixels x BN channels; CTA rank r of the
+  // pair owns M tile 2 * m2 + r (it may lie past the end of the tensor: loads zero-fill, the store clips)
+  int m_tiles2, total_tiles2;
+  FastDiv fd_m_tiles2;
   // linear tiles (LIN): an M tile is 128 consecutive output pixels of the flattened (n, oh, ow) space
   int P_total;              // N * Ho * Wo
   int gp;                   // first output pixel of statistics group 1 (== P_total: single group)
@@ -97,7 +101,7 @@ struct Params {
   int ap_act;
   long long* timeline;      // debug: CTA 0 records (event id, clock) pairs; nullptr in production
   int timeline_cap;
-  int debug_flags;          // debug: 1 = skip the MMAs, 2 = skip the TMA loads (barriers still cycle), 4 = skip epilogue work
+  int debug_flags;          // debug: 1 = skip the MMAs, 2 = skip the TMA loads (barriers still cycle)
   float* dbg_f32;           // validation: fp32 accumulators [pixel][Cout] written next to the stored result (nullptr in production)
 };
 
@@ -157,6 +161,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 }
 
+__host__ __device__ constexpr uint32_t make_idesc_m(int n, int m) {      // M = 256: the cta_group::2 pair
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
 constexpr int kSlabCols = 64;                  // epilogue slab: 64 bf16 columns = one 128-byte swizzled row
 constexpr int kSlabBytes = kBlockM * 128;      // 16 KiB staging tile
 
@@ -177,22 +185,52 @@ struct Cfg {
 //              shared-memory descriptors into that halo (row pitch 16 pixels = 2 KiB, so every 8-pixel swizzle atom of a
 //              tap view keeps the phase of its first row).  3x3 stride-1 only.  Each input pixel crosses L2 -> SM once
 //              per tile instead of nine times: the tap re-reads are what bounds the 3x3 layers otherwise.
-template <int BN, bool TL, int AM>
+//
+// PAIR (cta_group::2, BN = 256 linear tiles with a long main loop): the grid is launched as clusters of two CTAs (one TPC).  The
+// pair computes a 256-pixel x 256-channel tile with ONE tcgen05.mma.cta_group::2 stream issued by the leader (cluster rank 0):
+// every CTA stages its own 128 A rows and only its HALF of the weight slab (B rows [r * 128, +128) of the tile's 256 channels),
+// so a K block moves 32 KiB instead of 48 KiB through each SM's shared memory -- the operand bandwidth that holds the
+// single-CTA BN = 256 main loop at ~77 % of the tensor pipe -- and the ring gets six stages instead of four.  The
+// accumulator halves land in each CTA's own TMEM; epilogue, statistics and stores are those of two independent M tiles.
+//   full[s]   lives in the leader only: 4 arrivals (A and B producer of both CTAs; the peer's arrive remotely), the TMA
+//             loads of both CTAs complete their bytes there (.cta_group::2 load form)
+//   empty[s], tmem_full[a]   one per CTA, signalled together by the leader's multicast tcgen05.commit
+//   tmem_empty[a]   leader only: one elected arrival per convert warp of both CTAs (16)
+template <int BN, bool TL, int AM, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const Params p) {
   using C = Cfg<BN>;
   constexpr bool LIN = (AM == 1);
   constexpr bool HALO = (AM == 2);
+  static_assert(!PAIR || (LIN && BN == 256), "pair mode: linear tiles, BN = 256");
+  constexpr int kBB = PAIR ? C::kBBytes / 2 : C::kBBytes;   // weight bytes per 64-deep K block in THIS CTA's shared memory
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  // tile walk: (first, step, end) of this CTA's loop over tiles (pair mode: over pair tiles, shared by the two CTAs)
+  // (expressions, not variables: blockIdx / gridDim / kernel parameters cost no registers)
+#define SY_T_FIRST (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x)
+#define SY_T_STEP (PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x)
+#define SY_T_END (PAIR ? p.total_tiles2 : p.total_tiles)
+  auto tile_nm = [&](int tile, int& n_tile, int& m_tile) {
+    if constexpr (PAIR) {
+      n_tile = fdiv(tile, p.fd_m_tiles2);
+      m_tile = 2 * (tile - n_tile * p.m_tiles2) + (int)crank;
+    } else {
+      n_tile = fdiv(tile, p.fd_m_tiles);
+      m_tile = tile - n_tile * p.m_tiles;
+    }
+  };
   const int S = p.stages;                                  // patch/linear: A+B ring depth; halo: B ring depth
   // 64-deep K sub-blocks per ring stage; halo mode: filter taps per weight-ring stage (one barrier round per filter row)
-  constexpr int kSub = HALO ? (BN == 256 ? 1 : 3) : C::kSub;
+  // (pair mode: a stage is 32 KiB per sub-block, so two fit three deep -- and a producer warp needs ~300 cycles for the
+  // barrier round plus ~250 per load: one round per K = 128 keeps it below the MMA time of two K blocks)
+  constexpr int kSub = HALO ? (BN == 256 ? 1 : 3) : (PAIR ? 2 : C::kSub);
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms; plain pointer arithmetic keeps the shared address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = sA + (HALO ? p.stagesA * p.halo_bytes : S * kSub * kABytes);
-  uint8_t* sStage = sB + S * kSub * C::kBBytes;                                 // 1024-aligned: the rings are multiples of 1 KiB
+  uint8_t* sStage = sB + S * kSub * kBB;                                 // 1024-aligned: the rings are multiples of 1 KiB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + p.stage_tiles * kSlabBytes);
   const int sflip = p.stage_tiles - 1;                                          // slab parity toggles the tile iff there are two
   // bars: [0,8) full, [8,16) empty, [16,18) tmem_full, [18,20) tmem_empty, then the tmem base slot
@@ -219,7 +257,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmY);
     for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), HALO ? 1 : 2);     // A producer + B producer (halo: B only)
+      mbar_init(full_bar(s), HALO ? 1 : (PAIR ? 4 : 2));     // A producer + B producer (halo: B only; pair: of both CTAs)
       mbar_init(empty_bar(s), 1);
     }
     if (HALO) {
@@ -232,13 +270,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(tfull_bar(a), 1);
       // arrivals per accumulator hand-back: both convert warpgroups, except in team mode at BN = 64 (one slab per tile:
       // only the warpgroup that owns the tile's slab ever reads the accumulator)
-      mbar_init(tempty_bar(a), (p.team && BN == kSlabCols) ? kEpiThreads / 2 : kEpiThreads);
+      mbar_init(tempty_bar(a), PAIR ? 16 : ((p.team && BN == kSlabCols) ? kEpiThreads / 2 : kEpiThreads));
     }
     fence_barrier_init();
   }
-  if (warp == 17) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
+  if (warp == 17) {
+    if constexpr (PAIR) tmem_alloc_2cta(smem_u32(tmem_slot), C::kTmemCols);
+    else tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
+  }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync();     // both CTAs' barriers and TMEM exist before anybody signals / writes them
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above touched only smem / TMEM / kernel parameters; from here on we read what the previous kernels wrote
@@ -255,8 +297,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 18) {                            // A: one halo box [18 rows][pitch px][64 ch] per (tile, channel block)
       int sa = 0;
       uint32_t pha = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
+      for (int tile = SY_T_FIRST; tile < SY_T_END; tile += SY_T_STEP) {
+        int n_tile, m_tile;
+        tile_nm(tile, n_tile, m_tile);
         const int img = fdiv(m_tile, p.fd_per_img), rem = m_tile - img * per_img;
         const int py = fdiv(rem, p.fd_tiles_x), px = rem - py * p.tiles_x;
         for (int cb = 0; cb < p.cblocks; ++cb) {
@@ -272,8 +315,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {                                     // B: one [BN][64] weight slab per (channel block, tap)
       int sb = 0;
       uint32_t phb = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n_tile = fdiv(tile, p.fd_m_tiles);
+      for (int tile = SY_T_FIRST; tile < SY_T_END; tile += SY_T_STEP) {
+        int n_tile, m_tile_unused;
+        tile_nm(tile, n_tile, m_tile_unused);
         for (int cb = 0; cb < p.cblocks; ++cb) {
           for (int t0 = 0; t0 < 9; t0 += kSub) {
             mbar_wait(empty_bar(sb), phb ^ 1u);
@@ -295,7 +339,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int sa = 0, sb = 0, it = 0;
     uint32_t pha = 0, phb = 0;
     const uint32_t row_bytes = (uint32_t)p.halo_pitch * 128u;            // one halo row; also the stride between 8-pixel atoms
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = SY_T_FIRST; tile < SY_T_END; tile += SY_T_STEP, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -341,8 +385,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int tl_n = is_a ? 0 : p.timeline_cap / 8;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
+      for (int tile = SY_T_FIRST; tile < SY_T_END; tile += SY_T_STEP) {
+        int n_tile, m_tile;
+        tile_nm(tile, n_tile, m_tile);
         int img, y0, x0;
         if constexpr (LIN) {
           const int p0 = m_tile * kBlockM;
@@ -361,19 +406,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int sb0 = 0; sb0 < p.kblocks; sb0 += kSub) {
           const int nsub = min(kSub, p.kblocks - sb0);
           mbar_wait(empty_bar(stage), phase ^ 1u);          // whole warp waits: control flow stays uniform
+          // pair mode: the full barrier is the LEADER's (cluster address); the leader's producers expect the bytes of both CTAs
+          const uint32_t fbar = PAIR ? mapa(full_bar(stage), 0u) : full_bar(stage);
           if (elect_one()) {
             tl_rec<TL>(p, tl_n, is_a ? 0 : 3, 0, tile, sb0);
-            if (p.debug_flags & 2) {
+            if constexpr (PAIR) {
+              if (crank != 0u || (p.debug_flags & 2)) mbar_arrive_cluster(fbar);
+              else mbar_expect_tx(full_bar(stage), 2u * (uint32_t)nsub * (is_a ? a_bytes : (uint32_t)kBB));
+            } else if (p.debug_flags & 2) {
               mbar_arrive(full_bar(stage));
             } else if (is_a) {
               mbar_expect_tx(full_bar(stage), a_bytes * (uint32_t)nsub);
             } else {
               mbar_expect_tx(full_bar(stage), (uint32_t)(C::kBBytes * nsub));
             }
+            tl_rec<TL>(p, tl_n, is_a ? 0 : 3, 1, tile, sb0);
           }
           for (int j = 0; j < nsub; ++j) {
             if (!(p.debug_flags & 2) && elect_one()) {
-              if (is_a) {
+              if constexpr (PAIR) {
+                if (is_a)
+                  tma_load_im2col_4d_2cta(smem_u32(sA + (stage * kSub + j) * kABytes), &tmA, fbar, cb * kBlockK, x0, y0, img, (uint16_t)sx,
+                                          (uint16_t)r);
+                else                        // this CTA's half of the tile's 256 weight rows
+                  tma_load_3d_2cta(smem_u32(sB + (stage * kSub + j) * kBB), &tmB, fbar, cb * kBlockK, r * p.kw + sx,
+                                   n_tile * BN + (int)crank * (BN / 2));
+              } else if (is_a) {
                 if constexpr (LIN)
                   tma_load_im2col_4d(smem_u32(sA + (stage * kSub + j) * kABytes), &tmA, full_bar(stage), cb * kBlockK, x0,
                                      y0, img, (uint16_t)sx, (uint16_t)r);
@@ -386,6 +444,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (++cb == p.cblocks) { cb = 0; if (++sx == p.kw) { sx = 0; ++r; } }
           }
+          if (TL && elect_one()) tl_rec<TL>(p, tl_n, is_a ? 0 : 3, 2, tile, sb0);
           __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
@@ -395,12 +454,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // -------------------------------------------------------------- MMA issuer
     // The whole warp walks the pipeline (uniform control flow, operands in uniform registers); one elected
     // lane issues the tcgen05 instructions.
-    constexpr uint32_t idesc = make_idesc(BN);
+    constexpr uint32_t idesc = PAIR ? make_idesc_m(BN, 2 * kBlockM) : make_idesc(BN);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     int tl_n = p.timeline_cap / 4;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = (PAIR && crank != 0u) ? SY_T_END : SY_T_FIRST; tile < SY_T_END; tile += SY_T_STEP, ++it) {   // pair: the leader issues
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -415,16 +474,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (!(p.debug_flags & 1)) {
             for (int j = 0; j < nsub; ++j) {
               const uint64_t da = make_smem_desc(smem_u32(sA + (stage * kSub + j) * kABytes));
-              const uint64_t db = make_smem_desc(smem_u32(sB + (stage * kSub + j) * C::kBBytes));
+              const uint64_t db = make_smem_desc(smem_u32(sB + (stage * kSub + j) * kBB));
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k) {
                 // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-                umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (sb0 | j | k) != 0);
+                if constexpr (PAIR) umma_bf16_2cta(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (sb0 | j | k) != 0);
+                else umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (sb0 | j | k) != 0);
               }
             }
           }
-          umma_commit(empty_bar(stage));            // frees the smem slot when these MMAs retire
-          if (sb0 + kSub >= p.kblocks) umma_commit(tfull_bar(acc));
+          tl_rec<TL>(p, tl_n, 1, 2, tile, sb0);
+          if constexpr (PAIR) {                     // the same barrier offsets in BOTH CTAs
+            umma_commit_2cta(empty_bar(stage));
+            if (sb0 + kSub >= p.kblocks) umma_commit_2cta(tfull_bar(acc));
+          } else {
+            umma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
+            if (sb0 + kSub >= p.kblocks) umma_commit(tfull_bar(acc));
+          }
+          tl_rec<TL>(p, tl_n, 1, 3, tile, sb0);
         }
         __syncwarp();
         if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -440,8 +507,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nbar = p.team ? 416 : 544;
     bar_free_arrive(0, nbar);                    // both tiles start out free
     if (sflip) bar_free_arrive(1, nbar);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
+    for (int tile = SY_T_FIRST; tile < SY_T_END; tile += SY_T_STEP) {
+      int n_tile, m_tile;
+        tile_nm(tile, n_tile, m_tile);
       int c1, c2, c3;                            // store coordinates below the channel: (x, y, image) | (pixel, 0, 0)
       if constexpr (LIN) {
         c1 = m_tile * kBlockM; c2 = 0; c3 = 0;
@@ -563,8 +631,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int j = 0; j < kAccSlabs; ++j) reduce_store(acc[j], pend_grp, pend_n0 + j * kSlabCols);
       pend_grp = -1;
     };
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
+    for (int tile = SY_T_FIRST; tile < SY_T_END; tile += SY_T_STEP) {
+      int n_tile, m_tile;
+        tile_nm(tile, n_tile, m_tile);
       const int n0 = n_tile * BN;
       // rows [0, cut) of the tile belong to statistics group 0, rows [cut, 128) to group 1 (a patch tile lies in one
       // image = one group; a linear tile can straddle the boundary; rows past the end of the tensor were staged as zeros)
@@ -651,7 +720,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int team = half;
       constexpr int kSlabs = BN / kSlabCols;
       const uint32_t my_tile_row = my_row + (uint32_t)(team * kSlabBytes);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = SY_T_FIRST; tile < SY_T_END; tile += SY_T_STEP, ++it) {
         const int gs0 = it * kSlabs;                                   // global index of this tile's first slab
         int first = ((gs0 & 1) == team) ? 0 : 1;                       // first slab of the tile this warpgroup owns
         if (first >= kSlabs) continue;
@@ -659,7 +728,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         while (last + 2 < kSlabs) last += 2;
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-        const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
+        int n_tile, m_tile;
+        tile_nm(tile, n_tile, m_tile);
         bool valid;
         long long pix;
         if constexpr (LIN) {
@@ -725,10 +795,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       bar_free_wait(team, 416);                                        // drain the last arrivals of this warpgroup's tile
       asm volatile("bar.sync 4, 288;" ::: "memory");
     } else {
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = SY_T_FIRST; tile < SY_T_END; tile += SY_T_STEP, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
+      int n_tile, m_tile;
+        tile_nm(tile, n_tile, m_tile);
       bool valid;
       long long pix;                             // this thread's output pixel in the flattened (n, oh, ow) space
       if constexpr (LIN) {
@@ -768,7 +839,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (slab == BN / kSlabCols - 1) {
           // every TMEM read of this accumulator is complete: hand it back to the MMA warp
           tcgen05_fence_before();
-          mbar_arrive(tempty_bar(acc));
+          if constexpr (PAIR) {                      // ... of the leader: one arrival per warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(acc), 0u));
+          } else {
+            mbar_arrive(tempty_bar(acc));
+          }
         }
         if (p.dbg_f32 != nullptr && valid) {       // validation only: the accumulators before any rounding
           float* o = p.dbg_f32 + pix * p.Cout + n0 + cl;
@@ -915,8 +991,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           constexpr int CPR = BN / 8;                              // 16-byte chunks per pixel row of a tile
           constexpr int RPP = kTailThreads / CPR;                  // tile rows handled per pass of the 512 threads
           const int chunk = et % CPR, r0 = et / CPR;
-          for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int n_tile = fdiv(tile, p.fd_m_tiles), m_tile = tile - n_tile * p.m_tiles;
+          for (int tile = SY_T_FIRST; tile < SY_T_END; tile += SY_T_STEP) {
+            int n_tile, m_tile;
+        tile_nm(tile, n_tile, m_tile);
             const int cg = n_tile * BN + chunk * 8;
             if (cg >= p.Cout) continue;
             int img = 0, py = 0, px = 0;
@@ -993,14 +1070,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync();     // the peer's MMAs read this CTA's operands and write its TMEM: leave together
+  else __syncthreads();
   if (threadIdx.x == 16 * 32) tl_rec<TL>(p, tl_k, 4, 3, 0, 0);
   if (warp == 17) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if constexpr (PAIR) tmem_dealloc_2cta(tmem_base, C::kTmemCols);
+    else tmem_dealloc(tmem_base, C::kTmemCols);
   }
   if (threadIdx.x == 17 * 32) { int k2 = tl_k + 8; tl_rec<TL>(p, k2, 4, 4, 0, 0); }
 }
+
+#undef SY_T_FIRST
+#undef SY_T_STEP
+#undef SY_T_END
 
 // ------------------------------------------------------------------ host side
 
@@ -1041,6 +1124,10 @@ static void pick_patch(int ho, int wo, int* th, int* tw) {
 static double epi_cycles_per_slab(int bn) { (void)bn; return 1900.0; }
 
 static int pick_bn(int cout, int m_tiles, int kblocks) {
+  if (const char* e = getenv("SY_CONV_BN")) {            // tuning / test aid: force the tile width
+    const int v = atoi(e);
+    if (v == 64 || v == 128 || v == 256) return v;
+  }
   const int cands[3] = {256, 128, 64};
   const double kbc[3] = {665.0, 515.0, 560.0};
   int best_bn = 64;
@@ -1122,6 +1209,85 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   else
     SY_CUDA(launch_pdl(conv_tc_kernel<BN, false, AM>, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
   return launch_status("conv_tc_kernel");
+}
+
+// ---- pair mode (cta_group::2) ------------------------------------------------------------------------------------------
+// How many 2-CTA clusters of the pair kernel can be resident at once (the BatchNorm tail's grid barrier needs all of them;
+// 74 on a B200: 148 SMs in TPC pairs).  0 = clusters cannot be launched.
+static int resident_pairs(size_t smem) {
+  static size_t seen_smem[4] = {0, 0, 0, 0};
+  static int seen_n[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 4; ++i)
+    if (seen_smem[i] == smem) return seen_n[i];
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<256, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc_kernel<256, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(num_sms() & ~1);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<256, false, 1, true>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  for (int i = 0; i < 4; ++i)
+    if (seen_smem[i] == 0) { seen_smem[i] = smem; seen_n[i] = n; break; }
+  return n;
+}
+
+// Decide pair mode for a linear-tile BN = 256 layer and, if chosen, fill the pair fields of p (tiles, ring depth, grid).
+// Main-loop-bound layers only (the epilogue of a tile hides behind the next tile's K loop), and only when pairing M tiles
+// does not add a round of the persistent grid.  SY_CONV_PAIR=0 disables, =1 forces it on every eligible layer.
+static bool plan_pair(Params& p, int* grid_out, int* smem_out) {
+  const char* e = getenv("SY_CONV_PAIR");
+  if (e != nullptr && e[0] == '0') return false;
+  const bool force = e != nullptr && e[0] == '1';
+  if (p.ap_y != nullptr && !force) return false;
+  const int m2 = cdiv(p.m_tiles, 2), total2 = m2 * p.n_tiles;
+  const int acc_bytes = (p.mode == SY_CONV_RAW && p.partials) ? 16 * p.Cout : 2048;
+  const int fixed_bytes = Cfg<256>::kFixedBytes;
+  const int stage_bytes = 2 * (kABytes + Cfg<256>::kBBytes / 2);          // two 64-deep sub-blocks per stage (kernel: kSub)
+  int stages = (kSmemLimit - fixed_bytes - acc_bytes) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if ((p.debug_flags >> 8) & 15) stages = min(stages, (p.debug_flags >> 8) & 15);
+  if (stages < 2) return false;
+  const int smem = fixed_bytes + acc_bytes + stages * stage_bytes;
+  if (!force) {
+    if (p.kblocks * 665.0 < epi_cycles_per_slab(256) * 4) return false;          // epilogue-bound: nothing to gain
+  }
+  const int pairs = resident_pairs((size_t)smem);
+  if (pairs < 1) return false;
+  if (!force && cdiv(total2, pairs) > cdiv(p.total_tiles, num_sms())) return false;
+  p.m_tiles2 = m2;
+  p.total_tiles2 = total2;
+  p.fd_m_tiles2 = make_fastdiv((uint32_t)m2);
+  p.stages = stages;
+  p.stage_tiles = 1;
+  p.team = 0;
+  *grid_out = 2 * (total2 < pairs ? total2 : pairs);
+  *smem_out = smem;
+  return true;
+}
+
+static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, Params& p, int grid, int smem,
+                       cudaStream_t stream) {
+  if (p.timeline != nullptr)
+    SY_CUDA(launch_pdl_cluster(conv_tc_kernel<256, true, 1, true>, 2, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
+  else
+    SY_CUDA(launch_pdl_cluster(conv_tc_kernel<256, false, 1, true>, 2, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
+  return launch_status("conv_tc_kernel(pair)");
 }
 
 template <int AM>
@@ -1260,7 +1426,9 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
       }
     }
   }
-  if (d->rows_written) *d->rows_written = p.total_tiles < tc::num_sms() ? p.total_tiles : tc::num_sms();
+  int pair_grid = 0, pair_smem = 0;
+  const bool pair = lin && bn == 256 && tc::plan_pair(p, &pair_grid, &pair_smem);
+  if (d->rows_written) *d->rows_written = pair ? pair_grid : (p.total_tiles < tc::num_sms() ? p.total_tiles : tc::num_sms());
 
   // A: input view as (C, W, H, N), box (64, TW*s, TH*s, 1) traversed with element strides (1, s, s, 1)
   CUtensorMap ta, tb, ty;
@@ -1308,7 +1476,7 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
     const int taps = d->kh * d->kw;
     cuuint64_t dims[3] = {(cuuint64_t)x.c, (cuuint64_t)taps, (cuuint64_t)y.c};
     cuuint64_t strides[2] = {(cuuint64_t)x.c * 2, (cuuint64_t)x.c * 2 * taps};
-    cuuint32_t box[3] = {(cuuint32_t)tc::kBlockK, 1, (cuuint32_t)bn};
+    cuuint32_t box[3] = {(cuuint32_t)tc::kBlockK, 1, (cuuint32_t)(pair ? bn / 2 : bn)};   // pair: each CTA loads half a slab
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->w), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1336,6 +1504,7 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SY_REQUIRE(r == CUDA_SUCCESS, SY_ELAUNCH, "cuTensorMapEncodeTiled(Y) failed: %d", (int)r);
   }
+  if (pair) return tc::launch_pair(ta, tb, ty, p, pair_grid, pair_smem, stream);
   if (halo) return tc::launch_bn<2>(bn, ta, tb, ty, p, stream);
   if (lin) return tc::launch_bn<1>(bn, ta, tb, ty, p, stream);
   return tc::launch_bn<0>(bn, ta, tb, ty, p, stream);

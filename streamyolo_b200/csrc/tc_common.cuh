@@ -63,6 +63,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// (Tried and rejected, round 2: polling with ONE lane per warp + __syncwarp instead of all 32 lanes -- 31.4 -> 36.0 us on the
+// 3x3 256->256 layer: the wake-up after the phase flip gets slower, and nothing else gets faster.)
 // one lane of a fully converged warp; keeps the surrounding control flow warp-uniform so that the
 // compiler holds descriptors / addresses in uniform registers (no per-lane serialisation loops)
 __device__ __forceinline__ bool elect_one() {
@@ -157,6 +159,67 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// ---- cta_group::2: a cluster of two CTAs (one TPC) works on ONE 256-row tile; CTA rank 0 (the leader) issues the MMAs.
+// Forms as in the CUTLASS headers vendored in the image (cute/arch/copy_sm100_tma.hpp SM100_TMA_2SM_LOAD_IM2COL_4D,
+// cute/arch/mma_sm100_umma.hpp SM100_MMA_F16BF16_2x1SM_SS, cutlass/arch/barrier.h umma_arrive_multicast_2x1SM),
+// verified on hardware with tools/cta2_probe.cu.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> the same offset in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  // default semantics (as cutlass::arch::ClusterBarrier::arrive(cta_id)): an explicit .release.cluster costs ~1000 cycles
+  // per arrival (it waits for the thread's outstanding global accesses) and made the peer's producers the bottleneck
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// loads into THIS CTA's shared memory whose bytes complete on a barrier that may live in the peer CTA (cluster address)
+__device__ __forceinline__ void tma_load_im2col_4d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0,
+                                                        int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(cluster_bar), "r"(c0), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1,
+                                                 int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// completion of the pair's MMAs -> the mbarrier at this shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+// D[tmem of both CTAs, 256 rows] (+)= A[128 rows from each CTA's smem] * B[N/2 rows from each CTA's smem]
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }

@@ -40,7 +40,7 @@ t = tl.view(cap, 2).cpu().numpy()
 ev = [(int(c), int(e) >> 28, (int(e) >> 24) & 15, (int(e) >> 8) & 0xffff, int(e) & 255) for e, c in t if c != 0]
 ev.sort()
 t0 = ev[0][0]
-names = {(0, 0): "PA slot-free", (3, 0): "PB slot-free", (1, 0): "M acc-free", (1, 1): "M data-landed", (1, 2): "M issued", (1, 3): "M committed", (4, 0): "K entry", (4, 1): "K setup-done", (4, 2): "K tiles-done", (4, 3): "K all-synced", (4, 4): "K tmem-freed", (2, 0): "E tile-start", (2, 1): "E acc-ready",
+names = {(0, 0): "PA slot-free", (3, 0): "PB slot-free", (0, 1): "PA expect-tx", (3, 1): "PB expect-tx", (0, 2): "PA tma-issued", (3, 2): "PB tma-issued", (1, 0): "M acc-free", (1, 1): "M data-landed", (1, 2): "M issued", (1, 3): "M committed", (4, 0): "K entry", (4, 1): "K setup-done", (4, 2): "K tiles-done", (4, 3): "K all-synced", (4, 4): "K tmem-freed", (2, 0): "E tile-start", (2, 1): "E acc-ready",
          (2, 2): "E converted", (2, 3): "E staged", (2, 4): "E slab-done", (5, 0): "S staged-seen", (5, 1): "S rows-loaded",
          (5, 2): "S reduced", (6, 0): "T staged-seen", (6, 1): "T store-read-done"}
 tiles = sorted({e[3] for e in ev})
