@@ -186,7 +186,7 @@ struct Cfg {
 //              tap view keeps the phase of its first row).  3x3 stride-1 only.  Each input pixel crosses L2 -> SM once
 //              per tile instead of nine times: the tap re-reads are what bounds the 3x3 layers otherwise.
 //
-// PAIR (cta_group::2, BN = 256 linear tiles with a long main loop): the grid is launched as clusters of two CTAs (one TPC).  The
+// PAIR (cta_group::2, linear or halo tiles with a long main loop): the grid is launched as clusters of two CTAs (one TPC).  The
 // pair computes a 256-pixel x 256-channel tile with ONE tcgen05.mma.cta_group::2 stream issued by the leader (cluster rank 0):
 // every CTA stages its own 128 A rows and only its HALF of the weight slab (B rows [r * 128, +128) of the tile's 256 channels),
 // so a K block moves 32 KiB instead of 48 KiB through each SM's shared memory -- the operand bandwidth that holds the
@@ -203,7 +203,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using C = Cfg<BN>;
   constexpr bool LIN = (AM == 1);
   constexpr bool HALO = (AM == 2);
-  static_assert(!PAIR || (LIN && BN == 256), "pair mode: linear tiles, BN = 256");
+  static_assert(!PAIR || AM != 0, "pair mode: linear or halo tiles");
   constexpr int kBB = PAIR ? C::kBBytes / 2 : C::kBBytes;   // weight bytes per 64-deep K block in THIS CTA's shared memory
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
   // tile walk: (first, step, end) of this CTA's loop over tiles (pair mode: over pair tiles, shared by the two CTAs)
@@ -225,6 +225,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // (pair mode: a stage is 32 KiB per sub-block, so two fit three deep -- and a producer warp needs ~300 cycles for the
   // barrier round plus ~250 per load: one round per K = 128 keeps it below the MMA time of two K blocks)
   constexpr int kSub = HALO ? (BN == 256 ? 1 : 3) : (PAIR ? 2 : C::kSub);
+  static_assert(!PAIR || C::kSub <= 2, "pair mode: the host sizes the ring for two sub-blocks per stage");
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms; plain pointer arithmetic keeps the shared address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -257,12 +258,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmY);
     for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), HALO ? 1 : (PAIR ? 4 : 2));     // A producer + B producer (halo: B only; pair: of both CTAs)
+      mbar_init(full_bar(s), (HALO ? 1 : 2) * (PAIR ? 2 : 1));     // A producer + B producer (halo: B only; pair: of both CTAs)
       mbar_init(empty_bar(s), 1);
     }
     if (HALO) {
       for (int s = 0; s < p.stagesA; ++s) {
-        mbar_init(fullA_bar(s), 1);
+        mbar_init(fullA_bar(s), PAIR ? 2 : 1);
         mbar_init(emptyA_bar(s), 1);
       }
     }
@@ -305,8 +306,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int cb = 0; cb < p.cblocks; ++cb) {
           mbar_wait(emptyA_bar(sa), pha ^ 1u);
           if (elect_one()) {
-            mbar_expect_tx(fullA_bar(sa), (uint32_t)p.halo_tx);
-            tma_load_4d(smem_u32(sA + sa * p.halo_bytes), &tmA, fullA_bar(sa), cb * kBlockK, px * p.tw - 1, py * p.th - 1, img);
+            if constexpr (PAIR) {                // the leader's barrier collects the bytes of both CTAs' halos
+              const uint32_t fbar = mapa(fullA_bar(sa), 0u);
+              if (crank != 0u) mbar_arrive_cluster(fbar);
+              else mbar_expect_tx(fullA_bar(sa), 2u * (uint32_t)p.halo_tx);
+              tma_load_4d_2cta(smem_u32(sA + sa * p.halo_bytes), &tmA, fbar, cb * kBlockK, px * p.tw - 1, py * p.th - 1, img);
+            } else {
+              mbar_expect_tx(fullA_bar(sa), (uint32_t)p.halo_tx);
+              tma_load_4d(smem_u32(sA + sa * p.halo_bytes), &tmA, fullA_bar(sa), cb * kBlockK, px * p.tw - 1, py * p.th - 1, img);
+            }
           }
           __syncwarp();
           if (++sa == p.stagesA) { sa = 0; pha ^= 1u; }
@@ -321,11 +329,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int cb = 0; cb < p.cblocks; ++cb) {
           for (int t0 = 0; t0 < 9; t0 += kSub) {
             mbar_wait(empty_bar(sb), phb ^ 1u);
-            if (elect_one()) mbar_expect_tx(full_bar(sb), (uint32_t)(kSub * C::kBBytes));
+            const uint32_t fbar = PAIR ? mapa(full_bar(sb), 0u) : full_bar(sb);
+            if (elect_one()) {
+              if (PAIR && crank != 0u) mbar_arrive_cluster(fbar);
+              else mbar_expect_tx(full_bar(sb), (uint32_t)(kSub * kBB) * (PAIR ? 2u : 1u));
+            }
 #pragma unroll
             for (int j = 0; j < kSub; ++j) {
-              if (elect_one())
-                tma_load_3d(smem_u32(sB + (sb * kSub + j) * C::kBBytes), &tmB, full_bar(sb), cb * kBlockK, t0 + j, n_tile * BN);
+              if (elect_one()) {
+                if constexpr (PAIR)              // this CTA's half of the tile's weight rows
+                  tma_load_3d_2cta(smem_u32(sB + (sb * kSub + j) * kBB), &tmB, fbar, cb * kBlockK, t0 + j,
+                                   n_tile * BN + (int)crank * (BN / 2));
+                else
+                  tma_load_3d(smem_u32(sB + (sb * kSub + j) * kBB), &tmB, full_bar(sb), cb * kBlockK, t0 + j, n_tile * BN);
+              }
             }
             __syncwarp();
             if (++sb == S) { sb = 0; phb ^= 1u; }
@@ -335,11 +352,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (HALO && warp == 19) {
     // ----------------------------------------------- halo mode MMA issuer: K order = (channel block, tap)
-    constexpr uint32_t idesc = make_idesc(BN);
+    constexpr uint32_t idesc = PAIR ? make_idesc_m(BN, 2 * kBlockM) : make_idesc(BN);
     int sa = 0, sb = 0, it = 0;
     uint32_t pha = 0, phb = 0;
     const uint32_t row_bytes = (uint32_t)p.halo_pitch * 128u;            // one halo row; also the stride between 8-pixel atoms
-    for (int tile = SY_T_FIRST; tile < SY_T_END; tile += SY_T_STEP, ++it) {
+    for (int tile = (PAIR && crank != 0u) ? SY_T_END : SY_T_FIRST; tile < SY_T_END; tile += SY_T_STEP, ++it) {   // pair: the leader issues
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -359,15 +376,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t a_addr = halo + (uint32_t)r * row_bytes + (uint32_t)sx * 128u;
               const uint32_t boff = (p.debug_flags & 64) ? ((a_addr >> 7) & 7u) : 0u;
               const uint64_t da = make_smem_desc_ex(a_addr, row_bytes, boff);
-              const uint64_t db = make_smem_desc(smem_u32(sB + (sb * kSub + j) * C::kBBytes));
+              const uint64_t db = make_smem_desc(smem_u32(sB + (sb * kSub + j) * kBB));
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cb | tap | k) != 0);
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                if constexpr (PAIR) umma_bf16_2cta(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cb | tap | k) != 0);
+                else umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cb | tap | k) != 0);
+              }
             }
-            umma_commit(empty_bar(sb));                       // the weight slabs are free when these MMAs retire
-            if (t0 + kSub >= 9) {
-              umma_commit(emptyA_bar(sa));                    // ... and so is the halo after its ninth tap
-              if (cb == p.cblocks - 1) umma_commit(tfull_bar(acc));
+            if constexpr (PAIR) {                             // (the same barrier offsets in both CTAs)
+              umma_commit_2cta(empty_bar(sb));
+              if (t0 + kSub >= 9) {
+                umma_commit_2cta(emptyA_bar(sa));
+                if (cb == p.cblocks - 1) umma_commit_2cta(tfull_bar(acc));
+              }
+            } else {
+              umma_commit(empty_bar(sb));                     // the weight slabs are free when these MMAs retire
+              if (t0 + kSub >= 9) {
+                umma_commit(emptyA_bar(sa));                  // ... and so is the halo after its ninth tap
+                if (cb == p.cblocks - 1) umma_commit(tfull_bar(acc));
+              }
             }
           }
           __syncwarp();
@@ -1147,46 +1174,141 @@ static int pick_bn(int cout, int m_tiles, int kblocks) {
 
 static const int kSmemLimit = 232448;   // 227 KiB opt-in maximum per CTA
 
-template <int BN, int AM>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, Params& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, false, AM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    SY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, true, AM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    attr_set = true;
+struct Plan {
+  int smem, grid;
+  bool pair;
+};
+
+template <int BN, int AM, bool PAIR>
+static bool set_smem_attr() {
+  static int state = 0;                 // 0 = not tried, 1 = ok, -1 = failed
+  if (state == 0) {
+    const bool ok =
+        cudaFuncSetAttribute(conv_tc_kernel<BN, false, AM, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) == cudaSuccess &&
+        cudaFuncSetAttribute(conv_tc_kernel<BN, true, AM, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    state = ok ? 1 : -1;
   }
+  return state == 1;
+}
+
+// How many 2-CTA clusters of the pair kernel can be resident at once (the BatchNorm tail's grid barrier needs all of them;
+// 74 on a B200: 148 SMs in TPC pairs).  0 = clusters cannot be launched.
+template <int BN, int AM>
+static int resident_pairs(size_t smem) {
+  if constexpr (AM == 0) {
+    return 0;
+  } else {
+    static size_t seen_smem[4] = {0, 0, 0, 0};
+    static int seen_n[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i)
+      if (seen_smem[i] == smem) return seen_n[i];
+    if (!set_smem_attr<BN, AM, true>()) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms() & ~1);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<BN, false, AM, true>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      n = 0;
+    }
+    for (int i = 0; i < 4; ++i)
+      if (seen_smem[i] == 0) { seen_smem[i] = smem; seen_n[i] = n; break; }
+    return n;
+  }
+}
+
+// Ring depth, staging tiles, shared-memory size and grid of one launch; decides pair mode (cta_group::2).
+// Pair mode is for main-loop-bound layers (the epilogue of a tile hides behind the next tile's K loop), and only when pairing
+// the M tiles does not add a round of the persistent grid.  SY_CONV_PAIR=0 disables it, =1 forces it on every layer with
+// linear or halo tiles.
+template <int BN, int AM>
+static int make_plan(Params& p, Plan* out) {
   const int acc_bytes = (p.mode == SY_CONV_RAW && p.partials) ? 16 * p.Cout : 2048;
   // epilogue-bound layers (main loop of a tile shorter than its epilogue: 1x1 convs with few input channels, the
   // stem) get a second staging tile: the store + statistics of a slab then overlap the conversion of the next
-  {
-    const double kbc = BN == 256 ? 665.0 : (BN == 128 ? 515.0 : 560.0);
-    p.stage_tiles = (p.kblocks * kbc < epi_cycles_per_slab(BN) * (BN / 64)) ? 2 : 1;
+  const double kbc = BN == 256 ? 665.0 : (BN == 128 ? 515.0 : 560.0);
+  const bool main_loop_bound = !(p.kblocks * kbc < epi_cycles_per_slab(BN) * (BN / 64));
+  bool pair = false;
+  if (AM != 0) {
+    const char* e = getenv("SY_CONV_PAIR");
+    const bool off = e != nullptr && e[0] == '0', force = e != nullptr && e[0] == '1';
+    pair = !off && (force || (main_loop_bound && p.ap_y == nullptr));
+  }
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    p.stage_tiles = main_loop_bound ? 1 : 2;
     if (const char* e = getenv("SY_STAGE_TILES")) p.stage_tiles = (e[0] == '2') ? 2 : 1;   // tuning aid
     // epilogue-bound layers in RAW mode: the two convert warpgroups take alternate slabs (SY_CONV_TEAM=0 turns it off)
     p.team = (p.stage_tiles == 2 && p.mode == SY_CONV_RAW) ? 1 : 0;
     if (const char* e = getenv("SY_CONV_TEAM")) p.team = (e[0] != '0' && p.stage_tiles == 2 && p.mode == SY_CONV_RAW) ? 1 : 0;
+    if (pair) { p.stage_tiles = 1; p.team = 0; }
+    const int bbytes = Cfg<BN>::kBBytes / (pair ? 2 : 1);          // weight bytes per 64-deep K block in one CTA
+    const int fixed_bytes = Cfg<BN>::kFixedBytes + (p.stage_tiles - 1) * kSlabBytes;
+    int smem;
+    if (AM == 2) {
+      // halo ring (2-3 stages of 23 KiB) + weight-slab ring (the rest, `taps` slabs per stage)
+      const int taps = (BN == 256) ? 1 : 3;                        // filter taps per weight-ring stage (kernel: kSub)
+      p.stagesA = (BN == 64 && p.cblocks > 1) ? 3 : 2;
+      int stages = (kSmemLimit - fixed_bytes - acc_bytes - p.stagesA * p.halo_bytes) / (taps * bbytes);
+      if (stages > kMaxStages) stages = kMaxStages;
+      SY_REQUIRE(stages >= 2, SY_EINVAL, "conv2d_tc(halo): Cout=%d leaves no room for the weight ring", p.Cout);
+      p.stages = stages;
+      smem = fixed_bytes + acc_bytes + p.stagesA * p.halo_bytes + stages * taps * bbytes;
+    } else {
+      const int ksub = pair ? 2 : Cfg<BN>::kSub;                   // 64-deep sub-blocks per stage (kernel: kSub)
+      const int stage_bytes = ksub * (kABytes + bbytes);
+      int stages = (kSmemLimit - fixed_bytes - acc_bytes) / stage_bytes;
+      if (stages > kMaxStages) stages = kMaxStages;
+      if ((p.debug_flags >> 8) & 15) stages = min(stages, (p.debug_flags >> 8) & 15);   // debug: cap the ring depth
+      SY_REQUIRE(stages >= 2, SY_EINVAL, "conv2d_tc: Cout=%d leaves no room for the operand ring", p.Cout);
+      p.stages = stages;
+      smem = fixed_bytes + acc_bytes + stages * stage_bytes;
+    }
+    out->smem = smem;
+    out->pair = pair;
+    if (!pair) {
+      out->grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+      return SY_OK;
+    }
+    // pair tiles: CTA rank r of a pair owns M tile 2 * m2 + r
+    const int m2 = cdiv(p.m_tiles, 2), total2 = m2 * p.n_tiles;
+    const int pairs = resident_pairs<BN, AM>((size_t)smem);
+    const bool forced = getenv("SY_CONV_PAIR") != nullptr;
+    if (pairs < 1 || (!forced && cdiv(total2, pairs) > cdiv(p.total_tiles, num_sms()))) {
+      pair = false;                                                // not launchable / would add a round: plan again without
+      continue;
+    }
+    p.m_tiles2 = m2;
+    p.total_tiles2 = total2;
+    p.fd_m_tiles2 = make_fastdiv((uint32_t)m2);
+    out->grid = 2 * (total2 < pairs ? total2 : pairs);
+    return SY_OK;
   }
-  const int fixed_bytes = Cfg<BN>::kFixedBytes + (p.stage_tiles - 1) * kSlabBytes;
-  int smem;
-  if (AM == 2) {
-    // halo ring (2-3 stages of 36 KiB) + weight-slab ring (the rest, one [BN][64] slab per stage)
-    const int taps = (BN == 256) ? 1 : 3;                        // filter taps per weight-ring stage (kernel: kSub)
-    p.stagesA = (BN == 64 && p.cblocks > 1) ? 3 : 2;
-    int stages = (kSmemLimit - fixed_bytes - acc_bytes - p.stagesA * p.halo_bytes) / (taps * Cfg<BN>::kBBytes);
-    if (stages > kMaxStages) stages = kMaxStages;
-    SY_REQUIRE(stages >= 2, SY_EINVAL, "conv2d_tc(halo): Cout=%d leaves no room for the weight ring", p.Cout);
-    p.stages = stages;
-    smem = fixed_bytes + acc_bytes + p.stagesA * p.halo_bytes + stages * taps * Cfg<BN>::kBBytes;
-  } else {
-    const int stage_bytes = Cfg<BN>::kSub * (kABytes + Cfg<BN>::kBBytes);
-    int stages = (kSmemLimit - fixed_bytes - acc_bytes) / stage_bytes;
-    if (stages > kMaxStages) stages = kMaxStages;
-    if ((p.debug_flags >> 8) & 15) stages = min(stages, (p.debug_flags >> 8) & 15);   // debug: cap the ring depth
-    SY_REQUIRE(stages >= 2, SY_EINVAL, "conv2d_tc: Cout=%d leaves no room for the operand ring", p.Cout);
-    p.stages = stages;
-    smem = fixed_bytes + acc_bytes + stages * stage_bytes;
+  return SY_OK;
+}
+
+template <int BN, int AM>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, Params& p, const Plan& pl, cudaStream_t stream) {
+  const int smem = pl.smem, grid = pl.grid;
+  if (pl.pair) {
+    if constexpr (AM != 0) {
+      // (co-residency of the clusters was checked by make_plan: grid <= 2 * resident pairs)
+      if (p.timeline != nullptr)
+        SY_CUDA(launch_pdl_cluster(conv_tc_kernel<BN, true, AM, true>, 2, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
+      else
+        SY_CUDA(launch_pdl_cluster(conv_tc_kernel<BN, false, AM, true>, 2, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
+      return launch_status("conv_tc_kernel(pair)");
+    } else {
+      SY_REQUIRE(false, SY_EINVAL, "conv2d_tc: pair mode needs linear or halo tiles");
+    }
   }
-  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  SY_REQUIRE((set_smem_attr<BN, AM, false>()), SY_ELAUNCH, "conv2d_tc: cannot opt in to %d bytes of shared memory", kSmemLimit);
   if (p.n_seg > 0) {
     // The BatchNorm tail ends in a grid-wide barrier: every CTA of this launch must be resident at once.  The launch is
     // not a cooperative launch (it carries the programmatic-dependent-launch attribute instead), so check what a
@@ -1196,7 +1318,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     for (int i = 0; i < 8; ++i) seen = seen || ok_smem[i] == smem;
     if (!seen) {
       int per_sm = 0;
-      SY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_tc_kernel<BN, false, AM>, kThreads, (size_t)smem));
+      SY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_tc_kernel<BN, false, AM, false>, kThreads, (size_t)smem));
       SY_REQUIRE(per_sm >= 1 && per_sm * num_sms() >= grid, SY_ELAUNCH,
                  "conv2d_tc: %d CTAs cannot be co-resident (%d per SM x %d SMs): the BatchNorm grid barrier would hang", grid,
                  per_sm, num_sms());
@@ -1205,97 +1327,28 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     }
   }
   if (p.timeline != nullptr)
-    SY_CUDA(launch_pdl(conv_tc_kernel<BN, true, AM>, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
+    SY_CUDA(launch_pdl(conv_tc_kernel<BN, true, AM, false>, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
   else
-    SY_CUDA(launch_pdl(conv_tc_kernel<BN, false, AM>, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
+    SY_CUDA(launch_pdl(conv_tc_kernel<BN, false, AM, false>, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
   return launch_status("conv_tc_kernel");
 }
 
-// ---- pair mode (cta_group::2) ------------------------------------------------------------------------------------------
-// How many 2-CTA clusters of the pair kernel can be resident at once (the BatchNorm tail's grid barrier needs all of them;
-// 74 on a B200: 148 SMs in TPC pairs).  0 = clusters cannot be launched.
-static int resident_pairs(size_t smem) {
-  static size_t seen_smem[4] = {0, 0, 0, 0};
-  static int seen_n[4] = {0, 0, 0, 0};
-  for (int i = 0; i < 4; ++i)
-    if (seen_smem[i] == smem) return seen_n[i];
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<256, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc_kernel<256, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess) {
-      cudaGetLastError();
-      return 0;
-    }
-    attr_set = true;
+template <int AM>
+static int plan_bn(int bn, Params& p, Plan* out) {
+  switch (bn) {
+    case 64: return make_plan<64, AM>(p, out);
+    case 128: return make_plan<128, AM>(p, out);
+    default: return make_plan<256, AM>(p, out);
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(num_sms() & ~1);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<256, false, 1, true>, &cfg) != cudaSuccess) {
-    cudaGetLastError();
-    n = 0;
-  }
-  for (int i = 0; i < 4; ++i)
-    if (seen_smem[i] == 0) { seen_smem[i] = smem; seen_n[i] = n; break; }
-  return n;
-}
-
-// Decide pair mode for a linear-tile BN = 256 layer and, if chosen, fill the pair fields of p (tiles, ring depth, grid).
-// Main-loop-bound layers only (the epilogue of a tile hides behind the next tile's K loop), and only when pairing M tiles
-// does not add a round of the persistent grid.  SY_CONV_PAIR=0 disables, =1 forces it on every eligible layer.
-static bool plan_pair(Params& p, int* grid_out, int* smem_out) {
-  const char* e = getenv("SY_CONV_PAIR");
-  if (e != nullptr && e[0] == '0') return false;
-  const bool force = e != nullptr && e[0] == '1';
-  if (p.ap_y != nullptr && !force) return false;
-  const int m2 = cdiv(p.m_tiles, 2), total2 = m2 * p.n_tiles;
-  const int acc_bytes = (p.mode == SY_CONV_RAW && p.partials) ? 16 * p.Cout : 2048;
-  const int fixed_bytes = Cfg<256>::kFixedBytes;
-  const int stage_bytes = 2 * (kABytes + Cfg<256>::kBBytes / 2);          // two 64-deep sub-blocks per stage (kernel: kSub)
-  int stages = (kSmemLimit - fixed_bytes - acc_bytes) / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  if ((p.debug_flags >> 8) & 15) stages = min(stages, (p.debug_flags >> 8) & 15);
-  if (stages < 2) return false;
-  const int smem = fixed_bytes + acc_bytes + stages * stage_bytes;
-  if (!force) {
-    if (p.kblocks * 665.0 < epi_cycles_per_slab(256) * 4) return false;          // epilogue-bound: nothing to gain
-  }
-  const int pairs = resident_pairs((size_t)smem);
-  if (pairs < 1) return false;
-  if (!force && cdiv(total2, pairs) > cdiv(p.total_tiles, num_sms())) return false;
-  p.m_tiles2 = m2;
-  p.total_tiles2 = total2;
-  p.fd_m_tiles2 = make_fastdiv((uint32_t)m2);
-  p.stages = stages;
-  p.stage_tiles = 1;
-  p.team = 0;
-  *grid_out = 2 * (total2 < pairs ? total2 : pairs);
-  *smem_out = smem;
-  return true;
-}
-
-static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, Params& p, int grid, int smem,
-                       cudaStream_t stream) {
-  if (p.timeline != nullptr)
-    SY_CUDA(launch_pdl_cluster(conv_tc_kernel<256, true, 1, true>, 2, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
-  else
-    SY_CUDA(launch_pdl_cluster(conv_tc_kernel<256, false, 1, true>, 2, dim3(grid), dim3(kThreads), (size_t)smem, stream, ta, tb, ty, p));
-  return launch_status("conv_tc_kernel(pair)");
 }
 
 template <int AM>
-static int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, Params& p, cudaStream_t stream) {
+static int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, Params& p, const Plan& pl,
+                     cudaStream_t stream) {
   switch (bn) {
-    case 64: return launch<64, AM>(ta, tb, ty, p, stream);
-    case 128: return launch<128, AM>(ta, tb, ty, p, stream);
-    default: return launch<256, AM>(ta, tb, ty, p, stream);
+    case 64: return launch<64, AM>(ta, tb, ty, p, pl, stream);
+    case 128: return launch<128, AM>(ta, tb, ty, p, pl, stream);
+    default: return launch<256, AM>(ta, tb, ty, p, pl, stream);
   }
 }
 
@@ -1426,9 +1479,13 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
       }
     }
   }
-  int pair_grid = 0, pair_smem = 0;
-  const bool pair = lin && bn == 256 && tc::plan_pair(p, &pair_grid, &pair_smem);
-  if (d->rows_written) *d->rows_written = pair ? pair_grid : (p.total_tiles < tc::num_sms() ? p.total_tiles : tc::num_sms());
+  tc::Plan pl{};
+  {
+    const int rc = halo ? tc::plan_bn<2>(bn, p, &pl) : (lin ? tc::plan_bn<1>(bn, p, &pl) : tc::plan_bn<0>(bn, p, &pl));
+    if (rc != SY_OK) return rc;
+  }
+  const bool pair = pl.pair;
+  if (d->rows_written) *d->rows_written = pl.grid;
 
   // A: input view as (C, W, H, N), box (64, TW*s, TH*s, 1) traversed with element strides (1, s, s, 1)
   CUtensorMap ta, tb, ty;
@@ -1504,10 +1561,9 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SY_REQUIRE(r == CUDA_SUCCESS, SY_ELAUNCH, "cuTensorMapEncodeTiled(Y) failed: %d", (int)r);
   }
-  if (pair) return tc::launch_pair(ta, tb, ty, p, pair_grid, pair_smem, stream);
-  if (halo) return tc::launch_bn<2>(bn, ta, tb, ty, p, stream);
-  if (lin) return tc::launch_bn<1>(bn, ta, tb, ty, p, stream);
-  return tc::launch_bn<0>(bn, ta, tb, ty, p, stream);
+  if (halo) return tc::launch_bn<2>(bn, ta, tb, ty, p, pl, stream);
+  if (lin) return tc::launch_bn<1>(bn, ta, tb, ty, p, pl, stream);
+  return tc::launch_bn<0>(bn, ta, tb, ty, p, pl, stream);
 }
 
 // Host-only query (no launch, works without a GPU): the tiling decisions sy_conv2d_tc takes for a layer shape.

@@ -1,6 +1,6 @@
 """GPU: the cta_group::2 ("pair") variant of the tensor-core convolution (conv_tc.cu, PAIR): two CTAs of one cluster compute a
 256-pixel x 256-channel tile with one tcgen05.mma.cta_group::2 stream.  SY_CONV_PAIR=1 forces it on every eligible layer
-(linear tiles, BN = 256), SY_CONV_PAIR=0 switches it off; the two must agree with each other and with F.conv2d on
+(linear or halo tiles, any tile width), SY_CONV_PAIR=0 switches it off; the two must agree with each other and with F.conv2d on
   * the fp32 accumulators (debug store), the stored bf16 values, the per-channel statistics and the BatchNorm finalize,
   * pair tiles whose second half lies past the end of the tensor, channel counts that leave the peer's weight half empty,
   * more pair tiles than resident pairs (several rounds: barrier phases wrap), repeated launches (grid barrier counters)."""
@@ -15,23 +15,38 @@ from streamyolo_b200.ops import View  # noqa: E402
 from test_gpu_ops import DEV, check_close, rand_act, rand_w  # noqa: E402
 
 CASES = [
-    # n, cin, cout, h, w, k, s
-    (4, 256, 256, 38, 60, 3, 1),       # 72 M tiles -> 36 pair tiles
-    (16, 256, 256, 38, 60, 3, 1),      # 285 M tiles -> 143 pair tiles: two rounds of 74 pairs
-    (3, 256, 512, 19, 30, 3, 1),       # 14 M tiles, two N tiles
-    (3, 128, 512, 21, 30, 3, 1),       # 15 M tiles (odd): the last pair's second half is past the end
-    (2, 512, 1024, 38, 60, 3, 2),      # stride 2
-    (1, 2048, 1024, 19, 30, 1, 1),     # 1x1, 32 K blocks
-    (2, 256, 384, 19, 30, 3, 1),       # Cout = 384: the second N tile's upper weight half is empty
-    (1, 256, 256, 9, 7, 3, 1),         # 63 pixels: one pair tile, the peer CTA has no pixel at all
+    # (n, cin, cout, h, w, k, s), tile width BN, A mode
+    ((4, 256, 256, 38, 60, 3, 1), 256, "off"),       # 72 M tiles -> 36 pair tiles
+    ((16, 256, 256, 38, 60, 3, 1), 256, "off"),      # 285 M tiles -> 143 pair tiles: two rounds of 74 pairs
+    ((3, 256, 512, 19, 30, 3, 1), 256, "off"),       # 14 M tiles, two N tiles
+    ((3, 128, 512, 21, 30, 3, 1), 256, "off"),       # 15 M tiles (odd): the last pair's second half is past the end
+    ((2, 512, 1024, 38, 60, 3, 2), 256, "off"),      # stride 2
+    ((1, 2048, 1024, 19, 30, 1, 1), 256, "off"),     # 1x1, 32 K blocks
+    ((2, 256, 384, 19, 30, 3, 1), 256, "off"),       # Cout = 384: the second N tile's upper weight half is empty
+    ((1, 256, 256, 9, 7, 3, 1), 256, "off"),         # 63 pixels: one pair tile, the peer CTA has no pixel at all
+    ((2, 64, 128, 150, 240, 3, 2), 128, "off"),      # linear tiles, BN = 128 (each CTA stages 64 weight rows)
+    ((4, 128, 128, 38, 60, 1, 1), 128, "off"),
+    ((2, 64, 64, 75, 120, 1, 1), 64, "off"),         # BN = 64: 32 weight rows per CTA
+    ((2, 192, 96, 19, 30, 3, 1), 128, "off"),        # Cout = 96 < BN: the peer's weight half is partly out of bounds
+    ((4, 128, 128, 75, 120, 3, 1), 128, "halo"),     # halo tiles (16 x 8 patches): a pair = two patches, two halos
+    ((2, 64, 64, 150, 240, 3, 1), 64, "halo"),
+    ((3, 128, 128, 19, 30, 3, 1), 128, "halo"),      # ragged patches on a small map, odd patch count per image
+    ((2, 256, 256, 38, 60, 3, 1), 256, "halo"),
+    ((2, 96, 96, 19, 30, 3, 1), 128, "halo"),        # channel counts that are not multiples of 64
 ]
 
 
-def run(case, pair, monkeypatch, reps=1):
+def n_m_tiles(case, amode):
+    n, ci, co, h, w, k, s = case
+    ho, wo = ops.conv_out_hw(h, w, k, s)
+    return n * -(-ho // 16) * -(-wo // 8) if amode == "halo" else -(-n * ho * wo // 128)
+
+
+def run(case, bn, amode, pair, monkeypatch, reps=1):
     n, ci, co, h, w, k, s = case
     monkeypatch.setenv("SY_CONV_PAIR", "1" if pair else "0")
-    monkeypatch.setenv("SY_CONV_A", "off")
-    monkeypatch.setenv("SY_CONV_BN", "256")
+    monkeypatch.setenv("SY_CONV_A", amode)
+    monkeypatch.setenv("SY_CONV_BN", str(bn))
     x, wt = rand_act(n, ci, h, w, 71), rand_w(co, ci, k, 72)
     ho, wo = ops.conv_out_hw(h, w, k, s)
     g = torch.Generator().manual_seed(73)
@@ -57,14 +72,13 @@ def run(case, pair, monkeypatch, reps=1):
                 rm=rm, rv=rv, nbt=int(nbt), ref=ref, groups=2 if 0 < split < n else 1)
 
 
-@pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c)))
-def test_pair_conv_matches_reference_and_single_cta(case, monkeypatch):
+@pytest.mark.parametrize("case,bn,amode", CASES, ids=lambda c: "x".join(map(str, c)) if isinstance(c, tuple) else str(c))
+def test_pair_conv_matches_reference_and_single_cta(case, bn, amode, monkeypatch):
     n, ci, co, h, w, k, s = case
     ho, wo = ops.conv_out_hw(h, w, k, s)
-    a = run(case, True, monkeypatch, reps=3)
-    b = run(case, False, monkeypatch, reps=3)
-    m_tiles = -(-n * ho * wo // 128)
-    pair_tiles = -(-m_tiles // 2) * -(-co // 256)
+    a = run(case, bn, amode, True, monkeypatch, reps=3)
+    b = run(case, bn, amode, False, monkeypatch, reps=3)
+    pair_tiles = -(-n_m_tiles(case, amode) // 2) * -(-co // bn)
     assert a["rows"] == 2 * min(74, pair_tiles), f"pair mode did not run: {a['rows']} statistic rows for {pair_tiles} pair tiles"
     check_close(a["y"], a["ref"], f"pair conv {case}")
     # fp32 accumulators: same K order, same operands -> within fp32 summation noise of the single-CTA kernel and of cuDNN
