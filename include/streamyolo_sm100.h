@@ -86,7 +86,7 @@ typedef struct {
   SyTensor res;          /* FUSED: optional residual added after the activation (ptr NULL = none) */
   /* ---- RAW mode: per-channel batch statistics of the stored output (sy_conv2d_tc only) ---- */
   int32_t split_n;       /* images >= split_n form statistics group 1 (0 or >= n: one group) */
-  float* stat_partials;  /* [n_partials][2 groups][2 (sum, sumsq)][Cout] floats, one row per CTA, or NULL */
+  float* stat_partials;  /* [n_partials][Cout][2 groups][2 (sum, sumsq)] floats, one row per CTA (16B aligned), or NULL */
   int32_t n_partials;    /* >= sy_conv_stat_rows(); rows of CTAs that did not run are NOT written */
   int32_t* rows_written; /* out (host int, may be NULL): number of partial rows this launch writes */
   SyBnSegment bn[2];     /* bn[0].gamma != NULL: finalize BatchNorm in the kernel tail (1-2 parameter segments) */

@@ -87,10 +87,12 @@ struct Params {
   const float* shift;
   // statistics / BatchNorm finalize (RAW mode)
   int split_n;              // images >= split_n form statistics group 1
-  float* partials;          // [gridDim][2 groups][2][Cout] or nullptr (no statistics)
+  float* partials;          // [gridDim][Cout][2 groups][2 (sum, sumsq)] or nullptr (no statistics)
   int n_seg;                // > 0: finalize BatchNorm in the kernel tail (grid barrier + parallel reduce)
   BnSeg seg[2];
   float momentum, eps;
+  double inv_cnt[2];        // 1 / (values per channel) of statistics group 0 | 1 (host-computed: no fp64 division in the tail)
+  float unbias[2];          // cnt / (cnt - 1) of each group: biased -> unbiased variance for the running statistics
   float* ss;                // [2 (scale|shift)][2 groups][Cout]
   float* mi;                // optional [2 (mean|invstd)][2 groups][Cout] for the backward pass
   unsigned int* sync;       // three counters (two grid barriers + exit ticket), zero between launches
@@ -936,8 +938,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (et == 0) tl_rec<TL>(p, tl_epi, 4, 2, 0, 0);
     bar_stats_done();                                // every sAcc update is done; convert warps have seen the stores drain
     if (do_stats) {
-      float* mine = p.partials + (size_t)blockIdx.x * 4 * p.Cout;
-      for (int i = et; i < 4 * p.Cout; i += kTailThreads) mine[i] = sAcc[i];
+      // partial row of this CTA, channel-major: the four sums of a channel are one 16-byte word (the finalize below loads
+      // one word per row and channel; with the shared-memory layout [4][Cout] in global memory it needed four loads, and the
+      // 640 sector requests per warp made the partial-row sums the longest part of the tail)
+      float4* mine = reinterpret_cast<float4*>(p.partials) + (size_t)blockIdx.x * p.Cout;
+      for (int c = et; c < p.Cout; c += kTailThreads)
+        mine[c] = make_float4(sAcc[c], sAcc[p.Cout + c], sAcc[2 * p.Cout + c], sAcc[3 * p.Cout + c]);
       if (p.n_seg > 0) {
         auto grid_barrier = [&](unsigned int* ctr) {    // all CTAs of the persistent grid are resident (1 per SM)
           __threadfence();
@@ -948,65 +954,103 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           bar_stats_done();
         };
-        grid_barrier(&p.sync[0]);
-        // This CTA finalizes channels [b*cpc, (b+1)*cpc): one WARP per channel (no block barriers): lane l sums the
-        // partial rows l, l+32, ... in order, a fixed shuffle tree combines the lanes (deterministic), lane 0 finalizes.
+        if (et == 0) tl_rec<TL>(p, tl_epi, 4, 5, 0, 0);
+        // This CTA finalizes channels [b*cpc, (b+1)*cpc), one warp per channel.  The BatchNorm parameters and running
+        // statistics of the warp's first channel do not depend on the other CTAs: load them BEFORE the grid barrier (they
+        // come from DRAM -- behind the barrier their latency, twice in a row, was most of the finalize)
         const int groups = p.split_n < p.N ? 2 : 1;
         const int cpc = (p.Cout + (int)gridDim.x - 1) / (int)gridDim.x;
         const int c_end = min(p.Cout, ((int)blockIdx.x + 1) * cpc);
-        for (int c = (int)blockIdx.x * cpc + warp; c < c_end; c += kTailThreads / 32) {
+        const int c_first = (int)blockIdx.x * cpc + warp;
+        float pre_gamma = 1.f, pre_beta = 0.f, pre_rm = 0.f, pre_rv = 1.f;
+        if (c_first < c_end && lane < 2) {
+          const BnSeg& sg = (p.n_seg > 1 && c_first >= p.seg[1].c_begin) ? p.seg[1] : p.seg[0];
+          const int cs = c_first - sg.c_begin;
+          pre_gamma = sg.gamma[cs];
+          pre_beta = sg.beta[cs];
+          if (lane == 0) {
+            if (sg.rmean) pre_rm = sg.rmean[cs];
+            if (sg.rvar) pre_rv = sg.rvar[cs];
+          }
+        }
+        grid_barrier(&p.sync[0]);
+        if (et == 0) tl_rec<TL>(p, tl_epi, 4, 6, 0, 0);
+        // exit ticket (the last CTA past the barriers re-arms the counters): taken as early as possible -- right after the
+        // last grid barrier -- so that the atomic's round trip overlaps the finalize instead of ending the kernel
+        unsigned int ticket = 0xffffffffu;
+        if (et == 0 && p.ap_y == nullptr) ticket = atomicAdd(&p.sync[2], 1u);
+        // one WARP per channel (no block barriers): lane l sums the partial rows l, l+32, ... in order, a fixed shuffle tree
+        // combines the lanes (deterministic), lanes 0 / 1 finalize one statistics group each.
+        for (int c = c_first; c < c_end; c += kTailThreads / 32) {
           // all loads first (<= 148 rows: five per lane), then the sums in the same fixed order: one L2 round trip instead
           // of five serialised ones (the fp64 adds used to sit between the loads of consecutive rows)
-          float buf[5][4];
+          const float4* rows4 = reinterpret_cast<const float4*>(p.partials) + c;
+          float4 buf[5];
 #pragma unroll
           for (int j = 0; j < 5; ++j) {
             const int r = lane + 32 * j;
-            const float* rowp = p.partials + (size_t)r * 4 * p.Cout + c;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) buf[j][i] = r < (int)gridDim.x ? __ldcg(rowp + i * p.Cout) : 0.f;
+            buf[j] = r < (int)gridDim.x ? __ldcg(rows4 + (size_t)r * p.Cout) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           double v[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-          for (int j = 0; j < 5; ++j)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] += (double)buf[j][i];
+          for (int j = 0; j < 5; ++j) {
+            v[0] += (double)buf[j].x; v[1] += (double)buf[j].y; v[2] += (double)buf[j].z; v[3] += (double)buf[j].w;
+          }
+          if (et == 0) tl_rec<TL>(p, tl_epi, 4, 8, 0, 0);
           for (int r = lane + 160; r < (int)gridDim.x; r += 32) {          // (more than 160 CTAs: not on a B200)
-            const float* rowp = p.partials + (size_t)r * 4 * p.Cout + c;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] += (double)__ldcg(rowp + i * p.Cout);
+            const float4 q = __ldcg(rows4 + (size_t)r * p.Cout);
+            v[0] += (double)q.x; v[1] += (double)q.y; v[2] += (double)q.z; v[3] += (double)q.w;
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], m);
           }
+          if (et == 0) tl_rec<TL>(p, tl_epi, 4, 9, 0, 0);
+          // every lane holds the four sums: lane g finalizes statistics group g (fp64 only for mean / E[x^2] - mean^2; the
+          // reciprocal square root is IEEE fp32 -- the fp64 sqrt / divisions of the first version cost ~3 us per launch),
+          // lane 0 then folds both groups into the running statistics in order
+          const BnSeg& sg = (p.n_seg > 1 && c >= p.seg[1].c_begin) ? p.seg[1] : p.seg[0];
+          const int cs = c - sg.c_begin;
+          float mean_f = 0.f, var_f = 0.f;
+          if (lane < groups) {
+            const int g = lane;
+            const double s1 = g ? v[2] : v[0], s2 = g ? v[3] : v[1];
+            const double mean = s1 * p.inv_cnt[g];
+            double var = s2 * p.inv_cnt[g] - mean * mean;
+            if (var < 0.0) var = 0.0;
+            mean_f = (float)mean;
+            var_f = (float)var;
+            const float istd = 1.0f / sqrtf(var_f + p.eps);
+            const float sc = (c == c_first ? pre_gamma : sg.gamma[cs]) * istd;
+            p.ss[(0 * 2 + g) * p.Cout + c] = sc;
+            p.ss[(1 * 2 + g) * p.Cout + c] = (c == c_first ? pre_beta : sg.beta[cs]) - mean_f * sc;
+            if (p.mi != nullptr) {
+              p.mi[(0 * 2 + g) * p.Cout + c] = mean_f;
+              p.mi[(1 * 2 + g) * p.Cout + c] = istd;
+            }
+          }
+          const float mean1 = __shfl_sync(0xffffffffu, mean_f, 1), var1 = __shfl_sync(0xffffffffu, var_f, 1);
           if (lane == 0) {
-            const BnSeg& sg = (p.n_seg > 1 && c >= p.seg[1].c_begin) ? p.seg[1] : p.seg[0];
-            const int cs = c - sg.c_begin;
-            float rm = sg.rmean ? sg.rmean[cs] : 0.f, rv = sg.rvar ? sg.rvar[cs] : 1.f;
-            for (int g = 0; g < groups; ++g) {
-              const double cnt = (double)(g == 0 ? (groups == 2 ? p.split_n : p.N) : p.N - p.split_n) * p.Ho * p.Wo;
-              const double mean = v[2 * g] / cnt;
-              double var = v[2 * g + 1] / cnt - mean * mean;
-              if (var < 0.0) var = 0.0;
-              const float sc = sg.gamma[cs] * (float)(1.0 / sqrt(var + (double)p.eps));
-              p.ss[(0 * 2 + g) * p.Cout + c] = sc;
-              p.ss[(1 * 2 + g) * p.Cout + c] = sg.beta[cs] - (float)mean * sc;
-              if (p.mi != nullptr) {
-                p.mi[(0 * 2 + g) * p.Cout + c] = (float)mean;
-                p.mi[(1 * 2 + g) * p.Cout + c] = (float)(1.0 / sqrt(var + (double)p.eps));
-              }
-              const double unbiased = cnt > 1.0 ? var * (cnt / (cnt - 1.0)) : var;
-              rm = (1.f - p.momentum) * rm + p.momentum * (float)mean;
-              rv = (1.f - p.momentum) * rv + p.momentum * (float)unbiased;
+            float rm = pre_rm, rv = pre_rv;
+            if (c != c_first) {
+              rm = sg.rmean ? sg.rmean[cs] : 0.f;
+              rv = sg.rvar ? sg.rvar[cs] : 1.f;
+            }
+            rm = (1.f - p.momentum) * rm + p.momentum * mean_f;
+            rv = (1.f - p.momentum) * rv + p.momentum * (var_f * p.unbias[0]);
+            if (groups == 2) {
+              rm = (1.f - p.momentum) * rm + p.momentum * mean1;
+              rv = (1.f - p.momentum) * rv + p.momentum * (var1 * p.unbias[1]);
             }
             if (sg.rmean) sg.rmean[cs] = rm;
             if (sg.rvar) sg.rvar[cs] = rv;
           }
         }
+        if (et == 0) tl_rec<TL>(p, tl_epi, 4, 7, 0, 0);
         if (et == 0 && blockIdx.x == 0) {
-          for (int sgi = 0; sgi < p.n_seg; ++sgi)
-            if (p.seg[sgi].nbt) *p.seg[sgi].nbt += groups;
+          for (int sgi = 0; sgi < p.n_seg; ++sgi)          // (a reduction: no round trip -- a load-add-store ended CTA 0 ~1 us late)
+            if (p.seg[sgi].nbt) atomicAdd(reinterpret_cast<unsigned long long*>(p.seg[sgi].nbt), (unsigned long long)groups);
         }
         if (p.ap_y != nullptr) {
           // ---- second grid barrier: scale/shift of every channel are published; normalise this CTA's own tiles,
@@ -1085,8 +1129,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (et == 0) {
-          const unsigned int old = atomicAdd(&p.sync[2], 1u);
-          if (old == gridDim.x - 1) {               // every CTA is past both barriers: re-arm for the next launch
+          if (p.ap_y != nullptr) ticket = atomicAdd(&p.sync[2], 1u);
+          if (ticket == gridDim.x - 1) {            // every CTA is past both barriers: re-arm for the next launch
             p.sync[0] = 0u;
             p.sync[1] = 0u;
             p.sync[2] = 0u;
@@ -1440,6 +1484,7 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
   p.gp = p.split_n * ho * wo;
   p.partials = (d->mode == SY_CONV_RAW) ? d->stat_partials : nullptr;
   if (p.partials) {
+    SY_REQUIRE(((uintptr_t)p.partials % 16) == 0, SY_EINVAL, "conv2d_tc: statistic rows not 16B aligned");
     SY_REQUIRE(d->n_partials >= tc::num_sms(), SY_EWORKSPACE, "conv2d_tc: %d statistic rows, need %d (sy_conv_stat_rows)",
                d->n_partials, tc::num_sms());
   }
@@ -1461,6 +1506,14 @@ extern "C" int sy_conv2d_tc(const SyConvDesc* d, sy_stream_t stream_) {
     }
     SY_REQUIRE(p.seg[0].c_begin == 0, SY_EINVAL, "conv2d_tc: first BN segment must start at channel 0");
     p.momentum = d->momentum; p.eps = d->eps;
+    {
+      const int groups = p.split_n < x.n ? 2 : 1;
+      for (int g = 0; g < 2; ++g) {
+        const double cnt = (double)(g == 0 ? (groups == 2 ? p.split_n : x.n) : x.n - p.split_n) * ho * wo;
+        p.inv_cnt[g] = cnt > 0.0 ? 1.0 / cnt : 0.0;
+        p.unbias[g] = cnt > 1.0 ? (float)(cnt / (cnt - 1.0)) : 1.0f;
+      }
+    }
     p.ss = d->scale_shift;
     p.mi = d->mean_invstd;
     p.sync = d->sync;

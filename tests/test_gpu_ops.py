@@ -105,8 +105,8 @@ def test_conv_raw(case, impl, monkeypatch):
     got = y.nchw_float()
     check_close(got, ref, f"conv_{impl}{case}")
     if impl == "tc":
-        # per-CTA partial rows [cta][group][sum|sumsq][c]; rows of CTAs that did not run stay NaN
-        pr = torch.nan_to_num(partials.view(rows, 2, 2, co)).sum(0)
+        # per-CTA partial rows [cta][c][group][sum|sumsq]; rows of CTAs that did not run stay NaN
+        pr = torch.nan_to_num(partials.view(rows, co, 2, 2)).sum(0).permute(1, 2, 0)
         st = got    # statistics are defined on the stored (rounded) values
         groups = [(0, split), (split, n)] if split else [(0, n)]
         for g, (a0, a1) in enumerate(groups):
