@@ -349,9 +349,9 @@ int sy_pack_conv_weight(const float* w, int32_t cout, int32_t cin, int32_t kh, i
                         int64_t out_pitch, int32_t co_offset, sy_stream_t stream);
 
 /* The same for MANY parameters in one launch: items (a DEVICE array) lists (parameter, layout) pairs with the arguments of
- * sy_pack_conv_weight; `begin` = index of the item's first element in the launch (prefix sum of the element counts:
- * cout*cin*kh*kw for modes 0 / 1, cout*kh*64 for mode 2), `total` = their sum.  The trainer re-packs every conv operand of the
- * model (forward and data-gradient layouts) with it after each optimiser step. */
+ * sy_pack_conv_weight.  The launch works in TILES (64 output x 32 input channels of one item; 64 output channels of a stem
+ * item): `begin` = index of the item's first tile (prefix sum of sy_pack_item_tiles over the items), `total` = their sum.
+ * The trainer re-packs every conv operand of the model (forward and data-gradient layouts) with it after each optimiser step. */
 typedef struct SyPackItem {
   const float* w;
   void* out;
@@ -359,6 +359,7 @@ typedef struct SyPackItem {
   int64_t out_pitch;
   int64_t begin;
 } SyPackItem;
+int64_t sy_pack_item_tiles(int32_t cout, int32_t cin, int32_t mode);
 int sy_pack_conv_weights_batch(const SyPackItem* items_dev, int32_t n_items, int64_t total, sy_stream_t stream);
 
 /* The optimiser step of the reference trainer as one launch over flat fp32 state:

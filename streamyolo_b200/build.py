@@ -43,21 +43,52 @@ def _digest():
     return h.hexdigest()
 
 
+def _file_digest(src, extra):
+    """digest of one translation unit: its source, every header of csrc/ and include/, and its flags"""
+    h = hashlib.sha256()
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    files = [os.path.join(CSRC, src)] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))]
+    files += [os.path.join(inc, f) for f in sorted(os.listdir(inc))]
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(f.encode())
+            h.update(fh.read())
+    h.update(" ".join(COMMON + extra).encode())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every translation unit whose digest changed (in parallel) and link.  The driver's build check calls this
+    from a clean tree, which compiles all of them."""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "build.stamp")
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
-    objs = []
     log = []
-    for src, extra in SOURCES.items():
+
+    def compile_one(item):
+        src, extra = item
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        fd = _file_digest(src, extra)
+        fstamp = obj + ".stamp"
+        if not force and os.path.exists(obj) and os.path.exists(fstamp) and open(fstamp).read() == fd:
+            return obj, f"(up to date) {src}", 0
         cmd = [NVCC] + COMMON + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        log.append(f"$ {' '.join(cmd)}\n{r.stdout}{r.stderr}")
-        if r.returncode != 0:
-            sys.stderr.write(log[-1])
+        if r.returncode == 0:
+            with open(fstamp, "w") as fh:
+                fh.write(fd)
+        return obj, f"$ {' '.join(cmd)}\n{r.stdout}{r.stderr}", r.returncode
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, SOURCES.items()))
+    objs = []
+    for (obj, text, rc), src in zip(results, SOURCES):
+        log.append(text)
+        if rc != 0:
+            sys.stderr.write(text)
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
     cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]

@@ -1088,7 +1088,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else {
                   const int tyy = fdiv(rr, p.fd_tw), txx = rr - tyy * p.tw;
                   const int oy = py * p.th + tyy, ox = px * p.tw + txx;
-                  pixv[j] = (rr < rows_in_patch && oy < p.Ho && ox < p.Wo) ? ((long long)img * p.Ho + oy) * p.Wo + ox : -1;
+                  // (img >= N: the second M tile of the last pair may lie past the end of the tensor)
+                  pixv[j] = (rr < rows_in_patch && img < p.N && oy < p.Ho && ox < p.Wo) ? ((long long)img * p.Ho + oy) * p.Wo + ox : -1;
                 }
               }
 #pragma unroll
@@ -1283,7 +1284,10 @@ static int make_plan(Params& p, Plan* out) {
   if (AM != 0) {
     const char* e = getenv("SY_CONV_PAIR");
     const bool off = e != nullptr && e[0] == '0', force = e != nullptr && e[0] == '1';
-    pair = !off && (force || (main_loop_bound && p.ap_y == nullptr));
+    // (the in-kernel normalise pass works on pair tiles too; SY_PAIR_APPLY=1 lets such launches pair up -- A/B switch)
+    const char* pa = getenv("SY_PAIR_APPLY");
+    const bool pair_apply = pa != nullptr && pa[0] == '1';
+    pair = !off && (force || (main_loop_bound && (p.ap_y == nullptr || pair_apply)));
   }
   for (int attempt = 0; attempt < 2; ++attempt) {
     p.stage_tiles = main_loop_bound ? 1 : 2;

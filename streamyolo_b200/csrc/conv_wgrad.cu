@@ -235,7 +235,12 @@ static int make_plan(const SyConvWgradDesc* d, Plan* pl) {
   pl->taps = d->kh * d->kw;
   pl->kb_total = cdiv(x.n * pl->ho * pl->wo, kPixK);
   const int base = pl->m_tiles * pl->n_tiles * pl->taps;
-  int ks = cdiv(2 * num_sms(), base);                       // about two waves of work items
+  int waves = 2;                                            // about two waves of work items
+  if (const char* e = getenv("SY_WGRAD_WAVES")) {           // tuning aid: fewer waves = less split-K partial traffic
+    const int v = atoi(e);
+    if (v >= 1 && v <= 8) waves = v;
+  }
+  int ks = cdiv(waves * num_sms(), base);
   const int ks_max = pl->kb_total / 8 > 1 ? pl->kb_total / 8 : 1;   // at least 8 K blocks per split
   if (ks > ks_max) ks = ks_max;
   if (ks < 1) ks = 1;

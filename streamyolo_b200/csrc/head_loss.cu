@@ -17,7 +17,11 @@ namespace sy {
 // Output row layout [reg4, obj1, cls*] (tal_head.py:174,197-199); anchors row-major y then x (:236-239).
 constexpr int kMaxPred = 5 + 32;
 
-template <int NO>
+// PT pixels per thread (64 * PT pixels per block and pass): every weight chunk read from shared memory is used for PT
+// pixels.  With one pixel per thread the kernel was bound by its shared-memory weight reads (26 LDS.128 per 104 FMAs: 51 us
+// for the 73 MB of level-0 features = 1.4 TB/s); the per-pixel arithmetic (order of the products and sums) is unchanged, so
+// the results are bit-identical for every PT.
+template <int NO, int PT>
 __global__ void __launch_bounds__(256)
 head_pred_kernel(const SyHeadPredDesc d, int B, int H, int W, int C) {
   extern __shared__ float wsm[];   // [NO][C] : reg(4), obj(1), cls(NO-5)
@@ -31,79 +35,205 @@ head_pred_kernel(const SyHeadPredDesc d, int B, int H, int W, int C) {
   const __nv_bfloat16* cf = reinterpret_cast<const __nv_bfloat16*>(d.cls_feat.ptr);
   const __nv_bfloat16* rf = reinterpret_cast<const __nv_bfloat16*>(d.reg_feat.ptr);
   const int chunks = C / 8;
-  for (long long pix0 = (long long)blockIdx.x * 64; pix0 < npix; pix0 += (long long)gridDim.x * 64) {
-    const long long pix = pix0 + (threadIdx.x >> 2);
-    const bool live = pix < npix;
-    float acc[NO];
+  for (long long pix0 = (long long)blockIdx.x * (64 * PT); pix0 < npix; pix0 += (long long)gridDim.x * (64 * PT)) {
+    long long pix[PT];
+    bool live[PT];
 #pragma unroll
-    for (int o = 0; o < NO; ++o) acc[o] = 0.f;
-    if (live) {
-      for (int ch = ks; ch < chunks; ch += 4) {
-        const uint4 rv = *reinterpret_cast<const uint4*>(rf + pix * d.reg_feat.pitch + ch * 8);
-        const uint4 cv = *reinterpret_cast<const uint4*>(cf + pix * d.cls_feat.pitch + ch * 8);
-        const float r[8] = {bf16_lo(rv.x), bf16_hi(rv.x), bf16_lo(rv.y), bf16_hi(rv.y),
-                            bf16_lo(rv.z), bf16_hi(rv.z), bf16_lo(rv.w), bf16_hi(rv.w)};
-        const float c[8] = {bf16_lo(cv.x), bf16_hi(cv.x), bf16_lo(cv.y), bf16_hi(cv.y),
-                            bf16_lo(cv.z), bf16_hi(cv.z), bf16_lo(cv.w), bf16_hi(cv.w)};
+    for (int j = 0; j < PT; ++j) {
+      pix[j] = pix0 + 64 * j + (threadIdx.x >> 2);
+      live[j] = pix[j] < npix;
+    }
+    float acc[PT][NO];
 #pragma unroll
-        for (int o = 0; o < NO; ++o) {
+    for (int j = 0; j < PT; ++j)
+#pragma unroll
+      for (int o = 0; o < NO; ++o) acc[j][o] = 0.f;
+    for (int ch = ks; ch < chunks; ch += 4) {
+      uint4 rv[PT], cv[PT];
+#pragma unroll
+      for (int j = 0; j < PT; ++j) {             // all loads of the pass first: 2 * PT independent 16-byte requests in flight
+        rv[j] = live[j] ? *reinterpret_cast<const uint4*>(rf + pix[j] * d.reg_feat.pitch + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
+        cv[j] = live[j] ? *reinterpret_cast<const uint4*>(cf + pix[j] * d.cls_feat.pitch + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {     // reg | obj outputs read the reg features, the class outputs the cls features
+        float v[PT][8];
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+          const uint4 u = part == 0 ? rv[j] : cv[j];
+          v[j][0] = bf16_lo(u.x); v[j][1] = bf16_hi(u.x); v[j][2] = bf16_lo(u.y); v[j][3] = bf16_hi(u.y);
+          v[j][4] = bf16_lo(u.z); v[j][5] = bf16_hi(u.z); v[j][6] = bf16_lo(u.w); v[j][7] = bf16_hi(u.w);
+        }
+#pragma unroll
+        for (int o = (part == 0 ? 0 : 5); o < (part == 0 ? 5 : NO); ++o) {
           const float4 w0 = *reinterpret_cast<const float4*>(wsm + o * C + ch * 8);
           const float4 w1 = *reinterpret_cast<const float4*>(wsm + o * C + ch * 8 + 4);
-          const float* v = (o < 5) ? r : c;
-          float s = v[0] * w0.x;          // explicit FMAs: this unit is compiled with -fmad=false for the loss
-          s = __fmaf_rn(v[1], w0.y, s); s = __fmaf_rn(v[2], w0.z, s); s = __fmaf_rn(v[3], w0.w, s);
-          s = __fmaf_rn(v[4], w1.x, s); s = __fmaf_rn(v[5], w1.y, s); s = __fmaf_rn(v[6], w1.z, s);
-          s = __fmaf_rn(v[7], w1.w, s);
-          acc[o] += s;
+#pragma unroll
+          for (int j = 0; j < PT; ++j) {
+            float s = v[j][0] * w0.x;     // explicit FMAs: this unit is compiled with -fmad=false for the loss
+            s = __fmaf_rn(v[j][1], w0.y, s); s = __fmaf_rn(v[j][2], w0.z, s); s = __fmaf_rn(v[j][3], w0.w, s);
+            s = __fmaf_rn(v[j][4], w1.x, s); s = __fmaf_rn(v[j][5], w1.y, s); s = __fmaf_rn(v[j][6], w1.z, s);
+            s = __fmaf_rn(v[j][7], w1.w, s);
+            acc[j][o] += s;
+          }
         }
       }
     }
 #pragma unroll
-    for (int o = 0; o < NO; ++o) {
-      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
-      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
-    }
-    if (live && ks == 0) {
-      const int x = (int)(pix % W), y = (int)((pix / W) % H);
-      const int b = (int)(pix / ((long long)W * H));
-      const long long a = (long long)b * d.a_total + d.anchor_offset + (long long)y * W + x;
-      float* out = d.out + a * NO;
-      float reg[4];
+    for (int j = 0; j < PT; ++j) {
 #pragma unroll
-      for (int o = 0; o < 4; ++o) reg[o] = acc[o] + d.b_reg[o];
-      if (d.origin) {
-        float* og = d.origin + a * 4;
-        og[0] = reg[0]; og[1] = reg[1]; og[2] = reg[2]; og[3] = reg[3];
+      for (int o = 0; o < NO; ++o) {
+        acc[j][o] += __shfl_xor_sync(0xffffffffu, acc[j][o], 1);
+        acc[j][o] += __shfl_xor_sync(0xffffffffu, acc[j][o], 2);
       }
-      const float s = (float)d.stride;
-      if (d.decode) {
-        out[0] = (reg[0] + (float)x) * s;
-        out[1] = (reg[1] + (float)y) * s;
-        out[2] = expf(reg[2]) * s;
-        out[3] = expf(reg[3]) * s;
-      } else {
-        out[0] = reg[0]; out[1] = reg[1]; out[2] = reg[2]; out[3] = reg[3];
-      }
-      const float obj = acc[4] + d.b_obj[0];
-      out[4] = d.sigmoid ? 1.0f / (1.0f + expf(-obj)) : obj;
+      if (live[j] && ks == 0) {
+        const int x = (int)(pix[j] % W), y = (int)((pix[j] / W) % H);
+        const int b = (int)(pix[j] / ((long long)W * H));
+        const long long a = (long long)b * d.a_total + d.anchor_offset + (long long)y * W + x;
+        float* out = d.out + a * NO;
+        float reg[4];
 #pragma unroll
-      for (int o = 5; o < NO; ++o) {
-        const float v = acc[o] + d.b_cls[o - 5];
-        out[o] = d.sigmoid ? 1.0f / (1.0f + expf(-v)) : v;
+        for (int o = 0; o < 4; ++o) reg[o] = acc[j][o] + d.b_reg[o];
+        if (d.origin) {
+          float* og = d.origin + a * 4;
+          og[0] = reg[0]; og[1] = reg[1]; og[2] = reg[2]; og[3] = reg[3];
+        }
+        const float s = (float)d.stride;
+        if (d.decode) {
+          out[0] = (reg[0] + (float)x) * s;
+          out[1] = (reg[1] + (float)y) * s;
+          out[2] = expf(reg[2]) * s;
+          out[3] = expf(reg[3]) * s;
+        } else {
+          out[0] = reg[0]; out[1] = reg[1]; out[2] = reg[2]; out[3] = reg[3];
+        }
+        const float obj = acc[j][4] + d.b_obj[0];
+        out[4] = d.sigmoid ? 1.0f / (1.0f + expf(-obj)) : obj;
+#pragma unroll
+        for (int o = 5; o < NO; ++o) {
+          const float v = acc[j][o] + d.b_cls[o - 5];
+          out[o] = d.sigmoid ? 1.0f / (1.0f + expf(-v)) : v;
+        }
       }
     }
   }
 }
 
+// Any class count (the reference head takes `num_classes` freely, tal_head.py:27): the outputs are walked in groups of eight
+// compile-time accumulators, re-reading the pixel's features (L1 / L2) for every group.  Same per-output arithmetic as above.
+__global__ void __launch_bounds__(256)
+head_pred_generic_kernel(const SyHeadPredDesc d, int B, int H, int W, int C, int NO) {
+  extern __shared__ float wsm[];   // [NO][C]
+  for (int i = threadIdx.x; i < NO * C; i += blockDim.x) {
+    const int o = i / C, c = i % C;
+    wsm[i] = (o < 4) ? d.w_reg[o * C + c] : (o == 4 ? d.w_obj[c] : d.w_cls[(o - 5) * C + c]);
+  }
+  __syncthreads();
+  const int ks = threadIdx.x & 3;
+  const long long npix = (long long)B * H * W;
+  const __nv_bfloat16* cf = reinterpret_cast<const __nv_bfloat16*>(d.cls_feat.ptr);
+  const __nv_bfloat16* rf = reinterpret_cast<const __nv_bfloat16*>(d.reg_feat.ptr);
+  const int chunks = C / 8;
+  for (long long pix0 = (long long)blockIdx.x * 64; pix0 < npix; pix0 += (long long)gridDim.x * 64) {
+    const long long pix = pix0 + (threadIdx.x >> 2);
+    const bool live = pix < npix;
+    const int x = live ? (int)(pix % W) : 0, y = live ? (int)((pix / W) % H) : 0;
+    const int b = live ? (int)(pix / ((long long)W * H)) : 0;
+    const long long a = (long long)b * d.a_total + d.anchor_offset + (long long)y * W + x;
+    for (int o0 = 0; o0 < NO; o0 += 8) {       // group 0 = reg(4) + obj + 3 classes
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      if (live) {
+        for (int ch = ks; ch < chunks; ch += 4) {
+          const uint4 rv = *reinterpret_cast<const uint4*>(rf + pix * d.reg_feat.pitch + ch * 8);
+          const uint4 cv = *reinterpret_cast<const uint4*>(cf + pix * d.cls_feat.pitch + ch * 8);
+          const float r[8] = {bf16_lo(rv.x), bf16_hi(rv.x), bf16_lo(rv.y), bf16_hi(rv.y),
+                              bf16_lo(rv.z), bf16_hi(rv.z), bf16_lo(rv.w), bf16_hi(rv.w)};
+          const float c[8] = {bf16_lo(cv.x), bf16_hi(cv.x), bf16_lo(cv.y), bf16_hi(cv.y),
+                              bf16_lo(cv.z), bf16_hi(cv.z), bf16_lo(cv.w), bf16_hi(cv.w)};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int o = o0 + i;
+            if (o < NO) {
+              const float4 w0 = *reinterpret_cast<const float4*>(wsm + o * C + ch * 8);
+              const float4 w1 = *reinterpret_cast<const float4*>(wsm + o * C + ch * 8 + 4);
+              const bool use_r = o < 5;
+              float s = (use_r ? r[0] : c[0]) * w0.x;
+              s = __fmaf_rn(use_r ? r[1] : c[1], w0.y, s); s = __fmaf_rn(use_r ? r[2] : c[2], w0.z, s);
+              s = __fmaf_rn(use_r ? r[3] : c[3], w0.w, s); s = __fmaf_rn(use_r ? r[4] : c[4], w1.x, s);
+              s = __fmaf_rn(use_r ? r[5] : c[5], w1.y, s); s = __fmaf_rn(use_r ? r[6] : c[6], w1.z, s);
+              s = __fmaf_rn(use_r ? r[7] : c[7], w1.w, s);
+              acc[i] += s;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 2);
+      }
+      if (live && ks == 0) {
+        float* out = d.out + a * NO;
+        const float s = (float)d.stride;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int o = o0 + i;
+          if (o >= NO) continue;
+          if (o < 4) {
+            const float reg = acc[i] + d.b_reg[o];
+            if (d.origin) d.origin[a * 4 + o] = reg;
+            out[o] = !d.decode ? reg : (o == 0 ? (reg + (float)x) * s : (o == 1 ? (reg + (float)y) * s : expf(reg) * s));
+          } else {
+            const float v = acc[i] + (o == 4 ? d.b_obj[0] : d.b_cls[o - 5]);
+            out[o] = d.sigmoid ? 1.0f / (1.0f + expf(-v)) : v;
+          }
+        }
+      }
+    }
+  }
+}
+
+static int head_pixels_per_thread(long long npix) {
+  if (const char* e = getenv("SY_HEAD_PT")) {            // tuning aid
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) return v;
+  }
+  return npix >= 32768 ? 2 : 1;                          // small levels: more blocks matter more than the weight reuse
+}
+
+template <int NO, int PT>
+static int launch_head_pred_pt(const SyHeadPredDesc* d, const SyTensor& f, cudaStream_t stream) {
+  const size_t smem = sizeof(float) * NO * f.c;
+  if (smem > 48 * 1024)
+    SY_CUDA(cudaFuncSetAttribute(head_pred_kernel<NO, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long npix = (long long)f.n * f.h * f.w;
+  int blocks = (int)((npix + 64 * PT - 1) / (64 * PT));
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  head_pred_kernel<NO, PT><<<blocks, 256, smem, stream>>>(*d, f.n, f.h, f.w, f.c);
+  return launch_status("head_pred_kernel");
+}
+
 template <int NO>
 static int launch_head_pred(const SyHeadPredDesc* d, const SyTensor& f, cudaStream_t stream) {
+  switch (head_pixels_per_thread((long long)f.n * f.h * f.w)) {
+    case 4: return launch_head_pred_pt<NO, 4>(d, f, stream);
+    case 2: return launch_head_pred_pt<NO, 2>(d, f, stream);
+    default: return launch_head_pred_pt<NO, 1>(d, f, stream);
+  }
+}
+
+static int launch_head_pred_generic(const SyHeadPredDesc* d, const SyTensor& f, cudaStream_t stream) {
+  const int NO = 5 + d->num_classes;
   const size_t smem = sizeof(float) * NO * f.c;
-  if (smem > 48 * 1024) SY_CUDA(cudaFuncSetAttribute(head_pred_kernel<NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024)
+    SY_CUDA(cudaFuncSetAttribute(head_pred_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long npix = (long long)f.n * f.h * f.w;
   int blocks = (int)((npix + 63) / 64);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  head_pred_kernel<NO><<<blocks, 256, smem, stream>>>(*d, f.n, f.h, f.w, f.c);
-  return launch_status("head_pred_kernel");
+  head_pred_generic_kernel<<<blocks, 256, smem, stream>>>(*d, f.n, f.h, f.w, f.c, NO);
+  return launch_status("head_pred_generic_kernel");
 }
 
 // ======================================================================= loss
@@ -201,19 +331,22 @@ __device__ __forceinline__ void in_tests(const Box g, float xc, float yc, float 
 // ---- 1. label counts + trend IoU per future GT (tal_head.py:285-286, 394-403)
 __global__ void k_labels(const float* fut, const float* cur, int L, float thr, float ign, int* ngt, int* nsup, float* tal) {
   const int b = blockIdx.x;
-  __shared__ int s_n[2];
-  if (threadIdx.x == 0) {
-    int n0 = 0, n1 = 0;
-    for (int i = 0; i < L; ++i) {
-      const float* r0 = fut + ((size_t)b * L + i) * 5;
-      const float* r1 = cur + ((size_t)b * L + i) * 5;
-      if ((((r0[0] + r0[1]) + r0[2]) + r0[3]) + r0[4] > 0.f) ++n0;
-      if ((((r1[0] + r1[1]) + r1[2]) + r1[3]) + r1[4] > 0.f) ++n1;
-    }
-    s_n[0] = n0; s_n[1] = n1; ngt[b] = n0; nsup[b] = n1;
+  // counts of non-empty label rows, all threads in parallel (a single thread walking 2 x 120 rows took ~30 us)
+  int c0 = 0, c1 = 0;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const float* r0 = fut + ((size_t)b * L + i) * 5;
+    const float* r1 = cur + ((size_t)b * L + i) * 5;
+    if ((((r0[0] + r0[1]) + r0[2]) + r0[3]) + r0[4] > 0.f) ++c0;
+    if ((((r1[0] + r1[1]) + r1[2]) + r1[3]) + r1[4] > 0.f) ++c1;
   }
+  __shared__ int s_n[2];
+  if (threadIdx.x == 0) { s_n[0] = 0; s_n[1] = 0; }
+  __syncthreads();
+  if (c0) atomicAdd(&s_n[0], c0);
+  if (c1) atomicAdd(&s_n[1], c1);
   __syncthreads();
   const int G = s_n[0], GS = s_n[1];
+  if (threadIdx.x == 0) { ngt[b] = G; nsup[b] = GS; }
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     float v = 1.0f;
     if (GS > 0) {
@@ -317,45 +450,71 @@ __device__ __forceinline__ void block_arg(float v, int i, float* s_v, int* s_i, 
 }
 
 // ---- 4. dynamic-k matching per (image, gt) (tal_head.py:679-692)
-__global__ void k_dynk(const int* ngt, const float* iou_m, const float* cost_m, int A, int L, int* cnt, int* match) {
-  extern __shared__ float row[];   // [A]
+// Only the image's candidate anchors (in some box or centre region: a few hundred to a few thousand of the 11 850) can be
+// selected -- every other entry of the row is -inf (IoU) / +inf (cost) -- so the block first compacts the candidates'
+// (anchor, IoU) pairs into shared memory and runs the ten arg-max / dynamic-k arg-min rounds over that short list.
+// Selection order is by (value, anchor index): independent of the order in which the list was filled.
+__global__ void k_dynk(const int* ngt, const int* cand, const float* iou_m, const float* cost_m, int A, int L, int* cnt,
+                       int* match) {
+  extern __shared__ float row[];   // [A] values, then [A] anchor indices
+  int* idx = reinterpret_cast<int*>(row + A);
   __shared__ float s_v[33];
   __shared__ int s_i[33];
+  __shared__ int s_n;
   const int b = blockIdx.y, g = blockIdx.x;
   if (g >= ngt[b]) return;
   const float* ir = iou_m + ((size_t)b * L + g) * A;
   const float* cr = cost_m + ((size_t)b * L + g) * A;
-  for (int a = threadIdx.x; a < A; a += blockDim.x) row[a] = ir[a];
+  const int* cd = cand + (size_t)b * A;
+  if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
+  for (int a0 = 0; a0 < A; a0 += blockDim.x) {              // warp-aggregated compaction
+    const int a = a0 + threadIdx.x;
+    const bool is = a < A && cd[a] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, is);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (is) {
+      const int pos = base + __popc(m & ((1u << lane) - 1u));
+      idx[pos] = a;
+      row[pos] = ir[a];
+    }
+  }
+  __syncthreads();
+  const int n = s_n;
   float acc = 0.f;
   for (int k = 0; k < 10; ++k) {
-    float bv = -INFINITY; int bi = 0x7fffffff;
-    for (int a = threadIdx.x; a < A; a += blockDim.x) {
-      const float v = row[a];
-      if (v > bv) { bv = v; bi = a; }
+    float bv = -INFINITY; int bi = 0x7fffffff, bp = -1;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const float v = row[j];
+      const int a = idx[j];
+      if (v > bv || (v == bv && a < bi)) { bv = v; bi = a; bp = j; }
     }
     float wv; int wi;
     block_arg<true>(bv, bi, s_v, s_i, &wv, &wi);
     if (!(wv > -INFINITY)) break;     // fewer than 10 candidates (uniform across the block)
     acc += wv;
-    if (threadIdx.x == 0) row[wi] = -INFINITY;
+    if (bp >= 0 && bi == wi) row[bp] = -INFINITY;   // the one thread that holds the winner retires it
     __syncthreads();
   }
   int dk = (int)acc;
   if (dk < 1) dk = 1;
-  for (int a = threadIdx.x; a < A; a += blockDim.x) row[a] = cr[a];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) row[j] = cr[idx[j]];
   __syncthreads();
   for (int k = 0; k < dk; ++k) {
-    float bv = INFINITY; int bi = 0x7fffffff;
-    for (int a = threadIdx.x; a < A; a += blockDim.x) {
-      const float v = row[a];
-      if (v < bv) { bv = v; bi = a; }
+    float bv = INFINITY; int bi = 0x7fffffff, bp = -1;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const float v = row[j];
+      const int a = idx[j];
+      if (v < bv || (v == bv && a < bi)) { bv = v; bi = a; bp = j; }
     }
     float wv; int wi;
     block_arg<false>(bv, bi, s_v, s_i, &wv, &wi);
     if (!(wv < INFINITY)) break;      // ran out of candidates
-    if (threadIdx.x == 0) {
-      row[wi] = INFINITY;
+    if (bp >= 0 && bi == wi) {
+      row[bp] = INFINITY;
       atomicAdd(&cnt[(size_t)b * A + wi], 1);
       match[(size_t)b * A + wi] = g;
     }
@@ -440,11 +599,15 @@ __global__ void k_resolve_loss(const LossArgs q) {
 
 // ---- 6. final scalars (tal_head.py:441-470)
 __global__ void k_final(const double* part, int nblk, const int* ngt, int B, int use_l1, float* out, double* tot_out) {
+  // 7 sums over nblk partial rows: warp w (of 8) owns sum w; its lanes take rows lane, lane+32, ... in order and a fixed
+  // shuffle tree combines them (deterministic; one thread per sum walking ~380 rows cost ~25 us of serial L2 latency)
   __shared__ double tot[7];
-  if (threadIdx.x < 7) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < 7) {
     double s = 0.0;
-    for (int i = 0; i < nblk; ++i) s += part[(size_t)i * 8 + threadIdx.x];
-    tot[threadIdx.x] = s;
+    for (int i = lane; i < nblk; i += 32) s += part[(size_t)i * 8 + warp];
+    for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    if (lane == 0) tot[warp] = s;
   }
   __syncthreads();
   if (threadIdx.x < 7) tot_out[threadIdx.x] = tot[threadIdx.x];
@@ -578,19 +741,19 @@ extern "C" int sy_head_pred_decode(const SyHeadPredDesc* d, sy_stream_t stream_)
   const SyTensor& f = d->cls_feat;
   SY_REQUIRE(d->reg_feat.n == f.n && d->reg_feat.h == f.h && d->reg_feat.w == f.w && d->reg_feat.c == f.c, SY_EINVAL,
              "head_pred: cls/reg feature mismatch");
-  SY_REQUIRE(d->num_classes >= 1 && d->num_classes <= 32 && d->out && d->w_reg && d->w_obj && d->w_cls && d->b_reg &&
+  SY_REQUIRE(d->num_classes >= 1 && d->num_classes <= 251 && d->out && d->w_reg && d->w_obj && d->w_cls && d->b_reg &&
                  d->b_obj && d->b_cls,
              SY_EINVAL, "head_pred: null weights or num_classes out of range");
   SY_REQUIRE(d->anchor_offset >= 0 && d->anchor_offset + f.h * f.w <= d->a_total, SY_EINVAL, "head_pred: anchor range");
-  SY_REQUIRE(sizeof(float) * (5 + d->num_classes) * f.c <= 160 * 1024, SY_EINVAL, "head_pred: too many channels (%d)", f.c);
-  switch (d->num_classes) {           // compile-time output counts for the class counts in use (Argoverse-HD: 8; COCO: 80 -> generic)
+  SY_REQUIRE((f.c % 8) == 0 && sizeof(float) * (5 + d->num_classes) * f.c <= 200 * 1024, SY_EINVAL,
+             "head_pred: %d channels x %d outputs do not fit the shared-memory weight tile", f.c, 5 + d->num_classes);
+  switch (d->num_classes) {           // compile-time output counts for the class counts in use (Argoverse-HD: 8); any other: generic
     case 8: return launch_head_pred<13>(d, f, stream);
     case 1: return launch_head_pred<6>(d, f, stream);
     case 20: return launch_head_pred<25>(d, f, stream);
     default: break;
   }
-  SY_REQUIRE(false, SY_EINVAL, "head_pred: num_classes=%d not instantiated (8, 1, 20)", d->num_classes);
-  return SY_EINVAL;
+  return launch_head_pred_generic(d, f, stream);
 }
 
 extern "C" size_t sy_tal_loss_workspace_bytes(int32_t b, int32_t a_total, int32_t max_labels, int32_t num_classes) {
@@ -622,10 +785,10 @@ extern "C" int sy_tal_loss(const SyTalLossDesc* d, sy_stream_t stream_) {
   k_anchor_prep<<<dim3(ab, B), kLossThreads, 0, stream>>>(d->outputs, d->labels_fut, w.ngt, lv, A, L, NC, w.cand, w.clsterm);
   k_pair<<<dim3(ab, L, B), kLossThreads, 0, stream>>>(d->outputs, d->labels_fut, w.ngt, w.cand, w.clsterm, lv, A, L, NC,
                                                       w.iou, w.cost);
-  const size_t row_bytes = sizeof(float) * (size_t)A;
+  const size_t row_bytes = 2 * sizeof(float) * (size_t)A;       // candidate values + anchor indices
   SY_REQUIRE(row_bytes <= 200 * 1024, SY_EINVAL, "tal_loss: %d anchors exceed the shared-memory row", A);
   if (row_bytes > 48 * 1024) SY_CUDA(cudaFuncSetAttribute(k_dynk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes));
-  k_dynk<<<dim3(L, B), 256, row_bytes, stream>>>(w.ngt, w.iou, w.cost, A, L, w.cnt, w.match);
+  k_dynk<<<dim3(L, B), 256, row_bytes, stream>>>(w.ngt, w.cand, w.iou, w.cost, A, L, w.cnt, w.match);
   LossArgs q{};
   q.outputs = d->outputs; q.origin = d->origin; q.fut = d->labels_fut; q.ngt = w.ngt; q.tal = w.tal;
   q.iou_m = w.iou; q.cost_m = w.cost; q.cnt = w.cnt; q.match = w.match; q.lv = lv; q.A = A; q.L = L; q.NC = NC;
@@ -633,7 +796,7 @@ extern "C" int sy_tal_loss(const SyTalLossDesc* d, sy_stream_t stream_) {
   q.fg_out = d->fg_out; q.matched_out = d->matched_out; q.piou_out = d->pred_iou_out;
   q.mres = w.mres; q.piou_ws = w.piou;
   k_resolve_loss<<<dim3(ab, B), kLossThreads, 0, stream>>>(q);
-  k_final<<<1, 32, 0, stream>>>(w.part, ab * B, w.ngt, B, d->use_l1, d->loss_out, w.tot);
+  k_final<<<1, 256, 0, stream>>>(w.part, ab * B, w.ngt, B, d->use_l1, d->loss_out, w.tot);
   return launch_status("tal_loss kernels");
 }
 

@@ -50,34 +50,82 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int O, int I, in
   }
 }
 
-// All conv operands of a model in ONE launch: items[k] describes one (parameter, layout) pair like the arguments of
-// pack_weight_kernel; element idx of the launch belongs to the item with begin <= idx < next begin (binary search).
-__global__ void pack_weights_batch_kernel(const SyPackItem* __restrict__ items, int n_items, long long total) {
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    int lo = 0, hi = n_items - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (items[mid].begin <= idx) lo = mid; else hi = mid - 1;
+// All conv operands of a model in ONE launch.  Work unit = TILE: 64 output channels x 32 input channels (x all taps) of one
+// item (modes 0 / 1), or 64 output channels of a stem item (mode 2); items[k].begin = first tile of item k (prefix sum of
+// sy_pack_item_tiles), found by binary search once per tile.  A tile is read with coalesced loads along the source's
+// contiguous (ci, tap) run, converted, staged in shared memory and written with coalesced stores along the destination's
+// contiguous dimension (ci for the forward operand, co for the data-gradient operand).  The first version moved one element
+// per thread with the source index computed from the destination index: the data-gradient layout then read one 32-byte
+// sector per element (1.19 ms for StreamYOLO-l; this version: the 660 MB of traffic at HBM speed).
+constexpr int kPackTO = 64, kPackTI = 32, kPackMaxTaps = 9;
+constexpr int kPackPitch = kPackTI * kPackMaxTaps + 2;      // bf16 elements; (pitch / 2) odd: column reads are conflict-free
+
+__host__ __device__ inline long long pack_item_tiles(int cout, int cin, int mode) {
+  const long long to = (cout + kPackTO - 1) / kPackTO;
+  return mode == 2 ? to : to * ((cin + kPackTI - 1) / kPackTI);
+}
+
+__global__ void __launch_bounds__(256) pack_weights_batch_kernel(const SyPackItem* __restrict__ items, int n_items, long long total) {
+  __shared__ __nv_bfloat16 tile[kPackTO][kPackPitch];
+  __shared__ int s_item;
+  for (long long tidx = blockIdx.x; tidx < total; tidx += gridDim.x) {
+    if (threadIdx.x == 0) {
+      int lo = 0, hi = n_items - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (items[mid].begin <= tidx) lo = mid; else hi = mid - 1;
+      }
+      s_item = lo;
     }
-    const SyPackItem it = items[lo];
-    const long long l = idx - it.begin;
+    __syncthreads();
+    const SyPackItem it = items[s_item];
+    const int l = (int)(tidx - it.begin);
     const int taps = it.taps, O = it.cout, I = it.cin;
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(it.out);
-    if (it.mode == 2) {
-      const int kh = it.kh;
-      const int col = (int)(l % 64), r = (int)((l / 64) % kh), o = (int)(l / (64 * kh));
-      const int s = col >> 4, i = col & 15, kw = taps / kh;
-      float v = 0.f;
-      if (s < kw && i < I) v = it.w[(((long long)o * I + i) * kh + r) * kw + s];
-      out[l] = __float2bfloat16_rn(v);
-    } else if (it.mode == 0) {
-      const int i = (int)(l % I), t = (int)((l / I) % taps), o = (int)(l / ((long long)I * taps));
-      out[l] = __float2bfloat16_rn(it.w[((long long)o * I + i) * taps + t]);
+    if (it.mode == 2) {                                     // Focus stem: out[o][r][s * 16 + i], 64 columns per (o, r)
+      const int kh = it.kh, kw = taps / kh;
+      const int o0 = l * kPackTO, no = min(kPackTO, O - o0);
+      const int n = no * kh * 64;
+      for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int col = e % 64, r = (e / 64) % kh, o = o0 + e / (64 * kh);
+        const int sx = col >> 4, i = col & 15;
+        float v = 0.f;
+        if (sx < kw && i < I) v = it.w[(((long long)o * I + i) * kh + r) * kw + sx];
+        out[(long long)o0 * kh * 64 + e] = __float2bfloat16_rn(v);
+      }
+    } else if (taps > kPackMaxTaps) {                       // (no such conv in the path: element-wise fallback)
+      const int tiles_i = (I + kPackTI - 1) / kPackTI;
+      const int o0 = (l / tiles_i) * kPackTO, i0 = (l % tiles_i) * kPackTI;
+      const int no = min(kPackTO, O - o0), ni = min(kPackTI, I - i0);
+      for (int e = threadIdx.x; e < no * ni * taps; e += blockDim.x) {
+        const int t = e % taps, i = i0 + (e / taps) % ni, o = o0 + e / (taps * ni);
+        const __nv_bfloat16 v = __float2bfloat16_rn(it.w[((long long)o * I + i) * taps + t]);
+        if (it.mode == 0) out[((long long)o * taps + t) * I + i] = v;
+        else out[((long long)i * taps + (taps - 1 - t)) * it.out_pitch + it.co_offset + o] = v;
+      }
     } else {
-      const int o = (int)(l % O), t2 = (int)((l / O) % taps), i = (int)(l / ((long long)O * taps));
-      out[((long long)i * taps + t2) * it.out_pitch + it.co_offset + o] =
-          __float2bfloat16_rn(it.w[((long long)o * I + i) * taps + (taps - 1 - t2)]);
+      const int tiles_i = (I + kPackTI - 1) / kPackTI;
+      const int o0 = (l / tiles_i) * kPackTO, i0 = (l % tiles_i) * kPackTI;
+      const int no = min(kPackTO, O - o0), ni = min(kPackTI, I - i0);
+      const int cols = ni * taps;                           // contiguous floats of source row o: w[o][i0 .. i0 + ni)[taps]
+      for (int e = threadIdx.x; e < no * cols; e += blockDim.x) {
+        const int o = e / cols, c = e - o * cols;
+        tile[o][c] = __float2bfloat16_rn(it.w[((long long)(o0 + o) * I + i0) * taps + c]);
+      }
+      __syncthreads();
+      if (it.mode == 0) {                                   // out[o][t][i]: runs of ni consecutive input channels
+        for (int e = threadIdx.x; e < no * cols; e += blockDim.x) {
+          const int i = e % ni, t = (e / ni) % taps, o = e / cols;
+          out[((long long)(o0 + o) * taps + t) * I + i0 + i] = tile[o][i * taps + t];
+        }
+      } else {                                              // out[i][taps - 1 - t][co_offset + o]: runs of no consecutive output channels
+        for (int e = threadIdx.x; e < no * cols; e += blockDim.x) {
+          const int o = e % no, t2 = (e / no) % taps, i = e / (no * taps);
+          out[((long long)(i0 + i) * taps + t2) * it.out_pitch + it.co_offset + o0 + o] = tile[o][i * taps + (taps - 1 - t2)];
+        }
+      }
     }
+    __syncthreads();                                        // the tile (and s_item) are reused by the next iteration
   }
 }
 
@@ -165,10 +213,13 @@ extern "C" int sy_pack_conv_weight(const float* w, int32_t cout, int32_t cin, in
   return launch_status("pack_weight_kernel");
 }
 
+extern "C" int64_t sy_pack_item_tiles(int32_t cout, int32_t cin, int32_t mode) { return pack_item_tiles(cout, cin, mode); }
+
 extern "C" int sy_pack_conv_weights_batch(const SyPackItem* items_dev, int32_t n_items, int64_t total, sy_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SY_REQUIRE(items_dev != nullptr && n_items > 0 && total > 0, SY_EINVAL, "pack_conv_weights_batch: bad arguments");
-  pack_weights_batch_kernel<<<grid_for(total, 256), 256, 0, stream>>>(items_dev, n_items, total);
+  const int grid = (int)(total < 148ll * 8 ? total : 148ll * 8);
+  pack_weights_batch_kernel<<<grid, 256, 0, stream>>>(items_dev, n_items, total);
   return launch_status("pack_weights_batch_kernel");
 }
 

@@ -35,24 +35,88 @@ DEBUG_HOOK = None     # tests: callable(stage, record, **tensors) invoked inside
                       # recorded conv's backward in situ against torch on the very tensors the kernels saw)
 
 
+POISON = False        # tests: fill the gradient arena with NaN instead of leaving it uninitialised -- a region that is read
+                      # before anything was written to it then poisons the parameter gradients (tests/test_cpu_backward.py)
+
+
 class Tape:
     def __init__(self, device):
         self.device = device
         self.ops = []
-        self.gbuf = {}          # id(activation buffer) -> gradient buffer (bf16, zero-initialised)
+        self.gbuf = {}          # id(activation buffer) -> gradient buffer (bf16)
         self.keep = []          # keeps the activation buffers (and so their ids) alive
         self.uses = {}          # id(BaseConv) -> number of recorded launches (a module used twice accumulates: DFP jian)
+        self.cover = {}         # id(activation buffer) -> bool [images, channels]: which part of its gradient has been written
 
     def g(self, v: View) -> View:
         key = id(v.buf)
         if key not in self.gbuf:
-            self.gbuf[key] = torch.zeros_like(v.buf)
+            self.gbuf[key] = torch.zeros_like(v.buf)                 # (not in the arena: zero-filled, i.e. written)
+            self.cover[key] = torch.ones((v.buf.shape[0], v.buf.shape[3]), dtype=torch.bool)
             self.keep.append(v.buf)
         return View(self.gbuf[key], v.c0, v.c, v.n0, v.n)
 
+    # The arena is NOT zero-filled (the memset plus the reads of those zeros by every first accumulation were ~0.9 ms of a
+    # 20 ms StreamYOLO-l step).  Instead the walk asks before every gradient write whether the region already holds a
+    # contribution: the first contribution is WRITTEN (copy instead of add, the conv data gradient without its residual
+    # input), later ones accumulate; a region that is read before any consumer wrote to it is zero-filled on the spot
+    # (a tensor without consumers -- does not happen in this network, kept for safety).  Host-side bookkeeping only.
+    def _cov(self, v: View):
+        c = self.cover[id(v.buf)]
+        return c[v.n0:v.n0 + v.n, v.c0:v.c0 + v.c]
+
+    def _zero_uncovered(self, v: View):
+        """zero-fill the not yet written part of the gradient region of ``v`` (rectangles of equal image rows)"""
+        cov = self._cov(v)
+        gb = self.gbuf[id(v.buf)]
+        n = 0
+        while n < v.n:
+            m = n + 1
+            while m < v.n and torch.equal(cov[m], cov[n]):
+                m += 1
+            row = cov[n]
+            c = 0
+            while c < v.c:
+                if row[c]:
+                    c += 1
+                    continue
+                e = c
+                while e < v.c and not row[e]:
+                    e += 1
+                gb[v.n0 + n:v.n0 + m, :, :, v.c0 + c:v.c0 + e].zero_()
+                c = e
+            n = m
+        cov[:] = True
+
+    def first(self, v: View) -> bool:
+        """True: nothing has been written to the gradient of ``v`` yet -- the caller must WRITE it (the region counts as
+        written from now on); False: it holds contributions -- the caller accumulates."""
+        cov = self._cov(v)
+        if not bool(cov.any()):
+            cov[:] = True
+            return True
+        if not bool(cov.all()):
+            self._zero_uncovered(v)              # partly written: complete it with zeros, then accumulate
+        return False
+
+    def gread(self, v: View) -> View:
+        """gradient of ``v`` for READING: everything that was never written is zero"""
+        g = self.g(v)
+        if not bool(self._cov(v).all()):
+            self._zero_uncovered(v)
+        return g
+
+    def accumulate(self, src: View, v: View):
+        """g(v) (+)= src"""
+        g = self.g(v)
+        if self.first(v):
+            ops.copy(src, g)
+        else:
+            ops.add_(src, g)
+
     def prepare_grads(self):
-        """One zero-filled arena (ONE memset) holding the gradient buffer of every activation buffer the walk will touch,
-        instead of one allocation + fill per buffer."""
+        """ONE uninitialised arena holding the gradient buffer of every activation buffer the walk will touch, instead of
+        one allocation per buffer (see ``first`` for why it needs no memset)."""
         bufs, seen = [], set()
 
         def add(v):
@@ -79,10 +143,13 @@ class Tape:
         if not bufs:
             return
         sizes = [(b.numel() + 127) // 128 * 128 for b in bufs]            # 256-byte aligned slots
-        arena = torch.zeros(sum(sizes), dtype=bufs[0].dtype, device=self.device)
+        arena = torch.empty(sum(sizes), dtype=bufs[0].dtype, device=self.device)
+        if POISON:
+            arena.fill_(float("nan"))
         off = 0
         for b, n in zip(bufs, sizes):
             self.gbuf[id(b)] = arena[off:off + b.numel()].view(b.shape)
+            self.cover[id(b)] = torch.zeros((b.shape[0], b.shape[3]), dtype=torch.bool)
             self.keep.append(b)
             off += n
 
@@ -315,9 +382,9 @@ def _conv_backward(T: Tape, r, sink):
     dev = T.device
     cout, cin = raw.c, x.c
     stem = r["kind"] == "stem"
-    gy = T.g(y)
+    gy = T.gread(y)
     if res is not None:
-        ops.add_(gy, T.g(res))                                   # shortcut / "+ cur" branch
+        T.accumulate(gy, res)                                    # shortcut / "+ cur" branch
     draw = View.empty(raw.n, raw.h, raw.w, cout, dev)
     dgamma, dbeta, acc_bn = sink.bn(mods)
     if DEBUG_HOOK is not None:
@@ -337,18 +404,20 @@ def _conv_backward(T: Tape, r, sink):
         sink.done([mods[0].conv.weight, mods[0].bn.weight, mods[0].bn.bias])
         return                                                    # the input frames need no gradient
     dw, acc_w = sink.conv_weight(mods, cin, kh, kw)
+    gx = T.g(x)
+    fresh = T.first(x)                                            # no consumer has written this input's gradient yet
     if DEBUG_HOOK is not None:
-        DEBUG_HOOK("pre_w", r, dw=dw, acc_w=acc_w, gx=T.g(x))
+        DEBUG_HOOK("pre_w", r, dw=dw, acc_w=acc_w, gx=None if fresh else gx)
     ops.conv2d_wgrad(x, draw, (kh, kw), s, dw, accumulate=acc_w)
     sink.done([p for m in mods for p in (m.conv.weight, m.bn.weight, m.bn.bias)])
-    gx = T.g(x)
     one, zero = _one_zero(T, cin)
     src = draw
     if s == 2:
         src = View.empty(x.n, x.h, x.w, cout, dev)
         ops.dilate2(draw, src)
-    # data gradient, accumulated in place: gx = conv(src, flipped / transposed filter) * 1 + 0 + gx
-    ops.conv2d(src, engine._packed_dgrad(mods), gx, (kh, kw), 1, ops.SY_CONV_FUSED, scale=one, shift=zero, act=0, res=gx)
+    # data gradient: gx = conv(src, flipped / transposed filter) * 1 + 0 (+ gx: accumulated in place through the residual input)
+    ops.conv2d(src, engine._packed_dgrad(mods), gx, (kh, kw), 1, ops.SY_CONV_FUSED, scale=one, shift=zero, act=0,
+               res=None if fresh else gx)
     if DEBUG_HOOK is not None:
         DEBUG_HOOK("post", r, draw=draw, dgamma=dgamma, dbeta=dbeta, dw=dw, gx=gx)
 
@@ -369,7 +438,9 @@ def _head_backward(T: Tape, head, r, grad_scale, sink):
     for k, cf, rf, off in r["levels"]:
         regp, objp, clsp = head.reg_preds[k], head.obj_preds[k], head.cls_preds[k]
         dws, dbs, acc = sink.head(head, k)
-        ops.head_pred_backward(g_raw, cf, rf, T.g(cf), T.g(rf), _f32(regp.weight), _f32(objp.weight), _f32(clsp.weight),
+        gcf, grf = T.g(cf), T.g(rf)
+        assert T.first(cf) and T.first(rf), "the prediction convs are the only consumers of the tower outputs"
+        ops.head_pred_backward(g_raw, cf, rf, gcf, grf, _f32(regp.weight), _f32(objp.weight), _f32(clsp.weight),
                                r["a_total"], off, dws[0], dws[1], dws[2], dbs[0], dbs[1], dbs[2], accumulate=acc)
         sink.done([regp.weight, objp.weight, clsp.weight, regp.bias, objp.bias, clsp.bias])
 
@@ -383,16 +454,25 @@ def _walk(T: Tape, head, grad_scale, sink):
         elif t == "head":
             _head_backward(T, head, r, grad_scale, sink)
         elif t == "copy":
-            ops.add_(T.g(r["dst"]), T.g(r["src"]))
+            T.accumulate(T.gread(r["dst"]), r["src"])
         elif t == "upsample":
-            tmp = View.empty(r["x"].n, r["x"].h, r["x"].w, r["x"].c, T.device)
-            ops.upsample_nearest_backward(T.g(r["y"]), tmp)
-            ops.add_(tmp, T.g(r["x"]))
+            x = r["x"]
+            gy, gx = T.gread(r["y"]), T.g(x)
+            if T.first(x):
+                ops.upsample_nearest_backward(gy, gx)
+            else:
+                tmp = View.empty(x.n, x.h, x.w, x.c, T.device)
+                ops.upsample_nearest_backward(gy, tmp)
+                ops.add_(tmp, gx)
         elif t == "spp":
             x = r["x"]
-            tmp = View.empty(x.n, x.h, x.w, x.c, T.device)
-            ops.spp_maxpool_backward(x, T.g(r["y5"]), T.g(r["y9"]), T.g(r["y13"]), tmp)
-            ops.add_(tmp, T.g(x))
+            g5, g9, g13, gx = T.gread(r["y5"]), T.gread(r["y9"]), T.gread(r["y13"]), T.g(x)
+            if T.first(x):
+                ops.spp_maxpool_backward(x, g5, g9, g13, gx)
+            else:
+                tmp = View.empty(x.n, x.h, x.w, x.c, T.device)
+                ops.spp_maxpool_backward(x, g5, g9, g13, tmp)
+                ops.add_(tmp, gx)
         else:
             raise RuntimeError(t)
     sink.finish()

@@ -156,6 +156,7 @@ _SIG = {
     "sy_conv2d_wgrad_tc": (C.c_int, [C.POINTER(SyConvWgradDesc), C.c_void_p]),
     "sy_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_int64, C.c_int32, C.c_void_p]),
+    "sy_pack_item_tiles": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "sy_pack_conv_weights_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "sy_sgd_nesterov_ema_step": (C.c_int, [C.POINTER(SySgdEmaDesc), C.c_void_p]),
     "sy_resize_bilinear": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
@@ -637,7 +638,7 @@ class PackBatch:
         o, i, kh, kw = w.shape
         it = SyPackItem(w.data_ptr(), out.data_ptr(), o, i, kh, kh * kw, mode, co_offset, out_pitch, self.total)
         self.items.append(it)
-        self.total += o * kh * 64 if mode == 2 else o * i * kh * kw
+        self.total += load_library().sy_pack_item_tiles(o, i, mode)      # work tiles (see include/streamyolo_sm100.h)
 
     def run(self):
         if self.table is None:

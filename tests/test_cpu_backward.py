@@ -33,6 +33,9 @@ def build_product(c):
 
 def _run(c, monkeypatch, exact):
     emul_ops.install(monkeypatch, exact=exact)
+    # the activation-gradient arena starts as NaN instead of uninitialised memory: a region the walk reads before any
+    # consumer wrote it (first-write bookkeeping of backward.Tape) would poison the parameter gradients checked below
+    monkeypatch.setattr(backward, "POISON", True)
     x = synth.synth_frames(c["B"], c["H"], c["W"])
     tg = synth.synth_labels(c["B"], c["H"], c["W"], empty_image=c["empty"])
     model = build_product(c)

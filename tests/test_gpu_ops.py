@@ -281,8 +281,13 @@ def test_spp_and_copy_exact():
     assert torch.equal(s.nchw_float(), ref)
 
 
-def test_head_pred_decode():
-    b, c, h, w, nc = 2, 64, 15, 20, 8
+@pytest.mark.parametrize("shape", [(2, 64, 15, 20, 8), (2, 64, 15, 20, 3), (1, 32, 9, 11, 80), (8, 256, 75, 120, 8)],
+                         ids=["nc8", "nc3-generic", "nc80-generic", "level0-l"])
+def test_head_pred_decode(shape, monkeypatch):
+    """Prediction convs + decode against F.conv2d.  Class counts without a compiled instantiation take the generic kernel
+    (the reference head accepts any num_classes, tal_head.py:27); the benchmark's level-0 shape takes the two-pixels-per-thread
+    variant, whose output must be bit-identical to the one-pixel variant (same per-pixel arithmetic)."""
+    b, c, h, w, nc = shape
     cf, rf = rand_act(b, c, h, w, 51), rand_act(b, c, h, w, 52)
     g = torch.Generator().manual_seed(53)
     wr, br = (torch.randn(4, c, generator=g) * 0.05).to(DEV), (torch.randn(4, generator=g) * 0.1).to(DEV)
@@ -310,6 +315,17 @@ def test_head_pred_decode():
         if train:
             assert torch.allclose(origin[:, off:], raw[..., :4], rtol=1e-4, atol=1e-5)
         assert (out[:, :off] == 0).all()
+        if nc == 8:
+            outs = []
+            for pt in ("1", "2", "4"):
+                monkeypatch.setenv("SY_HEAD_PT", pt)
+                o2 = torch.zeros((b, a_total, 5 + nc), device=DEV)
+                ops.head_pred_decode(ops.from_nchw(cf), ops.from_nchw(rf), wr, br, wo_, bo, wc, bc, stride, off, a_total, o2,
+                                     None, sigmoid=not train, decode=True)
+                torch.cuda.synchronize()
+                outs.append(o2)
+            monkeypatch.delenv("SY_HEAD_PT")
+            assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]) and torch.equal(outs[0], out)
 
 
 # ---------------------------------------------------------------------------------------------- backward bricks

@@ -169,7 +169,8 @@ def test_walk_in_situ_every_conv_backward():
             return
         if stage == "pre_w":
             snap["dw"] = kw["dw"].clone() if kw["acc_w"] else None
-            snap["gx"] = nchw(kw["gx"]).clone()
+            # gx is None when this launch is the first contribution to its input's gradient (written, not accumulated)
+            snap["gx"] = nchw(kw["gx"]).clone() if kw["gx"] is not None else 0.0
             return
         mods, raw, xin = r["mods"], nchw(r["raw"]), nchw(r["x"])
         name = getattr(mods[0], "_sy_name", "?")
@@ -211,11 +212,15 @@ def test_walk_in_situ_every_conv_backward():
     from streamyolo_b200.model import engine
     engine.name_modules(m)
     backward.DEBUG_HOOK = hook
+    backward.POISON = True        # the gradient arena starts as NaN: a region read before it was written would show up
     try:
         backward.forward_backward(m, x, tg)
         torch.cuda.synchronize()
     finally:
         backward.DEBUG_HOOK = None
+        backward.POISON = False
+    for n_, p_ in m.named_parameters():
+        assert p_.grad is not None and bool(torch.isfinite(p_.grad).all()), n_
     # 77 BaseConvs: 8 CSP conv2 ride with their conv1, 3 head reg towers with their cls twin, jian x2, the stem has no dx
     assert len(seen) == 77 - 8 - 3 + 3 - 1, len(seen)
 
@@ -266,3 +271,23 @@ def test_pack_batch_equals_single_packs():
     assert torch.equal(f0, ops.pack_conv_weight(ws[0])) and torch.equal(d0, ops.pack_conv_weight_dgrad(ws[0]))
     assert torch.equal(pair_f, ops.pack_conv_weight(ws[1], ws[2])) and torch.equal(pair_d, ops.pack_conv_weight_dgrad(ws[1], ws[2]))
     assert torch.equal(stem, ops.pack_stem_weight(ws[3])) and torch.equal(f4, ops.pack_conv_weight(ws[4]))
+    # ragged tiles (the launch works in 64 x 32 channel tiles) and a stem with more than 64 outputs
+    for shape in ((96, 80, 3, 3), (200, 24, 3, 3), (520, 264, 1, 1), (8, 8, 3, 3)):
+        w = torch.randn(shape, generator=g).cuda()
+        o, i, kh, kw = shape
+        f = torch.full((o, kh * kw, i), 7.0, dtype=torch.bfloat16, device="cuda")
+        d = torch.full((i, kh * kw, o + 8), 7.0, dtype=torch.bfloat16, device="cuda")
+        pb2 = ops.PackBatch(torch.device("cuda"))
+        pb2.add(w, f, 0)
+        pb2.add(w, d, 1, out_pitch=o + 8, co_offset=8)
+        pb2.run()
+        torch.cuda.synchronize()
+        assert torch.equal(f, ops.pack_conv_weight(w))
+        assert torch.equal(d[:, :, 8:], ops.pack_conv_weight_dgrad(w)) and (d[:, :, :8] == 7.0).all()
+    w = torch.randn((80, 12, 3, 3), generator=g).cuda()
+    st = torch.empty((80, 3, 64), dtype=torch.bfloat16, device="cuda")
+    pb3 = ops.PackBatch(torch.device("cuda"))
+    pb3.add(w, st, 2)
+    pb3.run()
+    torch.cuda.synchronize()
+    assert torch.equal(st, ops.pack_stem_weight(w))

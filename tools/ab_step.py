@@ -28,6 +28,14 @@ SETTINGS = [
     ("team epilogue off", {"SY_CONV_TEAM": "0"}, 0),
     ("pair mode off (no cta_group::2)", {"SY_CONV_PAIR": "0"}, 0),
     ("pair mode forced on every BN=256 linear layer", {"SY_CONV_PAIR": "1"}, 0),
+    ("fuse apply <= 10 MB", {}, 10),
+    ("fuse apply <= 20 MB", {}, 20),
+    ("fuse apply <= 40 MB", {}, 40),
+    ("fuse apply <= 10 MB +pair", {"SY_PAIR_APPLY": "1"}, 10),
+    ("fuse apply <= 20 MB +pair", {"SY_PAIR_APPLY": "1"}, 20),
+    ("fuse apply <= 40 MB +pair", {"SY_PAIR_APPLY": "1"}, 40),
+    ("head pred 1 px/thread", {"SY_HEAD_PT": "1"}, 0),
+    ("head pred 4 px/thread", {"SY_HEAD_PT": "4"}, 0),
     ("raw arena off (no L2 window)", {"SY_RAW_ARENA_MB": "0"}, 0),
     ("halo off", {"SY_CONV_A": "off"}, 0),
     ("halo forced", {"SY_CONV_A": "halo"}, 0),
@@ -53,7 +61,7 @@ SETTINGS = [
 ]
 if len(sys.argv) > 3:
     SETTINGS = [s for s in SETTINGS if any(k in s[0] for k in sys.argv[3].split(","))]
-SWITCHES = ("SY_RAW_ARENA_MB", "SY_CONV_TEAM", "SY_CONV_PAIR", "SY_DBG_SKIP_APPLY", "SY_CONV_TILES", "SY_PDL", "SY_APPLY", "SY_APPLY_CAP", "SY_STAGE_TILES", "SY_APPLY_CARVEOUT", "SY_CONV_DEBUG", "SY_CONV_A")
+SWITCHES = ("SY_HEAD_PT", "SY_PAIR_APPLY", "SY_RAW_ARENA_MB", "SY_CONV_TEAM", "SY_CONV_PAIR", "SY_DBG_SKIP_APPLY", "SY_CONV_TILES", "SY_PDL", "SY_APPLY", "SY_APPLY_CAP", "SY_STAGE_TILES", "SY_APPLY_CARVEOUT", "SY_CONV_DEBUG", "SY_CONV_A")
 
 
 def measure(label, env, fuse_mb, steps=20, warmup=4):
