@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(kBwdThreads) bn_act_bwd_reduce_kernel(const Bw
 //   with A = scale, B = shift, C1 = -scale * mb * invstd, C0 = -scale * (ma - mb * mean * invstd),
 //   ma = mean_g(dz), mb = mean_g(dz * xhat)     (draw = scale * (dz - ma - xhat * mb), xhat = (r - mean) * invstd)
 // coef layout [2 groups][4 (A | B | C1 | C0)][C].
-__global__ void __launch_bounds__(256) bn_act_bwd_finalize_kernel(const float* __restrict__ partials, int rows0, int rows1, double cnt0,
-                                                                  double cnt1, int C, const float* __restrict__ scale,
+__global__ void __launch_bounds__(256) bn_act_bwd_finalize_kernel(const float* __restrict__ partials, int rows0, int rows1, double inv_cnt0,
+                                                                  double inv_cnt1, int C, const float* __restrict__ scale,
                                                                   const float* __restrict__ shift, const float* __restrict__ mean,
                                                                   const float* __restrict__ invstd, float* dgamma, float* dbeta,
                                                                   int accumulate, float* coef) {
@@ -158,8 +158,8 @@ __global__ void __launch_bounds__(256) bn_act_bwd_finalize_kernel(const float* _
       for (int m = 16; m >= 1; m >>= 1) s[g][i] += __shfl_xor_sync(0xffffffffu, s[g][i], m);
   if (lane != 0) return;
   for (int g = 0; g < 2; ++g) {
-    const double cnt = g ? cnt1 : cnt0;
-    const float ma = cnt > 0.0 ? (float)(s[g][0] / cnt) : 0.f, mb = cnt > 0.0 ? (float)(s[g][1] / cnt) : 0.f;
+    const double inv_cnt = g ? inv_cnt1 : inv_cnt0;       // 1 / pixels of the group, host-computed (0: empty group) -- no fp64
+    const float ma = (float)(s[g][0] * inv_cnt), mb = (float)(s[g][1] * inv_cnt);   // division on the device (software, ~1 us)
     const float A = scale[g * C + c], B = shift[g * C + c], mu = mean[g * C + c], is = invstd[g * C + c];
     coef[(g * 4 + 0) * C + c] = A;
     coef[(g * 4 + 1) * C + c] = B;
@@ -270,8 +270,9 @@ extern "C" int sy_bn_act_backward(const SyBnActBwdDesc* d, sy_stream_t stream_) 
   const int rows = q.rows0 + q.rows1;
   SY_REQUIRE(d->n_partials >= rows, SY_EWORKSPACE, "bn_act_backward: %d partial rows, need %d", d->n_partials, rows);
   bn_act_bwd_reduce_kernel<<<rows, kBwdThreads, 0, stream>>>(q, d->partials);
-  bn_act_bwd_finalize_kernel<<<cdiv(raw.c, 8), 256, 0, stream>>>(d->partials, q.rows0, q.rows1, (double)q.split_pix,
-                                                                 (double)(q.npix - q.split_pix), raw.c, d->scale, d->shift, d->mean,
+  const double inv0 = q.split_pix > 0 ? 1.0 / (double)q.split_pix : 0.0;
+  const double inv1 = q.npix - q.split_pix > 0 ? 1.0 / (double)(q.npix - q.split_pix) : 0.0;
+  bn_act_bwd_finalize_kernel<<<cdiv(raw.c, 8), 256, 0, stream>>>(d->partials, q.rows0, q.rows1, inv0, inv1, raw.c, d->scale, d->shift, d->mean,
                                                                  d->invstd, d->dgamma, d->dbeta, d->accumulate, d->coef);
   const int G = raw.c / 8, ppb = kBwdThreads / G;
   long long blocks = (q.npix + (long long)ppb * kBwdUnroll - 1) / ((long long)ppb * kBwdUnroll);
