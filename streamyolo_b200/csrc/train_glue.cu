@@ -113,7 +113,20 @@ __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const SyPackIte
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
       for (int o = warp; o < no; o += 8) {
         const float* src = it.w + ((long long)(o0 + o) * I + i0) * taps;
-        for (int c = lane; c < cols; c += 32) tile[o][c] = __float2bfloat16_rn(src[c]);
+        // nine loads in flight per lane (a whole 3x3 row in one pass): one load per iteration left the tile latency-bound
+        for (int c0 = 0; c0 < cols; c0 += 32 * kPackMaxTaps) {
+          float v[kPackMaxTaps];
+#pragma unroll
+          for (int j = 0; j < kPackMaxTaps; ++j) {
+            const int c = c0 + 32 * j + lane;
+            v[j] = c < cols ? src[c] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < kPackMaxTaps; ++j) {
+            const int c = c0 + 32 * j + lane;
+            if (c < cols) tile[o][c] = __float2bfloat16_rn(v[j]);
+          }
+        }
       }
       __syncthreads();
       if (it.mode == 0) {                                   // out[o][t][i]: runs of ni consecutive input channels
