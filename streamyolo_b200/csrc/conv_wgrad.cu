@@ -68,11 +68,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int S = p.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * kStageBytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
-  const uint32_t tfull = bar0 + 8u * (2 * kMaxStages), tempty = bar0 + 8u * (2 * kMaxStages + 1);
+  // two accumulators (2 x BN TMEM columns): the epilogue of work item i (TMEM -> 128 x BN fp32 partial in global memory)
+  // overlaps the main loop of item i + 1 (with one accumulator the MMA warp idled through every epilogue)
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + 2 + a); };
+  constexpr int kTmemCols = 2 * BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   (void)lane;
 
@@ -83,11 +87,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tfull, 1);
-    mbar_init(tempty, 128);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), BN < 32 ? 32 : BN);
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -139,8 +145,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       int m_tile, n_tile, tap, kb0, kb1;
       decode(item, m_tile, n_tile, tap, kb0, kb1);
-      mbar_wait(tempty, ((uint32_t)it & 1u) ^ 1u);          // the epilogue has drained the accumulator
+      const int acc = it & 1;
+      mbar_wait(tempty_bar(acc), (((uint32_t)it >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator
       tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tcgen05_fence_after();
@@ -148,14 +156,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           const uint32_t a0 = smem_u32(smem + stage * kStageBytes), b0 = a0 + 2 * kBoxBytes;
 #pragma unroll
           for (int k = 0; k < kPixK / 16; ++k)
-            umma_bf16(tmem_base, make_desc_mn(a0 + k * 2048), make_desc_mn(b0 + k * 2048), idesc, (kb != kb0) || (k != 0));
+            umma_bf16(tmem_d, make_desc_mn(a0 + k * 2048), make_desc_mn(b0 + k * 2048), idesc, (kb != kb0) || (k != 0));
           umma_commit(empty_bar(stage));
-          if (kb == kb1 - 1) umma_commit(tfull);
+          if (kb == kb1 - 1) umma_commit(tfull_bar(acc));
         }
         __syncwarp();
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
-      if (kb1 <= kb0 && elect_one()) umma_commit(tfull);     // empty split (cannot happen with the host's ksplit; keeps the protocol safe)
+      if (kb1 <= kb0 && elect_one()) umma_commit(tfull_bar(acc));     // empty split (cannot happen with the host's ksplit; keeps the protocol safe)
       __syncwarp();
     }
   } else {
@@ -164,7 +172,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       int m_tile, n_tile, tap, kb0, kb1;
       decode(item, m_tile, n_tile, tap, kb0, kb1);
-      mbar_wait(tfull, (uint32_t)it & 1u);
+      const int acc = it & 1;
+      mbar_wait(tfull_bar(acc), ((uint32_t)it >> 1) & 1u);
       tcgen05_fence_after();
       const int row = warp * 32 + lane;
       float* dst = p.partial + ((size_t)item * 128 + row) * BN;
@@ -172,7 +181,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
@@ -181,14 +190,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                     : make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
       }
       tcgen05_fence_before();
-      mbar_arrive(tempty);
+      mbar_arrive(tempty_bar(acc));
     }
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 4) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
