@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kApplyThreads, 3)
 bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const float* __restrict__ scale,
                     const float* __restrict__ shift, long long split_pix, int act,
                     const __nv_bfloat16* res, long long rp, __nv_bfloat16* y, long long yp,
-                    long long npix, int C, long long y_goff1, long long r_goff1) {
+                    long long npix, int C, long long y_goff1, long long r_goff1, int hints) {
   pdl_launch_dependents();
   const int G = C >> 3;                           // 16-byte chunks per pixel (<= 256)
   const int ppb = kApplyThreads / G;              // pixels per block pass
@@ -136,7 +136,8 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const flo
 #pragma unroll
     for (int j = 0; j < kApplyUnroll; ++j) {
       const long long pix = pix0 + j * step;
-      if (pix < npix) v[j] = *reinterpret_cast<const uint4*>(xg + pix * xp);
+      // hints & 1: the raw tensor is dead after this pass -- read it with the streaming (evict-first) policy (A/B switch)
+      if (pix < npix) v[j] = (hints & 1) ? __ldcs(reinterpret_cast<const uint4*>(xg + pix * xp)) : *reinterpret_cast<const uint4*>(xg + pix * xp);
     }
     if (RES) {
 #pragma unroll
@@ -164,7 +165,8 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const flo
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] += r[i];
       }
-      *reinterpret_cast<uint4*>(yg + pix * yp + (g1 ? y_goff1 : 0)) = pack8(f);
+      if (hints & 2) __stcg(reinterpret_cast<uint4*>(yg + pix * yp + (g1 ? y_goff1 : 0)), pack8(f));
+      else *reinterpret_cast<uint4*>(yg + pix * yp + (g1 ? y_goff1 : 0)) = pack8(f);
     }
   }
 }
@@ -346,13 +348,15 @@ extern "C" int sy_bn_act_apply(SyTensor x, const float* scale, const float* shif
   if (const char* e = getenv("SY_APPLY_CAP")) cap = 148LL * (atoi(e) > 0 ? atoi(e) : 3);   // tuning aid: blocks per SM
   const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
   const bool has_res = rp != nullptr;
+  int hints = 0;
+  if (const char* e = getenv("SY_APPLY_HINTS")) hints = atoi(e);                             // tuning aid: cache-policy bits
   auto launch = [&](auto kernel) -> int {
     // L1/shared split: measured on the whole step (StreamYOLO-l, 8 pairs): carveout 0 (all L1) 6.40 ms, default and
     // 100 (all shared, the conv kernels' split) 6.51 ms.
     SY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
     SY_CUDA(launch_pdl(kernel, dim3(grid), dim3(kApplyThreads), 0, stream, CBF(x.ptr), (long long)x.pitch, scale, shift,
                        split_pix, act, rp, rpitch, BF(y.ptr), (long long)y.pitch, npix, x.c, (long long)y_goff1,
-                       (long long)r_goff1));
+                       (long long)r_goff1, hints));
     return SY_OK;
   };
   int rc;

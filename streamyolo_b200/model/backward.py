@@ -47,6 +47,7 @@ class Tape:
         self.keep = []          # keeps the activation buffers (and so their ids) alive
         self.uses = {}          # id(BaseConv) -> number of recorded launches (a module used twice accumulates: DFP jian)
         self.cover = {}         # id(activation buffer) -> bool [images, channels]: which part of its gradient has been written
+        self.pending = {}       # id(activation buffer) -> [(dst view, src gradient view)]: deferred first contributions (see defer)
 
     def g(self, v: View) -> View:
         key = id(v.buf)
@@ -88,9 +89,62 @@ class Tape:
             n = m
         cov[:] = True
 
+    # A shortcut's gradient (g(res) += g(y)) that would be the FIRST contribution to g(res) is not copied: it is remembered and
+    # handed to the conv data-gradient launch that writes the same region next, as that launch's residual input
+    # (g(x) = conv(...) + g(y) in one epilogue).  Any other access to the region first materialises the copy.
+    @staticmethod
+    def _same(a: View, b: View):
+        return a.buf is b.buf and (a.c0, a.c, a.n0, a.n) == (b.c0, b.c, b.n0, b.n)
+
+    @staticmethod
+    def _overlap(a: View, b: View):
+        return (a.buf is b.buf and a.c0 < b.c0 + b.c and b.c0 < a.c0 + a.c and a.n0 < b.n0 + b.n and b.n0 < a.n0 + a.n)
+
+    def defer(self, src: View, v: View):
+        """g(v) (+)= src, deferred when it would be the first write"""
+        self.g(v)
+        self._resolve(v)
+        if bool(self._cov(v).any()):
+            self.accumulate(src, v)
+        else:
+            self.pending.setdefault(id(v.buf), []).append((v, src))
+
+    def take_pending(self, v: View):
+        """the deferred source for EXACTLY the region of ``v`` (removed from the table), or None; other deferred regions that
+        overlap ``v`` are materialised"""
+        lst = self.pending.get(id(v.buf), [])
+        hit = None
+        for i, (dv, src) in enumerate(lst):
+            if self._same(dv, v):
+                hit = lst.pop(i)[1]
+                break
+        self._resolve(v)
+        return hit
+
+    def _resolve(self, v: View):
+        lst = self.pending.get(id(v.buf))
+        if not lst:
+            return
+        keep = []
+        for dv, src in lst:
+            if self._overlap(dv, v):
+                gd = View(self.gbuf[id(dv.buf)], dv.c0, dv.c, dv.n0, dv.n)
+                cov = self._cov(dv)
+                if not bool(cov.any()):
+                    cov[:] = True
+                    ops.copy(src, gd)
+                else:
+                    if not bool(cov.all()):
+                        self._zero_uncovered(dv)
+                    ops.add_(src, gd)
+            else:
+                keep.append((dv, src))
+        self.pending[id(v.buf)] = keep
+
     def first(self, v: View) -> bool:
         """True: nothing has been written to the gradient of ``v`` yet -- the caller must WRITE it (the region counts as
         written from now on); False: it holds contributions -- the caller accumulates."""
+        self._resolve(v)
         cov = self._cov(v)
         if not bool(cov.any()):
             cov[:] = True
@@ -102,6 +156,7 @@ class Tape:
     def gread(self, v: View) -> View:
         """gradient of ``v`` for READING: everything that was never written is zero"""
         g = self.g(v)
+        self._resolve(v)
         if not bool(self._cov(v).all()):
             self._zero_uncovered(v)
         return g
@@ -384,7 +439,7 @@ def _conv_backward(T: Tape, r, sink):
     stem = r["kind"] == "stem"
     gy = T.gread(y)
     if res is not None:
-        T.accumulate(gy, res)                                    # shortcut / "+ cur" branch
+        T.defer(gy, res)                                         # shortcut / "+ cur" branch
     draw = View.empty(raw.n, raw.h, raw.w, cout, dev)
     dgamma, dbeta, acc_bn = sink.bn(mods)
     if DEBUG_HOOK is not None:
@@ -405,9 +460,11 @@ def _conv_backward(T: Tape, r, sink):
         return                                                    # the input frames need no gradient
     dw, acc_w = sink.conv_weight(mods, cin, kh, kw)
     gx = T.g(x)
+    shortcut = T.take_pending(x)                                  # a deferred shortcut gradient for exactly this region
     fresh = T.first(x)                                            # no consumer has written this input's gradient yet
+    assert shortcut is None or fresh
     if DEBUG_HOOK is not None:
-        DEBUG_HOOK("pre_w", r, dw=dw, acc_w=acc_w, gx=None if fresh else gx)
+        DEBUG_HOOK("pre_w", r, dw=dw, acc_w=acc_w, gx=shortcut if shortcut is not None else (None if fresh else gx))
     ops.conv2d_wgrad(x, draw, (kh, kw), s, dw, accumulate=acc_w)
     sink.done([p for m in mods for p in (m.conv.weight, m.bn.weight, m.bn.bias)])
     one, zero = _one_zero(T, cin)
@@ -417,7 +474,7 @@ def _conv_backward(T: Tape, r, sink):
         ops.dilate2(draw, src)
     # data gradient: gx = conv(src, flipped / transposed filter) * 1 + 0 (+ gx: accumulated in place through the residual input)
     ops.conv2d(src, engine._packed_dgrad(mods), gx, (kh, kw), 1, ops.SY_CONV_FUSED, scale=one, shift=zero, act=0,
-               res=None if fresh else gx)
+               res=shortcut if shortcut is not None else (None if fresh else gx))
     if DEBUG_HOOK is not None:
         DEBUG_HOOK("post", r, draw=draw, dgamma=dgamma, dbeta=dbeta, dw=dw, gx=gx)
 
@@ -475,6 +532,7 @@ def _walk(T: Tape, head, grad_scale, sink):
                 ops.add_(tmp, gx)
         else:
             raise RuntimeError(t)
+    assert not any(T.pending.values()), "deferred shortcut gradients left over"
     sink.finish()
 
 

@@ -12,18 +12,16 @@ from .. import ops
 from .network_blocks import BaseConv, DWConv
 
 
-SUPPORTED_NUM_CLASSES = (8, 1, 20)     # head_pred_kernel<5 + nc> instantiations
+MAX_NUM_CLASSES = 251     # sy_head_pred_decode: compiled instantiations for 8 / 1 / 20 classes, a generic kernel for any other count
+                          # (the reference head takes num_classes freely, tal_head.py:27); training backward: <= 27 classes
 
 
 class TALHead(nn.Module):
     def __init__(self, num_classes, width=1.0, strides=[8, 16, 32], in_channels=[256, 512, 1024], act="silu",
                  depthwise=False, gamma=1.5, ignore_thr=0.2, ignore_value=0.2):
         super().__init__()
-        if num_classes not in SUPPORTED_NUM_CLASSES:
-            # the prediction-conv + decode kernel is instantiated per class count (csrc/head_loss.cu): fail at construction,
-            # not at the first forward
-            raise NotImplementedError(f"num_classes={num_classes}: libstreamyolo_sm100 builds the head kernels for "
-                                      f"{SUPPORTED_NUM_CLASSES} (Argoverse-HD: 8)")
+        if not 1 <= num_classes <= MAX_NUM_CLASSES:
+            raise NotImplementedError(f"num_classes={num_classes}: the head kernels take 1..{MAX_NUM_CLASSES} classes")
         self.gamma, self.ignore_thr, self.ignore_value = gamma, ignore_thr, ignore_value
         self.n_anchors = 1
         self.num_classes = num_classes

@@ -288,5 +288,6 @@ def test_pipe_head_is_tal_head_without_trend_weights(monkeypatch):
     ref = o.forward(x, (fut, fut))
     for k in ("total_loss", "iou_loss", "l1_loss", "conf_loss", "cls_loss", "num_fg"):
         assert abs(float(loss[k]) - float(ref[k])) <= 2e-5 * abs(float(ref[k])) + 1e-6, k
+    assert TALHead(80, 0.25).num_classes == 80          # any class count constructs (generic head kernel; tal_head.py:27)
     with pytest.raises(NotImplementedError):
-        TALHead(80)
+        TALHead(1000)

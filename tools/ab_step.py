@@ -36,6 +36,12 @@ SETTINGS = [
     ("fuse apply <= 40 MB +pair", {"SY_PAIR_APPLY": "1"}, 40),
     ("head pred 1 px/thread", {"SY_HEAD_PT": "1"}, 0),
     ("head pred 4 px/thread", {"SY_HEAD_PT": "4"}, 0),
+    ("apply: raw loads streaming (ld.cs)", {"SY_APPLY_HINTS": "1"}, 0),
+    ("apply: stores .cg", {"SY_APPLY_HINTS": "2"}, 0),
+    ("apply: ld.cs + st.cg", {"SY_APPLY_HINTS": "3"}, 0),
+    ("raw arena 20 MB", {"SY_RAW_ARENA_MB": "20"}, 0),
+    ("raw arena 60 MB", {"SY_RAW_ARENA_MB": "60"}, 0),
+    ("raw arena 80 MB", {"SY_RAW_ARENA_MB": "80"}, 0),
     ("raw arena off (no L2 window)", {"SY_RAW_ARENA_MB": "0"}, 0),
     ("halo off", {"SY_CONV_A": "off"}, 0),
     ("halo forced", {"SY_CONV_A": "halo"}, 0),
@@ -61,7 +67,7 @@ SETTINGS = [
 ]
 if len(sys.argv) > 3:
     SETTINGS = [s for s in SETTINGS if any(k in s[0] for k in sys.argv[3].split(","))]
-SWITCHES = ("SY_HEAD_PT", "SY_PAIR_APPLY", "SY_RAW_ARENA_MB", "SY_CONV_TEAM", "SY_CONV_PAIR", "SY_DBG_SKIP_APPLY", "SY_CONV_TILES", "SY_PDL", "SY_APPLY", "SY_APPLY_CAP", "SY_STAGE_TILES", "SY_APPLY_CARVEOUT", "SY_CONV_DEBUG", "SY_CONV_A")
+SWITCHES = ("SY_APPLY_HINTS", "SY_HEAD_PT", "SY_PAIR_APPLY", "SY_RAW_ARENA_MB", "SY_CONV_TEAM", "SY_CONV_PAIR", "SY_DBG_SKIP_APPLY", "SY_CONV_TILES", "SY_PDL", "SY_APPLY", "SY_APPLY_CAP", "SY_STAGE_TILES", "SY_APPLY_CARVEOUT", "SY_CONV_DEBUG", "SY_CONV_A")
 
 
 def measure(label, env, fuse_mb, steps=20, warmup=4):
@@ -69,7 +75,11 @@ def measure(label, env, fuse_mb, steps=20, warmup=4):
         os.environ.pop(k, None)
     os.environ.update(env)
     engine.FUSE_APPLY_MAX_BYTES = fuse_mb * 1e6
-    engine.RAW_ARENA_MB = float(os.environ.get("SY_RAW_ARENA_MB", "40"))
+    mb = float(os.environ.get("SY_RAW_ARENA_MB", "40"))
+    if mb != engine.RAW_ARENA_MB:
+        engine._RAW_ARENAS.clear()          # the arena is allocated once at its configured size: re-create it
+        engine._CAPTURE_STREAMS.clear()
+    engine.RAW_ARENA_MB = mb
     with torch.no_grad():
         ops.LAUNCHES = 0
         out = model(x, (fut, cur))
