@@ -79,6 +79,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   constexpr int kTmemCols = 2 * BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   (void)lane;
+  pdl_launch_dependents();               // (launch_pdl) the next kernel on the stream may start its own prologue
 
   if (threadIdx.x == 5 * 32) {
     prefetch_tmap(&tmDY);
@@ -99,6 +100,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int hw = p.Ho * p.Wo;
+  // everything above touched only smem / TMEM / kernel parameters; from here on we read what the previous kernels wrote
+  // (and write the partial tiles, which may alias a workspace an earlier reduction is still reading)
+  pdl_wait();
 
   auto decode = [&](int item, int& m_tile, int& n_tile, int& tap, int& kb0, int& kb1) {
     const int ks = item % p.ksplit;
@@ -204,20 +208,53 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 // dw[co][ci][r][s] (+)= sum over the K splits, fixed order.  Threads walk (co, tap, ci) with ci fastest: the partial reads
 // (the bulk: ksplit per output) are coalesced along the N = input-channel dimension; only the single store per output is
 // strided (by the tap count) in the optimizer's OIHW layout.
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int BN, int m_tiles, int n_tiles, int taps, int ksplit,
-                                    int Cout, int Cin, float* dw, int accumulate) {
+// SG > 1 (layers with few outputs and many splits: the 1x1 convs have up to 296 splits for 16 K - 260 K outputs): a block's
+// 256 threads are 256 / SG outputs x SG split groups; group g sums the splits [g * ksplit / SG, (g + 1) * ksplit / SG) and
+// the first group adds the SG sums in group order (deterministic).  One thread per output walked its 296 partials in a
+// dependent-latency chain: ~13 us per 1x1 layer for 16 MB of partials.
+template <int SG>
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int BN, int m_tiles, int n_tiles, int taps,
+                                                           int ksplit, int Cout, int Cin, float* dw, int accumulate) {
+  constexpr int kOut = 256 / SG;                  // outputs per block pass
+  __shared__ float part[SG][kOut];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int ol = (int)threadIdx.x % kOut, sg = (int)threadIdx.x / kOut;
   const long long total = (long long)Cout * Cin * taps;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int ci = (int)(idx % Cin);
-    const int tap = (int)((idx / Cin) % taps);
-    const int co = (int)(idx / ((long long)taps * Cin));
-    const int m_tile = co / 128, row = co % 128, n_tile = ci / BN, col = ci % BN;
-    const size_t item0 = ((size_t)(m_tile * n_tiles + n_tile) * taps + tap) * ksplit;
-    const float* src = partial + (item0 * 128 + row) * BN + col;
+  const int k0 = (int)((long long)ksplit * sg / SG), k1 = (int)((long long)ksplit * (sg + 1) / SG);
+  for (long long base = (long long)blockIdx.x * kOut; base < total; base += (long long)gridDim.x * kOut) {
+    const long long idx = base + ol;
     float acc = 0.f;
-    for (int ks = 0; ks < ksplit; ++ks) acc += __ldg(src + (size_t)ks * 128 * BN);
-    const long long o = ((long long)co * Cin + ci) * taps + tap;
-    dw[o] = accumulate ? dw[o] + acc : acc;
+    long long o = 0;
+    if (idx < total) {
+      const int ci = (int)(idx % Cin);
+      const int tap = (int)((idx / Cin) % taps);
+      const int co = (int)(idx / ((long long)taps * Cin));
+      const int m_tile = co / 128, row = co % 128, n_tile = ci / BN, col = ci % BN;
+      const size_t item0 = ((size_t)(m_tile * n_tiles + n_tile) * taps + tap) * ksplit;
+      const float* src = partial + (item0 * 128 + row) * BN + col;
+      int ks = k0;
+      for (; ks + 4 <= k1; ks += 4) {             // four loads in flight; summed in split order
+        const float v0 = __ldg(src + (size_t)ks * 128 * BN), v1 = __ldg(src + (size_t)(ks + 1) * 128 * BN);
+        const float v2 = __ldg(src + (size_t)(ks + 2) * 128 * BN), v3 = __ldg(src + (size_t)(ks + 3) * 128 * BN);
+        acc += v0; acc += v1; acc += v2; acc += v3;
+      }
+      for (; ks < k1; ++ks) acc += __ldg(src + (size_t)ks * 128 * BN);
+      o = ((long long)co * Cin + ci) * taps + tap;
+    }
+    if (SG > 1) {
+      part[sg][ol] = acc;
+      __syncthreads();
+      if (sg == 0 && idx < total) {
+        float t = part[0][ol];
+#pragma unroll
+        for (int g = 1; g < SG; ++g) t += part[g][ol];
+        dw[o] = accumulate ? dw[o] + t : t;
+      }
+      __syncthreads();
+    } else if (idx < total) {
+      dw[o] = accumulate ? dw[o] + acc : acc;
+    }
   }
 }
 
@@ -273,7 +310,7 @@ static int launch(const CUtensorMap& tdy, const CUtensorMap& tx, WParams& p, cud
   p.stages = stages;
   const int smem = 1024 + 512 + stages * stage_bytes;
   const int grid = p.items < num_sms() ? p.items : num_sms();
-  conv_wgrad_kernel<BN><<<grid, kThreads, smem, stream>>>(tdy, tx, p);
+  SY_CUDA(launch_pdl(conv_wgrad_kernel<BN>, dim3(grid), dim3(kThreads), (size_t)smem, stream, tdy, tx, p));
   return launch_status("conv_wgrad_kernel");
 }
 
@@ -341,8 +378,19 @@ extern "C" int sy_conv2d_wgrad_tc(const SyConvWgradDesc* d, sy_stream_t stream_)
   }
   if (lrc != SY_OK) return lrc;
   const long long total = (long long)dy.c * x.c * pl.taps;
-  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  wg::wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.partial, pl.bn, pl.m_tiles, pl.n_tiles, pl.taps, pl.ksplit, dy.c, x.c,
-                                                      d->dw, d->accumulate);
+  // split groups per output: enough threads to cover the GPU (~148 x 2048) and at least 8 splits per group
+  int sg = 1;
+  if (getenv("SY_WGRAD_SG1") == nullptr) {
+    while (sg < 8 && total * sg < 148LL * 2048 && pl.ksplit >= 16 * sg) sg *= 2;
+  }
+  const long long per_block = 256 / sg;
+  const long long want = (total + per_block - 1) / per_block;
+  const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+  switch (sg) {
+    case 8: SY_CUDA(launch_pdl(wg::wgrad_reduce_kernel<8>, dim3(blocks), dim3(256), 0, stream, (const float*)p.partial, pl.bn, pl.m_tiles, pl.n_tiles, pl.taps, pl.ksplit, (int)dy.c, (int)x.c, d->dw, (int)d->accumulate)); break;
+    case 4: SY_CUDA(launch_pdl(wg::wgrad_reduce_kernel<4>, dim3(blocks), dim3(256), 0, stream, (const float*)p.partial, pl.bn, pl.m_tiles, pl.n_tiles, pl.taps, pl.ksplit, (int)dy.c, (int)x.c, d->dw, (int)d->accumulate)); break;
+    case 2: SY_CUDA(launch_pdl(wg::wgrad_reduce_kernel<2>, dim3(blocks), dim3(256), 0, stream, (const float*)p.partial, pl.bn, pl.m_tiles, pl.n_tiles, pl.taps, pl.ksplit, (int)dy.c, (int)x.c, d->dw, (int)d->accumulate)); break;
+    default: SY_CUDA(launch_pdl(wg::wgrad_reduce_kernel<1>, dim3(blocks), dim3(256), 0, stream, (const float*)p.partial, pl.bn, pl.m_tiles, pl.n_tiles, pl.taps, pl.ksplit, (int)dy.c, (int)x.c, d->dw, (int)d->accumulate)); break;
+  }
   return launch_status("wgrad_reduce_kernel");
 }
