@@ -79,7 +79,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   constexpr int kTmemCols = 2 * BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   (void)lane;
-  pdl_launch_dependents();               // (launch_pdl) the next kernel on the stream may start its own prologue
 
   if (threadIdx.x == 5 * 32) {
     prefetch_tmap(&tmDY);
@@ -100,9 +99,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int hw = p.Ho * p.Wo;
-  // everything above touched only smem / TMEM / kernel parameters; from here on we read what the previous kernels wrote
-  // (and write the partial tiles, which may alias a workspace an earlier reduction is still reading)
-  pdl_wait();
 
   auto decode = [&](int item, int& m_tile, int& n_tile, int& tap, int& kb0, int& kb1) {
     const int ks = item % p.ksplit;
@@ -217,8 +213,6 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
                                                            int ksplit, int Cout, int Cin, float* dw, int accumulate) {
   constexpr int kOut = 256 / SG;                  // outputs per block pass
   __shared__ float part[SG][kOut];
-  pdl_launch_dependents();
-  pdl_wait();
   const int ol = (int)threadIdx.x % kOut, sg = (int)threadIdx.x / kOut;
   const long long total = (long long)Cout * Cin * taps;
   const int k0 = (int)((long long)ksplit * sg / SG), k1 = (int)((long long)ksplit * (sg + 1) / SG);
@@ -310,7 +304,7 @@ static int launch(const CUtensorMap& tdy, const CUtensorMap& tx, WParams& p, cud
   p.stages = stages;
   const int smem = 1024 + 512 + stages * stage_bytes;
   const int grid = p.items < num_sms() ? p.items : num_sms();
-  SY_CUDA(launch_pdl(conv_wgrad_kernel<BN>, dim3(grid), dim3(kThreads), (size_t)smem, stream, tdy, tx, p));
+  conv_wgrad_kernel<BN><<<grid, kThreads, smem, stream>>>(tdy, tx, p);
   return launch_status("conv_wgrad_kernel");
 }
 
@@ -387,10 +381,10 @@ extern "C" int sy_conv2d_wgrad_tc(const SyConvWgradDesc* d, sy_stream_t stream_)
   const long long want = (total + per_block - 1) / per_block;
   const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
   switch (sg) {
-    case 8: SY_CUDA(launch_pdl(wg::wgrad_reduce_kernel<8>, dim3(blocks), dim3(256), 0, stream, (const float*)p.partial, pl.bn, pl.m_tiles, pl.n_tiles, pl.taps, pl.ksplit, (int)dy.c, (int)x.c, d->dw, (int)d->accumulate)); break;
-    case 4: SY_CUDA(launch_pdl(wg::wgrad_reduce_kernel<4>, dim3(blocks), dim3(256), 0, stream, (const float*)p.partial, pl.bn, pl.m_tiles, pl.n_tiles, pl.taps, pl.ksplit, (int)dy.c, (int)x.c, d->dw, (int)d->accumulate)); break;
-    case 2: SY_CUDA(launch_pdl(wg::wgrad_reduce_kernel<2>, dim3(blocks), dim3(256), 0, stream, (const float*)p.partial, pl.bn, pl.m_tiles, pl.n_tiles, pl.taps, pl.ksplit, (int)dy.c, (int)x.c, d->dw, (int)d->accumulate)); break;
-    default: SY_CUDA(launch_pdl(wg::wgrad_reduce_kernel<1>, dim3(blocks), dim3(256), 0, stream, (const float*)p.partial, pl.bn, pl.m_tiles, pl.n_tiles, pl.taps, pl.ksplit, (int)dy.c, (int)x.c, d->dw, (int)d->accumulate)); break;
+    case 8: wg::wgrad_reduce_kernel<8><<<blocks, 256, 0, stream>>>(p.partial, pl.bn, pl.m_tiles, pl.n_tiles, pl.taps, pl.ksplit, dy.c, x.c, d->dw, d->accumulate); break;
+    case 4: wg::wgrad_reduce_kernel<4><<<blocks, 256, 0, stream>>>(p.partial, pl.bn, pl.m_tiles, pl.n_tiles, pl.taps, pl.ksplit, dy.c, x.c, d->dw, d->accumulate); break;
+    case 2: wg::wgrad_reduce_kernel<2><<<blocks, 256, 0, stream>>>(p.partial, pl.bn, pl.m_tiles, pl.n_tiles, pl.taps, pl.ksplit, dy.c, x.c, d->dw, d->accumulate); break;
+    default: wg::wgrad_reduce_kernel<1><<<blocks, 256, 0, stream>>>(p.partial, pl.bn, pl.m_tiles, pl.n_tiles, pl.taps, pl.ksplit, dy.c, x.c, d->dw, d->accumulate); break;
   }
   return launch_status("wgrad_reduce_kernel");
 }
