@@ -136,19 +136,23 @@ __global__ void __launch_bounds__(256) bn_act_bwd_finalize_kernel(const float* _
   // a lane owns at most ceil(296 / 32) = 10 rows per group: all loads first, then the sums in row order (one L2 round trip
   // per group instead of ten dependent ones)
   constexpr int kPerLane = (kBwdRowsPerGroup + 31) / 32;
-  for (int g = 0; g < 2; ++g) {
+  float v0[2][kPerLane], v1[2][kPerLane];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {                  // the loads of BOTH groups first (40 independent requests per lane)
     const int rb = g ? rows0 : 0, re = g ? rows0 + rows1 : rows0;
-    float v0[kPerLane], v1[kPerLane];
 #pragma unroll
     for (int j = 0; j < kPerLane; ++j) {
       const int r = rb + lane + 32 * j;
-      v0[j] = r < re ? __ldg(partials + (size_t)r * 2 * C + c) : 0.f;
-      v1[j] = r < re ? __ldg(partials + (size_t)r * 2 * C + C + c) : 0.f;
+      v0[g][j] = r < re ? __ldg(partials + (size_t)r * 2 * C + c) : 0.f;
+      v1[g][j] = r < re ? __ldg(partials + (size_t)r * 2 * C + C + c) : 0.f;
     }
+  }
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
 #pragma unroll
     for (int j = 0; j < kPerLane; ++j) {
-      s[g][0] += (double)v0[j];
-      s[g][1] += (double)v1[j];
+      s[g][0] += (double)v0[g][j];
+      s[g][1] += (double)v1[g][j];
     }
   }
 #pragma unroll

@@ -660,6 +660,132 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int j = 0; j < kAccSlabs; ++j) reduce_store(acc[j], pend_grp, pend_n0 + j * kSlabCols);
       pend_grp = -1;
     };
+    if constexpr (BN == 256) {
+      // ---- BN = 256: four slabs per tile.  Per-lane accumulators for every slab would need 64 registers with the row split
+      // above (32 lanes = 32 row classes); here a warp OWNS one slab (warp ew: slab ew >> 1, logical 16-byte chunks
+      // 4 * (ew & 1) .. +4 of its rows) and its lanes split the rows eight ways (lane = chunk-in-warp * 8 + row class; rows
+      // rc, rc + 8, ...: the 128B swizzle puts the eight row classes of one logical chunk into eight different bank groups, so
+      // the quarter-warp accesses are conflict-free).  16 accumulators per lane, kept across tiles like above; a flush
+      // combines the eight row classes with three halving shuffles.  The other six warps only keep the barrier protocol going
+      // for a slab, so consecutive slabs are handled by different warps and their arithmetic overlaps the next slab's
+      // loads.  (Per-slab full shuffle reductions held the epilogue of every BN = 256 RAW layer at ~1450 cycles per slab:
+      // profiles/r02_timeline_1x1_256_38x60_*.)
+      const int own_slab = ew >> 1;
+      const int jlog = (ew & 1) * 4 + (lane >> 3);            // logical chunk (8 columns) of the slab
+      const int rc = lane & 7;                                // row class
+      const uint32_t lane_off = (uint32_t)rc * 128u + ((((uint32_t)jlog) ^ (uint32_t)rc) << 4);
+      float a0[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a0[i] = 0.f;
+      int pgrp = -1, pn0 = 0;
+      // eight row classes -> one: recursive halving over lane bits 2, 1, 0; lane keeps 2 of the 16 values
+      auto reduce_store8 = [&](float (&a)[16], int grp, int n0v) {
+        float b8[8], c4[4], d2[2];
+        {
+          const bool up = (lane & 4) != 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float send = up ? a[i] : a[8 + i], keep = up ? a[8 + i] : a[i];
+            b8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+        }
+        {
+          const bool up = (lane & 2) != 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float send = up ? b8[i] : b8[4 + i], keep = up ? b8[4 + i] : b8[i];
+            c4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+        }
+        {
+          const bool up = (lane & 1) != 0;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float send = up ? c4[i] : c4[2 + i], keep = up ? c4[2 + i] : c4[i];
+            d2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+          }
+        }
+        // lane bits: 2 = sum | sumsq, 1 = columns 0-3 | 4-7 of the chunk, 0 = columns (0,1) | (2,3) of that half
+        const int kind = (lane >> 2) & 1;
+        const int col = n0v + own_slab * kSlabCols + jlog * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          if (col + i < p.Cout) sAcc[(grp * 2 + kind) * p.Cout + col + i] += d2[i];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = 0.f;
+      };
+      for (int tile = SY_T_FIRST; tile < SY_T_END; tile += SY_T_STEP) {
+        int n_tile, m_tile;
+        tile_nm(tile, n_tile, m_tile);
+        const int n0 = n_tile * BN;
+        int cut;
+        if constexpr (LIN) {
+          cut = min(max(p.gp - m_tile * kBlockM, 0), kBlockM);
+        } else {
+          cut = fdiv(m_tile, p.fd_per_img) >= p.split_n ? 0 : kBlockM;
+        }
+        const bool pure = (cut <= 0) || (cut >= kBlockM);
+        const int tgrp = cut <= 0 ? 1 : 0;
+        if (do_stats && pgrp >= 0 && (!pure || pgrp != tgrp || pn0 != n0)) {      // warp-uniform
+          reduce_store8(a0, pgrp, pn0);
+          pgrp = -1;
+        }
+        for (int slab = 0; slab < kSlabs; ++slab, sbuf ^= sflip) {
+          bar_staged_wait(sbuf, nbar);
+          tl_rec<TL>(p, tl_t, 5, 0, tile, slab);
+          if (!do_stats || slab != own_slab) {
+            bar_free_arrive(sbuf, nbar);
+            continue;
+          }
+          const uint32_t base = stage_base + (uint32_t)(sbuf * kSlabBytes) + lane_off;
+          if (pure) {
+            // two batches of eight rows (all sixteen chunks in registers at once spill at the 96-register budget): the
+            // second batch's loads are in flight while the first is accumulated; the tile is handed back after them
+            uint4 u[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) u[i] = lds128(base + (uint32_t)(h * 8 + i) * 1024u);       // rows rc + 8 (8 h + i)
+              if (h == 1) {
+                bar_free_arrive(sbuf, nbar);         // the values are in registers: the tile may be overwritten
+                tl_rec<TL>(p, tl_t, 5, 1, tile, slab);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float x8[8] = {bf16_lo(u[i].x), bf16_hi(u[i].x), bf16_lo(u[i].y), bf16_hi(u[i].y),
+                                     bf16_lo(u[i].z), bf16_hi(u[i].z), bf16_lo(u[i].w), bf16_hi(u[i].w)};
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { a0[c] += x8[c]; a0[8 + c] += x8[c] * x8[c]; }
+              }
+            }
+            pgrp = tgrp; pn0 = n0;
+          } else {
+            // the tile straddles the group boundary (at most one M tile per layer and N tile): one group after the other
+            // straight from shared memory, masked, reduced at once; the tile is handed back afterwards
+#pragma unroll 1
+            for (int grp = 0; grp < 2; ++grp) {
+              const int lo = grp ? cut : 0, hi = grp ? kBlockM : cut;
+#pragma unroll 4
+              for (int i = 0; i < 16; ++i) {
+                const int r = rc + 8 * i;
+                if (r >= lo && r < hi) {
+                  const uint4 v = lds128(base + (uint32_t)i * 1024u);
+                  const float x8[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
+                                       bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) { a0[c] += x8[c]; a0[8 + c] += x8[c] * x8[c]; }
+                }
+              }
+              reduce_store8(a0, grp, n0);
+            }
+            bar_free_arrive(sbuf, nbar);
+            tl_rec<TL>(p, tl_t, 5, 1, tile, slab);
+          }
+          tl_rec<TL>(p, tl_t, 5, 2, tile, slab);
+        }
+      }
+      if (do_stats && pgrp >= 0) reduce_store8(a0, pgrp, pn0);
+    } else {
     for (int tile = SY_T_FIRST; tile < SY_T_END; tile += SY_T_STEP) {
       int n_tile, m_tile;
         tile_nm(tile, n_tile, m_tile);
@@ -728,6 +854,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (do_stats) flush();
+    }   // BN != 256
   } else if (warp < 8) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
