@@ -95,7 +95,7 @@ struct Params {
   float unbias[2];          // cnt / (cnt - 1) of each group: biased -> unbiased variance for the running statistics
   float* ss;                // [2 (scale|shift)][2 groups][Cout]
   float* mi;                // optional [2 (mean|invstd)][2 groups][Cout] for the backward pass
-  unsigned int* sync;       // three counters (two grid barriers + exit ticket), zero between launches
+  unsigned int* sync;       // two sense-reversing grid barriers: {arrival count, generation} x 2; the counts are zero between launches
   // normalise + act (+ residual) pass done by this kernel after the statistics are final (nullptr: separate launch)
   __nv_bfloat16* ap_y; long long ap_y_pitch;
   const __nv_bfloat16* ap_res; long long ap_res_pitch;
@@ -760,26 +760,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             pgrp = tgrp; pn0 = n0;
           } else {
-            // the tile straddles the group boundary (at most one M tile per layer and N tile): one group after the other
-            // straight from shared memory, masked, reduced at once; the tile is handed back afterwards
-#pragma unroll 1
-            for (int grp = 0; grp < 2; ++grp) {
-              const int lo = grp ? cut : 0, hi = grp ? kBlockM : cut;
-#pragma unroll 4
-              for (int i = 0; i < 16; ++i) {
-                const int r = rc + 8 * i;
-                if (r >= lo && r < hi) {
-                  const uint4 v = lds128(base + (uint32_t)i * 1024u);
-                  const float x8[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
-                                       bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+            // the tile straddles the group boundary (at most one M tile per layer and N tile): same two batches, the rows
+            // below `cut` go to a0 (group 0), the others to a second accumulator set (group 1); both are reduced at once.
+            // (The tile is handed back after the loads like in the pure case: this CTA must not fall behind the others --
+            //  the whole grid waits for it at the BatchNorm barrier.)
+            float a1[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a1[i] = 0.f;
+            uint4 u[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) u[i] = lds128(base + (uint32_t)(h * 8 + i) * 1024u);
+              if (h == 1) {
+                bar_free_arrive(sbuf, nbar);
+                tl_rec<TL>(p, tl_t, 5, 1, tile, slab);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float x8[8] = {bf16_lo(u[i].x), bf16_hi(u[i].x), bf16_lo(u[i].y), bf16_hi(u[i].y),
+                                     bf16_lo(u[i].z), bf16_hi(u[i].z), bf16_lo(u[i].w), bf16_hi(u[i].w)};
+                if (rc + 8 * (h * 8 + i) < cut) {
 #pragma unroll
                   for (int c = 0; c < 8; ++c) { a0[c] += x8[c]; a0[8 + c] += x8[c] * x8[c]; }
+                } else {
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) { a1[c] += x8[c]; a1[8 + c] += x8[c] * x8[c]; }
                 }
               }
-              reduce_store8(a0, grp, n0);
             }
-            bar_free_arrive(sbuf, nbar);
-            tl_rec<TL>(p, tl_t, 5, 1, tile, slab);
+            reduce_store8(a0, 0, n0);
+            reduce_store8(a1, 1, n0);
           }
           tl_rec<TL>(p, tl_t, 5, 2, tile, slab);
         }
@@ -1072,15 +1083,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int c = et; c < p.Cout; c += kTailThreads)
         mine[c] = make_float4(sAcc[c], sAcc[p.Cout + c], sAcc[2 * p.Cout + c], sAcc[3 * p.Cout + c]);
       if (p.n_seg > 0) {
-        auto grid_barrier = [&](unsigned int* ctr) {    // all CTAs of the persistent grid are resident (1 per SM)
+        // Grid barrier (all CTAs of the persistent grid are resident, one per SM): sense reversing -- the LAST CTA to arrive
+        // zeroes the arrival count and then bumps the generation word the others spin on, so the counters re-arm themselves
+        // without a second round of atomics.  (The first version took an exit ticket after the barrier to find the CTA that
+        // may reset the count: 148 simultaneous atomics with return value on ONE address, ~4000 cycles for the last of them --
+        // the kernel tail of every train-mode conv waited ~1-2 us for it.)  The generation is read before this CTA arrives,
+        // i.e. before this launch's bump; launches that share a slot are ordered by the stream.
+        auto grid_barrier = [&](unsigned int* cnt_gen, unsigned int my_gen) {
           __threadfence();
           bar_stats_done();
           if (et == 0) {
-            atomicAdd(ctr, 1u);
-            while (ld_acquire_u32(ctr) < gridDim.x) __nanosleep(32);
+            const unsigned int old = atomicAdd(cnt_gen, 1u);
+            if (old == gridDim.x - 1) {
+              cnt_gen[0] = 0u;
+              __threadfence();
+              st_release_u32(cnt_gen + 1, my_gen + 1u);
+            } else {
+              while (ld_acquire_u32(cnt_gen + 1) == my_gen) __nanosleep(32);
+            }
           }
           bar_stats_done();
         };
+        unsigned int gen0 = 0u, gen1 = 0u;
+        if (et == 0) {
+          gen0 = ld_acquire_u32(&p.sync[1]);
+          if (p.ap_y != nullptr) gen1 = ld_acquire_u32(&p.sync[3]);
+        }
         if (et == 0) tl_rec<TL>(p, tl_epi, 4, 5, 0, 0);
         // This CTA finalizes channels [b*cpc, (b+1)*cpc), one warp per channel.  The BatchNorm parameters and running
         // statistics of the warp's first channel do not depend on the other CTAs: load them BEFORE the grid barrier (they
@@ -1100,12 +1128,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (sg.rvar) pre_rv = sg.rvar[cs];
           }
         }
-        grid_barrier(&p.sync[0]);
+        grid_barrier(&p.sync[0], gen0);
         if (et == 0) tl_rec<TL>(p, tl_epi, 4, 6, 0, 0);
-        // exit ticket (the last CTA past the barriers re-arms the counters): taken as early as possible -- right after the
-        // last grid barrier -- so that the atomic's round trip overlaps the finalize instead of ending the kernel
-        unsigned int ticket = 0xffffffffu;
-        if (et == 0 && p.ap_y == nullptr) ticket = atomicAdd(&p.sync[2], 1u);
         // one WARP per channel (no block barriers): lane l sums the partial rows l, l+32, ... in order, a fixed shuffle tree
         // combines the lanes (deterministic), lanes 0 / 1 finalize one statistics group each.
         for (int c = c_first; c < c_end; c += kTailThreads / 32) {
@@ -1182,7 +1206,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.ap_y != nullptr) {
           // ---- second grid barrier: scale/shift of every channel are published; normalise this CTA's own tiles,
           //      re-reading the raw bf16 values it just stored (L2 resident for all but the largest layers)
-          grid_barrier(&p.sync[1]);
+          grid_barrier(&p.sync[2], gen1);
           for (int i = et; i < p.Cout; i += kTailThreads)          // [2 (scale|shift)][2 groups][Cout] -> smem (over sAcc)
             reinterpret_cast<float4*>(sAcc)[i] = __ldcg(reinterpret_cast<const float4*>(p.ss) + i);
           bar_stats_done();
@@ -1254,15 +1278,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
               }
             }
-          }
-        }
-        if (et == 0) {
-          if (p.ap_y != nullptr) ticket = atomicAdd(&p.sync[2], 1u);
-          if (ticket == gridDim.x - 1) {            // every CTA is past both barriers: re-arm for the next launch
-            p.sync[0] = 0u;
-            p.sync[1] = 0u;
-            p.sync[2] = 0u;
-            __threadfence();
           }
         }
       }
