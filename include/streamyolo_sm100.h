@@ -94,8 +94,7 @@ typedef struct {
   float* scale_shift;    /* [2 (scale|shift)][2 groups][Cout]: y = x*scale + shift, ready when the kernel ends */
   float* mean_invstd;    /* optional [2 (mean|invstd)][2 groups][Cout]: the batch statistics themselves, saved for
                           * sy_bn_act_backward (NULL: not written) */
-  uint32_t* sync;        /* four zero-initialised words: {arrival count, generation} of two grid barriers; the kernel leaves the
-                          * counts at zero, the generations advance (any value is a valid start) */
+  uint32_t* sync;        /* four zero-initialised counters (grid barriers); the kernel leaves them at zero */
   /* With bn[]: optional normalise + act (+ residual) pass INSIDE the same launch (after a second grid barrier
    * every CTA re-reads the raw tiles it stored -- L2 resident -- and writes apply_y = act(y*scale+shift) (+ apply_res)).
    * apply_y.ptr == NULL: leave it to sy_bn_act_apply.  The *_group1_offset are element offsets added to the

@@ -95,7 +95,7 @@ struct Params {
   float unbias[2];          // cnt / (cnt - 1) of each group: biased -> unbiased variance for the running statistics
   float* ss;                // [2 (scale|shift)][2 groups][Cout]
   float* mi;                // optional [2 (mean|invstd)][2 groups][Cout] for the backward pass
-  unsigned int* sync;       // two sense-reversing grid barriers: {arrival count, generation} x 2; the counts are zero between launches
+  unsigned int* sync;       // three counters (two grid barriers + exit ticket), zero between launches
   // normalise + act (+ residual) pass done by this kernel after the statistics are final (nullptr: separate launch)
   __nv_bfloat16* ap_y; long long ap_y_pitch;
   const __nv_bfloat16* ap_res; long long ap_res_pitch;
@@ -660,143 +660,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int j = 0; j < kAccSlabs; ++j) reduce_store(acc[j], pend_grp, pend_n0 + j * kSlabCols);
       pend_grp = -1;
     };
-    if constexpr (BN == 256) {
-      // ---- BN = 256: four slabs per tile.  Per-lane accumulators for every slab would need 64 registers with the row split
-      // above (32 lanes = 32 row classes); here a warp OWNS one slab (warp ew: slab ew >> 1, logical 16-byte chunks
-      // 4 * (ew & 1) .. +4 of its rows) and its lanes split the rows eight ways (lane = chunk-in-warp * 8 + row class; rows
-      // rc, rc + 8, ...: the 128B swizzle puts the eight row classes of one logical chunk into eight different bank groups, so
-      // the quarter-warp accesses are conflict-free).  16 accumulators per lane, kept across tiles like above; a flush
-      // combines the eight row classes with three halving shuffles.  The other six warps only keep the barrier protocol going
-      // for a slab, so consecutive slabs are handled by different warps and their arithmetic overlaps the next slab's
-      // loads.  (Per-slab full shuffle reductions held the epilogue of every BN = 256 RAW layer at ~1450 cycles per slab:
-      // profiles/r02_timeline_1x1_256_38x60_*.)
-      const int own_slab = ew >> 1;
-      const int jlog = (ew & 1) * 4 + (lane >> 3);            // logical chunk (8 columns) of the slab
-      const int rc = lane & 7;                                // row class
-      const uint32_t lane_off = (uint32_t)rc * 128u + ((((uint32_t)jlog) ^ (uint32_t)rc) << 4);
-      float a0[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) a0[i] = 0.f;
-      int pgrp = -1, pn0 = 0;
-      // eight row classes -> one: recursive halving over lane bits 2, 1, 0; lane keeps 2 of the 16 values
-      auto reduce_store8 = [&](float (&a)[16], int grp, int n0v) {
-        float b8[8], c4[4], d2[2];
-        {
-          const bool up = (lane & 4) != 0;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float send = up ? a[i] : a[8 + i], keep = up ? a[8 + i] : a[i];
-            b8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-          }
-        }
-        {
-          const bool up = (lane & 2) != 0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float send = up ? b8[i] : b8[4 + i], keep = up ? b8[4 + i] : b8[i];
-            c4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-          }
-        }
-        {
-          const bool up = (lane & 1) != 0;
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const float send = up ? c4[i] : c4[2 + i], keep = up ? c4[2 + i] : c4[i];
-            d2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-          }
-        }
-        // lane bits: 2 = sum | sumsq, 1 = columns 0-3 | 4-7 of the chunk, 0 = columns (0,1) | (2,3) of that half
-        const int kind = (lane >> 2) & 1;
-        const int col = n0v + own_slab * kSlabCols + jlog * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2;
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-          if (col + i < p.Cout) sAcc[(grp * 2 + kind) * p.Cout + col + i] += d2[i];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a[i] = 0.f;
-      };
-      for (int tile = SY_T_FIRST; tile < SY_T_END; tile += SY_T_STEP) {
-        int n_tile, m_tile;
-        tile_nm(tile, n_tile, m_tile);
-        const int n0 = n_tile * BN;
-        int cut;
-        if constexpr (LIN) {
-          cut = min(max(p.gp - m_tile * kBlockM, 0), kBlockM);
-        } else {
-          cut = fdiv(m_tile, p.fd_per_img) >= p.split_n ? 0 : kBlockM;
-        }
-        const bool pure = (cut <= 0) || (cut >= kBlockM);
-        const int tgrp = cut <= 0 ? 1 : 0;
-        if (do_stats && pgrp >= 0 && (!pure || pgrp != tgrp || pn0 != n0)) {      // warp-uniform
-          reduce_store8(a0, pgrp, pn0);
-          pgrp = -1;
-        }
-        for (int slab = 0; slab < kSlabs; ++slab, sbuf ^= sflip) {
-          bar_staged_wait(sbuf, nbar);
-          tl_rec<TL>(p, tl_t, 5, 0, tile, slab);
-          if (!do_stats || slab != own_slab) {
-            bar_free_arrive(sbuf, nbar);
-            continue;
-          }
-          const uint32_t base = stage_base + (uint32_t)(sbuf * kSlabBytes) + lane_off;
-          if (pure) {
-            // two batches of eight rows (all sixteen chunks in registers at once spill at the 96-register budget): the
-            // second batch's loads are in flight while the first is accumulated; the tile is handed back after them
-            uint4 u[8];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) u[i] = lds128(base + (uint32_t)(h * 8 + i) * 1024u);       // rows rc + 8 (8 h + i)
-              if (h == 1) {
-                bar_free_arrive(sbuf, nbar);         // the values are in registers: the tile may be overwritten
-                tl_rec<TL>(p, tl_t, 5, 1, tile, slab);
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float x8[8] = {bf16_lo(u[i].x), bf16_hi(u[i].x), bf16_lo(u[i].y), bf16_hi(u[i].y),
-                                     bf16_lo(u[i].z), bf16_hi(u[i].z), bf16_lo(u[i].w), bf16_hi(u[i].w)};
-#pragma unroll
-                for (int c = 0; c < 8; ++c) { a0[c] += x8[c]; a0[8 + c] += x8[c] * x8[c]; }
-              }
-            }
-            pgrp = tgrp; pn0 = n0;
-          } else {
-            // the tile straddles the group boundary (at most one M tile per layer and N tile): same two batches, the rows
-            // below `cut` go to a0 (group 0), the others to a second accumulator set (group 1); both are reduced at once.
-            // (The tile is handed back after the loads like in the pure case: this CTA must not fall behind the others --
-            //  the whole grid waits for it at the BatchNorm barrier.)
-            float a1[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) a1[i] = 0.f;
-            uint4 u[8];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) u[i] = lds128(base + (uint32_t)(h * 8 + i) * 1024u);
-              if (h == 1) {
-                bar_free_arrive(sbuf, nbar);
-                tl_rec<TL>(p, tl_t, 5, 1, tile, slab);
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float x8[8] = {bf16_lo(u[i].x), bf16_hi(u[i].x), bf16_lo(u[i].y), bf16_hi(u[i].y),
-                                     bf16_lo(u[i].z), bf16_hi(u[i].z), bf16_lo(u[i].w), bf16_hi(u[i].w)};
-                if (rc + 8 * (h * 8 + i) < cut) {
-#pragma unroll
-                  for (int c = 0; c < 8; ++c) { a0[c] += x8[c]; a0[8 + c] += x8[c] * x8[c]; }
-                } else {
-#pragma unroll
-                  for (int c = 0; c < 8; ++c) { a1[c] += x8[c]; a1[8 + c] += x8[c] * x8[c]; }
-                }
-              }
-            }
-            reduce_store8(a0, 0, n0);
-            reduce_store8(a1, 1, n0);
-          }
-          tl_rec<TL>(p, tl_t, 5, 2, tile, slab);
-        }
-      }
-      if (do_stats && pgrp >= 0) reduce_store8(a0, pgrp, pn0);
-    } else {
     for (int tile = SY_T_FIRST; tile < SY_T_END; tile += SY_T_STEP) {
       int n_tile, m_tile;
         tile_nm(tile, n_tile, m_tile);
@@ -865,7 +728,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (do_stats) flush();
-    }   // BN != 256
   } else if (warp < 8) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
@@ -1083,32 +945,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int c = et; c < p.Cout; c += kTailThreads)
         mine[c] = make_float4(sAcc[c], sAcc[p.Cout + c], sAcc[2 * p.Cout + c], sAcc[3 * p.Cout + c]);
       if (p.n_seg > 0) {
-        // Grid barrier (all CTAs of the persistent grid are resident, one per SM): sense reversing -- the LAST CTA to arrive
-        // zeroes the arrival count and then bumps the generation word the others spin on, so the counters re-arm themselves
-        // without a second round of atomics.  (The first version took an exit ticket after the barrier to find the CTA that
-        // may reset the count: 148 simultaneous atomics with return value on ONE address, ~4000 cycles for the last of them --
-        // the kernel tail of every train-mode conv waited ~1-2 us for it.)  The generation is read before this CTA arrives,
-        // i.e. before this launch's bump; launches that share a slot are ordered by the stream.
-        auto grid_barrier = [&](unsigned int* cnt_gen, unsigned int my_gen) {
+        auto grid_barrier = [&](unsigned int* ctr) {    // all CTAs of the persistent grid are resident (1 per SM)
           __threadfence();
           bar_stats_done();
           if (et == 0) {
-            const unsigned int old = atomicAdd(cnt_gen, 1u);
-            if (old == gridDim.x - 1) {
-              cnt_gen[0] = 0u;
-              __threadfence();
-              st_release_u32(cnt_gen + 1, my_gen + 1u);
-            } else {
-              while (ld_acquire_u32(cnt_gen + 1) == my_gen) __nanosleep(32);
-            }
+            atomicAdd(ctr, 1u);
+            while (ld_acquire_u32(ctr) < gridDim.x) __nanosleep(32);
           }
           bar_stats_done();
         };
-        unsigned int gen0 = 0u, gen1 = 0u;
-        if (et == 0) {
-          gen0 = ld_acquire_u32(&p.sync[1]);
-          if (p.ap_y != nullptr) gen1 = ld_acquire_u32(&p.sync[3]);
-        }
         if (et == 0) tl_rec<TL>(p, tl_epi, 4, 5, 0, 0);
         // This CTA finalizes channels [b*cpc, (b+1)*cpc), one warp per channel.  The BatchNorm parameters and running
         // statistics of the warp's first channel do not depend on the other CTAs: load them BEFORE the grid barrier (they
@@ -1128,8 +973,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (sg.rvar) pre_rv = sg.rvar[cs];
           }
         }
-        grid_barrier(&p.sync[0], gen0);
+        grid_barrier(&p.sync[0]);
         if (et == 0) tl_rec<TL>(p, tl_epi, 4, 6, 0, 0);
+        // exit ticket (the last CTA past the barriers re-arms the counters): taken as early as possible -- right after the
+        // last grid barrier -- so that the atomic's round trip overlaps the finalize instead of ending the kernel
+        unsigned int ticket = 0xffffffffu;
+        if (et == 0 && p.ap_y == nullptr) ticket = atomicAdd(&p.sync[2], 1u);
         // one WARP per channel (no block barriers): lane l sums the partial rows l, l+32, ... in order, a fixed shuffle tree
         // combines the lanes (deterministic), lanes 0 / 1 finalize one statistics group each.
         for (int c = c_first; c < c_end; c += kTailThreads / 32) {
@@ -1206,7 +1055,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.ap_y != nullptr) {
           // ---- second grid barrier: scale/shift of every channel are published; normalise this CTA's own tiles,
           //      re-reading the raw bf16 values it just stored (L2 resident for all but the largest layers)
-          grid_barrier(&p.sync[2], gen1);
+          grid_barrier(&p.sync[1]);
           for (int i = et; i < p.Cout; i += kTailThreads)          // [2 (scale|shift)][2 groups][Cout] -> smem (over sAcc)
             reinterpret_cast<float4*>(sAcc)[i] = __ldcg(reinterpret_cast<const float4*>(p.ss) + i);
           bar_stats_done();
@@ -1278,6 +1127,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
               }
             }
+          }
+        }
+        if (et == 0) {
+          if (p.ap_y != nullptr) ticket = atomicAdd(&p.sync[2], 1u);
+          if (ticket == gridDim.x - 1) {            // every CTA is past both barriers: re-arm for the next launch
+            p.sync[0] = 0u;
+            p.sync[1] = 0u;
+            p.sync[2] = 0u;
+            __threadfence();
           }
         }
       }
