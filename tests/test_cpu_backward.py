@@ -291,3 +291,48 @@ def test_pipe_head_is_tal_head_without_trend_weights(monkeypatch):
     assert TALHead(80, 0.25).num_classes == 80          # any class count constructs (generic head kernel; tal_head.py:27)
     with pytest.raises(NotImplementedError):
         TALHead(1000)
+
+
+def test_tape_gradient_regions_first_write_accumulate_and_zero_fill(monkeypatch):
+    """The bookkeeping behind the memset-free gradient arena (backward.Tape): first write vs accumulate, reads of regions
+    nobody wrote (zero-filled on the spot), partly written regions (completed with zeros, then accumulated), deferred
+    shortcut gradients (handed to an exact-match consumer, materialised by any other access).  The network itself never
+    takes the zero-fill / partial paths; this drives them directly on a NaN-poisoned arena."""
+    from streamyolo_b200.ops import View
+    emul_ops.install(monkeypatch, exact=True)
+    monkeypatch.setattr(backward, "POISON", True)
+    T = backward.Tape(torch.device("cpu"))
+    act = View(torch.zeros((4, 3, 5, 16)))
+    other = View(torch.zeros((4, 3, 5, 8)))
+    T.rec(t="copy", src=act, dst=other)
+    T.prepare_grads()
+    g = T.g(act)
+    assert torch.isnan(g.torch()).all()                          # poisoned, nothing written yet
+    one = View(torch.ones((2, 3, 5, 4)))
+    # first write to a sub-rectangle, then an accumulate on the same rectangle
+    T.accumulate(one, act.imgs(0, 2).ch(0, 4))
+    T.accumulate(one, act.imgs(0, 2).ch(0, 4))
+    assert (g.torch()[0:2, :, :, 0:4] == 2).all() and torch.isnan(g.torch()[2:]).all()
+    # a read of a region that is only partly written: the rest becomes zero, the written part is kept
+    r = T.gread(act.imgs(0, 4).ch(0, 8))
+    assert (r.torch()[0:2, :, :, 0:4] == 2).all() and (r.torch()[2:4] == 0).all() and (r.torch()[0:2, :, :, 4:8] == 0).all()
+    assert torch.isnan(g.torch()[:, :, :, 8:]).all()
+    # first() on a partly covered region completes it with zeros and asks for accumulation
+    assert T.first(act.imgs(0, 4).ch(4, 8)) is False
+    assert (g.torch()[:, :, :, 8:12] == 0).all() and torch.isnan(g.torch()[:, :, :, 12:]).all()
+    # a fresh region: first() says "write"
+    assert T.first(act.imgs(0, 4).ch(12, 4)) is True
+    # deferred shortcut: exact-match consumer takes it, nothing is copied
+    T2 = backward.Tape(torch.device("cpu"))
+    T2.rec(t="copy", src=act, dst=other)
+    T2.prepare_grads()
+    src = View(torch.full((4, 3, 5, 8), 3.0))
+    T2.defer(src, other)
+    assert torch.isnan(T2.g(other).torch()).all()                 # still untouched
+    assert T2.take_pending(other) is src and T2.first(other) is True
+    # ... and any other access materialises it (copy), a second contribution then accumulates
+    T2.defer(src, act.ch(0, 8))
+    got = T2.gread(act.ch(0, 4))
+    assert (got.torch() == 3).all() and (T2.g(act).torch()[:, :, :, 0:8] == 3).all()
+    T2.defer(src, act.ch(0, 8))
+    assert (T2.g(act).torch()[:, :, :, 0:8] == 6).all() and not any(T2.pending.values())
