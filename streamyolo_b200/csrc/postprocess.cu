@@ -83,21 +83,73 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsArgs q) {
     removed[j] = 0;
   }
   __syncthreads();
-  // ---- 4. greedy suppression in score order
-  for (int i = 0; i < n; ++i) {
-    if (!removed[i]) {                                     // uniform: every thread reads the same flag after the barrier
-      const float ix1 = BX[i * 4], iy1 = BX[i * 4 + 1], ix2 = BX[i * 4 + 2], iy2 = BX[i * 4 + 3];
-      const float iarea = (ix2 - ix1) * (iy2 - iy1);
-      const int ic = CL[i];
-      for (int j = i + 1 + tid; j < n; j += kNmsThreads) {
-        if (removed[j] || (!q.class_agnostic && CL[j] != ic)) continue;
-        const float xx1 = fmaxf(ix1, BX[j * 4]), yy1 = fmaxf(iy1, BX[j * 4 + 1]);
-        const float xx2 = fminf(ix2, BX[j * 4 + 2]), yy2 = fminf(iy2, BX[j * 4 + 3]);
-        const float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
-        const float inter = w * h;
-        const float jarea = (BX[j * 4 + 2] - BX[j * 4]) * (BX[j * 4 + 3] - BX[j * 4 + 1]);
-        const float ovr = inter / (iarea + jarea - inter);
-        if (ovr > q.nms_thre) removed[j] = 1;
+  // ---- 4. greedy suppression in score order, 32 candidates at a time.  (One block-wide barrier per candidate -- the first
+  //         version -- cost ~0.25 ms for 2000 candidates; now two barriers per 32.)
+  //   (a) warp 0 settles the chunk among its own members: lane l owns candidate c0 + l; for i = 0..31 in order, if candidate
+  //       i is still alive, the later lanes of the same class test their box against it (the box of i comes by shuffle);
+  //   (b) all threads apply the chunk's survivors to the candidates behind the chunk.
+  //   Same decisions as the sequential loop: a candidate is removed iff a kept earlier candidate of its class overlaps it.
+  __shared__ float s_kbox[32][4];
+  __shared__ float s_karea[32];
+  __shared__ int s_kcls[32];
+  __shared__ int s_nk;
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    if (tid < 32) {
+      const int j = c0 + tid;
+      const bool in = j < n;
+      float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+      int cl = -1;
+      bool alive = false;
+      if (in) {
+        x1 = BX[j * 4]; y1 = BX[j * 4 + 1]; x2 = BX[j * 4 + 2]; y2 = BX[j * 4 + 3];
+        cl = CL[j];
+        alive = removed[j] == 0;
+      }
+      const float area = (x2 - x1) * (y2 - y1);
+      for (int i = 0; i < 32; ++i) {
+        const unsigned live = __ballot_sync(0xffffffffu, alive);
+        if (!((live >> i) & 1u)) continue;                   // candidate i was removed (or lies past n): uniform
+        const float ix1 = __shfl_sync(0xffffffffu, x1, i), iy1 = __shfl_sync(0xffffffffu, y1, i);
+        const float ix2 = __shfl_sync(0xffffffffu, x2, i), iy2 = __shfl_sync(0xffffffffu, y2, i);
+        const float iarea = __shfl_sync(0xffffffffu, area, i);
+        const int ic = __shfl_sync(0xffffffffu, cl, i);
+        if (alive && tid > i && (q.class_agnostic || cl == ic)) {
+          const float xx1 = fmaxf(ix1, x1), yy1 = fmaxf(iy1, y1);
+          const float xx2 = fminf(ix2, x2), yy2 = fminf(iy2, y2);
+          const float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
+          const float inter = w * h;
+          const float ovr = inter / (iarea + area - inter);
+          if (ovr > q.nms_thre) alive = false;
+        }
+      }
+      if (in && !alive) removed[j] = 1;
+      // survivors of the chunk, compacted (order irrelevant for step (b))
+      const unsigned live = __ballot_sync(0xffffffffu, alive);
+      if (alive) {
+        const int k = __popc(live & ((1u << tid) - 1u));
+        s_kbox[k][0] = x1; s_kbox[k][1] = y1; s_kbox[k][2] = x2; s_kbox[k][3] = y2;
+        s_karea[k] = area;
+        s_kcls[k] = cl;
+      }
+      if (tid == 0) s_nk = __popc(live);
+    }
+    __syncthreads();
+    const int nk = s_nk;
+    if (nk > 0) {
+      for (int j = c0 + 32 + tid; j < n; j += kNmsThreads) {
+        if (removed[j]) continue;
+        const float x1 = BX[j * 4], y1 = BX[j * 4 + 1], x2 = BX[j * 4 + 2], y2 = BX[j * 4 + 3];
+        const float jarea = (x2 - x1) * (y2 - y1);
+        const int cl = CL[j];
+        for (int k = 0; k < nk; ++k) {
+          if (!q.class_agnostic && s_kcls[k] != cl) continue;
+          const float xx1 = fmaxf(s_kbox[k][0], x1), yy1 = fmaxf(s_kbox[k][1], y1);
+          const float xx2 = fminf(s_kbox[k][2], x2), yy2 = fminf(s_kbox[k][3], y2);
+          const float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
+          const float inter = w * h;
+          const float ovr = inter / (s_karea[k] + jarea - inter);
+          if (ovr > q.nms_thre) { removed[j] = 1; break; }
+        }
       }
     }
     __syncthreads();
