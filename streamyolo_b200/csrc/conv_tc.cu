@@ -33,6 +33,7 @@
 // Replaces the cuDNN conv + ATen BN/SiLU triplet behind [yolox] BaseConv
 // (/root/reference/exps/model/darknet.py:115-165, dfp_pafpn.py:33-105, tal_head.py:55-104).
 #include <cuda.h>
+#include <stdio.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -1199,6 +1200,10 @@ static int pick_bn(int cout, int m_tiles, int kblocks) {
   if (const char* e = getenv("SY_CONV_BN")) {            // tuning / test aid: force the tile width
     const int v = atoi(e);
     if (v == 64 || v == 128 || v == 256) return v;
+  }
+  if (const char* e = getenv("SY_BN128_RULE")) {         // tuning aid "max_m_tiles,max_kblocks": short-K wide layers on few tiles
+    int mt = 0, kb = 0;                                  // take BN = 128 (their epilogue, not the main loop, sets the time)
+    if (sscanf(e, "%d,%d", &mt, &kb) == 2 && cout >= 256 && m_tiles <= mt && kblocks <= kb) return 128;
   }
   const int cands[3] = {256, 128, 64};
   const double kbc[3] = {665.0, 515.0, 560.0};

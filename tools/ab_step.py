@@ -42,6 +42,11 @@ SETTINGS = [
     ("raw arena 20 MB", {"SY_RAW_ARENA_MB": "20"}, 0),
     ("raw arena 60 MB", {"SY_RAW_ARENA_MB": "60"}, 0),
     ("raw arena 80 MB", {"SY_RAW_ARENA_MB": "80"}, 0),
+    ("bn128 rule 300,4", {"SY_BN128_RULE": "300,4"}, 0),
+    ("bn128 rule 300,8", {"SY_BN128_RULE": "300,8"}, 0),
+    ("bn128 rule 300,16", {"SY_BN128_RULE": "300,16"}, 0),
+    ("bn128 rule 600,8", {"SY_BN128_RULE": "600,8"}, 0),
+    ("bn128 rule 1200,4", {"SY_BN128_RULE": "1200,4"}, 0),
     ("raw arena off (no L2 window)", {"SY_RAW_ARENA_MB": "0"}, 0),
     ("halo off", {"SY_CONV_A": "off"}, 0),
     ("halo forced", {"SY_CONV_A": "halo"}, 0),
@@ -67,7 +72,7 @@ SETTINGS = [
 ]
 if len(sys.argv) > 3:
     SETTINGS = [s for s in SETTINGS if any(k in s[0] for k in sys.argv[3].split(","))]
-SWITCHES = ("SY_APPLY_HINTS", "SY_HEAD_PT", "SY_PAIR_APPLY", "SY_RAW_ARENA_MB", "SY_CONV_TEAM", "SY_CONV_PAIR", "SY_DBG_SKIP_APPLY", "SY_CONV_TILES", "SY_PDL", "SY_APPLY", "SY_APPLY_CAP", "SY_STAGE_TILES", "SY_APPLY_CARVEOUT", "SY_CONV_DEBUG", "SY_CONV_A")
+SWITCHES = ("SY_BN128_RULE", "SY_APPLY_HINTS", "SY_HEAD_PT", "SY_PAIR_APPLY", "SY_RAW_ARENA_MB", "SY_CONV_TEAM", "SY_CONV_PAIR", "SY_DBG_SKIP_APPLY", "SY_CONV_TILES", "SY_PDL", "SY_APPLY", "SY_APPLY_CAP", "SY_STAGE_TILES", "SY_APPLY_CARVEOUT", "SY_CONV_DEBUG", "SY_CONV_A")
 
 
 def measure(label, env, fuse_mb, steps=20, warmup=4):
