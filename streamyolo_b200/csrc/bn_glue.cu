@@ -172,21 +172,23 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const flo
 }
 
 // PyTorch legacy "nearest": src = min((int)floorf(dst * scale), in - 1), scale = (float)in / out
+// One block pass per output row (n, oy): the source row is resolved once, the threads walk (ox, chunk) with 32-bit index
+// arithmetic (the first version did five 64-bit divisions per 16-byte chunk and was bound by them, not by memory).
 __global__ void upsample_nearest_kernel(const __nv_bfloat16* __restrict__ x, long long xp, int N, int Hi, int Wi,
                                         __nv_bfloat16* y, long long yp, int Ho, int Wo, int C) {
   const int G = C / 8;
   const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
-  const long long total = (long long)N * Ho * Wo * G;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % G);
-    const long long pix = idx / G;
-    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho);
-    const int n = (int)(pix / ((long long)Wo * Ho));
+  const int rows = N * Ho, per_row = Wo * G;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / Ho, oy = row - n * Ho;
     const int iy = min((int)floorf(__fmul_rn((float)oy, sh)), Hi - 1);
-    const int ix = min((int)floorf(__fmul_rn((float)ox, sw)), Wi - 1);
-    const uint4 v = *reinterpret_cast<const uint4*>(x + (((long long)n * Hi + iy) * Wi + ix) * xp + g * 8);
-    *reinterpret_cast<uint4*>(y + pix * yp + g * 8) = v;
+    const __nv_bfloat16* src = x + ((long long)n * Hi + iy) * Wi * xp;
+    __nv_bfloat16* dst = y + (long long)row * Wo * yp;
+    for (int e = threadIdx.x; e < per_row; e += blockDim.x) {
+      const int ox = e / G, g = e - ox * G;
+      const int ix = min((int)floorf(__fmul_rn((float)ox, sw)), Wi - 1);
+      *reinterpret_cast<uint4*>(dst + (long long)ox * yp + g * 8) = *reinterpret_cast<const uint4*>(src + (long long)ix * xp + g * 8);
+    }
   }
 }
 
@@ -274,15 +276,28 @@ __global__ void spp_maxpool_direct_kernel(const __nv_bfloat16* __restrict__ x, l
   }
 }
 
+// A thread keeps its 16-byte channel chunk and walks the pixels (no per-element index division), four copies in flight.
 __global__ void copy_kernel(const __nv_bfloat16* __restrict__ x, long long xp, __nv_bfloat16* y, long long yp,
                             long long npix, int C) {
   const int G = C / 8;
-  const long long total = npix * G;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % G);
-    const long long pix = idx / G;
-    *reinterpret_cast<uint4*>(y + pix * yp + g * 8) = *reinterpret_cast<const uint4*>(x + pix * xp + g * 8);
+  if (G <= (int)blockDim.x) {
+    const int ppb = (int)blockDim.x / G;
+    const int prow = (int)threadIdx.x / G, g = (int)threadIdx.x - prow * G;
+    if (prow >= ppb) return;
+    const long long step = (long long)gridDim.x * ppb;
+    for (long long pix0 = (long long)blockIdx.x * ppb + prow; pix0 < npix; pix0 += 4 * step) {
+      uint4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (pix0 + j * step < npix) v[j] = *reinterpret_cast<const uint4*>(x + (pix0 + j * step) * xp + g * 8);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (pix0 + j * step < npix) *reinterpret_cast<uint4*>(y + (pix0 + j * step) * yp + g * 8) = v[j];
+    }
+  } else {                                        // more than 2048 channels: one pixel per block pass
+    for (long long pix = blockIdx.x; pix < npix; pix += gridDim.x)
+      for (int g = threadIdx.x; g < G; g += blockDim.x)
+        *reinterpret_cast<uint4*>(y + pix * yp + g * 8) = *reinterpret_cast<const uint4*>(x + pix * xp + g * 8);
   }
 }
 
@@ -370,8 +385,10 @@ extern "C" int sy_upsample_nearest(SyTensor x, SyTensor y, sy_stream_t stream_) 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SY_REQUIRE(view_ok(x) && view_ok(y) && x.n == y.n && x.c == y.c, SY_EINVAL, "upsample: bad views");
   const long long total = (long long)y.n * y.h * y.w * (y.c / 8);
-  upsample_nearest_kernel<<<grid_for(total, 256), 256, 0, stream>>>(CBF(x.ptr), x.pitch, x.n, x.h, x.w, BF(y.ptr),
-                                                                    y.pitch, y.h, y.w, x.c);
+  (void)total;
+  const int up_rows = y.n * y.h;
+  upsample_nearest_kernel<<<up_rows < 148 * 8 ? up_rows : 148 * 8, 256, 0, stream>>>(CBF(x.ptr), x.pitch, x.n, x.h, x.w, BF(y.ptr),
+                                                                                     y.pitch, y.h, y.w, x.c);
   return launch_status("upsample_nearest_kernel");
 }
 
@@ -397,6 +414,11 @@ extern "C" int sy_copy(SyTensor x, SyTensor y, sy_stream_t stream_) {
   SY_REQUIRE(view_ok(x) && view_ok(y) && x.n == y.n && x.h == y.h && x.w == y.w && x.c == y.c, SY_EINVAL,
              "copy: view mismatch");
   const long long npix = (long long)x.n * x.h * x.w;
-  copy_kernel<<<grid_for(npix * (x.c / 8), 256), 256, 0, stream>>>(CBF(x.ptr), x.pitch, BF(y.ptr), y.pitch, npix, x.c);
+  {
+    const int G = x.c / 8, ppb = G <= 256 ? 256 / G : 1;
+    const long long want = (npix + 4LL * ppb - 1) / (4LL * ppb);
+    copy_kernel<<<(int)(want < 1 ? 1 : (want < 148 * 8 ? want : 148 * 8)), 256, 0, stream>>>(CBF(x.ptr), x.pitch, BF(y.ptr), y.pitch,
+                                                                                          npix, x.c);
+  }
   return launch_status("copy_kernel");
 }

@@ -20,17 +20,20 @@ __device__ __forceinline__ void unpack8g(const uint4& v, float* f) {
 // D[n, 2i, 2j, :] = g[n, i, j, :], zero elsewhere; D is [n, H, W, c] with H in {2h-1, 2h}, W in {2w-1, 2w}
 __global__ void dilate2_kernel(const __nv_bfloat16* g, long long gp, int N, int h, int w, __nv_bfloat16* D, long long dp, int H,
                                int W, int C) {
+  // one block pass per output row (n, y); threads walk (x, chunk) with 32-bit index arithmetic
   const int G = C / 8;
-  const long long total = (long long)N * H * W * G;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(idx % G);
-    const long long pix = idx / G;
-    const int x = (int)(pix % W), y = (int)((pix / W) % H);
-    const int n = (int)(pix / ((long long)W * H));
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (((x | y) & 1) == 0 && (y >> 1) < h && (x >> 1) < w)
-      v = *reinterpret_cast<const uint4*>(g + (((long long)n * h + (y >> 1)) * w + (x >> 1)) * gp + cg * 8);
-    *reinterpret_cast<uint4*>(D + pix * dp + cg * 8) = v;
+  const int rows = N * H, per_row = W * G;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / H, y = row - n * H;
+    const bool yrow = ((y & 1) == 0) && ((y >> 1) < h);
+    const __nv_bfloat16* src = g + ((long long)n * h + (y >> 1)) * w * gp;
+    __nv_bfloat16* dst = D + (long long)row * W * dp;
+    for (int e = threadIdx.x; e < per_row; e += blockDim.x) {
+      const int x = e / G, cg = e - x * G;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (yrow && (x & 1) == 0 && (x >> 1) < w) v = *reinterpret_cast<const uint4*>(src + (long long)(x >> 1) * gp + cg * 8);
+      *reinterpret_cast<uint4*>(dst + (long long)x * dp + cg * 8) = v;
+    }
   }
 }
 
@@ -175,17 +178,37 @@ __global__ void head_pred_bwd_finalize_kernel(const float* __restrict__ partial,
 // y += x (bf16, fp32 add, one rounding): gradient accumulation where a tensor feeds several consumers (residual
 // shortcuts, FPN features read by two branches, the DFP fusion's "+ cur")
 __global__ void add_kernel(const __nv_bfloat16* x, long long xp, __nv_bfloat16* y, long long yp, long long npix, int C) {
+  // a thread keeps its 16-byte channel chunk and walks the pixels (no per-element index division), two pairs in flight
   const int G = C / 8;
-  const long long total = npix * G;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(idx % G);
-    const long long pix = idx / G;
+  auto add8 = [](const uint4& xa, const uint4& ya) {
     float a[8], b[8];
-    unpack8g(*reinterpret_cast<const uint4*>(x + pix * xp + cg * 8), a);
-    unpack8g(*reinterpret_cast<const uint4*>(y + pix * yp + cg * 8), b);
-    *reinterpret_cast<uint4*>(y + pix * yp + cg * 8) =
-        make_uint4(pack_bf16(a[0] + b[0], a[1] + b[1]), pack_bf16(a[2] + b[2], a[3] + b[3]), pack_bf16(a[4] + b[4], a[5] + b[5]),
-                   pack_bf16(a[6] + b[6], a[7] + b[7]));
+    unpack8g(xa, a);
+    unpack8g(ya, b);
+    return make_uint4(pack_bf16(a[0] + b[0], a[1] + b[1]), pack_bf16(a[2] + b[2], a[3] + b[3]), pack_bf16(a[4] + b[4], a[5] + b[5]),
+                      pack_bf16(a[6] + b[6], a[7] + b[7]));
+  };
+  if (G <= (int)blockDim.x) {
+    const int ppb = (int)blockDim.x / G;
+    const int prow = (int)threadIdx.x / G, g = (int)threadIdx.x - prow * G;
+    if (prow >= ppb) return;
+    const long long step = (long long)gridDim.x * ppb;
+    for (long long pix0 = (long long)blockIdx.x * ppb + prow; pix0 < npix; pix0 += 2 * step) {
+      uint4 xa[2], ya[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (pix0 + j * step < npix) {
+          xa[j] = *reinterpret_cast<const uint4*>(x + (pix0 + j * step) * xp + g * 8);
+          ya[j] = *reinterpret_cast<const uint4*>(y + (pix0 + j * step) * yp + g * 8);
+        }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (pix0 + j * step < npix) *reinterpret_cast<uint4*>(y + (pix0 + j * step) * yp + g * 8) = add8(xa[j], ya[j]);
+    }
+  } else {
+    for (long long pix = blockIdx.x; pix < npix; pix += gridDim.x)
+      for (int g = threadIdx.x; g < G; g += blockDim.x)
+        *reinterpret_cast<uint4*>(y + pix * yp + g * 8) =
+            add8(*reinterpret_cast<const uint4*>(x + pix * xp + g * 8), *reinterpret_cast<const uint4*>(y + pix * yp + g * 8));
   }
 }
 

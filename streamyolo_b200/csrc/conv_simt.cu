@@ -73,34 +73,35 @@ __global__ void conv_simt_kernel(const SimtConvParams p) {
 // whose inner extent runs past a 96-byte pixel were measured 2.6x slower: 354 vs 133 us for the stem conv), so that
 // the stem is a 3x1 conv with three 64-deep K blocks for the tensor-core kernel.  thread = (pixel, tap | pad).
 // Input pixels are rounded to bf16.
+// One block pass per output row (image, oy); threads walk (ox, tap) with shifts only (the first version resolved
+// (tap, ox, oy, image, frame) from a flat index with five 64-bit divisions per thread).
 __global__ void focus_pack_kernel(const float* __restrict__ x, int B, int in_ch, int H, int W, int frames,
                                   __nv_bfloat16* y, long long y_pitch) {
   const int Ho = H / 2, Wo = W / 2;
-  const long long total = (long long)frames * B * Ho * Wo * 4;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int s = (int)(idx & 3);
-    const long long pix = idx >> 2;
-    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho);
-    const int n = (int)(pix / ((long long)Wo * Ho));
-    const int frame = n / B, b = n % B;
-    const int fx = ox + s - 1;
-    float v[12];
-    if (s < 3 && fx >= 0 && fx < Wo) {
-      const float* xb = x + ((long long)b * in_ch + frame * 3) * H * W;
+  const int rows = frames * B * Ho;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / Ho, oy = row - n * Ho;
+    const int frame = n / B, b = n - frame * B;
+    const float* xb = x + ((long long)b * in_ch + frame * 3) * H * W;
+    for (int e = threadIdx.x; e < Wo * 4; e += blockDim.x) {
+      const int s = e & 3, ox = e >> 2;
+      const int fx = ox + s - 1;
+      float v[12];
+      if (s < 3 && fx >= 0 && fx < Wo) {
 #pragma unroll
-      for (int fc = 0; fc < 12; ++fc) {
-        const int qd = fc / 3, c = fc % 3;
-        const int dy = qd & 1, dx = qd >> 1;   // TL(0,0) BL(1,0) TR(0,1) BR(1,1)
-        v[fc] = __ldg(xb + ((long long)c * H + (2 * oy + dy)) * W + 2 * fx + dx);
+        for (int fc = 0; fc < 12; ++fc) {
+          const int qd = fc / 3, c = fc % 3;
+          const int dy = qd & 1, dx = qd >> 1;   // TL(0,0) BL(1,0) TR(0,1) BR(1,1)
+          v[fc] = __ldg(xb + ((long long)c * H + (2 * oy + dy)) * W + 2 * fx + dx);
+        }
+      } else {
+#pragma unroll
+        for (int fc = 0; fc < 12; ++fc) v[fc] = 0.f;
       }
-    } else {
-#pragma unroll
-      for (int fc = 0; fc < 12; ++fc) v[fc] = 0.f;
+      uint4* dst = reinterpret_cast<uint4*>(y + ((long long)row * Wo + ox) * y_pitch + s * 16);
+      dst[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), 0u, 0u);
     }
-    uint4* dst = reinterpret_cast<uint4*>(y + pix * y_pitch + s * 16);
-    dst[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-    dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), 0u, 0u);
   }
 }
 
@@ -185,8 +186,8 @@ extern "C" int sy_focus_pack(const float* x, int32_t b, int32_t in_ch, int32_t h
              "focus_pack: h=%d w=%d must be even, frames=%d in_ch=%d", h, w_px, frames, in_ch);
   SY_REQUIRE(y.n == frames * b && y.h == h / 2 && y.w == w_px / 2 && y.c == 64, SY_EINVAL,
              "focus_pack: output view must be [frames*b, h/2, w/2, 64]");
-  const long long total = (long long)y.n * y.h * y.w * 4;
-  const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+  const int rows = y.n * y.h;                                   // one block pass per output row
+  const int blocks = rows < 148 * 16 ? rows : 148 * 16;
   focus_pack_kernel<<<blocks, 256, 0, stream>>>(x, b, in_ch, h, w_px, frames, reinterpret_cast<__nv_bfloat16*>(y.ptr),
                                                 y.pitch);
   return launch_status("focus_pack_kernel");

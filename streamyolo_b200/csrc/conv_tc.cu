@@ -1194,7 +1194,15 @@ static void pick_patch(int ho, int wo, int* th, int* tw) {
 // (register statistics, two slabs in flight) and ~1400 at BN = 256, but refitting the heuristic to those numbers moved the
 // 256->256 1x1 layers to BN = 128 and made them SLOWER in-graph (36 -> 44 us at 16x75x120, profiles/r02_layers_in_graph_*):
 // the round-1 constant stays.
-static double epi_cycles_per_slab(int bn) { (void)bn; return 1900.0; }
+static double epi_cycles_per_slab(int bn) {
+  if (const char* e = getenv("SY_EPI_CYCLES")) {          // tuning aid "c64,c128,c256": the heuristics' epilogue cost per slab
+    int c64 = 0, c128 = 0, c256 = 0;
+    if (sscanf(e, "%d,%d,%d", &c64, &c128, &c256) == 3) return (double)(bn == 64 ? c64 : (bn == 128 ? c128 : c256));
+  }
+  // BN = 256: 1000 (measured on the whole step, profiles/r02_ab_epi_cycles.txt: 5.432 -> 5.405 ms; it makes the 1x1 layers with
+  // 448 - 704 input channels "main-loop bound": one staging tile, pair mode); BN <= 128: lower values were slower
+  return bn == 256 ? 1000.0 : 1900.0;
+}
 
 static int pick_bn(int cout, int m_tiles, int kblocks) {
   if (const char* e = getenv("SY_CONV_BN")) {            // tuning / test aid: force the tile width

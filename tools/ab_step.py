@@ -47,6 +47,14 @@ SETTINGS = [
     ("bn128 rule 300,16", {"SY_BN128_RULE": "300,16"}, 0),
     ("bn128 rule 600,8", {"SY_BN128_RULE": "600,8"}, 0),
     ("bn128 rule 1200,4", {"SY_BN128_RULE": "1200,4"}, 0),
+    ("epi cycles 1500,1900,1900", {"SY_EPI_CYCLES": "1500,1900,1900"}, 0),
+    ("epi cycles 1200,1900,1900", {"SY_EPI_CYCLES": "1200,1900,1900"}, 0),
+    ("epi cycles 1900,1400,1900", {"SY_EPI_CYCLES": "1900,1400,1900"}, 0),
+    ("epi cycles 1900,1900,1450", {"SY_EPI_CYCLES": "1900,1900,1450"}, 0),
+    ("epi cycles 1900,1900,1000", {"SY_EPI_CYCLES": "1900,1900,1000"}, 0),
+    ("epi cycles 1900,1900,700", {"SY_EPI_CYCLES": "1900,1900,700"}, 0),
+    ("epi cycles 1900,1900,400", {"SY_EPI_CYCLES": "1900,1900,400"}, 0),
+    ("epi cycles 1900,1900,100", {"SY_EPI_CYCLES": "1900,1900,100"}, 0),
     ("raw arena off (no L2 window)", {"SY_RAW_ARENA_MB": "0"}, 0),
     ("halo off", {"SY_CONV_A": "off"}, 0),
     ("halo forced", {"SY_CONV_A": "halo"}, 0),
@@ -72,7 +80,7 @@ SETTINGS = [
 ]
 if len(sys.argv) > 3:
     SETTINGS = [s for s in SETTINGS if any(k in s[0] for k in sys.argv[3].split(","))]
-SWITCHES = ("SY_BN128_RULE", "SY_APPLY_HINTS", "SY_HEAD_PT", "SY_PAIR_APPLY", "SY_RAW_ARENA_MB", "SY_CONV_TEAM", "SY_CONV_PAIR", "SY_DBG_SKIP_APPLY", "SY_CONV_TILES", "SY_PDL", "SY_APPLY", "SY_APPLY_CAP", "SY_STAGE_TILES", "SY_APPLY_CARVEOUT", "SY_CONV_DEBUG", "SY_CONV_A")
+SWITCHES = ("SY_EPI_CYCLES", "SY_BN128_RULE", "SY_APPLY_HINTS", "SY_HEAD_PT", "SY_PAIR_APPLY", "SY_RAW_ARENA_MB", "SY_CONV_TEAM", "SY_CONV_PAIR", "SY_DBG_SKIP_APPLY", "SY_CONV_TILES", "SY_PDL", "SY_APPLY", "SY_APPLY_CAP", "SY_STAGE_TILES", "SY_APPLY_CARVEOUT", "SY_CONV_DEBUG", "SY_CONV_A")
 
 
 def measure(label, env, fuse_mb, steps=20, warmup=4):
