@@ -163,3 +163,24 @@ def test_conv_plan_query_without_gpu(monkeypatch):
     assert p["mode"] == 0 and p["rounds"] == 3
     with pytest.raises(RuntimeError):
         ops.conv2d_plan(1, 8, 8, 8, 8, 5, 1)
+
+
+def test_pack_batch_tile_table():
+    """Host side of sy_pack_conv_weights_batch: items are laid out in work TILES (64 output x 32 input channels; 64 outputs of a
+    stem item), `begin` is the prefix sum of sy_pack_item_tiles (a host-only entry point: no GPU needed)."""
+    import torch
+    from streamyolo_b200 import ops
+    lib = ops.load_library()
+    assert lib.sy_pack_item_tiles(64, 32, 0) == 1 and lib.sy_pack_item_tiles(65, 33, 1) == 4
+    assert lib.sy_pack_item_tiles(512, 256, 0) == 8 * 8 and lib.sy_pack_item_tiles(80, 12, 2) == 2
+    pb = ops.PackBatch(torch.device("cpu"))
+    shapes = [((96, 80, 3, 3), 0), ((96, 80, 3, 3), 1), ((16, 12, 3, 3), 2), ((520, 264, 1, 1), 0)]
+    want = 0
+    for shape, mode in shapes:
+        w = torch.zeros(shape)
+        o, i, kh, kw = shape
+        out = torch.zeros((o, kh * kw, i) if mode == 0 else ((i, kh * kw, o) if mode == 1 else (o, kh, 64)), dtype=torch.bfloat16)
+        pb.add(w, out, mode, out_pitch=o if mode == 1 else 0)
+        assert pb.items[-1].begin == want
+        want += lib.sy_pack_item_tiles(o, i, mode)
+    assert pb.total == want == 2 * 3 + 2 * 3 + 1 + 9 * 9
