@@ -81,14 +81,16 @@ struct HeadBwdArgs {
 };
 
 __global__ void head_pred_bwd_data_kernel(const HeadBwdArgs q) {
+  // a thread keeps its 8-channel chunk (its 2 x NO x 8 weights stay in L1) and walks the pixels; 32-bit index arithmetic
   const int G = q.C / 8;
-  const long long npix = (long long)q.B * q.H * q.W;
-  const long long total = npix * G;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(idx % G);
-    const long long pix = idx / G;
-    const int b = (int)(pix / ((long long)q.H * q.W));
-    const long long a = (long long)b * q.a_total + q.anchor_offset + (pix - (long long)b * q.H * q.W);
+  const int HW = q.H * q.W;
+  const int npix = q.B * HW;
+  const int ppb = (int)blockDim.x / G;             // G <= 256 (C <= 2048, checked by the host)
+  const int prow = (int)threadIdx.x / G, cg = (int)threadIdx.x - prow * G;
+  if (prow >= ppb) return;
+  for (int pix = blockIdx.x * ppb + prow; pix < npix; pix += gridDim.x * ppb) {
+    const int b = pix / HW;
+    const long long a = (long long)b * q.a_total + q.anchor_offset + (pix - b * HW);
     const float* g = q.g + a * q.NO;
     float dr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int o = 0; o < q.NO; ++o) {
@@ -98,9 +100,9 @@ __global__ void head_pred_bwd_data_kernel(const HeadBwdArgs q) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) dst[i] += gv * wrow[cg * 8 + i];
     }
-    *reinterpret_cast<uint4*>(q.drf + pix * q.drfp + cg * 8) =
+    *reinterpret_cast<uint4*>(q.drf + (long long)pix * q.drfp + cg * 8) =
         make_uint4(pack_bf16(dr[0], dr[1]), pack_bf16(dr[2], dr[3]), pack_bf16(dr[4], dr[5]), pack_bf16(dr[6], dr[7]));
-    *reinterpret_cast<uint4*>(q.dcf + pix * q.dcfp + cg * 8) =
+    *reinterpret_cast<uint4*>(q.dcf + (long long)pix * q.dcfp + cg * 8) =
         make_uint4(pack_bf16(dc[0], dc[1]), pack_bf16(dc[2], dc[3]), pack_bf16(dc[4], dc[5]), pack_bf16(dc[6], dc[7]));
   }
 }
@@ -360,6 +362,8 @@ extern "C" int sy_head_pred_backward(const SyHeadPredBwdDesc* d, sy_stream_t str
   q.dcf = reinterpret_cast<__nv_bfloat16*>(d->d_cls_feat.ptr); q.dcfp = d->d_cls_feat.pitch;
   q.drf = reinterpret_cast<__nv_bfloat16*>(d->d_reg_feat.ptr); q.drfp = d->d_reg_feat.pitch;
   q.partial = d->partials;
+  SY_REQUIRE(f.c % 8 == 0 && f.c <= 2048 && (long long)f.n * f.h * f.w < (1ll << 31), SY_EINVAL,
+             "head_pred_backward: %d channels / %d x %d x %d pixels unsupported", f.c, f.n, f.h, f.w);
   const long long total = (long long)f.n * f.h * f.w * (f.c / 8);
   head_pred_bwd_data_kernel<<<grid_cap(total, 256), 256, 0, stream>>>(q);
   const size_t wsm = sizeof(float) * kHeadBwdPix * q.NO;
