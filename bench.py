@@ -681,7 +681,7 @@ def main():
                             "algorithmic_flop_per_step": B * gf * 1e9,
                             # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the family's 114 launches of
                             # one step (ncu launch list of this command, profiles/r02_launch_summary_final.txt; StreamYOLO-l, 8 pairs only)
-                            "traffic": (50.6e6 if (args.model, B) == ("l", 8) else None), "traffic_unit": "bytes/launch (ncu launch list profiles/r02_launch_summary_final.txt: 5767 MB DRAM read+written over the 114 conv launches)",
+                            "traffic": (50.5e6 if (args.model, B) == ("l", 8) else None), "traffic_unit": "bytes/launch (ncu launch list profiles/r02_launch_summary_final.txt: 5761 MB DRAM read+written over the 114 conv launches)",
                             "how": "the step's conv launches re-issued alone, in order, as one CUDA graph on the step's own buffers; "
                                    "CUDA events around the replay, best of 5; ncu launch list of the step: profiles/"}
     if not args.no_cpu_baseline:
