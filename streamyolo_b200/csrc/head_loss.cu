@@ -788,7 +788,7 @@ extern "C" int sy_tal_loss(const SyTalLossDesc* d, sy_stream_t stream_) {
   const size_t row_bytes = 2 * sizeof(float) * (size_t)A;       // candidate values + anchor indices
   SY_REQUIRE(row_bytes <= 200 * 1024, SY_EINVAL, "tal_loss: %d anchors exceed the shared-memory row", A);
   if (row_bytes > 48 * 1024) SY_CUDA(cudaFuncSetAttribute(k_dynk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes));
-  k_dynk<<<dim3(L, B), 256, row_bytes, stream>>>(w.ngt, w.cand, w.iou, w.cost, A, L, w.cnt, w.match);
+  k_dynk<<<dim3(L, B), 1024, row_bytes, stream>>>(w.ngt, w.cand, w.iou, w.cost, A, L, w.cnt, w.match);
   LossArgs q{};
   q.outputs = d->outputs; q.origin = d->origin; q.fut = d->labels_fut; q.ngt = w.ngt; q.tal = w.tal;
   q.iou_m = w.iou; q.cost_m = w.cost; q.cnt = w.cnt; q.match = w.match; q.lv = lv; q.A = A; q.L = L; q.NC = NC;
