@@ -1,11 +1,12 @@
 // Implicit-GEMM convolution on the Blackwell tensor cores (sm_100a).
 //
-//   M = output pixels (a TH x TW spatial patch of one image, <= 128 rows)
+//   M = 128 output pixels: 128 consecutive pixels of the flattened (n, oh, ow) space ("linear" tiles, the default), a
+//       TH x TW patch of one image, or a 16 x 8 patch with its input halo (template parameter AM, see below)
 //   N = output channels (BN = 64/128/256 per tile, chosen per layer)
 //   K = taps * Cin, walked as (tap, 64-channel block)
 //
-// Operand movement is im2col-free: for every (tap, channel block) ONE 4-D TMA load
-// brings the shifted input patch [TH][TW][64ch] straight from the NHWC tensor into a
+// Operand movement is im2col-free: for every (tap, channel block) ONE TMA load (im2col mode for
+// linear tiles, tiled mode for patches) brings the shifted input pixels [128][64ch] straight from the NHWC tensor into a
 // 128B-swizzled shared-memory tile (out-of-bounds = zero padding = the conv padding;
 // stride-2 convs use the tensor map's element strides), and one 3-D TMA load brings the
 // [BN][64] weight slab.  A single elected thread issues tcgen05.mma (M=128, N=BN, K=16)
@@ -13,14 +14,13 @@
 // buffered), so the epilogue of tile i overlaps the main loop of tile i+1.
 //
 // Warp roles (640 threads, persistent CTA, one per SM):
-//   warps 0-7   convert: TMEM -> registers -> epilogue math -> bf16 -> swizzled smem staging tile
-//   warps 8-15  statistics: per-channel (sum, sum of squares) of the staged tile (overlaps the next slab's conversion)
-//   warp 16 TMA store   warp 17 TMEM alloc + weight (B) loads   warp 18 activation (A) loads   warp 19 MMA issuer
-//   warps 4-11 epilogue, per 64-column slab of the accumulator: TMEM -> registers -> (raw | folded BN +
-//             SiLU + residual) -> bf16 -> 128B-swizzled shared staging tile -> ONE 4-D TMA store (the
-//             tensor map clips the patch to the image and the channel slice) while the eight warps
-//             reduce the slab's per-channel (sum, sum of squares) from shared memory with 16-byte loads
-//             and a recursive-halving shuffle (16 shuffles for 16 values)
+//   warps 0-7   convert: per 64-column slab of the accumulator TMEM -> registers -> (raw | folded BN + SiLU + residual) ->
+//               bf16 -> 128B-swizzled shared staging tile (team mode: the two warpgroups take alternate slabs)
+//   warps 8-15  statistics: per-channel (sum, sum of squares) of the staged tile in per-lane register accumulators that persist
+//               across slabs and tiles (overlaps the next slab's conversion)
+//   warp 16 TMA store (one 4-D store per slab; the tensor map clips the tile to the tensor / the channel slice)
+//   warp 17 TMEM alloc + weight (B) loads   warp 18 activation (A) loads   warp 19 MMA issuer
+// PAIR = true: the grid is launched as clusters of two CTAs sharing ONE tcgen05.mma.cta_group::2 stream (see below).
 //
 // Train-mode BatchNorm is folded into this kernel as far as the grid-wide dependency allows:
 // every CTA accumulates per-channel (sum, sum of squares) of the values it stored, per
